@@ -1,0 +1,127 @@
+/* oracle/crt_oracle.h -- TEST INFRASTRUCTURE ONLY (the parity checker).
+ *
+ * A CPU restatement, in plain C, of the reference's composite modulate -> noise ->
+ * demodulate hot path.  It is NOT part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg may load it, and only as
+ * the checker.  The product library (ntsc-crt_b200/lib/libcrt_b200_*.so) never links or
+ * loads it and has no CPU fallback.
+ *
+ * Pinning: the reference ships no tests or golden vectors of its own (SURVEY.md
+ * section 4), so this restatement is pinned against the reference ITSELF, compiled
+ * unmodified into oracle/_ref/libref_*.so (oracle/Makefile) -- see
+ * tests/test_oracle_vs_ref.py -- and against the md5 anchors recorded in BASELINE.md.
+ *
+ * Unlike the reference (compile-time polymorphic via CRT_SYSTEM, crt_core.h:39-59)
+ * the oracle is runtime-polymorphic: one library, a system descriptor per variant.
+ * It is also decomposed the way the CUDA pipeline is (noise pass / sync pre-pass /
+ * per-line filter + resample) so every intermediate table the kernels exchange can
+ * be compared, not just the final image.
+ */
+#ifndef CRT_ORACLE_H
+#define CRT_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCRT_SYS_NTSC 0 /* crt_core.h:30 */
+#define OCRT_SYS_NES  1 /* crt_core.h:31 */
+#define OCRT_SYS_VHS  5 /* crt_core.h:35 */
+
+#define OCRT_MAX_VPER 3
+#define OCRT_PAD      2048 /* slack after analog/inp for the reference's over-reads */
+
+/* Everything the reference derives from macros (crt_ntsc.h:25-109, crt_nes.h:30-130,
+ * crt_ntscvhs.h:25-131) plus the coefficients its init code computes once
+ * (crt_core.c:263-289, crt_ntsc.c:95-106). */
+typedef struct ocrt_sys {
+    int system, chroma_pattern;
+    int hres, vres, input_size;
+    int top, bot, lines;
+    int cc_vper;
+    int hsync_window, vsync_window, hsync_thresh, vsync_thresh;
+    int sync_beg, bw_beg, cb_beg, av_beg, av_len, burst_len;
+    int white_level, burst_level, black_level, blank_level, sync_level;
+    int vhs_noise;              /* crt_ntscvhs.h:29 */
+    int nes_vsync_end;          /* PPUpx2pos(327), crt_nes.c:91 */
+    /* decoder equaliser: lf, hf, g[3] for Y, I, Q (crt_core.c:278-280) */
+    int eq[3][5];
+    /* encoder band-limit coefficients c for Y, I, Q (crt_ntsc.c:142-146) */
+    int iir_c[3];
+} ocrt_sys;
+
+/* Mirrors the caller-visible part of struct CRT (crt_core.h:74-92). */
+typedef struct ocrt_monitor {
+    signed char *analog; /* input_size + OCRT_PAD, owned */
+    signed char *inp;    /* input_size + OCRT_PAD, owned */
+    int outw, outh, out_format;
+    unsigned char *out;  /* caller-owned */
+    int hue, brightness, contrast, saturation;
+    int black_point, white_point;
+    int scanlines, blend;
+    unsigned v_fac;
+    int ccf[OCRT_MAX_VPER][4];
+    int hsync, vsync, rn;
+} ocrt_monitor;
+
+/* struct NTSC_SETTINGS of the RGB systems (crt_ntsc.h:111-124, crt_ntscvhs.h:133-147) */
+typedef struct ocrt_rgb_source {
+    const unsigned char *data;
+    int format, w, h, raw, as_color, field, frame, hue, xoffset, yoffset;
+    int do_aberration; /* VHS only */
+} ocrt_rgb_source;
+
+/* struct NTSC_SETTINGS of the NES system (crt_nes.h:132-143) */
+typedef struct ocrt_nes_source {
+    const unsigned short *data;
+    int w, h;
+    int dot_crawl_offset, hue, xoffset, yoffset;
+    int field_initialized;
+} ocrt_nes_source;
+
+/* glibc TYPE_3 rand() replica (the VHS variant draws from libc rand(),
+ * crt_core.c:344-351, crt_ntscvhs.c:206; glibc 2.39 stdlib/random_r.c) */
+typedef struct ocrt_rand {
+    unsigned r[31];
+    int f, b;
+} ocrt_rand;
+
+/* what the sync pre-pass decides for one decoded scanline (crt_core.c:409-479) */
+typedef struct ocrt_line {
+    int skip;       /* crt_core.c:431 */
+    int beg, end;   /* output rows, crt_core.c:428-432 */
+    int hsync;      /* after this line's search, crt_core.c:446 */
+    int pos;        /* xpos + ypos * hres, crt_core.c:452-454 */
+    int wave[4];    /* crt_core.c:476-479 */
+} ocrt_line;
+
+const ocrt_sys *ocrt_system(int system, int chroma_pattern);
+
+void ocrt_sincos14(int *s, int *c, int n);
+int  ocrt_bpp(int format);
+
+void ocrt_rand_seed(ocrt_rand *g, unsigned seed);
+int  ocrt_rand_next(ocrt_rand *g);
+
+int  ocrt_monitor_create(const ocrt_sys *sys, ocrt_monitor *m, int w, int h, int f, unsigned char *out);
+void ocrt_monitor_destroy(ocrt_monitor *m);
+void ocrt_monitor_reset(ocrt_monitor *m);
+
+/* crt_modulate */
+void ocrt_encode_rgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src, ocrt_rand *g);
+void ocrt_encode_nes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_nes_source *src);
+
+/* crt_demodulate, and its three stages on their own */
+void ocrt_decode(const ocrt_sys *sys, ocrt_monitor *m, int noise, ocrt_rand *g);
+void ocrt_noise_pass(const ocrt_sys *sys, ocrt_monitor *m, int noise, ocrt_rand *g);
+int  ocrt_sync_pass(const ocrt_sys *sys, ocrt_monitor *m, ocrt_line *table /* [lines] */);
+void ocrt_line_pass(const ocrt_sys *sys, ocrt_monitor *m, const ocrt_line *table, int first, int count);
+
+/* LCG jump-ahead of the noise generator: (mul, add) such that n steps of
+ * rn = 214019 * rn + 140327895 (crt_core.c:359) equal rn * mul + add (mod 2^32). */
+void ocrt_lcg_jump(unsigned n, unsigned *mul, unsigned *add);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,235 @@
+"""Pin the oracle (oracle/crt_oracle.c) against the reference itself.
+
+The reference has no tests or golden vectors, so the pin is the
+UNMODIFIED reference compiled into oracle/_ref/libref_*.so by oracle/Makefile.  Every
+case drives both through the same call sequence and compares analog / inp / out / ccf /
+hsync / vsync / rn bit for bit after every call.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import support as S
+from ntsc_crt_b200 import layout
+
+pytestmark = pytest.mark.skipif(not S.have_ref(), reason="oracle/_ref not built")
+
+
+def pair(variant, outw, outh, fmt=layout.PIX_BGRA, seed=1):
+    ref = S.RefEngine(variant, outw, outh, fmt, seed=seed)
+    ora = S.OracleEngine(variant, outw, outh, fmt, seed=seed)
+    return ref, ora
+
+
+def both(ref, ora, fn):
+    fn(ref)
+    fn(ora)
+
+
+def check(ref, ora, what):
+    S.assert_same_state(ref.state(), ora.state(), what)
+
+
+def test_struct_layout_matches_reference():
+    for variant in ("ntsc", "vhs", "nes", "nes_p0"):
+        spec = layout.system_spec(variant)
+        lib = C.CDLL(S.ref_path(variant))
+        assert lib.ref_sizeof_crt() == C.sizeof(layout.crt_struct(spec)), variant
+        assert lib.ref_sizeof_settings() == C.sizeof(layout.settings_struct(spec)), variant
+        g = (C.c_int * 20)()
+        lib.ref_geometry(g)
+        assert list(g)[:12] == [spec.hres, spec.vres, spec.input_size, spec.top, spec.bot,
+                                spec.vper, 4, spec.sync_beg, spec.bw_beg, spec.cb_beg,
+                                spec.av_beg, spec.av_len], variant
+        o = (C.c_int * 19)()
+        lib.ref_crt_offsets(o)
+        CRT = layout.crt_struct(spec)
+        names = ["analog", "inp", "outw", "outh", "out_format", "out", "hue", "brightness",
+                 "contrast", "saturation", "black_point", "white_point", "scanlines", "blend",
+                 "v_fac", "ccf", "hsync", "vsync", "rn"]
+        assert list(o) == [getattr(CRT, n).offset for n in names], variant
+
+
+def test_sincos_and_bpp():
+    lib = layout.bind_crt_api(C.CDLL(S.ref_path("ntsc")), layout.system_spec("ntsc"))
+    ora = S.oracle_lib()
+    s1, c1, s2, c2 = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    for n in list(range(-20000, 40000, 7)) + [0, 4095, 4096, 8191, 8192, 12288, 16383, 16384]:
+        lib.crt_sincos14(C.byref(s1), C.byref(c1), n)
+        ora.ocrt_sincos14(C.byref(s2), C.byref(c2), n)
+        assert (s1.value, c1.value) == (s2.value, c2.value), n
+    for f in range(-2, 9):
+        assert lib.crt_bpp4fmt(f) == ora.ocrt_bpp(f) == layout.bpp4fmt(f)
+
+
+def test_rand_replica_matches_glibc():
+    lib = C.CDLL(S.ref_path("vhs"))
+    lib.ref_srand.argtypes = [C.c_uint]
+    ora = S.oracle_lib()
+    g = S._ORand()
+    for seed in (1, 0, 42, 2**31 + 5, 0xFFFFFFFF):
+        lib.ref_srand(seed)
+        ora.ocrt_rand_seed(C.byref(g), seed)
+        for _ in range(2000):
+            assert lib.ref_rand() == ora.ocrt_rand_next(C.byref(g))
+
+
+def test_system_coefficients():
+    """eq / iir constants quoted in SURVEY.md 8a (probed from the compiled reference)."""
+    ora = S.oracle_lib()
+    nt = ora.ocrt_system(0, 1).contents
+    assert [list(r) for r in nt.eq] == [[42156, 79824, 65536, 8192, 9175],
+                                        [2252, 32636, 65536, 65536, 1311],
+                                        [2252, 28248, 65536, 65536, 0]]
+    assert list(nt.iir_c) == [1233, 574, 232]
+    assert list(ora.ocrt_system(5, 1).contents.iir_c) == [987, 262, 262]
+
+
+@pytest.mark.parametrize("progressive", [True, False])
+def test_ntsc_cli_sequence_config1(progressive):
+    """config 1: 256x240 in, noise 0 -> 832x624 and 256x240 (crt_main.c:221-255)."""
+    img = S.lcg_image(256, 240)
+    for outw, outh in ((832, 624), (256, 240)):
+        ref, ora = pair("ntsc", outw, outh)
+        both(ref, ora, lambda e: S.cli_sequence(e, img, 0, progressive, format=layout.PIX_BGRA))
+        check(ref, ora, "cfg1 %dx%d p=%d" % (outw, outh, progressive))
+
+
+def test_ntsc_every_call_config2():
+    """config 2: 832x624 interlaced colour, compare after every single call."""
+    img = S.rand_image(832, 624, seed=7)
+    ref, ora = pair("ntsc", 832, 624)
+    both(ref, ora, lambda e: e.set(blend=1, scanlines=1))
+    f, fr = 0, 0
+    for it in range(8):
+        both(ref, ora, lambda e: e.modulate(img, format=layout.PIX_BGRA, as_color=1, field=f, frame=fr))
+        check(ref, ora, "mod %d" % it)
+        both(ref, ora, lambda e: e.demodulate(0))
+        check(ref, ora, "demod %d" % it)
+        f ^= 1
+        if it % 2 == 1:
+            fr ^= 1
+
+
+@pytest.mark.parametrize("noise", [12, 24, 255])
+def test_ntsc_noise(noise):
+    img = S.bars_image(640, 480)
+    ref, ora = pair("ntsc", 640, 480)
+    both(ref, ora, lambda e: e.set(blend=0, scanlines=1))
+    for it in range(6):
+        both(ref, ora, lambda e: e.modulate(img, format=layout.PIX_BGRA, as_color=1, field=it & 1,
+                                            frame=(it >> 1) & 1))
+        both(ref, ora, lambda e: e.demodulate(noise))
+        check(ref, ora, "noise %d call %d" % (noise, it))
+
+
+@pytest.mark.parametrize("fmt", range(6))
+def test_ntsc_pixel_formats(fmt):
+    rgb = S.rand_image(320, 200, bpp=3, seed=fmt)
+    img = S.pack_rgb(rgb, fmt)
+    ref, ora = pair("ntsc", 400, 300, fmt)
+    both(ref, ora, lambda e: e.set(blend=1, scanlines=0))
+    for it in range(3):
+        both(ref, ora, lambda e: e.modulate(img, format=fmt, as_color=1, field=it & 1, frame=0))
+        both(ref, ora, lambda e: e.demodulate(5))
+        check(ref, ora, "fmt %d call %d" % (fmt, it))
+
+
+def test_ntsc_knobs_raw_mono_offsets():
+    img = S.bars_image(300, 200)
+    ref, ora = pair("ntsc", 512, 448)
+    both(ref, ora, lambda e: e.set(hue=37, brightness=9, contrast=200, saturation=14,
+                                   black_point=3, white_point=90, blend=0, scanlines=1))
+    cases = [dict(raw=1, as_color=1, hue=20, xoffset=8, yoffset=2),
+             dict(raw=0, as_color=0, hue=0, xoffset=0, yoffset=0),
+             dict(raw=1, as_color=1, hue=350, xoffset=4, yoffset=1),
+             dict(raw=0, as_color=1, hue=90, xoffset=0, yoffset=0)]
+    for it, kw in enumerate(cases * 2):
+        both(ref, ora, lambda e: e.modulate(img, format=layout.PIX_BGRA, field=it & 1,
+                                            frame=(it >> 1) & 1, **kw))
+        both(ref, ora, lambda e: e.demodulate(3 * it))
+        check(ref, ora, "knobs %d" % it)
+    both(ref, ora, lambda e: e.set(hue=-45, saturation=31, contrast=255, brightness=-20))
+    both(ref, ora, lambda e: e.demodulate(0))
+    check(ref, ora, "negative hue")
+
+
+def test_ntsc_unknown_format_is_silent_noop():
+    img = S.rand_image(64, 48)
+    ref, ora = pair("ntsc", 128, 96, 9)
+    both(ref, ora, lambda e: e.modulate(img, format=layout.PIX_BGRA, as_color=1))
+    both(ref, ora, lambda e: e.demodulate(4))
+    check(ref, ora, "bad out format")
+    ref, ora = pair("ntsc", 128, 96)
+    both(ref, ora, lambda e: e.modulate(img, format=17, as_color=1))
+    check(ref, ora, "bad in format")
+
+
+@pytest.mark.parametrize("variant", ["nes", "nes_p0"])
+def test_nes(variant):
+    """config 3: NES PPU pixels, dot crawl cycling 0,1,2 (crt_main.c:471)."""
+    for img in (S.nes_image(seed=5), S.nes_image(rainbow=True)):
+        ref, ora = pair(variant, 832, 624)
+        both(ref, ora, lambda e: e.set(blend=0, scanlines=1))
+        for it in range(5):
+            both(ref, ora, lambda e: e.modulate(img, dot_crawl_offset=it % 3, hue=(it * 30) % 360))
+            check(ref, ora, "%s mod %d" % (variant, it))
+            both(ref, ora, lambda e: e.demodulate(it * 4))
+            check(ref, ora, "%s demod %d" % (variant, it))
+
+
+@pytest.mark.parametrize("color,aberr", [(1, 0), (0, 0), (1, 1)])
+def test_vhs(color, aberr):
+    """config 5: VHS 832x624 noise 24 (libc rand() stream seeded identically).
+
+    With do_aberration the bottom lines lose their sync pulse, hsync runs away and the
+    reference reads its decode window PAST inp[] into the rest of struct CRT (which holds
+    an ASLR-dependent pointer): those output rows are outside the parity domain
+     and are masked; blend=0 keeps them from leaking into later fields.
+    """
+    img = S.bars_image(832, 624)
+    ref, ora = pair("vhs", 832, 624, seed=1)
+    both(ref, ora, lambda e: e.set(blend=0 if aberr else 1, scanlines=1))
+    for it in range(4):
+        both(ref, ora, lambda e: e.modulate(img, format=layout.PIX_BGRA, as_color=color,
+                                            field=it & 1, frame=(it >> 1) & 1, do_aberration=aberr))
+        check(ref, ora, "vhs mod %d" % it)
+        ref.demodulate(24)
+        ora.noise_pass(24)
+        _, table = ora.sync_pass()
+        ora.line_pass(table)
+        a, b = ref.state(), ora.state()
+        for rec in table:
+            if not rec.skip and rec.pos + ora.spec.av_len > ora.spec.input_size:
+                assert aberr, "decode window left inp[] without aberration"
+                a["out"][rec.beg:rec.end] = 0
+                b["out"][rec.beg:rec.end] = 0
+                ref.out[rec.beg:rec.end] = 0
+                ora.out[rec.beg:rec.end] = 0
+        S.assert_same_state(a, b, "vhs demod %d" % it)
+
+
+def test_staged_decode_equals_whole_decode():
+    """The oracle's three-stage split (what the kernels mirror) is the same function."""
+    img = S.bars_image(400, 300)
+    a = S.OracleEngine("ntsc", 640, 480)
+    b = S.OracleEngine("ntsc", 640, 480)
+    for e in (a, b):
+        e.set(blend=1, scanlines=1)
+    for it in range(3):
+        for e in (a, b):
+            e.modulate(img, format=layout.PIX_BGRA, as_color=1, field=it & 1, frame=0)
+        a.demodulate(10)
+        b.noise_pass(10)
+        _, table = b.sync_pass()
+        b.line_pass(table, 0, 100)
+        b.line_pass(table, 100, 140)
+        S.assert_same_state(a.state(), b.state(), "staged %d" % it)
+
+
+def test_lcg_jump():
+    ora = S.oracle_lib()
+    m, a = C.c_uint(), C.c_uint()
+    ora.ocrt_lcg_jump(238420, C.byref(m), C.byref(a))
+    assert (m.value, a.value) == (0x5535B491, 0xF58BFA78)  # SURVEY.md 7.2 K1 probe
