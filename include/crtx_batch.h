@@ -1,0 +1,114 @@
+/* include/crtx_batch.h -- device-resident batch interface (C89, plain pointers and sizes).
+ *
+ * An additive extension beside the drop-in calls of crt_b200.h: a context owns N
+ * "monitors" -- N independent `struct CRT` instances (crt_core.h:74-92) whose signal
+ * buffers (analog / inp), persistent decoder state (ccf / hsync / vsync / rn) and
+ * per-line tables live in HBM.  One crtx_modulate + crtx_demodulate pair advances every
+ * monitor by one field, exactly as one crt_modulate + crt_demodulate call pair on each of
+ * N reference instances would (crt_ntsc.c:128, crt_nes.c:106, crt_ntscvhs.c:128,
+ * crt_core.c:291), but as a handful of kernel launches for the whole batch, asynchronously
+ * on the caller's CUDA stream.  Images are DEVICE pointers here; crtx_frames_host is the
+ * host-buffer entry point (pinned staging + async copies inside the call).
+ *
+ * The library variant fixes the emulated system, as in the reference (compile-time
+ * CRT_SYSTEM): query it with crtx_system().
+ *
+ * All functions return 0 on success, non-zero on failure (crtx_last_error() explains);
+ * they never fall back to a CPU path.
+ */
+#ifndef CRTX_BATCH_H
+#define CRTX_BATCH_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct crtx_ctx crtx_ctx;
+
+/* the caller-settable part of struct CRT, plus crt_demodulate's `noise` argument */
+typedef struct crtx_monitor {
+    void *out; /* DEVICE image, outw * outh * bpp bytes */
+    int outw, outh, out_format;
+    int hue, brightness, contrast, saturation;
+    int black_point, white_point;
+    int scanlines, blend;
+    unsigned v_fac;
+    int noise;
+} crtx_monitor;
+
+/* struct NTSC_SETTINGS with the image on the DEVICE; fields a system lacks are ignored */
+typedef struct crtx_source {
+    const void *data; /* RGB systems: w*h*bpp bytes; NES: w*h unsigned short */
+    int format, w, h;
+    int raw, as_color, field, frame;
+    int hue, xoffset, yoffset;
+    int do_aberration;    /* CRT_SYSTEM_NTSCVHS */
+    int dot_crawl_offset; /* CRT_SYSTEM_NES */
+    int reinit;           /* CRT_SYSTEM_NES: settings.field_initialized was 0 */
+} crtx_source;
+
+/* the persistent decoder state of struct CRT */
+typedef struct crtx_state {
+    int ccf[3][4];
+    int hsync, vsync;
+    int rn;
+} crtx_state;
+
+/* what the sync pre-pass decided for one decoded scanline (diagnostics / tests) */
+typedef struct crtx_line {
+    int pos;        /* start of the 1-line decode window in inp[] (crt_core.c:452-454) */
+    int wave0, wave1; /* hue-rotated carrier (crt_core.c:476-477) */
+    int beg;        /* first output row, or -1 when the line is skipped (crt_core.c:431) */
+    int end;        /* one past the last output row (crt_core.c:429,432) */
+    int hsync;      /* after this line's search (crt_core.c:446) */
+    int pad0, pad1;
+} crtx_line;
+
+/* geometry of this library variant */
+int crtx_system(void);          /* CRT_SYSTEM */
+int crtx_chroma_pattern(void);  /* CRT_CHROMA_PATTERN */
+int crtx_hres(void);            /* CRT_HRES */
+int crtx_input_size(void);      /* CRT_INPUT_SIZE */
+int crtx_lines(void);           /* CRT_LINES */
+int crtx_cc_vper(void);         /* CRT_CC_VPER */
+
+int  crtx_create(crtx_ctx **ctx, int n_monitors); /* on the current CUDA device */
+void crtx_destroy(crtx_ctx *ctx);
+
+/* configuration and state; `m` / `s` are HOST arrays of `count` entries */
+int crtx_set_monitors(crtx_ctx *ctx, int first, int count, const crtx_monitor *m);
+int crtx_set_state(crtx_ctx *ctx, int first, int count, const crtx_state *s, void *stream);
+int crtx_get_state(crtx_ctx *ctx, int first, int count, crtx_state *s, void *stream);
+int crtx_seed(crtx_ctx *ctx, int first, int count, unsigned seed); /* VHS libc-rand() replica */
+
+/* DEVICE pointers to monitor i's signal buffers (CRT_INPUT_SIZE + slack bytes each) */
+signed char *crtx_analog(crtx_ctx *ctx, int i);
+signed char *crtx_inp(crtx_ctx *ctx, int i);
+
+/* copy monitor i's analog[] (which = 0) or inp[] (which = 1), CRT_INPUT_SIZE bytes, to / from a HOST
+ * buffer; synchronises `stream` */
+int crtx_read_signal(crtx_ctx *ctx, int i, int which, signed char *host, void *stream);
+int crtx_write_signal(crtx_ctx *ctx, int i, int which, const signed char *host, void *stream);
+
+/* one field for monitors [first, first+count); asynchronous on `stream` (a cudaStream_t) */
+int crtx_modulate(crtx_ctx *ctx, int first, int count, const crtx_source *src, void *stream);
+int crtx_demodulate(crtx_ctx *ctx, int first, int count, void *stream);
+
+/* host-buffer convenience: src[i].data and out[i] are HOST pointers (pinned for full speed);
+ * copies the images in, runs modulate + demodulate, copies the decoded images out, all on
+ * `stream`; the monitors' `out` must have been set to device images of the right size. */
+int crtx_frames_host(crtx_ctx *ctx, int first, int count, const crtx_source *src,
+                     void *const *out_host, void *stream);
+
+/* diagnostics */
+int crtx_get_lines(crtx_ctx *ctx, int i, crtx_line *table /* crtx_lines() entries */, void *stream);
+long crtx_launch_count(crtx_ctx *ctx); /* kernels launched through this context so far */
+int crtx_set_option(crtx_ctx *ctx, const char *name, int value);
+const char *crtx_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,40 @@
+// crt_records.h -- the small records host code and kernels exchange.
+#pragma once
+
+#include "crtx_batch.h"
+
+namespace crt {
+
+// ---------------------------------------------------------------------------------------
+// device-side records
+// ---------------------------------------------------------------------------------------
+struct MonCfg { // host -> device, the caller-settable part of struct CRT
+    unsigned char *out;
+    int outw, outh, out_format, bpp;
+    int hue, brightness, contrast, saturation;
+    int black_point, white_point;
+    int scanlines, blend;
+    unsigned v_fac;
+    int noise;
+};
+
+struct MonState { // device resident, the persistent decoder state of struct CRT
+    int ccf[3][4];
+    int hsync, vsync, rn;
+    int field; // detected field * (ratio / 2) of the last demodulate (crt_core.c:398-407)
+};
+
+struct SrcCfg { // host -> device, struct NTSC_SETTINGS
+    const void *data;
+    int format, w, h;
+    int raw, as_color, field, frame;
+    int hue, xoffset, yoffset;
+    int aberration; // VHS: already drawn number of sync-less lines (crt_ntscvhs.c:205-207)
+    int dot_crawl_offset;
+    int reinit;
+    int pad;
+};
+
+typedef crtx_line LineRec; // 32 bytes
+
+} // namespace crt

@@ -1,0 +1,179 @@
+// crt_sys.cuh -- compile-time description of the emulated system and the integer
+// helpers shared by host and device code.
+//
+// The reference selects the system with -DCRT_SYSTEM=n (crt_core.h:39-59); so do we: one
+// shared library per variant, every timing constant a compile-time constant so ptxas can fold
+// them into immediates.  The filter coefficients the reference computes at run time in
+// crt_init (crt_core.c:263-289) and init_iir (crt_ntsc.c:98-106) are evaluated here by
+// constexpr restatements of the same integer formulas and pinned with static_asserts against
+// the values probed from the compiled reference.
+#pragma once
+
+#include <stdint.h>
+#include "crt_b200.h"
+
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#endif
+
+namespace crt {
+
+constexpr int kSystem = CRT_SYSTEM;
+constexpr int kPattern = CRT_CHROMA_PATTERN;
+constexpr bool kIsNes = (CRT_SYSTEM == CRT_SYSTEM_NES);
+constexpr bool kIsVhs = (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS);
+
+constexpr int kHres = CRT_HRES;
+constexpr int kVres = CRT_VRES;
+constexpr int kInputSize = CRT_INPUT_SIZE;
+constexpr int kTop = CRT_TOP;
+constexpr int kBot = CRT_BOT;
+constexpr int kLines = CRT_LINES;
+constexpr int kVper = CRT_CC_VPER;
+constexpr int kHsyncWindow = CRT_HSYNC_WINDOW;
+constexpr int kVsyncWindow = CRT_VSYNC_WINDOW;
+constexpr int kHsyncLevel = CRT_HSYNC_THRESH * SYNC_LEVEL;
+constexpr int kVsyncLevel = CRT_VSYNC_THRESH * SYNC_LEVEL;
+constexpr int kSyncBeg = SYNC_BEG;
+constexpr int kBwBeg = BW_BEG;
+constexpr int kCbBeg = CB_BEG;
+constexpr int kAvBeg = AV_BEG;
+constexpr int kAvLen = AV_LEN;
+constexpr int kBurstLen = CB_CYCLES * CRT_CB_FREQ;
+constexpr int kWhite = WHITE_LEVEL;
+constexpr int kBurst = BURST_LEVEL;
+constexpr int kBlack = BLACK_LEVEL;
+constexpr int kBlank = BLANK_LEVEL;
+constexpr int kSync = SYNC_LEVEL;
+#if (CRT_SYSTEM == CRT_SYSTEM_NES)
+constexpr int kNesVsyncEnd = PPUpx2pos(327); // crt_nes.c:91
+#endif
+
+// Slack after each signal buffer: the reference reads its decode windows up to one line past
+// inp[] when sync is lost (crt_core.c:438-441,458,511); those reads are outside the parity
+// domain but must stay inside our allocation.
+constexpr int kSignalPad = 4096;
+constexpr int kSignalBytes = ((kInputSize + kSignalPad + 255) / 256) * 256;
+
+// ---------------------------------------------------------------------------------------
+// 14-bit-angle sine/cosine (crt_core.c:19-61)
+// ---------------------------------------------------------------------------------------
+#define CRT_QUARTER15                                                                    \
+    { 0x0000, 0x0c88, 0x18f8, 0x2528, 0x30f8, 0x3c50, 0x4718, 0x5130, 0x5a80, 0x62f0,    \
+      0x6a68, 0x70e0, 0x7640, 0x7a78, 0x7d88, 0x7f60, 0x8000, 0x7f60 }
+
+constexpr int kQuarter15[18] = CRT_QUARTER15;
+
+constexpr int quarter_c(int a)
+{
+    return kQuarter15[(a >> 8) & 0xff]
+         + (((kQuarter15[((a >> 8) & 0xff) + 1] - kQuarter15[(a >> 8) & 0xff]) * (a & 0xff)) >> 8);
+}
+
+constexpr int sin14_c(int n)
+{
+    return ((n & 16383) >= 8192 ? -1 : 1)
+         * (((n & 8191) >= 4096) ? quarter_c(8192 - (n & 8191)) : quarter_c(n & 8191));
+}
+
+// host run-time version (used by the exported crt_sincos14 and by host-side set-up)
+inline void sincos14_host(int *s, int *c, int n)
+{
+    n &= 16383;
+    int h = n & 8191;
+    if (h >= 4096) {
+        *c = -quarter_c(h - 4096);
+        *s = quarter_c(8192 - h);
+    } else {
+        *c = quarter_c(4096 - h);
+        *s = quarter_c(h);
+    }
+    if (n >= 8192) {
+        *c = -*c;
+        *s = -*s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// decoder equaliser coefficients (crt_core.c:171-196, 272-280), EQ_P = 16
+// ---------------------------------------------------------------------------------------
+constexpr int khz2l(int khz) { return kHres * (khz * 100) / 1431818; }
+constexpr int eq_frac(int khz) { return 2 * (sin14_c(8192 * khz2l(khz) / kHres) << 1); }
+
+constexpr int kEqYlf = eq_frac(1500), kEqYhf = eq_frac(3000);
+constexpr int kEqIlf = eq_frac(80), kEqIhf = eq_frac(1150);
+constexpr int kEqQlf = eq_frac(80), kEqQhf = eq_frac(1000);
+// band gains, Q16 (crt_core.c:278-280): Y {65536, 8192, 9175}, I {65536, 65536, 1311},
+// Q {65536, 65536, 0}
+constexpr int kEqYg1 = 8192, kEqYg2 = 9175, kEqIg2 = 1311;
+
+#if (CRT_SYSTEM != CRT_SYSTEM_NES)
+static_assert(kHres == 910 && kAvBeg == 156 && kAvLen == 753 && kCbBeg == 97 && kSyncBeg == 21
+              && kBwBeg == 88, "NTSC timing (SURVEY.md 8a)");
+static_assert(kEqYlf == 42156 && kEqYhf == 79824 && kEqIlf == 2252 && kEqIhf == 32636
+              && kEqQlf == 2252 && kEqQhf == 28248, "equaliser fractions (SURVEY.md 8a)");
+#endif
+
+// ---------------------------------------------------------------------------------------
+// encoder band-limit coefficients (crt_ntsc.c:25-106)
+// ---------------------------------------------------------------------------------------
+constexpr int exp_q11_c(int n)
+{
+    // only ever evaluated for -2048 < n < 0 here (idx == 0 branch of crt_ntsc.c:41-83)
+    long long a = n < 0 ? -(long long) n : n;
+    long long term = 2048, sum = 0, fact = 1;
+    for (int k = 1; k < 17; k++) {
+        sum += term / fact;
+        term = (term * a) >> 11;
+        fact *= k;
+        if (fact > term || term <= 0 || fact <= 0) break;
+    }
+    long long res = (2048 * sum) >> 11;
+    if (n < 0) res = (2048LL << 11) / res;
+    return (int) res;
+}
+
+constexpr int bandlimit_c(int limit)
+{
+    return 2048 - exp_q11_c(-((6434 << 9) / ((1431818 << 9) / limit)));
+}
+
+#if (CRT_SYSTEM == CRT_SYSTEM_NTSC)
+constexpr int kIirY = bandlimit_c(420000), kIirI = bandlimit_c(150000), kIirQ = bandlimit_c(55000);
+static_assert(kIirY == 1233 && kIirI == 574 && kIirQ == 232, "NTSC band-limit (SURVEY.md 8a)");
+#elif (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
+constexpr int kIirY = bandlimit_c(300000), kIirI = bandlimit_c(62700), kIirQ = bandlimit_c(62700);
+static_assert(kIirY == 987 && kIirI == 262 && kIirQ == 262, "VHS band-limit (SURVEY.md 8a)");
+#endif
+
+// ---------------------------------------------------------------------------------------
+// noise LCG (crt_core.c:359) and its jump-ahead
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t kLcgMul = 214019u, kLcgAdd = 140327895u;
+
+struct Affine { // x -> x * mul + add (mod 2^32)
+    uint32_t mul, add;
+};
+
+constexpr Affine lcg_jump(uint32_t n)
+{
+    uint32_t am = kLcgMul, ac = kLcgAdd, rm = 1u, rc = 0u;
+    while (n) {
+        if (n & 1u) { rc = rc * am + ac; rm = rm * am; }
+        ac = ac * am + ac;
+        am = am * am;
+        n >>= 1;
+    }
+    return Affine{ rm, rc };
+}
+
+constexpr Affine kLcgField = lcg_jump((uint32_t) kInputSize); // one whole crt_demodulate call
+#if (CRT_SYSTEM == CRT_SYSTEM_NTSC)
+static_assert(kLcgField.mul == 0x5535b491u && kLcgField.add == 0xf58bfa78u, "SURVEY.md 7.2 K1");
+#endif
+
+// pixel formats (crt_core.h:62-67): byte positions of R, G, B, A(-1 = none)
+__host__ __device__ inline int bpp_of(int f) { return (f == 0 || f == 1) ? 3 : ((f >= 2 && f <= 5) ? 4 : 0); }
+
+} // namespace crt

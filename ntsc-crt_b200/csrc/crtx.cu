@@ -1,0 +1,392 @@
+// crtx.cu -- context, launches and the crtx_* C-ABI (include/crtx_batch.h).
+//
+// A context owns, in HBM, for each of its N monitors: analog[] and inp[] (CRT_INPUT_SIZE + slack,
+// same flat layout as the host struct so they can be memcpy'd), the persistent decoder state, the
+// per-line table the sync pre-pass hands to the line kernel, and the small configuration records.
+// There is no CPU implementation behind any of these calls: a CUDA failure is reported, never
+// papered over.
+#include <cuda_runtime.h>
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "crt_kernels.cuh"
+#include "crtx_internal.h"
+
+namespace crt {
+
+static thread_local char g_error[512] = "";
+
+int fail(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+#define CUDA_TRY(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+static int check_range(const crtx_ctx *ctx, int first, int count)
+{
+    if (!ctx) return fail("null context");
+    if (first < 0 || count < 0 || first + count > ctx->n) return fail("monitor range [%d, %d) outside [0, %d)", first, first + count, ctx->n);
+    return 0;
+}
+
+static int upload_cfg(crtx_ctx *ctx, cudaStream_t stream)
+{
+    if (ctx->cfg_dirty_lo < ctx->cfg_dirty_hi) {
+        const int lo = ctx->cfg_dirty_lo, hi = ctx->cfg_dirty_hi;
+        // pageable source: staged before the call returns, so h_cfg may be edited right after
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_cfg + lo, ctx->h_cfg.data() + lo, sizeof(MonCfg) * (hi - lo),
+                                 cudaMemcpyHostToDevice, stream));
+        ctx->cfg_dirty_lo = ctx->n;
+        ctx->cfg_dirty_hi = 0;
+    }
+    return 0;
+}
+
+int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cudaStream_t stream)
+{
+    if (check_range(ctx, first, count)) return 1;
+    if (count == 0) return 0;
+    if (upload_cfg(ctx, stream)) return 1;
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_src + first, src, sizeof(SrcCfg) * count, cudaMemcpyHostToDevice, stream));
+#if (CRT_SYSTEM == CRT_SYSTEM_NES)
+    dim3 grid((kHres + 255) / 256, kVres, count);
+    k_mod_nes<<<grid, 256, 0, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_state, ctx->d_analog, first);
+    ctx->launches += 1;
+#else
+    k_mod_skeleton_rgb<<<count, 256, 0, stream>>>(ctx->d_src + first, ctx->d_state, ctx->d_analog, first);
+    k_mod_picture_rgb<<<count, 256, kModSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog, first);
+    ctx->launches += 2;
+#endif
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, const short *d_noise_terms)
+{
+    if (check_range(ctx, first, count)) return 1;
+    if (count == 0) return 0;
+    if (upload_cfg(ctx, stream)) return 1;
+#if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
+    if (!d_noise_terms) return fail("VHS demodulate needs host-drawn noise terms (device rand() replica not built yet)");
+    dim3 tgrid((kInputSize + 255) / 256, count);
+    k_noise_terms<<<tgrid, 256, 0, stream>>>(ctx->d_cfg, ctx->d_analog, ctx->d_inp, d_noise_terms, first);
+#else
+    (void) d_noise_terms;
+    dim3 ngrid(kNoiseBlocks, count);
+    k_noise<<<ngrid, 256, 0, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_analog, ctx->d_inp, ctx->d_jump_lo,
+                                       ctx->d_jump_hi, first);
+#endif
+    k_sync<<<count, 32, 0, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, first);
+    k_lines<<<count, kLinesWarps * 32, kLinesSmem, stream>>>(ctx->d_cfg, ctx->d_lines, ctx->d_inp, first,
+                                                             ctx->opt_tma, ctx->opt_generic);
+    ctx->launches += 3;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+void fill_src(SrcCfg *d, const crtx_source *s)
+{
+    memset(d, 0, sizeof(*d));
+    d->data = s->data;
+    d->format = s->format;
+    d->w = s->w;
+    d->h = s->h;
+    d->raw = s->raw;
+    d->as_color = s->as_color;
+    d->field = s->field;
+    d->frame = s->frame;
+    d->hue = s->hue;
+    d->xoffset = s->xoffset;
+    d->yoffset = s->yoffset;
+    d->aberration = 0;
+    d->dot_crawl_offset = s->dot_crawl_offset;
+    d->reinit = s->reinit;
+#if (CRT_SYSTEM == CRT_SYSTEM_NES)
+    d->format = CRT_PIX_FORMAT_RGB; // unused by the NES encoder
+#endif
+}
+
+} // namespace crt
+
+using namespace crt;
+
+extern "C" {
+
+const char *crtx_last_error(void) { return g_error; }
+
+int crtx_system(void) { return kSystem; }
+int crtx_chroma_pattern(void) { return kPattern; }
+int crtx_hres(void) { return kHres; }
+int crtx_input_size(void) { return kInputSize; }
+int crtx_lines(void) { return kLines; }
+int crtx_cc_vper(void) { return kVper; }
+
+int crtx_create(crtx_ctx **out, int n)
+{
+    if (!out || n <= 0) return fail("crtx_create: bad arguments");
+    *out = NULL;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail("crtx_create: device %d is sm_%d%d, this library is built for sm_100a only", dev, prop.major, prop.minor);
+
+    crtx_ctx *ctx = new crtx_ctx();
+    ctx->n = n;
+    ctx->device = dev;
+    ctx->h_cfg.assign(n, MonCfg());
+    memset(ctx->h_cfg.data(), 0, sizeof(MonCfg) * n);
+    ctx->cfg_dirty_lo = 0;
+    ctx->cfg_dirty_hi = n;
+    ctx->opt_tma = 1;
+    ctx->opt_generic = 0;
+    const char *e = getenv("CRT_B200_NO_TMA");
+    if (e && *e == '1') ctx->opt_tma = 0;
+
+#define CTX_TRY(expr)                                                                            \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            fail("%s: %s", #expr, cudaGetErrorString(e_));                                       \
+            crtx_destroy(ctx);                                                                   \
+            return 1;                                                                            \
+        }                                                                                        \
+    } while (0)
+    CTX_TRY(cudaMalloc(&ctx->d_cfg, sizeof(MonCfg) * n));
+    CTX_TRY(cudaMalloc(&ctx->d_state, sizeof(MonState) * n));
+    CTX_TRY(cudaMalloc(&ctx->d_src, sizeof(SrcCfg) * n));
+    CTX_TRY(cudaMalloc(&ctx->d_lines, sizeof(LineRec) * (size_t) n * kLines));
+    CTX_TRY(cudaMalloc(&ctx->d_analog, (size_t) n * kSignalBytes));
+    CTX_TRY(cudaMalloc(&ctx->d_inp, (size_t) n * kSignalBytes));
+    CTX_TRY(cudaMalloc(&ctx->d_jump_lo, sizeof(Affine) * kJumpLo));
+    CTX_TRY(cudaMalloc(&ctx->d_jump_hi, sizeof(Affine) * kJumpHi));
+    CTX_TRY(cudaMemset(ctx->d_cfg, 0, sizeof(MonCfg) * n));
+    CTX_TRY(cudaMemset(ctx->d_lines, 0, sizeof(LineRec) * (size_t) n * kLines));
+    CTX_TRY(cudaMemset(ctx->d_analog, 0, (size_t) n * kSignalBytes)); // crt_init memsets the struct
+    CTX_TRY(cudaMemset(ctx->d_inp, 0, (size_t) n * kSignalBytes));
+    {
+        std::vector<MonState> st(n);
+        memset(st.data(), 0, sizeof(MonState) * n);
+        for (int i = 0; i < n; i++) st[i].rn = 194; // crt_core.c:269
+        CTX_TRY(cudaMemcpy(ctx->d_state, st.data(), sizeof(MonState) * n, cudaMemcpyHostToDevice));
+        std::vector<Affine> lo(kJumpLo), hi(kJumpHi);
+        for (int k = 0; k < kJumpLo; k++) lo[k] = lcg_jump((uint32_t) (kNoiseVec * k));
+        for (int k = 0; k < kJumpHi; k++) hi[k] = lcg_jump((uint32_t) (kNoiseVec * kJumpLo * k));
+        CTX_TRY(cudaMemcpy(ctx->d_jump_lo, lo.data(), sizeof(Affine) * kJumpLo, cudaMemcpyHostToDevice));
+        CTX_TRY(cudaMemcpy(ctx->d_jump_hi, hi.data(), sizeof(Affine) * kJumpHi, cudaMemcpyHostToDevice));
+    }
+    CTX_TRY(cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinesSmem));
+#if (CRT_SYSTEM != CRT_SYSTEM_NES)
+    CTX_TRY(cudaFuncSetAttribute(k_mod_picture_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSmem));
+#endif
+#undef CTX_TRY
+    *out = ctx;
+    return 0;
+}
+
+void crtx_destroy(crtx_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaFree(ctx->d_cfg);
+    cudaFree(ctx->d_state);
+    cudaFree(ctx->d_src);
+    cudaFree(ctx->d_lines);
+    cudaFree(ctx->d_analog);
+    cudaFree(ctx->d_inp);
+    cudaFree(ctx->d_jump_lo);
+    cudaFree(ctx->d_jump_hi);
+    cudaFree(ctx->d_src_img);
+    delete ctx;
+}
+
+int crtx_set_monitors(crtx_ctx *ctx, int first, int count, const crtx_monitor *m)
+{
+    if (check_range(ctx, first, count)) return 1;
+    for (int i = 0; i < count; i++) {
+        MonCfg &c = ctx->h_cfg[first + i];
+        c.out = static_cast<unsigned char *>(m[i].out);
+        c.outw = m[i].outw;
+        c.outh = m[i].outh;
+        c.out_format = m[i].out_format;
+        c.bpp = bpp_of(m[i].out_format);
+        c.hue = m[i].hue;
+        c.brightness = m[i].brightness;
+        c.contrast = m[i].contrast;
+        c.saturation = m[i].saturation;
+        c.black_point = m[i].black_point;
+        c.white_point = m[i].white_point;
+        c.scanlines = m[i].scanlines;
+        c.blend = m[i].blend;
+        c.v_fac = m[i].v_fac;
+        c.noise = m[i].noise;
+        if (c.bpp == 4 && (reinterpret_cast<uintptr_t>(c.out) & 3))
+            return fail("monitor %d: 4-byte pixel formats need a 4-byte aligned device image", first + i);
+    }
+    if (first < ctx->cfg_dirty_lo) ctx->cfg_dirty_lo = first;
+    if (first + count > ctx->cfg_dirty_hi) ctx->cfg_dirty_hi = first + count;
+    return 0;
+}
+
+int crtx_set_state(crtx_ctx *ctx, int first, int count, const crtx_state *s, void *stream)
+{
+    if (check_range(ctx, first, count)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<MonState> tmp(count);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), ctx->d_state + first, sizeof(MonState) * count, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < count; i++) {
+        memcpy(tmp[i].ccf, s[i].ccf, sizeof(tmp[i].ccf));
+        tmp[i].hsync = s[i].hsync;
+        tmp[i].vsync = s[i].vsync;
+        tmp[i].rn = s[i].rn;
+    }
+    CUDA_TRY(cudaMemcpyAsync(ctx->d_state + first, tmp.data(), sizeof(MonState) * count, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int crtx_get_state(crtx_ctx *ctx, int first, int count, crtx_state *s, void *stream)
+{
+    if (check_range(ctx, first, count)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::vector<MonState> tmp(count);
+    CUDA_TRY(cudaMemcpyAsync(tmp.data(), ctx->d_state + first, sizeof(MonState) * count, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int i = 0; i < count; i++) {
+        memcpy(s[i].ccf, tmp[i].ccf, sizeof(s[i].ccf));
+        s[i].hsync = tmp[i].hsync;
+        s[i].vsync = tmp[i].vsync;
+        s[i].rn = tmp[i].rn;
+    }
+    return 0;
+}
+
+int crtx_seed(crtx_ctx *ctx, int first, int count, unsigned seed)
+{
+    if (check_range(ctx, first, count)) return 1;
+    (void) seed;
+    if (!kIsVhs) return 0; // only the VHS variant draws from rand()
+    return fail("crtx_seed: the device rand() replica is not built yet in this variant");
+}
+
+signed char *crtx_analog(crtx_ctx *ctx, int i)
+{
+    if (check_range(ctx, i, 1)) return NULL;
+    return ctx->d_analog + (size_t) i * kSignalBytes;
+}
+
+signed char *crtx_inp(crtx_ctx *ctx, int i)
+{
+    if (check_range(ctx, i, 1)) return NULL;
+    return ctx->d_inp + (size_t) i * kSignalBytes;
+}
+
+int crtx_read_signal(crtx_ctx *ctx, int i, int which, signed char *host, void *stream)
+{
+    if (check_range(ctx, i, 1)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const signed char *src = (which ? ctx->d_inp : ctx->d_analog) + (size_t) i * kSignalBytes;
+    CUDA_TRY(cudaMemcpyAsync(host, src, kInputSize, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int crtx_write_signal(crtx_ctx *ctx, int i, int which, const signed char *host, void *stream)
+{
+    if (check_range(ctx, i, 1)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    signed char *dst = (which ? ctx->d_inp : ctx->d_analog) + (size_t) i * kSignalBytes;
+    CUDA_TRY(cudaMemcpyAsync(dst, host, kInputSize, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int crtx_modulate(crtx_ctx *ctx, int first, int count, const crtx_source *src, void *stream)
+{
+    if (check_range(ctx, first, count)) return 1;
+    if (kIsVhs) {
+        for (int i = 0; i < count; i++)
+            if (src[i].do_aberration) return fail("crtx_modulate: do_aberration needs the device rand() replica (not built yet)");
+    }
+    ctx->scratch_src.resize(count);
+    for (int i = 0; i < count; i++) fill_src(&ctx->scratch_src[i], &src[i]);
+    return modulate_launch(ctx, first, count, ctx->scratch_src.data(), static_cast<cudaStream_t>(stream));
+}
+
+int crtx_demodulate(crtx_ctx *ctx, int first, int count, void *stream)
+{
+    if (kIsVhs) return fail("crtx_demodulate: the VHS noise pass needs the device rand() replica (not built yet)");
+    return demodulate_launch(ctx, first, count, static_cast<cudaStream_t>(stream), NULL);
+}
+
+int crtx_frames_host(crtx_ctx *ctx, int first, int count, const crtx_source *src, void *const *out_host, void *stream)
+{
+    if (check_range(ctx, first, count)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // device staging for the source images, one slot per monitor
+    size_t need = 0;
+    for (int i = 0; i < count; i++) {
+        size_t b = (size_t) src[i].w * src[i].h * (kIsNes ? 2 : bpp_of(src[i].format));
+        b = (b + 255) & ~(size_t) 255;
+        if (b > need) need = b;
+    }
+    if (need > ctx->src_slot) {
+        CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(ctx->d_src_img);
+        ctx->d_src_img = NULL;
+        ctx->src_slot = 0;
+        CUDA_TRY(cudaMalloc(&ctx->d_src_img, need * ctx->n));
+        ctx->src_slot = need;
+    }
+    std::vector<crtx_source> dev(src, src + count);
+    for (int i = 0; i < count; i++) {
+        size_t b = (size_t) src[i].w * src[i].h * (kIsNes ? 2 : bpp_of(src[i].format));
+        unsigned char *slot = ctx->d_src_img + ctx->src_slot * (size_t) (first + i);
+        CUDA_TRY(cudaMemcpyAsync(slot, src[i].data, b, cudaMemcpyHostToDevice, st));
+        dev[i].data = slot;
+    }
+    if (crtx_modulate(ctx, first, count, dev.data(), stream)) return 1;
+    if (crtx_demodulate(ctx, first, count, stream)) return 1;
+    for (int i = 0; i < count; i++) {
+        const MonCfg &c = ctx->h_cfg[first + i];
+        if (!out_host || !out_host[i]) continue;
+        CUDA_TRY(cudaMemcpyAsync(out_host[i], c.out, (size_t) c.outw * c.outh * c.bpp, cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+}
+
+int crtx_get_lines(crtx_ctx *ctx, int i, crtx_line *table, void *stream)
+{
+    if (check_range(ctx, i, 1)) return 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemcpyAsync(table, ctx->d_lines + (size_t) i * kLines, sizeof(LineRec) * kLines, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}
+
+long crtx_launch_count(crtx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int crtx_set_option(crtx_ctx *ctx, const char *name, int value)
+{
+    if (!ctx || !name) return fail("crtx_set_option: bad arguments");
+    if (!strcmp(name, "tma")) ctx->opt_tma = value;
+    else if (!strcmp(name, "generic_eq")) ctx->opt_generic = value;
+    else return fail("crtx_set_option: unknown option '%s'", name);
+    return 0;
+}
+
+} // extern "C"

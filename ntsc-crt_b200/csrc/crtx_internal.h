@@ -1,0 +1,40 @@
+// crtx_internal.h -- what crtx.cu and crt_dropin.cu share (not part of the C-ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "crt_sys.cuh"
+#include "crtx_batch.h"
+
+#include "crt_records.h"
+
+struct crtx_ctx {
+    int n = 0;
+    int device = 0;
+    crt::MonCfg *d_cfg = nullptr;
+    crt::MonState *d_state = nullptr;
+    crt::SrcCfg *d_src = nullptr;
+    crtx_line *d_lines = nullptr;
+    signed char *d_analog = nullptr;
+    signed char *d_inp = nullptr;
+    crt::Affine *d_jump_lo = nullptr;
+    crt::Affine *d_jump_hi = nullptr;
+    unsigned char *d_src_img = nullptr; // crtx_frames_host staging, src_slot bytes per monitor
+    size_t src_slot = 0;
+    std::vector<crt::MonCfg> h_cfg;
+    std::vector<crt::SrcCfg> scratch_src;
+    int cfg_dirty_lo = 0, cfg_dirty_hi = 0;
+    long launches = 0;
+    int opt_tma = 1;
+    int opt_generic = 0;
+};
+
+namespace crt {
+int fail(const char *fmt, ...);
+void fill_src(SrcCfg *d, const crtx_source *s);
+int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cudaStream_t stream);
+// d_noise_terms: VHS only -- per-sample noise term already drawn on the host from libc rand()
+int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, const short *d_noise_terms);
+} // namespace crt

@@ -389,3 +389,27 @@ def cli_sequence(engine, img, noise=0, progressive=False, field=0, **settings):
             engine.demodulate(noise)
             if (it & 1) == 0:
                 fr ^= 1
+
+
+class ProductEngine(CEngine):
+    """The CUDA product library through the reference's own C interface (host buffers)."""
+
+    def __init__(self, variant, outw, outh, fmt=layout.PIX_BGRA, out=None):
+        from ntsc_crt_b200 import capi
+        capi.load(variant)  # raises if the library is not built: there is no fallback
+        super().__init__(capi.lib_path(variant), variant, outw, outh, fmt, out)
+
+
+def diff_report(name, x, y, shape_hint=None):
+    """One-line description of how two arrays differ (for the GPU diagnostics)."""
+    x = np.asarray(x)
+    y = np.asarray(y)
+    if x.shape != y.shape:
+        return "%s: SHAPE %r vs %r" % (name, x.shape, y.shape)
+    bad = np.argwhere(x != y)
+    if len(bad) == 0:
+        return "%s: identical (%d values)" % (name, x.size)
+    first = tuple(int(v) for v in bad[0])
+    last = tuple(int(v) for v in bad[-1])
+    return "%s: %d/%d differ, first %r got %r want %r, last %r" % (
+        name, len(bad), x.size, first, x[first], y[first], last)

@@ -1,0 +1,216 @@
+"""GPU parity: the CUDA product library against the oracle (and the compiled reference when
+oracle/_ref travelled with the snapshot), bit for bit, through the C-ABI.
+
+Two layers:
+  * drop-in: the reference's own interface (crt_init / crt_modulate / crt_demodulate on host
+    buffers), same call sequences as tests/test_oracle_vs_ref.py;
+  * stages: the crtx_* batch interface, checking each kernel's output on its own (analog after
+    modulate, inp after the noise pass, the per-line sync table, the decoded image).
+"""
+import numpy as np
+import pytest
+
+import support as S
+from ntsc_crt_b200 import layout
+
+pytestmark = pytest.mark.gpu
+
+
+def trio(variant, outw, outh, fmt=layout.PIX_BGRA):
+    gpu = S.ProductEngine(variant, outw, outh, fmt)
+    ora = S.OracleEngine(variant, outw, outh, fmt)
+    ref = S.RefEngine(variant, outw, outh, fmt, seed=1) if S.have_ref(variant) else None
+    return gpu, ora, ref
+
+
+def run_all(engines, fn):
+    for e in engines:
+        if e is not None:
+            fn(e)
+
+
+def check(gpu, ora, ref, what):
+    S.assert_same_state(gpu.state(), ora.state(), what + " [gpu vs oracle]")
+    if ref is not None:
+        S.assert_same_state(gpu.state(), ref.state(), what + " [gpu vs reference]")
+
+
+@pytest.mark.parametrize("progressive", [True, False])
+@pytest.mark.parametrize("size", [(832, 624), (256, 240)])
+def test_dropin_ntsc_config1(progressive, size):
+    """config 1: 256x240 in, noise 0, the CLI accumulate loop (crt_main.c:221-255)."""
+    img = S.lcg_image(256, 240)
+    gpu, ora, ref = trio("ntsc", *size)
+    run_all((gpu, ora, ref), lambda e: S.cli_sequence(e, img, 0, progressive, format=layout.PIX_BGRA))
+    check(gpu, ora, ref, "cfg1 %r p=%d" % (size, progressive))
+
+
+def test_dropin_ntsc_config2_every_call():
+    """config 2: 832x624 interlaced full colour, compared after every single call."""
+    img = S.rand_image(832, 624, seed=7)
+    gpu, ora, ref = trio("ntsc", 832, 624)
+    run_all((gpu, ora, ref), lambda e: e.set(blend=1, scanlines=1))
+    f, fr = 0, 0
+    for it in range(8):
+        run_all((gpu, ora, ref), lambda e: e.modulate(img, format=layout.PIX_BGRA, as_color=1, field=f, frame=fr))
+        check(gpu, ora, ref, "mod %d" % it)
+        run_all((gpu, ora, ref), lambda e: e.demodulate(0))
+        check(gpu, ora, ref, "demod %d" % it)
+        f ^= 1
+        if it % 2 == 1:
+            fr ^= 1
+
+
+@pytest.mark.parametrize("noise", [12, 24, 255])
+def test_dropin_ntsc_noise(noise):
+    img = S.bars_image(640, 480)
+    gpu, ora, ref = trio("ntsc", 640, 480)
+    run_all((gpu, ora, ref), lambda e: e.set(blend=0, scanlines=1))
+    for it in range(6):
+        run_all((gpu, ora, ref), lambda e: e.modulate(img, format=layout.PIX_BGRA, as_color=1,
+                                                      field=it & 1, frame=(it >> 1) & 1))
+        run_all((gpu, ora, ref), lambda e: e.demodulate(noise))
+        check(gpu, ora, ref, "noise %d call %d" % (noise, it))
+
+
+@pytest.mark.parametrize("fmt", range(6))
+def test_dropin_ntsc_pixel_formats(fmt):
+    rgb = S.rand_image(320, 200, bpp=3, seed=fmt)
+    img = S.pack_rgb(rgb, fmt)
+    gpu, ora, ref = trio("ntsc", 400, 300, fmt)
+    run_all((gpu, ora, ref), lambda e: e.set(blend=1, scanlines=0))
+    for it in range(3):
+        run_all((gpu, ora, ref), lambda e: e.modulate(img, format=fmt, as_color=1, field=it & 1, frame=0))
+        run_all((gpu, ora, ref), lambda e: e.demodulate(5))
+        check(gpu, ora, ref, "fmt %d call %d" % (fmt, it))
+
+
+def test_dropin_ntsc_knobs_raw_mono_offsets():
+    img = S.bars_image(300, 200)
+    gpu, ora, ref = trio("ntsc", 512, 448)
+    run_all((gpu, ora, ref), lambda e: e.set(hue=37, brightness=9, contrast=200, saturation=14,
+                                             black_point=3, white_point=90, blend=0, scanlines=1))
+    cases = [dict(raw=1, as_color=1, hue=20, xoffset=8, yoffset=2),
+             dict(raw=0, as_color=0, hue=0, xoffset=0, yoffset=0),
+             dict(raw=1, as_color=1, hue=350, xoffset=4, yoffset=1),
+             dict(raw=0, as_color=1, hue=90, xoffset=0, yoffset=0)]
+    for it, kw in enumerate(cases * 2):
+        run_all((gpu, ora, ref), lambda e: e.modulate(img, format=layout.PIX_BGRA, field=it & 1,
+                                                      frame=(it >> 1) & 1, **kw))
+        run_all((gpu, ora, ref), lambda e: e.demodulate(3 * it))
+        check(gpu, ora, ref, "knobs %d" % it)
+    # saturation 31 leaves the fast equaliser path's guaranteed range on some lines
+    run_all((gpu, ora, ref), lambda e: e.set(hue=-45, saturation=31, contrast=255, brightness=-20))
+    run_all((gpu, ora, ref), lambda e: e.demodulate(0))
+    check(gpu, ora, ref, "negative hue, high saturation")
+    run_all((gpu, ora, ref), lambda e: e.set(saturation=400, brightness=5000))
+    run_all((gpu, ora, ref), lambda e: e.demodulate(2))
+    check(gpu, ora, ref, "wrapping saturation / brightness (generic equaliser path)")
+
+
+def test_dropin_unknown_format_is_silent_noop():
+    img = S.rand_image(64, 48)
+    gpu, ora, ref = trio("ntsc", 128, 96, 9)
+    run_all((gpu, ora, ref), lambda e: e.modulate(img, format=layout.PIX_BGRA, as_color=1))
+    run_all((gpu, ora, ref), lambda e: e.demodulate(4))
+    check(gpu, ora, ref, "bad out format")
+    gpu, ora, ref = trio("ntsc", 128, 96)
+    run_all((gpu, ora, ref), lambda e: e.modulate(img, format=17, as_color=1))
+    check(gpu, ora, ref, "bad in format")
+
+
+@pytest.mark.parametrize("variant", ["nes", "nes_p0"])
+def test_dropin_nes(variant):
+    """config 3: NES PPU pixels incl. CRT_CHROMA_PATTERN 0, dot crawl cycling 0,1,2."""
+    for img in (S.nes_image(seed=5), S.nes_image(rainbow=True)):
+        gpu, ora, ref = trio(variant, 832, 624)
+        run_all((gpu, ora, ref), lambda e: e.set(blend=0, scanlines=1))
+        for it in range(5):
+            run_all((gpu, ora, ref), lambda e: e.modulate(img, dot_crawl_offset=it % 3, hue=(it * 30) % 360))
+            check(gpu, ora, ref, "%s mod %d" % (variant, it))
+            run_all((gpu, ora, ref), lambda e: e.demodulate(it * 4))
+            check(gpu, ora, ref, "%s demod %d" % (variant, it))
+
+
+@pytest.mark.parametrize("color", [1, 0])
+def test_dropin_vhs(color):
+    """config 5: VHS 832x624 noise 24; the drop-in draws from libc rand() like the reference, so the
+    comparison is against the compiled reference with the same srand (needs oracle/_ref)."""
+    import ctypes as C
+    if not S.have_ref("vhs"):
+        pytest.skip("oracle/_ref not present")
+    img = S.bars_image(832, 624)
+    libc = C.CDLL(None)
+    gpu = S.ProductEngine("vhs", 832, 624)
+    ora = S.OracleEngine("vhs", 832, 624, seed=1)
+    gpu.set(blend=1, scanlines=1)
+    ora.set(blend=1, scanlines=1)
+    libc.srand(1)
+    for it in range(4):
+        for e in (gpu, ora):
+            e.modulate(img, format=layout.PIX_BGRA, as_color=color, field=it & 1, frame=(it >> 1) & 1)
+        S.assert_same_state(gpu.state(), ora.state(), "vhs mod %d" % it)
+        for e in (gpu, ora):
+            e.demodulate(24)
+        S.assert_same_state(gpu.state(), ora.state(), "vhs demod %d" % it)
+
+
+def test_tma_and_plain_staging_agree():
+    """The TMA (cp.async.bulk) staging of the line kernel against plain loads, same kernel."""
+    import torch
+    from ntsc_crt_b200 import capi
+    img = torch.from_numpy(S.rand_image(832, 624, seed=11)).cuda()
+    outs = []
+    for tma in (1, 0):
+        b = capi.Batch("ntsc", 2)
+        b.set_option("tma", tma)
+        o = [torch.zeros(624, 832, 4, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        for i in range(2):
+            b.set_monitor(i, o[i], noise=7 * i, blend=1, scanlines=1)
+            b.set_source(i, img, format=layout.PIX_BGRA, as_color=1, field=i, frame=0)
+        b.commit_monitors()
+        for _ in range(2):
+            b.modulate()
+            b.demodulate()
+        torch.cuda.synchronize()
+        outs.append([x.cpu().numpy() for x in o])
+        b.close()
+    for i in range(2):
+        assert np.array_equal(outs[0][i], outs[1][i])
+    assert outs[0][0].any()
+
+
+def test_batch_matches_independent_oracles():
+    """crtx batch of 5 monitors with different knobs / noise = 5 independent reference instances."""
+    import torch
+    from ntsc_crt_b200 import capi
+    n = 5
+    imgs = [S.rand_image(200 + 40 * i, 150 + 30 * i, seed=i) for i in range(n)]
+    b = capi.Batch("ntsc", n)
+    outs = [torch.zeros(480, 640, 4, dtype=torch.uint8, device="cuda") for _ in range(n)]
+    dimg = [torch.from_numpy(x).cuda() for x in imgs]
+    oras = []
+    for i in range(n):
+        knobs = dict(hue=10 * i, saturation=8 + i, contrast=170 + 5 * i, blend=i & 1, scanlines=1)
+        b.set_monitor(i, outs[i], noise=6 * i, **knobs)
+        o = S.OracleEngine("ntsc", 640, 480)
+        o.set(**knobs)
+        oras.append(o)
+    b.commit_monitors()
+    for step in range(3):
+        for i in range(n):
+            b.set_source(i, dimg[i], format=layout.PIX_BGRA, as_color=1, field=step & 1, frame=0)
+        b.modulate()
+        b.demodulate()
+        for i in range(n):
+            oras[i].modulate(imgs[i], format=layout.PIX_BGRA, as_color=1, field=step & 1, frame=0)
+            oras[i].demodulate(6 * i)
+        torch.cuda.synchronize()
+        st = b.get_state()
+        for i in range(n):
+            got = dict(analog=b.signal(i, "analog"), inp=b.signal(i, "inp"), out=outs[i].cpu().numpy(),
+                       ccf=np.array([[st[i].ccf[r][x] for x in range(4)] for r in range(1)]),
+                       hsync=st[i].hsync, vsync=st[i].vsync, rn=st[i].rn)
+            S.assert_same_state(got, oras[i].state(), "batch monitor %d step %d" % (i, step))
+    assert b.launches == 3 * 5
+    b.close()
