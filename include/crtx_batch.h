@@ -102,6 +102,13 @@ int crtx_demodulate(crtx_ctx *ctx, int first, int count, void *stream);
 int crtx_frames_host(crtx_ctx *ctx, int first, int count, const crtx_source *src,
                      void *const *out_host, void *stream);
 
+/* per-kernel device timing.  After crtx_set_option(ctx, "timing", 1) every launch is bracketed by
+ * CUDA events on its stream; crtx_get_timing synchronises, then reports the summed milliseconds and
+ * the launch count of each kernel since the last call.  Index: 0 modulate skeleton (or the single
+ * NES encoder kernel), 1 modulate picture, 2 noise pass, 3 sync pre-pass, 4 line kernel. */
+#define CRTX_NUM_KERNELS 5
+int crtx_get_timing(crtx_ctx *ctx, float *ms /* [CRTX_NUM_KERNELS] */, long *launches /* [CRTX_NUM_KERNELS] */);
+
 /* diagnostics */
 int crtx_get_lines(crtx_ctx *ctx, int i, crtx_line *table /* crtx_lines() entries */, void *stream);
 long crtx_launch_count(crtx_ctx *ctx); /* kernels launched through this context so far */

@@ -51,7 +51,7 @@ CRTX_EXPORTS = ("crtx_system", "crtx_chroma_pattern", "crtx_hres", "crtx_input_s
                 "crtx_get_state", "crtx_seed", "crtx_analog", "crtx_inp", "crtx_read_signal",
                 "crtx_write_signal", "crtx_modulate",
                 "crtx_demodulate", "crtx_frames_host", "crtx_get_lines", "crtx_launch_count",
-                "crtx_set_option", "crtx_last_error")
+                "crtx_set_option", "crtx_get_timing", "crtx_last_error")
 
 _libs = {}
 
@@ -88,6 +88,7 @@ def load(variant):
     lib.crtx_launch_count.argtypes = [vp]
     lib.crtx_launch_count.restype = C.c_long
     lib.crtx_set_option.argtypes = [vp, C.c_char_p, ip]
+    lib.crtx_get_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_long)]
     lib.crtx_last_error.restype = C.c_char_p
     assert lib.crtx_system() == spec.system and lib.crtx_hres() == spec.hres, "variant mismatch"
     _libs[variant] = lib
@@ -209,6 +210,15 @@ class Batch:
         assert host.size == self.spec.input_size
         self._check(self.lib.crtx_write_signal(self._ctx, i, 0 if which == "analog" else 1,
                                                host.ctypes.data, stream))
+
+    KERNELS = ("mod_skeleton", "mod_picture", "noise", "sync", "lines")
+
+    def timing(self):
+        """{kernel: (total_ms, launches)} since the last call (needs set_option("timing", 1))."""
+        ms = (C.c_float * 5)()
+        cnt = (C.c_long * 5)()
+        self._check(self.lib.crtx_get_timing(self._ctx, ms, cnt))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KERNELS)}
 
     @property
     def launches(self):

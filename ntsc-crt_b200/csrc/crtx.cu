@@ -56,6 +56,39 @@ static int upload_cfg(crtx_ctx *ctx, cudaStream_t stream)
     return 0;
 }
 
+// RAII bracket: records start/stop events around one launch when timing is on
+struct LaunchTimer {
+    crtx_ctx *ctx;
+    cudaStream_t stream;
+    crtx_ctx::Timed t;
+    bool on;
+    static cudaEvent_t get(crtx_ctx *ctx)
+    {
+        cudaEvent_t e = nullptr;
+        if (!ctx->event_pool.empty()) {
+            e = ctx->event_pool.back();
+            ctx->event_pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
+    }
+    LaunchTimer(crtx_ctx *c, cudaStream_t s, int kernel) : ctx(c), stream(s), on(c->opt_timing != 0)
+    {
+        if (!on) return;
+        t.kernel = kernel;
+        t.start = get(ctx);
+        t.stop = get(ctx);
+        cudaEventRecord(t.start, stream);
+    }
+    ~LaunchTimer()
+    {
+        if (!on) return;
+        cudaEventRecord(t.stop, stream);
+        ctx->timed.push_back(t);
+    }
+};
+
 int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cudaStream_t stream)
 {
     if (check_range(ctx, first, count)) return 1;
@@ -64,11 +97,20 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
     CUDA_TRY(cudaMemcpyAsync(ctx->d_src + first, src, sizeof(SrcCfg) * count, cudaMemcpyHostToDevice, stream));
 #if (CRT_SYSTEM == CRT_SYSTEM_NES)
     dim3 grid((kHres + 255) / 256, kVres, count);
-    k_mod_nes<<<grid, 256, 0, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_state, ctx->d_analog, first);
+    {
+        LaunchTimer lt(ctx, stream, 0);
+        k_mod_nes<<<grid, 256, 0, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_state, ctx->d_analog, first);
+    }
     ctx->launches += 1;
 #else
-    k_mod_skeleton_rgb<<<count, 256, 0, stream>>>(ctx->d_src + first, ctx->d_state, ctx->d_analog, first);
-    k_mod_picture_rgb<<<count, 256, kModSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog, first);
+    {
+        LaunchTimer lt(ctx, stream, 0);
+        k_mod_skeleton_rgb<<<count, 256, 0, stream>>>(ctx->d_src + first, ctx->d_state, ctx->d_analog, first);
+    }
+    {
+        LaunchTimer lt(ctx, stream, 1);
+        k_mod_picture_rgb<<<count, 256, kModSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog, first);
+    }
     ctx->launches += 2;
 #endif
     CUDA_TRY(cudaGetLastError());
@@ -83,16 +125,28 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
 #if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
     if (!d_noise_terms) return fail("VHS demodulate needs host-drawn noise terms (device rand() replica not built yet)");
     dim3 tgrid((kInputSize + 255) / 256, count);
-    k_noise_terms<<<tgrid, 256, 0, stream>>>(ctx->d_cfg, ctx->d_analog, ctx->d_inp, d_noise_terms, first);
+    {
+        LaunchTimer lt(ctx, stream, 2);
+        k_noise_terms<<<tgrid, 256, 0, stream>>>(ctx->d_cfg, ctx->d_analog, ctx->d_inp, d_noise_terms, first);
+    }
 #else
     (void) d_noise_terms;
     dim3 ngrid(kNoiseBlocks, count);
-    k_noise<<<ngrid, 256, 0, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_analog, ctx->d_inp, ctx->d_jump_lo,
-                                       ctx->d_jump_hi, first);
+    {
+        LaunchTimer lt(ctx, stream, 2);
+        k_noise<<<ngrid, 256, 0, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_analog, ctx->d_inp, ctx->d_jump_lo,
+                                           ctx->d_jump_hi, first);
+    }
 #endif
-    k_sync<<<count, 32, 0, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, first);
-    k_lines<<<count, kLinesWarps * 32, kLinesSmem, stream>>>(ctx->d_cfg, ctx->d_lines, ctx->d_inp, first,
-                                                             ctx->opt_tma, ctx->opt_generic);
+    {
+        LaunchTimer lt(ctx, stream, 3);
+        k_sync<<<count, 32, 0, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, first);
+    }
+    {
+        LaunchTimer lt(ctx, stream, 4);
+        k_lines<<<count, kLinesWarps * 32, kLinesSmem, stream>>>(ctx->d_cfg, ctx->d_lines, ctx->d_inp, first,
+                                                                 ctx->opt_tma, ctx->opt_generic);
+    }
     ctx->launches += 3;
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -210,6 +264,11 @@ void crtx_destroy(crtx_ctx *ctx)
     cudaFree(ctx->d_jump_lo);
     cudaFree(ctx->d_jump_hi);
     cudaFree(ctx->d_src_img);
+    for (size_t i = 0; i < ctx->timed.size(); i++) {
+        cudaEventDestroy(ctx->timed[i].start);
+        cudaEventDestroy(ctx->timed[i].stop);
+    }
+    for (size_t i = 0; i < ctx->event_pool.size(); i++) cudaEventDestroy(ctx->event_pool[i]);
     delete ctx;
 }
 
@@ -380,11 +439,33 @@ int crtx_get_lines(crtx_ctx *ctx, int i, crtx_line *table, void *stream)
 
 long crtx_launch_count(crtx_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int crtx_get_timing(crtx_ctx *ctx, float *ms, long *launches)
+{
+    if (!ctx || !ms || !launches) return fail("crtx_get_timing: bad arguments");
+    for (int k = 0; k < CRTX_NUM_KERNELS; k++) {
+        ms[k] = 0.f;
+        launches[k] = 0;
+    }
+    for (size_t i = 0; i < ctx->timed.size(); i++) {
+        crtx_ctx::Timed &t = ctx->timed[i];
+        CUDA_TRY(cudaEventSynchronize(t.stop));
+        float e = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&e, t.start, t.stop));
+        ms[t.kernel] += e;
+        launches[t.kernel] += 1;
+        ctx->event_pool.push_back(t.start);
+        ctx->event_pool.push_back(t.stop);
+    }
+    ctx->timed.clear();
+    return 0;
+}
+
 int crtx_set_option(crtx_ctx *ctx, const char *name, int value)
 {
     if (!ctx || !name) return fail("crtx_set_option: bad arguments");
     if (!strcmp(name, "tma")) ctx->opt_tma = value;
     else if (!strcmp(name, "generic_eq")) ctx->opt_generic = value;
+    else if (!strcmp(name, "timing")) ctx->opt_timing = value;
     else return fail("crtx_set_option: unknown option '%s'", name);
     return 0;
 }

@@ -29,6 +29,13 @@ struct crtx_ctx {
     long launches = 0;
     int opt_tma = 1;
     int opt_generic = 0;
+    int opt_timing = 0;
+    struct Timed {
+        int kernel;
+        cudaEvent_t start, stop;
+    };
+    std::vector<Timed> timed;            // recorded, not yet read
+    std::vector<cudaEvent_t> event_pool; // recycled events
 };
 
 namespace crt {
