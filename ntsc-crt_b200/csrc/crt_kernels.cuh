@@ -502,7 +502,8 @@ __global__ void __launch_bounds__(256) k_noise_terms(const MonCfg *__restrict__ 
 // =======================================================================================
 __global__ void __launch_bounds__(32) k_sync(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states,
                                              LineRec *__restrict__ lines_base,
-                                             const signed char *__restrict__ inp_base, int first)
+                                             const signed char *__restrict__ inp_base, int first,
+                                             int force_generic)
 {
     const int m = first + blockIdx.x, lane = threadIdx.x;
     const MonCfg cfg = cfgs[m];
@@ -548,6 +549,9 @@ __global__ void __launch_bounds__(32) k_sync(const MonCfg *__restrict__ cfgs, Mo
 
     // ---- line chain.  Lane p < 4 carries ccf[row][p] for the three possible rows.
     int c0 = st->ccf[0][lane & 3], c1 = st->ccf[1 % kVper][lane & 3], c2 = st->ccf[2 % kVper][lane & 3];
+    // The fast equaliser path of k_lines is exact while |wave| <= 65536 and |bright| <= 4096
+    // (see eq_step in crt_lines.cuh); anything else sends the whole monitor down the generic one.
+    int generic = force_generic || abs(cfg.brightness - (kBlack + cfg.black_point)) > 4096;
     for (int k = 0; k < kLines; k++) {
         LineRec rec;
         rec.pad0 = rec.pad1 = 0;
@@ -600,6 +604,7 @@ __global__ void __launch_bounds__(32) k_sync(const MonCfg *__restrict__ cfgs, Mo
             rec.end = end;
             rec.hsync = hs;
             lines[k] = rec;
+            if (abs(rec.wave0) > 65536 || abs(rec.wave1) > 65536) generic = 1;
         }
     }
     if (lane < 4) {
@@ -611,277 +616,11 @@ __global__ void __launch_bounds__(32) k_sync(const MonCfg *__restrict__ cfgs, Mo
         st->vsync = vs;
         st->hsync = hs;
         st->field = field;
+        st->generic = generic;
         if (!kIsVhs) st->rn = (int) ((unsigned) st->rn * kLcgField.mul + kLcgField.add); // crt_core.c:367
     }
 }
 
-// =======================================================================================
-// line pass (crt_core.c:511-664): the roofline kernel.
-// =======================================================================================
-struct Eq { // crt_core.c:158-164
-    int l0, l1, l2, l3;
-    int h0, h1, h2, h3;
-    int s1, s2, s3; // input history, s3 oldest
-};
-
-__device__ __forceinline__ void eq_reset(Eq &f) { f.l0 = f.l1 = f.l2 = f.l3 = f.h0 = f.h1 = f.h2 = f.h3 = f.s1 = f.s2 = f.s3 = 0; }
-
-template <int C>
-__device__ __forceinline__ int pole(int f, int in) // crt_core.c:211-217
-{
-    return wadd(f, wadd(wmul(C, wsub(in, f)), 32768) >> 16);
-}
-
-// FAST: valid when every Q16 gain of 65536 is an exact identity and no product wraps, i.e.
-// |band| < 32768 (checked per warp from |wave| and |brightness|, see k_lines).  Then
-// r0 + r1 == hi-cascade output for I and Q (their lo cascades cancel and are not run at all), and
-// Y's middle gain 8192 is an arithmetic shift by 3.
-template <int LF, int HF, int G1, int G2, bool FAST, bool NEED_LO>
-__device__ __forceinline__ int eq_step(Eq &f, int s)
-{
-    f.h0 = pole<HF>(f.h0, s);
-    f.h1 = pole<HF>(f.h1, f.h0);
-    f.h2 = pole<HF>(f.h2, f.h1);
-    f.h3 = pole<HF>(f.h3, f.h2);
-    int r;
-    if (FAST && !NEED_LO) {
-        r = f.h3;
-        if (G2 != 0) r = wadd(r, wmul(wsub(f.s3, f.h3), G2) >> 16);
-    } else {
-        f.l0 = pole<LF>(f.l0, s);
-        f.l1 = pole<LF>(f.l1, f.l0);
-        f.l2 = pole<LF>(f.l2, f.l1);
-        f.l3 = pole<LF>(f.l3, f.l2);
-        if (FAST) {
-            static_assert(!FAST || !NEED_LO || G1 == 8192, "fast Y path assumes the 8192 mid gain");
-            r = wadd(wadd(f.l3, wsub(f.h3, f.l3) >> 3), wmul(wsub(f.s3, f.h3), G2) >> 16);
-        } else {
-            int r0 = wmul(f.l3, 65536) >> 16;
-            int r1 = wmul(wsub(f.h3, f.l3), G1) >> 16;
-            int r2 = wmul(wsub(f.s3, f.h3), G2) >> 16;
-            r = wadd(wadd(r0, r1), r2);
-        }
-    }
-    f.s3 = f.s2;
-    f.s2 = f.s1;
-    f.s1 = s;
-    return r;
-}
-
-__device__ __forceinline__ unsigned yiq_pixel(int ay, int ai, int aq, int by, int bi, int bq, int R, int contrast)
-{
-    const int L = 0xfff - R; // crt_core.c:559-575
-    int y = wadd(wmul(ay, L) >> 2, wmul(by, R) >> 2);
-    int i = wadd(wmul(ai, L) >> 14, wmul(bi, R) >> 14);
-    int q = wadd(wmul(aq, L) >> 14, wmul(bq, R) >> 14);
-    int r = wmul(wadd(wadd(y, wmul(3879, i)), wmul(2556, q)) >> 12, contrast) >> 8;
-    int g = wmul(wsub(wsub(y, wmul(1126, i)), wmul(2605, q)) >> 12, contrast) >> 8;
-    int b = wmul(wadd(wsub(y, wmul(4530, i)), wmul(7021, q)) >> 12, contrast) >> 8;
-    r = clampi(r, 0, 255);
-    g = clampi(g, 0, 255);
-    b = clampi(b, 0, 255);
-    return (unsigned) (r << 16 | g << 8 | b);
-}
-
-constexpr int kLinesWarps = 8;                       // 256 lane-lines per CTA, one monitor per CTA
-constexpr int kStageSamples = 64;                    // samples per staged chunk
-constexpr int kStageRow = kStageSamples + 16;        // bytes per line per stage (16-byte aligned window)
-constexpr int kStageBytes = 32 * kStageRow;          // per warp per stage
-constexpr int kTilePitch = 33;                       // words; [line][pixel] tile of finished pixels
-constexpr int kLinesWarpSmem = 2 * kStageBytes + 32 * kTilePitch * 4;
-constexpr int kLinesSmem = kLinesWarps * kLinesWarpSmem + kLinesWarps * 2 * 8;
-constexpr int kNumStages = (kAvLen + kStageSamples - 1) / kStageSamples;
-
-struct LinesCtx { // warp-uniform parameters of the pixel stage
-    unsigned char *out;
-    int outw, bpp, pitch, blend, contrast;
-    unsigned sel_store, sel_load; // PRMT selectors between 0x00RRGGBB and the pixel format
-    int rp, gp, bp, ap;
-};
-
-// Write `cnt` finished pixels [k0, k0 + cnt) of every active line of this warp: lanes across the
-// pixels (coalesced 128-byte row segments), loop over the 32 lines; blend with the previous
-// content and replicate into the duplicated rows (crt_core.c:584-664).
-__device__ __forceinline__ void flush_tile(const LinesCtx &cx, const unsigned *tile, int k0, int cnt, int lane,
-                                           int beg, int nrows)
-{
-    __syncwarp();
-    for (int l = 0; l < 32; l++) {
-        const int lbeg = __shfl_sync(0xffffffffu, beg, l);
-        const int lrows = __shfl_sync(0xffffffffu, nrows, l);
-        if (lbeg < 0) continue;
-        if (lane < cnt) {
-            unsigned rgb = tile[l * kTilePitch + lane];
-            unsigned char *p = cx.out + (size_t) lbeg * cx.pitch + (size_t) (k0 + lane) * cx.bpp;
-            if (cx.bpp == 4) {
-                if (cx.blend) {
-                    unsigned old = __byte_perm(*reinterpret_cast<const unsigned *>(p), 0u, cx.sel_load);
-                    rgb = ((rgb & 0xfefeffu) >> 1) + ((old & 0xfefeffu) >> 1);
-                }
-                const unsigned w = __byte_perm(rgb, 0xffu, cx.sel_store);
-                for (int r = 0; r < lrows; r++) *reinterpret_cast<unsigned *>(p + (size_t) r * cx.pitch) = w;
-            } else {
-                if (cx.blend) {
-                    unsigned old = (unsigned) p[cx.rp] << 16 | (unsigned) p[cx.gp] << 8 | (unsigned) p[cx.bp];
-                    rgb = ((rgb & 0xfefeffu) >> 1) + ((old & 0xfefeffu) >> 1);
-                }
-                for (int r = 0; r < lrows; r++) {
-                    unsigned char *q = p + (size_t) r * cx.pitch;
-                    q[cx.rp] = (unsigned char) (rgb >> 16);
-                    q[cx.gp] = (unsigned char) (rgb >> 8);
-                    q[cx.bp] = (unsigned char) rgb;
-                }
-            }
-        }
-    }
-    __syncwarp();
-}
-
-template <bool FAST>
-__device__ __forceinline__ void lines_body(const LinesCtx &cx, const signed char *inp, unsigned char *stage,
-                                           unsigned *tile, uint64_t *bars, int lane, bool active, int pos,
-                                           int wave0, int wave1, int beg, int nrows, int bright, bool use_tma)
-{
-    const int dx = ((kAvLen - 1) << 12) / cx.outw; // crt_core.c:527
-    const int nw0 = wsub(0, wave0), nw1 = wsub(0, wave1);
-    // wave[(i + 0) & 3] for I and wave[(i + 3) & 3] for Q (crt_core.c:538-543), i & 3 = 0..3
-    const int wi[4] = { wave0, wave1, nw0, nw1 };
-    const int wq[4] = { nw1, wave0, wave1, nw0 };
-    const int a = pos & 15;              // byte offset of the window inside its 16-byte aligned stage row
-    const signed char *src = inp + (pos & ~15);
-    const unsigned nactive = __popc(__ballot_sync(0xffffffffu, active));
-    const unsigned *row_base = reinterpret_cast<const unsigned *>(stage + lane * kStageRow) + (a >> 2);
-    const int sh = 8 * (a & 3);
-
-    auto issue = [&](int c) {
-        unsigned char *dst = stage + (c & 1) * kStageBytes + lane * kStageRow;
-        if (use_tma) {
-            if (lane == 0) mbar_expect_tx(&bars[c & 1], nactive * kStageRow);
-            __syncwarp();
-            if (active) tma_load_1d(dst, src + c * kStageSamples, kStageRow, &bars[c & 1]);
-        } else {
-            // plain path: each lane copies its own row with 16-byte loads (kept for A/B testing)
-            if (active) {
-#pragma unroll
-                for (int q = 0; q < kStageRow / 16; q++)
-                    reinterpret_cast<uint4 *>(dst)[q] =
-                        __ldg(reinterpret_cast<const uint4 *>(src + c * kStageSamples) + q);
-            }
-        }
-    };
-
-    Eq ey, ei, eq;
-    eq_reset(ey);
-    eq_reset(ei);
-    eq_reset(eq);
-    int py = 0, pi = 0, pq = 0;
-    int k = 0;             // next output pixel (warp uniform)
-    unsigned npos = 0;     // k * dx
-    int i = 0;             // sample index (warp uniform)
-
-    issue(0);
-    for (int c = 0; c < kNumStages; c++) {
-        if (c + 1 < kNumStages) issue(c + 1); // the other buffer was drained in iteration c - 1
-        if (use_tma) {
-            if (nactive) mbar_wait(&bars[c & 1], (c >> 1) & 1);
-        } else {
-            __syncwarp();
-        }
-        const unsigned *row = row_base + (c & 1) * (kStageBytes / 4);
-        unsigned lo = row[0];
-        const int ns = min(kStageSamples, kAvLen - c * kStageSamples);
-        for (int g = 0; 4 * g < ns; g++) {
-            const unsigned hi = row[g + 1];
-            const unsigned v4 = __funnelshift_r(lo, hi, sh);
-            lo = hi;
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                if (4 * g + b < ns) {
-                    const int s = (int) (signed char) (v4 >> (8 * b));
-                    const int cy = wmul(eq_step<kEqYlf, kEqYhf, kEqYg1, kEqYg2, FAST, true>(ey, s + bright), 16);
-                    const int ci = eq_step<kEqIlf, kEqIhf, 65536, kEqIg2, FAST, false>(ei, wmul(s, wi[b]) >> 9) >> 3;
-                    const int cq = eq_step<kEqQlf, kEqQhf, 65536, 0, FAST, false>(eq, wmul(s, wq[b]) >> 9) >> 3;
-                    // every output pixel whose left sample is i - 1 (crt_core.c:555-570)
-                    while (k < cx.outw && (int) (npos >> 12) == i - 1) {
-                        tile[lane * kTilePitch + (k & 31)] =
-                            yiq_pixel(py, pi, pq, cy, ci, cq, (int) (npos & 0xfff), cx.contrast);
-                        k++;
-                        npos += (unsigned) dx;
-                        if ((k & 31) == 0) flush_tile(cx, tile, k - 32, 32, lane, beg, nrows);
-                    }
-                    py = cy;
-                    pi = ci;
-                    pq = cq;
-                    i++;
-                }
-            }
-        }
-        __syncwarp(); // all lanes are done reading this stage buffer before it is refilled
-    }
-    if (k & 31) flush_tile(cx, tile, k & ~31, k & 31, lane, beg, nrows);
-}
-
-__global__ void __launch_bounds__(kLinesWarps * 32) k_lines(const MonCfg *__restrict__ cfgs,
-                                                            const LineRec *__restrict__ lines_base,
-                                                            const signed char *__restrict__ inp_base, int first,
-                                                            int use_tma, int force_generic)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m = first + blockIdx.x;
-    const MonCfg cfg = cfgs[m];
-    if (cfg.bpp == 0 || cfg.outw <= 0) return;
-
-    unsigned char *stage = smem_raw + warp * kLinesWarpSmem;
-    unsigned *tile = reinterpret_cast<unsigned *>(stage + 2 * kStageBytes);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + kLinesWarps * kLinesWarpSmem) + 2 * warp;
-    if (use_tma) {
-        if (lane == 0) {
-            mbar_init(&bars[0], 1);
-            mbar_init(&bars[1], 1);
-            mbar_fence_init();
-        }
-        __syncwarp();
-    }
-
-    const int k = warp * 32 + lane; // decoded line of this lane
-    LineRec rec;
-    rec.pos = 0; rec.wave0 = rec.wave1 = 0; rec.beg = -1; rec.end = -1; rec.hsync = 0;
-    if (k < kLines) rec = lines_base[(size_t) m * kLines + k];
-    const bool active = (k < kLines) && rec.beg >= 0;
-    const int beg = active ? rec.beg : -1;
-    const int nrows = active ? max(1, rec.end - cfg.scanlines - rec.beg) : 0; // crt_core.c:662-664
-    if (__ballot_sync(0xffffffffu, active) == 0) return;
-
-    LinesCtx cx;
-    cx.out = cfg.out;
-    cx.outw = cfg.outw;
-    cx.bpp = cfg.bpp;
-    cx.pitch = cfg.outw * cfg.bpp;
-    cx.blend = cfg.blend;
-    cx.contrast = cfg.contrast;
-    fmt_positions(cfg.out_format, cx.rp, cx.gp, cx.bp);
-    cx.ap = 0;
-    switch (cfg.out_format) {
-        case CRT_PIX_FORMAT_RGBA: cx.sel_store = 0x4012; cx.sel_load = 0x4012; break;
-        case CRT_PIX_FORMAT_ARGB: cx.sel_store = 0x0124; cx.sel_load = 0x4123; break;
-        case CRT_PIX_FORMAT_ABGR: cx.sel_store = 0x2104; cx.sel_load = 0x4321; break;
-        default:                  cx.sel_store = 0x4210; cx.sel_load = 0x4210; break; // BGRA
-    }
-
-    const int bright = cfg.brightness - (kBlack + cfg.black_point); // crt_core.c:304
-    const signed char *inp = inp_base + (size_t) m * kSignalBytes;
-
-    // FAST needs |I/Q band| < 32768 and no wrapping product: |wave| <= 65536 bounds the chroma
-    // inputs by 16257, |bright| <= 4096 bounds luma (see eq_step).  One vote per warp.
-    const bool lane_ok = !active || (abs(rec.wave0) <= 65536 && abs(rec.wave1) <= 65536);
-    const bool fast = !force_generic && abs(bright) <= 4096 && __all_sync(0xffffffffu, lane_ok);
-    if (fast)
-        lines_body<true>(cx, inp, stage, tile, bars, lane, active, rec.pos, rec.wave0, rec.wave1, beg, nrows, bright,
-                         use_tma != 0);
-    else
-        lines_body<false>(cx, inp, stage, tile, bars, lane, active, rec.pos, rec.wave0, rec.wave1, beg, nrows, bright,
-                          use_tma != 0);
-}
-
 } // namespace crt
+
+#include "crt_lines.cuh"

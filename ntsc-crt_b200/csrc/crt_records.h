@@ -21,7 +21,9 @@ struct MonCfg { // host -> device, the caller-settable part of struct CRT
 struct MonState { // device resident, the persistent decoder state of struct CRT
     int ccf[3][4];
     int hsync, vsync, rn;
-    int field; // detected field * (ratio / 2) of the last demodulate (crt_core.c:398-407)
+    int field;   // detected field * (ratio / 2) of the last demodulate (crt_core.c:398-407)
+    int generic; // last sync pass: some line needs the wrap-exact (generic) equaliser path
+    int pad[2];
 };
 
 struct SrcCfg { // host -> device, struct NTSC_SETTINGS

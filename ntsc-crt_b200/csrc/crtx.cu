@@ -56,6 +56,42 @@ static int upload_cfg(crtx_ctx *ctx, cudaStream_t stream)
     return 0;
 }
 
+template <bool FAST>
+static void launch_lines_mode(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
+{
+    const int mode = (geo.bpp == 4) ? (geo.blend ? 1 : 0) : 2;
+    const dim3 block(kLinesWarps * 32);
+    constexpr int smem = lines_smem<FAST>();
+    if (mode == 0)
+        k_lines<FAST, 0><<<count, block, smem, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, lo, geo);
+    else if (mode == 1)
+        k_lines<FAST, 1><<<count, block, smem, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, lo, geo);
+    else
+        k_lines<FAST, 2><<<count, block, smem, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, lo, geo);
+}
+
+static void launch_lines(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
+{
+    launch_lines_mode<true>(ctx, count, lo, geo, stream);
+    launch_lines_mode<false>(ctx, count, lo, geo, stream);
+}
+
+template <bool FAST, int MODE>
+static cudaError_t lines_attr()
+{
+    return cudaFuncSetAttribute(k_lines<FAST, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lines_smem<FAST>());
+}
+
+static cudaError_t lines_attr_all()
+{
+    cudaError_t e = cudaSuccess;
+#define LA(F, M)                                  \
+    if (e == cudaSuccess) e = lines_attr<F, M>();
+    LA(true, 0) LA(true, 1) LA(true, 2) LA(false, 0) LA(false, 1) LA(false, 2)
+#undef LA
+    return e;
+}
+
 // RAII bracket: records start/stop events around one launch when timing is on
 struct LaunchTimer {
     crtx_ctx *ctx;
@@ -140,14 +176,36 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
 #endif
     {
         LaunchTimer lt(ctx, stream, 3);
-        k_sync<<<count, 32, 0, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, first);
+        k_sync<<<count, 32, 0, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, first, ctx->opt_generic);
     }
-    {
-        LaunchTimer lt(ctx, stream, 4);
-        k_lines<<<count, kLinesWarps * 32, kLinesSmem, stream>>>(ctx->d_cfg, ctx->d_lines, ctx->d_inp, first,
-                                                                 ctx->opt_tma, ctx->opt_generic);
+    // The line kernel takes the output geometry as launch-uniform arguments: split the range into
+    // runs of monitors that share it (normally one run).
+    int launched = 0;
+    for (int lo = first; lo < first + count;) {
+        const MonCfg &c0 = ctx->h_cfg[lo];
+        int hi = lo + 1;
+        while (hi < first + count) {
+            const MonCfg &c = ctx->h_cfg[hi];
+            if (c.outw != c0.outw || c.out_format != c0.out_format || c.blend != c0.blend) break;
+            hi++;
+        }
+        LinesGeom geo;
+        geo.outw = c0.outw;
+        geo.out_format = c0.out_format;
+        geo.bpp = c0.bpp;
+        geo.blend = c0.blend ? 1 : 0;
+        geo.use_tma = ctx->opt_tma;
+        geo.rnd = 32768;
+        {
+            LaunchTimer lt(ctx, stream, 4);
+            // the second launch takes the monitors whose signal left the fast equaliser's exact range
+            // (flagged by k_sync); it is an empty pass otherwise
+            launch_lines(ctx, hi - lo, lo, geo, stream);
+        }
+        launched += 2;
+        lo = hi;
     }
-    ctx->launches += 3;
+    ctx->launches += 2 + launched;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -243,7 +301,7 @@ int crtx_create(crtx_ctx **out, int n)
         CTX_TRY(cudaMemcpy(ctx->d_jump_lo, lo.data(), sizeof(Affine) * kJumpLo, cudaMemcpyHostToDevice));
         CTX_TRY(cudaMemcpy(ctx->d_jump_hi, hi.data(), sizeof(Affine) * kJumpHi, cudaMemcpyHostToDevice));
     }
-    CTX_TRY(cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, kLinesSmem));
+    CTX_TRY(lines_attr_all());
 #if (CRT_SYSTEM != CRT_SYSTEM_NES)
     CTX_TRY(cudaFuncSetAttribute(k_mod_picture_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSmem));
 #endif
@@ -292,6 +350,8 @@ int crtx_set_monitors(crtx_ctx *ctx, int first, int count, const crtx_monitor *m
         c.blend = m[i].blend;
         c.v_fac = m[i].v_fac;
         c.noise = m[i].noise;
+        if (c.outw > kMaxOutw)
+            return fail("monitor %d: outw %d above the supported maximum %d", first + i, c.outw, kMaxOutw);
         if (c.bpp == 4 && (reinterpret_cast<uintptr_t>(c.out) & 3))
             return fail("monitor %d: 4-byte pixel formats need a 4-byte aligned device image", first + i);
     }
