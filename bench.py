@@ -241,6 +241,9 @@ def run_product(args):
     out = torch.zeros(B, H_OUT, W_OUT, 4, dtype=torch.uint8, device=dev)
     batch = capi.Batch(VARIANT, B)
     batch.set_option("timing", 1)
+    for kv in args.set:
+        name, val = kv.split("=")
+        batch.set_option(name, int(val))
     for i in range(B):
         batch.set_monitor(i, out[i], fmt=layout.PIX_BGRA, noise=0, blend=1, scanlines=1)
     batch.commit_monitors()
@@ -393,8 +396,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="monitors (frames per step) per GPU")
+    ap.add_argument("--batch", type=int, default=296,
+                    help="monitors (frames per step) per GPU; 296 = 2 resident CTAs x 148 SMs of the line kernel")
     ap.add_argument("--e2e-batch", type=int, default=64)
+    ap.add_argument("--set", action="append", default=[], help="library option name=value (A/B testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup

@@ -233,9 +233,13 @@ __device__ __forceinline__ void load_rgb(const unsigned char *data, size_t pix, 
     }
 }
 
+__device__ __forceinline__ bool mod_staged_ok(const SrcCfg &s, int destw);
+template <bool STAGED> __device__ __forceinline__ bool mod_takes(const SrcCfg &s);
+
 __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restrict__ srcs,
                                                          const MonCfg *__restrict__ cfgs,
-                                                         signed char *__restrict__ analog_base, int first)
+                                                         signed char *__restrict__ analog_base, int first,
+                                                         int skip_staged)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -248,6 +252,7 @@ __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restric
 
     const int bpp = bpp_of(s.format);
     if (bpp == 0) return;
+    if (skip_staged && mod_takes<true>(s)) return; // done by k_mod_picture_rgb_staged
     int destw = kAvLen, desth = (kLines * 64500) >> 16;
     if (s.raw) { // crt_ntsc.c:163-172
         destw = min(s.w, kAvLen);
@@ -340,6 +345,206 @@ __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restric
                 *reinterpret_cast<unsigned short *>(dst + 2 * lane) = (unsigned short) two;
             } else if (2 * lane < nx) {
                 dst[2 * lane] = (signed char) (two & 0xff);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Picture pass, staged variant (the one that normally runs).  Same arithmetic as above, different
+// data movement: a lane owns a picture line for the whole pass (the IIRs are serial along it), and
+// the stretch of its source row that a 32-sample chunk maps to is brought into shared memory by a
+// 1-D TMA bulk copy (one per lane, double buffered), so the serial loop reads pixels at
+// shared-memory latency and no transposition of the input is needed.  Finished samples are packed
+// 4 to a word and written back with coalesced 2-byte stores.
+// Usable when the chunk's source span fits a stage row; other monitors return at once and are
+// handled by k_mod_picture_rgb (gather variant), which in turn skips the ones done here.
+// The source image must be readable up to the next 16-byte boundary past its last pixel
+// (true of any cudaMalloc / torch allocation; include/crtx_batch.h).
+// ---------------------------------------------------------------------------------------
+constexpr int kModSChunk = 32;                     // samples per chunk
+constexpr int kModSRow = 192;                      // stage bytes per line per chunk
+constexpr int kModSOutPitch = kModSChunk / 4 + 1;  // words
+constexpr int kModSWarpSmem = 2 * 32 * kModSRow + 32 * kModSOutPitch * 4 + 32 * 4;
+constexpr int kModSSmem = 8 * kModSWarpSmem + 8 * 2 * 8;
+
+__device__ __forceinline__ bool mod_staged_ok(const SrcCfg &s, int destw)
+{
+    const int bpp = bpp_of(s.format);
+    if (bpp == 0 || destw <= 0 || s.w <= 0) return false;
+    // widest source span of a chunk: ceil(32 * w / destw) + 1 pixels, plus 15 bytes of alignment
+    const long long span = ((long long) kModSChunk * s.w + destw - 1) / destw + 1;
+    return span * bpp + 15 + 16 <= kModSRow && (bpp != 4 || (reinterpret_cast<uintptr_t>(s.data) & 3) == 0);
+}
+
+template <bool STAGED>
+__device__ __forceinline__ bool mod_takes(const SrcCfg &s)
+{
+    int destw = kAvLen;
+    if (s.raw) destw = min(s.w, kAvLen);
+    return mod_staged_ok(s, destw) == STAGED;
+}
+
+__global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg *__restrict__ srcs,
+                                                                   const MonCfg *__restrict__ cfgs,
+                                                                   signed char *__restrict__ analog_base, int first,
+                                                                   int use_tma)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const SrcCfg s = srcs[blockIdx.x];
+    if (!mod_takes<true>(s)) return;
+    const MonCfg cfg = cfgs[first + blockIdx.x];
+    signed char *analog = analog_base + (size_t) (first + blockIdx.x) * kSignalBytes;
+
+    unsigned char *stage = smem_raw + warp * kModSWarpSmem;
+    unsigned *obuf = reinterpret_cast<unsigned *>(stage + 2 * 32 * kModSRow);
+    int *coltab = reinterpret_cast<int *>(obuf + 32 * kModSOutPitch);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 8 * kModSWarpSmem) + 2 * warp;
+
+    const int bpp = bpp_of(s.format);
+    int destw = kAvLen, desth = (kLines * 64500) >> 16;
+    if (s.raw) { // crt_ntsc.c:163-172
+        destw = min(s.w, kAvLen);
+        desth = min(s.h, desth);
+    }
+    if (desth <= 0 || s.h <= 0) return;
+    const int y0 = warp * 32;
+    if (y0 >= desth) return;
+    const int nlines = min(32, desth - y0);
+    if (use_tma) {
+        if (lane == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+    }
+    const int field = s.field & 1, frame = s.frame & 1;
+    const int flip = (field == frame);
+    const int ph = flip ? -1 : 1;
+    const int xo = (kAvBeg + s.xoffset + (kAvLen - destw) / 2) & ~3;
+    const int yo = kTop + s.yoffset + (kLines - desth) / 2;
+    const int white = kWhite * cfg.white_point / 100;
+    const int ire0 = kBlack + cfg.black_point;
+    int rp, gp, bp;
+    fmt_positions(s.format, rp, gp, bp);
+    const unsigned char *data = static_cast<const unsigned char *>(s.data);
+    const bool color = s.as_color != 0;
+
+    int mI[4], mQ[4]; // ph * ccmodI/Q (crt_ntsc.c:174-188, 314-315)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        mI[k] = mQ[k] = 0;
+        if (color) {
+            int sn, cs, deg = s.hue + k * 90;
+            sincos14_d(sn, cs, deg * 8192 / 180);
+            mI[k] = ph * (sn >> 10);
+            sincos14_d(sn, cs, (deg - 90) * 8192 / 180);
+            mQ[k] = ph * (sn >> 10);
+        }
+    }
+
+    const bool active = lane < nlines;
+    const int y = y0 + min(lane, nlines - 1);
+    // source row of this lane's line (crt_ntsc.c:258-266); row == h (one past the image, undefined in
+    // the reference) is clamped to the last row
+    int row = (int) (((long long) y * s.h) / desth) + (field * s.h + desth) / desth / 2;
+    if (row >= s.h) row = s.h - 1;
+    const unsigned char *rowp = data + (size_t) row * s.w * bpp;
+    const int nchunks = (destw + kModSChunk - 1) / kModSChunk;
+
+    // chunk c covers samples [32c, 32c + 32): source columns f0..f1, staged from the 16-byte
+    // aligned address at or below the first pixel
+    auto span = [&](int c, int &f0, int &bytes) {
+        const int x0 = c * kModSChunk, x1 = min(x0 + kModSChunk, destw) - 1;
+        f0 = (int) (((long long) x0 * s.w) / destw);
+        const int f1 = (int) (((long long) x1 * s.w) / destw);
+        bytes = (f1 - f0 + 1) * bpp;
+    };
+    auto issue = [&](int c) {
+        int f0, bytes;
+        span(c, f0, bytes);
+        const unsigned char *p = rowp + (size_t) f0 * bpp;
+        const int a = (int) (reinterpret_cast<uintptr_t>(p) & 15);
+        const unsigned copy = (unsigned) ((a + bytes + 15) & ~15);
+        unsigned char *dst = stage + (c & 1) * 32 * kModSRow + lane * kModSRow;
+        if (use_tma) {
+            // every lane copies the same number of bytes only if all rows share `a`; sum them up
+            unsigned total = active ? copy : 0;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+            if (lane == 0) mbar_expect_tx(&bars[c & 1], total);
+            __syncwarp();
+            if (active) tma_load_1d(dst, p - a, copy, &bars[c & 1]);
+        } else if (active) {
+            for (unsigned q = 0; q < copy / 16; q++)
+                reinterpret_cast<uint4 *>(dst)[q] = __ldg(reinterpret_cast<const uint4 *>(p - a) + q);
+        }
+    };
+
+    int hy = 0, hi = 0, hq = 0;
+    issue(0);
+#pragma unroll 1
+    for (int c = 0; c < nchunks; c++) {
+        if (c + 1 < nchunks) issue(c + 1);
+        int f0, bytes;
+        span(c, f0, bytes);
+        const int c0 = c * kModSChunk;
+        const int nx = min(kModSChunk, destw - c0);
+        { // byte offset of sample x's pixel inside the stage row, relative to the first pixel
+            const int x = min(c0 + lane, destw - 1);
+            coltab[lane] = ((int) (((long long) x * s.w) / destw) - f0) * bpp;
+        }
+        if (use_tma) mbar_wait(&bars[c & 1], (c >> 1) & 1);
+        __syncwarp();
+        const unsigned char *srow = stage + (c & 1) * 32 * kModSRow + lane * kModSRow
+                                  + (int) (reinterpret_cast<uintptr_t>(rowp + (size_t) f0 * bpp) & 15);
+#pragma unroll 1
+        for (int x4 = 0; x4 < nx; x4 += 4) {
+            unsigned packed = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int off = coltab[min(x4 + k, kModSChunk - 1)];
+                int r, g, b;
+                if (bpp == 4) {
+                    const unsigned v = *reinterpret_cast<const unsigned *>(srow + off);
+                    r = (v >> (8 * rp)) & 0xff;
+                    g = (v >> (8 * gp)) & 0xff;
+                    b = (v >> (8 * bp)) & 0xff;
+                } else {
+                    r = srow[off + rp];
+                    g = srow[off + gp];
+                    b = srow[off + bp];
+                }
+                const int fy = (19595 * r + 38470 * g + 7471 * b) >> 14; // crt_ntsc.c:308-310
+                hy += wmul(fy - hy, kIirY) >> 11; // iirf, crt_ntsc.c:117-126
+                int sum = hy;
+                if (color) {
+                    const int fi = (39059 * r - 18022 * g - 21103 * b) >> 14;
+                    const int fq = (13894 * r - 34275 * g + 20382 * b) >> 14;
+                    hi += wmul(fi - hi, kIirI) >> 11;
+                    hq += wmul(fq - hq, kIirQ) >> 11;
+                    // (x + xo) & 3 == k: xo, c0 and x4 are multiples of 4
+                    sum += (wmul(hi, mI[k]) >> 4) + (wmul(hq, mQ[k]) >> 4);
+                }
+                int ire = ire0 + (wmul(sum, white) >> 10);
+                ire = clampi(ire, 0, 110);
+                packed |= (unsigned) ire << (8 * k);
+            }
+            obuf[lane * kModSOutPitch + (x4 >> 2)] = packed;
+        }
+        __syncwarp();
+        // coalesced stores: 16 lanes x 2 bytes per line, two lines per pass
+        for (int l2 = 0; l2 < nlines; l2 += 2) {
+            const int l = l2 + (lane >> 4), j = lane & 15;
+            if (l < nlines) {
+                signed char *dst = analog + (c0 + xo) + (y0 + l + yo) * kHres;
+                const unsigned w = obuf[l * kModSOutPitch + (j >> 1)];
+                const unsigned two = (w >> (16 * (j & 1))) & 0xffffu;
+                if (2 * j + 1 < nx) *reinterpret_cast<unsigned short *>(dst + 2 * j) = (unsigned short) two;
+                else if (2 * j < nx) dst[2 * j] = (signed char) (two & 0xff);
             }
         }
         __syncwarp();
@@ -494,133 +699,7 @@ __global__ void __launch_bounds__(256) k_noise_terms(const MonCfg *__restrict__ 
 }
 #endif
 
-// =======================================================================================
-// sync pre-pass: one warp per monitor (crt_core.c:379-479).
-// vsync search in parallel over a line (segment sums + warp scan), then the serial line-to-line
-// chain: hsync search (16 samples: one load per lane + scan + ballot) and the colour-burst lock
-// (4 lanes, one per carrier phase, 10 truncating steps each).  Emits one LineRec per decoded line.
-// =======================================================================================
-__global__ void __launch_bounds__(32) k_sync(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states,
-                                             LineRec *__restrict__ lines_base,
-                                             const signed char *__restrict__ inp_base, int first,
-                                             int force_generic)
-{
-    const int m = first + blockIdx.x, lane = threadIdx.x;
-    const MonCfg cfg = cfgs[m];
-    if (cfg.bpp == 0) return;
-    MonState *st = &states[m];
-    const signed char *inp = inp_base + (size_t) m * kSignalBytes;
-    LineRec *lines = lines_base + (size_t) m * kLines;
-
-    int huesn, huecs;
-    {
-        int sn, cs;
-        sincos14_d(sn, cs, ((cfg.hue % 360) + 33) * 8192 / 180); // crt_core.c:318-320
-        huesn = sn >> 11;
-        huecs = cs >> 11;
-    }
-    int vs = st->vsync, hs = st->hsync;
-
-    // ---- vsync (crt_core.c:379-396)
-    constexpr int kSeg = (kHres + 31) / 32;
-    int line = 0, j = kHres;
-    bool found = false;
-    for (int i = -kVsyncWindow; i < kVsyncWindow && !found; i++) {
-        line = posmod(vs + i, kVres);
-        const signed char *sig = inp + line * kHres;
-        const int b0 = lane * kSeg, b1 = min(kHres, b0 + kSeg);
-        int sum = 0;
-        for (int t = b0; t < b1; t++) sum += __ldg(sig + t);
-        int acc = warp_scan_incl(sum, lane) - sum, idx = -1;
-        for (int t = b0; t < b1; t++) {
-            acc += __ldg(sig + t);
-            if (idx < 0 && acc <= kVsyncLevel) idx = t;
-        }
-        unsigned hit = __ballot_sync(0xffffffffu, idx >= 0);
-        if (hit) {
-            j = __shfl_sync(0xffffffffu, idx, __ffs(hit) - 1);
-            found = true;
-        }
-    }
-    vs = line;
-    int field = (j > kHres / 2);
-    const int ratio = (((cfg.outh << 16) / kLines) + 32768) >> 16; // crt_core.c:404-407
-    field *= ratio / 2;
-
-    // ---- line chain.  Lane p < 4 carries ccf[row][p] for the three possible rows.
-    int c0 = st->ccf[0][lane & 3], c1 = st->ccf[1 % kVper][lane & 3], c2 = st->ccf[2 % kVper][lane & 3];
-    // The fast equaliser path of k_lines is exact while |wave| <= 65536 and |bright| <= 4096
-    // (see eq_step in crt_lines.cuh); anything else sends the whole monitor down the generic one.
-    int generic = force_generic || abs(cfg.brightness - (kBlack + cfg.black_point)) > 4096;
-    for (int k = 0; k < kLines; k++) {
-        LineRec rec;
-        rec.pad0 = rec.pad1 = 0;
-        int beg = (int) ((unsigned) k * ((unsigned) cfg.outh + cfg.v_fac) / (unsigned) kLines + (unsigned) field);
-        int end = (int) ((unsigned) (k + 1) * ((unsigned) cfg.outh + cfg.v_fac) / (unsigned) kLines + (unsigned) field);
-        if (beg >= cfg.outh) { // crt_core.c:431: no state is touched
-            if (lane == 0) {
-                rec.pos = 0; rec.wave0 = rec.wave1 = 0; rec.beg = -1; rec.end = -1; rec.hsync = hs;
-                lines[k] = rec;
-            }
-            continue;
-        }
-        if (end > cfg.outh) end = cfg.outh;
-
-        const int ln = posmod(kTop + k + vs, kVres) * kHres;
-        { // hsync (crt_core.c:437-450)
-            int v = 0;
-            if (lane < 2 * kHsyncWindow) v = __ldg(inp + ln + hs + kSyncBeg - kHsyncWindow + lane);
-            int acc = warp_scan_incl(v, lane);
-            unsigned hit = __ballot_sync(0xffffffffu, lane < 2 * kHsyncWindow && acc <= kHsyncLevel);
-            int i = (hit ? __ffs(hit) - 1 : 2 * kHsyncWindow) - kHsyncWindow;
-            hs = posmod(i + hs, kHres);
-        }
-        const int xpos = posmod(kAvBeg + hs - 3, kHres);
-        const int ypos = posmod(kTop + k + vs + 3, kVres);
-        const int row = ypos % kVper;
-
-        // burst lock (crt_core.c:456-467): ccr[i & 3] = ccr[i & 3] * 127 / 128 + sig[i]
-        int x = (row == 0) ? c0 : ((row == 1) ? c1 : c2);
-        if (lane < 4) {
-            const signed char *bs = inp + ln + (hs & ~3) + kCbBeg;
-            const int t0 = (lane - kCbBeg) & 3;
-            int smp[kBurstLen / 4];
-#pragma unroll
-            for (int q = 0; q < kBurstLen / 4; q++) smp[q] = __ldg(bs + t0 + 4 * q);
-#pragma unroll
-            for (int q = 0; q < kBurstLen / 4; q++) x = wadd(wmul(x, 127) / 128, smp[q]);
-        }
-        if (row == 0) c0 = x; else if (row == 1) c1 = x; else c2 = x;
-
-        const int pa = hs & 3; // crt_core.c:469-479
-        const int a0 = __shfl_sync(0xffffffffu, x, pa), a1 = __shfl_sync(0xffffffffu, x, (pa + 1) & 3);
-        const int a2 = __shfl_sync(0xffffffffu, x, (pa + 2) & 3), a3 = __shfl_sync(0xffffffffu, x, (pa + 3) & 3);
-        const int dci = wsub(a1, a3), dcq = wsub(a2, a0);
-        if (lane == 0) {
-            rec.pos = xpos + ypos * kHres;
-            rec.wave0 = wmul(wsub(wmul(dci, huecs), wmul(dcq, huesn)) >> 4, cfg.saturation);
-            rec.wave1 = wmul(wadd(wmul(dcq, huecs), wmul(dci, huesn)) >> 4, cfg.saturation);
-            rec.beg = beg;
-            rec.end = end;
-            rec.hsync = hs;
-            lines[k] = rec;
-            if (abs(rec.wave0) > 65536 || abs(rec.wave1) > 65536) generic = 1;
-        }
-    }
-    if (lane < 4) {
-        st->ccf[0][lane] = c0;
-        if (kVper > 1) st->ccf[1 % kVper][lane] = c1;
-        if (kVper > 2) st->ccf[2 % kVper][lane] = c2;
-    }
-    if (lane == 0) {
-        st->vsync = vs;
-        st->hsync = hs;
-        st->field = field;
-        st->generic = generic;
-        if (!kIsVhs) st->rn = (int) ((unsigned) st->rn * kLcgField.mul + kLcgField.add); // crt_core.c:367
-    }
-}
-
 } // namespace crt
 
+#include "crt_sync.cuh"
 #include "crt_lines.cuh"

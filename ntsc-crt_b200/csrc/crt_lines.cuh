@@ -9,8 +9,8 @@
 // datapath and the per-lane instruction stream is almost pure filter + pixel arithmetic.
 //   in : each lane's 753-sample window of inp[] arrives in shared memory through 1-D TMA bulk copies
 //        (cp.async.bulk + mbarrier), 64 samples per stage, double buffered;
-//   out: finished pixels go to a [line][32 px] shared-memory tile; every 32 pixels the warp turns
-//        the tile around and writes 128-byte row segments with 128-bit stores (8 lanes per row, 4
+//   out: finished pixels go to a [line][16 px] shared-memory tile; every 16 pixels the warp turns
+//        the tile around and writes 64-byte row segments with 128-bit stores (4 lanes per row, 8
 //        rows per instruction), blending with the previous image and replicating duplicated rows.
 #pragma once
 
@@ -104,7 +104,7 @@ constexpr int kSub = 12;                      // samples filtered between two pi
 constexpr int kStageSamples = 48;             // samples per staged chunk (4 sub-chunks)
 constexpr int kStageRow = kStageSamples + 16; // bytes per line per stage: a 16-byte aligned superset
 constexpr int kStageBytes = 32 * kStageRow;   // per warp per stage
-constexpr int kTilePitch = 36;                // words; pitch/4 odd -> conflict-free 128-bit row reads
+constexpr int kTilePitch = 20;                // words: 16 pixel columns per line, pitch/4 odd
 constexpr int kTileBytes = 32 * kTilePitch * 4;
 // The line is filtered in whole sub-chunks: up to kSub - 1 samples past AV_LEN are run through the
 // equalisers (they exist in the padded signal buffer) but no pixel ever reads them, because the
@@ -136,61 +136,82 @@ struct LinesGeom { // uniform over a launch: host groups monitors by these (crtx
 };
 
 // Write `cnt` (<= 16) finished pixels [k0, k0 + cnt) of every active line of this warp
-// (crt_core.c:584-664).  The tile is a ring of 32 pixel columns per line; pixels are already in
-// storage byte order and, when blending, pre-halved with the alpha byte forced to 0xff, so the blend
-// is (old >> 1 & mask) + new on whole words.  128-bit path: 4 lanes per row, 8 rows per pass.
-__device__ __forceinline__ void flush16(const unsigned *tile, const LinesGeom &geo, unsigned char *out, int k0,
-                                        int cnt, int lane, int beg, int nrows, unsigned blend_mask, bool vec)
+// (crt_core.c:584-664).  The tile holds 16 pixel columns per line; pixels are already in storage byte
+// order and, when blending, pre-halved with the alpha byte forced to 0xff, so the blend is
+// (old >> 1 & mask) + new on whole words.
+//
+// 128-bit path (4-byte pixels, 16-byte aligned rows): 4 lanes per row, 8 rows per pass, 4 passes.  Each
+// lane keeps, for its 4 (row, quad) slots, the row pointer and the number of rows to write
+// (crt_core.c:662-664), and -- when blending -- the previous image's pixels of the NEXT 16-pixel block,
+// fetched right after this block is written so that the DRAM latency hides behind a whole sub-chunk
+// of filter work instead of stalling the flush.
+struct RowSlots {
+    unsigned char *ptr[4]; // row start of line it * 8 + (lane >> 2), plus this lane's quad offset
+    int rows[4];           // rows to write, 0 = slot inactive
+};
+
+template <bool BLEND>
+__device__ __forceinline__ void load_old(const RowSlots &rs, int k0, int cnt, int lane, uint4 (&oldv)[4])
+{
+    if (!BLEND) return;
+#pragma unroll
+    for (int it = 0; it < 4; it++)
+        if (rs.rows[it] > 0 && 4 * (lane & 3) < cnt)
+            oldv[it] = *reinterpret_cast<const uint4 *>(rs.ptr[it] + (size_t) k0 * 4);
+}
+
+template <bool BLEND>
+__device__ __forceinline__ void flush16_vec(const unsigned *tile, const RowSlots &rs, int pitch, int k0, int cnt,
+                                            int lane, unsigned blend_mask, const uint4 (&oldv)[4])
+{
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        if (rs.rows[it] > 0 && 4 * (lane & 3) < cnt) {
+            uint4 v = *reinterpret_cast<const uint4 *>(tile + (it * 8 + (lane >> 2)) * kTilePitch + 4 * (lane & 3));
+            if (BLEND) {
+                v.x += (oldv[it].x >> 1) & blend_mask;
+                v.y += (oldv[it].y >> 1) & blend_mask;
+                v.z += (oldv[it].z >> 1) & blend_mask;
+                v.w += (oldv[it].w >> 1) & blend_mask;
+            }
+            unsigned char *p = rs.ptr[it] + (size_t) k0 * 4;
+            for (int r = 0; r < rs.rows[it]; r++) *reinterpret_cast<uint4 *>(p + (size_t) r * pitch) = v;
+        }
+    }
+    __syncwarp();
+}
+
+// scalar path: 3-byte pixels, or rows that are not 16-byte aligned; 16 lanes per row, 2 rows per pass
+__device__ __forceinline__ void flush16_scalar(const unsigned *tile, const LinesGeom &geo, unsigned char *out, int k0,
+                                               int cnt, int lane, int beg, int nrows, unsigned blend_mask)
 {
     const int pitch = geo.outw * geo.bpp;
-    const int col0 = k0 & 31;
+    int rp, gp, bp;
+    fmt_positions(geo.out_format, rp, gp, bp);
+    const int j = lane & 15;
     __syncwarp();
-    if (vec) {
-        const int q = lane & 3;
 #pragma unroll 1
-        for (int it = 0; it < 4; it++) {
-            const int l = it * 8 + (lane >> 2);
-            const int lbeg = __shfl_sync(0xffffffffu, beg, l);
-            const int lrows = __shfl_sync(0xffffffffu, nrows, l);
-            if (lbeg >= 0 && 4 * q < cnt) {
-                uint4 v = *reinterpret_cast<const uint4 *>(tile + l * kTilePitch + col0 + 4 * q);
-                unsigned char *p = out + (size_t) lbeg * pitch + (size_t) (k0 + 4 * q) * 4;
+    for (int it = 0; it < 16; it++) {
+        const int l = it * 2 + (lane >> 4);
+        const int lbeg = __shfl_sync(0xffffffffu, beg, l);
+        const int lrows = __shfl_sync(0xffffffffu, nrows, l);
+        if (lbeg >= 0 && j < cnt) {
+            unsigned v = tile[l * kTilePitch + j];
+            unsigned char *p = out + (size_t) lbeg * pitch + (size_t) (k0 + j) * geo.bpp;
+            if (geo.bpp == 4) {
+                if (geo.blend) v += (*reinterpret_cast<const unsigned *>(p) >> 1) & blend_mask;
+                for (int r = 0; r < lrows; r++) *reinterpret_cast<unsigned *>(p + (size_t) r * pitch) = v;
+            } else { // 3 bytes per pixel: the tile word is 0x00RRGGBB (pre-halved when blending)
                 if (geo.blend) {
-                    const uint4 o = *reinterpret_cast<const uint4 *>(p);
-                    v.x += (o.x >> 1) & blend_mask;
-                    v.y += (o.y >> 1) & blend_mask;
-                    v.z += (o.z >> 1) & blend_mask;
-                    v.w += (o.w >> 1) & blend_mask;
+                    const unsigned old = (unsigned) p[rp] << 16 | (unsigned) p[gp] << 8 | (unsigned) p[bp];
+                    v += (old >> 1) & 0x7f7f7fu;
                 }
-                for (int r = 0; r < lrows; r++) *reinterpret_cast<uint4 *>(p + (size_t) r * pitch) = v;
-            }
-        }
-    } else {
-        int rp, gp, bp;
-        fmt_positions(geo.out_format, rp, gp, bp);
-        const int j = lane & 15;
-#pragma unroll 1
-        for (int it = 0; it < 16; it++) {
-            const int l = it * 2 + (lane >> 4);
-            const int lbeg = __shfl_sync(0xffffffffu, beg, l);
-            const int lrows = __shfl_sync(0xffffffffu, nrows, l);
-            if (lbeg >= 0 && j < cnt) {
-                unsigned v = tile[l * kTilePitch + col0 + j];
-                unsigned char *p = out + (size_t) lbeg * pitch + (size_t) (k0 + j) * geo.bpp;
-                if (geo.bpp == 4) {
-                    if (geo.blend) v += (*reinterpret_cast<const unsigned *>(p) >> 1) & blend_mask;
-                    for (int r = 0; r < lrows; r++) *reinterpret_cast<unsigned *>(p + (size_t) r * pitch) = v;
-                } else { // 3 bytes per pixel: the tile word is 0x00RRGGBB (pre-halved when blending)
-                    if (geo.blend) {
-                        const unsigned old = (unsigned) p[rp] << 16 | (unsigned) p[gp] << 8 | (unsigned) p[bp];
-                        v += (old >> 1) & 0x7f7f7fu;
-                    }
-                    for (int r = 0; r < lrows; r++) {
-                        unsigned char *d = p + (size_t) r * pitch;
-                        d[rp] = (unsigned char) (v >> 16);
-                        d[gp] = (unsigned char) (v >> 8);
-                        d[bp] = (unsigned char) v;
-                    }
+                for (int r = 0; r < lrows; r++) {
+                    unsigned char *d = p + (size_t) r * pitch;
+                    d[rp] = (unsigned char) (v >> 16);
+                    d[gp] = (unsigned char) (v >> 8);
+                    d[bp] = (unsigned char) v;
                 }
             }
         }
@@ -249,9 +270,21 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
     const int beg = active ? rec.beg : -1;
     const int nrows = active ? max(1, rec.end - cfg->scanlines - rec.beg) : 0; // crt_core.c:662-664
     const bool vec = (MODE != 2) && ((geo.outw & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    LinesGeom fgeo = geo; // what flush16 branches on, pinned to the template mode
+    LinesGeom fgeo = geo; // what the scalar flush branches on, pinned to the template mode
     fgeo.bpp = (MODE == 2) ? 3 : 4;
     if (MODE != 2) fgeo.blend = (MODE == 1);
+    const int pitch = geo.outw * fgeo.bpp;
+    RowSlots rs;
+    uint4 oldv[4];
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        const int l = it * 8 + (lane >> 2);
+        const int lbeg = __shfl_sync(0xffffffffu, beg, l);
+        const int lrows = __shfl_sync(0xffffffffu, nrows, l);
+        rs.ptr[it] = out + (size_t) max(lbeg, 0) * pitch + (size_t) (lane & 3) * 16;
+        rs.rows[it] = (vec && lbeg >= 0) ? lrows : 0;
+        oldv[it] = make_uint4(0u, 0u, 0u, 0u);
+    }
 
     // storage byte order of 0x00RRGGBB (+ alpha 0xff) for the 4-byte formats (crt_core.h:62-67)
     unsigned sel_store, alpha_ff;
@@ -305,7 +338,7 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
         if (FAST) {
             const uint2 v = *reinterpret_cast<const uint2 *>(yiq + slot * kEntry);
             cy = (int) v.x;
-            ci = (int) __byte_perm(v.y, 0u, 0x9910); // sign-extended low half
+            ci = (int) (short) (unsigned short) v.y; // sign-extended low half
             cq = ((int) v.y) >> 16;
         } else {
             const uint4 v = *reinterpret_cast<const uint4 *>(yiq + slot * kEntry);
@@ -323,7 +356,17 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
     int kdone = 0;     // pixels already flushed  (uniform, multiple of 16)
     unsigned npos = 0; // k * dx, 20.12 position  (uniform)
 
+    auto drain = [&](int cnt) { // write pixels [kdone, kdone + cnt), then fetch the next block's old pixels
+        if (vec) {
+            flush16_vec<MODE == 1>(tile, rs, pitch, kdone, cnt, lane, blend_mask, oldv);
+            load_old<MODE == 1>(rs, kdone + 16, min(16, geo.outw - kdone - 16), lane, oldv);
+        } else {
+            flush16_scalar(tile, fgeo, out, kdone, cnt, lane, beg, nrows, blend_mask);
+        }
+    };
+
     issue(0);
+    if (vec) load_old<MODE == 1>(rs, 0, min(16, geo.outw), lane, oldv);
 #pragma unroll 1
     for (int c = 0; c < kNumStages; c++) {
         if (c + 1 < kNumStages) issue(c + 1); // the other buffer was drained in iteration c - 1
@@ -367,11 +410,11 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
                 } else if (geo.blend) {
                     px = (px >> 1) & 0x7f7f7fu;
                 }
-                tile_row[k & 31] = px;
+                tile_row[k & 15] = px;
                 k++;
                 npos += (unsigned) dx;
                 if (k - kdone == 16) {
-                    flush16(tile, fgeo, out, kdone, 16, lane, beg, nrows, blend_mask, vec);
+                    drain(16);
                     kdone += 16;
                 }
             }
@@ -385,7 +428,7 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
         }
         __syncwarp(); // all lanes are done with this stage buffer before it is refilled
     }
-    if (k - kdone > 0) flush16(tile, fgeo, out, kdone, k - kdone, lane, beg, nrows, blend_mask, vec);
+    if (k - kdone > 0) drain(k - kdone);
 }
 
 } // namespace crt

@@ -145,9 +145,14 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
     }
     {
         LaunchTimer lt(ctx, stream, 1);
-        k_mod_picture_rgb<<<count, 256, kModSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog, first);
+        if (ctx->opt_mod_staged)
+            k_mod_picture_rgb_staged<<<count, 256, kModSSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog,
+                                                                        first, ctx->opt_tma);
+        // monitors whose source span does not fit a stage row (or all of them when staging is off)
+        k_mod_picture_rgb<<<count, 256, kModSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog, first,
+                                                            ctx->opt_mod_staged);
     }
-    ctx->launches += 2;
+    ctx->launches += 2 + (ctx->opt_mod_staged ? 1 : 0);
 #endif
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -176,7 +181,8 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
 #endif
     {
         LaunchTimer lt(ctx, stream, 3);
-        k_sync<<<count, 32, 0, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, first, ctx->opt_generic);
+        k_sync<<<count, kSyncThreads, kSyncSmem, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, first,
+                                                           ctx->opt_generic);
     }
     // The line kernel takes the output geometry as launch-uniform arguments: split the range into
     // runs of monitors that share it (normally one run).
@@ -302,8 +308,10 @@ int crtx_create(crtx_ctx **out, int n)
         CTX_TRY(cudaMemcpy(ctx->d_jump_hi, hi.data(), sizeof(Affine) * kJumpHi, cudaMemcpyHostToDevice));
     }
     CTX_TRY(lines_attr_all());
+    CTX_TRY(cudaFuncSetAttribute(k_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
 #if (CRT_SYSTEM != CRT_SYSTEM_NES)
     CTX_TRY(cudaFuncSetAttribute(k_mod_picture_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSmem));
+    CTX_TRY(cudaFuncSetAttribute(k_mod_picture_rgb_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSSmem));
 #endif
 #undef CTX_TRY
     *out = ctx;
@@ -526,6 +534,7 @@ int crtx_set_option(crtx_ctx *ctx, const char *name, int value)
     if (!strcmp(name, "tma")) ctx->opt_tma = value;
     else if (!strcmp(name, "generic_eq")) ctx->opt_generic = value;
     else if (!strcmp(name, "timing")) ctx->opt_timing = value;
+    else if (!strcmp(name, "mod_staged")) ctx->opt_mod_staged = value;
     else return fail("crtx_set_option: unknown option '%s'", name);
     return 0;
 }
