@@ -184,20 +184,19 @@ __global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restri
     const int field = s.field & 1, frame = s.frame & 1;
     const int flip = (field == frame);
 
-    for (int idx = threadIdx.x; idx < kTotal; idx += blockDim.x) {
-        int n, t;
-        if (idx < kTop * kFullPairs) {
-            n = idx / kFullPairs;
-            t = 2 * (idx - n * kFullPairs);
-        } else {
-            int r = idx - kTop * kFullPairs;
-            n = kTop + r / kHeadPairs;
-            t = 2 * (r % kHeadPairs);
+    (void) kTotal;
+    // 16 bytes per thread per pass where alignment allows would need HRES % 16 == 0; lines start on
+    // even addresses only, so the unit is a byte pair.  The line type is warp-uniform per iteration.
+    const int aberration = s.aberration;
+    for (int n = threadIdx.x >> 5; n < kVres; n += blockDim.x >> 5) { // one warp per line
+        const int extent = (n < kTop) ? kHres : kAvBeg;
+        signed char *line = analog + n * kHres;
+        for (int t = 2 * (threadIdx.x & 31); t < extent; t += 64) {
+            char2 v;
+            v.x = (signed char) skeleton_level(n, t, field, flip, aberration, burst);
+            v.y = (signed char) skeleton_level(n, t + 1, field, flip, aberration, burst);
+            *reinterpret_cast<char2 *>(line + t) = v;
         }
-        char2 v;
-        v.x = (signed char) skeleton_level(n, t, field, flip, s.aberration, burst);
-        v.y = (signed char) skeleton_level(n, t + 1, field, flip, s.aberration, burst);
-        *reinterpret_cast<char2 *>(analog + n * kHres + t) = v;
     }
     if (threadIdx.x < 4) { // prime the burst lock (crt_ntsc.c:325-329 / crt_ntscvhs.c:332-336)
         MonState *st = &states[first + blockIdx.x];
@@ -375,7 +374,8 @@ __device__ __forceinline__ bool mod_staged_ok(const SrcCfg &s, int destw)
     if (bpp == 0 || destw <= 0 || s.w <= 0) return false;
     // widest source span of a chunk: ceil(32 * w / destw) + 1 pixels, plus 15 bytes of alignment
     const long long span = ((long long) kModSChunk * s.w + destw - 1) / destw + 1;
-    return span * bpp + 15 + 16 <= kModSRow && (bpp != 4 || (reinterpret_cast<uintptr_t>(s.data) & 3) == 0);
+    return span * bpp + 15 + 16 <= kModSRow && s.w <= 65535
+        && (bpp != 4 || (reinterpret_cast<uintptr_t>(s.data) & 3) == 0);
 }
 
 template <bool STAGED>
@@ -455,23 +455,23 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
     const unsigned char *rowp = data + (size_t) row * s.w * bpp;
     const int nchunks = (destw + kModSChunk - 1) / kModSChunk;
 
-    // chunk c covers samples [32c, 32c + 32): source columns f0..f1, staged from the 16-byte
-    // aligned address at or below the first pixel
-    auto span = [&](int c, int &f0, int &bytes) {
-        const int x0 = c * kModSChunk, x1 = min(x0 + kModSChunk, destw) - 1;
-        f0 = (int) (((long long) x0 * s.w) / destw);
-        const int f1 = (int) (((long long) x1 * s.w) / destw);
-        bytes = (f1 - f0 + 1) * bpp;
+    // chunk c covers samples [32c, 32c + 32): lane l maps sample 32c + l to source column
+    // (x * w) / destw (crt_ntsc.c:272) -- one 32-bit division per lane per chunk, computed one chunk
+    // ahead; the chunk's span f0..f1 is staged from the 16-byte aligned address at or below pixel f0
+    auto colof = [&](int c) {
+        const unsigned x = (unsigned) min(c * kModSChunk + lane, destw - 1);
+        return (int) (x * (unsigned) s.w / (unsigned) destw);
     };
-    auto issue = [&](int c) {
-        int f0, bytes;
-        span(c, f0, bytes);
+    auto issue = [&](int c, int col) {
+        const int nxc = min(kModSChunk, destw - c * kModSChunk);
+        const int f0 = __shfl_sync(0xffffffffu, col, 0), f1 = __shfl_sync(0xffffffffu, col, nxc - 1);
+        const int bytes = (f1 - f0 + 1) * bpp;
         const unsigned char *p = rowp + (size_t) f0 * bpp;
         const int a = (int) (reinterpret_cast<uintptr_t>(p) & 15);
         const unsigned copy = (unsigned) ((a + bytes + 15) & ~15);
         unsigned char *dst = stage + (c & 1) * 32 * kModSRow + lane * kModSRow;
         if (use_tma) {
-            // every lane copies the same number of bytes only if all rows share `a`; sum them up
+            // rows may sit at different 16-byte phases, so the copies differ in size: sum them up
             unsigned total = active ? copy : 0;
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
@@ -485,18 +485,20 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
     };
 
     int hy = 0, hi = 0, hq = 0;
-    issue(0);
+    int col_cur = colof(0);
+    issue(0, col_cur);
 #pragma unroll 1
     for (int c = 0; c < nchunks; c++) {
-        if (c + 1 < nchunks) issue(c + 1);
-        int f0, bytes;
-        span(c, f0, bytes);
+        int col_nxt = 0;
+        if (c + 1 < nchunks) {
+            col_nxt = colof(c + 1);
+            issue(c + 1, col_nxt);
+        }
+        const int f0 = __shfl_sync(0xffffffffu, col_cur, 0);
         const int c0 = c * kModSChunk;
         const int nx = min(kModSChunk, destw - c0);
-        { // byte offset of sample x's pixel inside the stage row, relative to the first pixel
-            const int x = min(c0 + lane, destw - 1);
-            coltab[lane] = ((int) (((long long) x * s.w) / destw) - f0) * bpp;
-        }
+        coltab[lane] = (col_cur - f0) * bpp; // byte offset of sample x's pixel from the chunk's first pixel
+        col_cur = col_nxt;
         if (use_tma) mbar_wait(&bars[c & 1], (c >> 1) & 1);
         __syncwarp();
         const unsigned char *srow = stage + (c & 1) * 32 * kModSRow + lane * kModSRow

@@ -10,9 +10,9 @@
 //      sync holds) into shared memory with coalesced loads -- the chains then run at shared-memory
 //      latency instead of L2 latency;
 //   2. the 2W vsync candidates are integrated in parallel, 4 lines at a time, one per warp;
-//   3. warp 0 runs the hsync chain (window prefix sums by byte dot-products, no shuffles) and
-//      publishes hsync[k]; warp 1 trails it with the burst-lock chain (4 lanes per colour row) and
-//      emits the per-line records k_lines consumes.  The two chains overlap.
+//   3. the hsync chain is solved by verified speculation (parallel sweeps to a fixed point, see 3a);
+//      one warp then runs the burst-lock chain, 4 lanes per colour row, next line prefetched;
+//   4. all threads emit the per-line records k_lines consumes.
 // Lines whose windows leave the staged heads (sync lost, |hsync| large) fall back to global loads.
 #pragma once
 
@@ -37,10 +37,38 @@ struct SyncShared {
     SyncLine ln[kLines];
     int hs[kLines];     // hsync after each decoded line's search
     int ccr[kLines][4]; // burst-lock accumulator of the line's colour row after its 10 steps
-    volatile int ready; // lines published by the hsync warp
+    short rowlist[3][kLines]; // decoded lines of each colour row, in order
+    int rowcount[3];
     int vs_found[2 * kVsyncWindow]; // per vsync candidate: crossing index or -1
     int generic;
 };
+
+// hsync search of one decoded line given the hsync it enters with (crt_core.c:437-447):
+// integrate 2W samples starting W before the expected sync edge, stop at the threshold.
+__device__ __forceinline__ int hsync_step(const unsigned *heads, const signed char *inp, int jl, int hs)
+{
+    const int p0 = jl * kHres + hs + kSyncBeg - kHsyncWindow; // first window sample
+    const int j = (hs > kHres / 2) ? jl + 1 : jl;             // line whose staged head holds the window
+    const int off = p0 - ((j * kHres - kHeadBefore) & ~3);
+    int i = 2 * kHsyncWindow, acc = 0;
+    if (j < kVres && off >= 0 && off + 2 * kHsyncWindow <= kHeadWords * 4) {
+        const signed char *hb = reinterpret_cast<const signed char *>(heads + j * kHeadWords) + off;
+#pragma unroll
+        for (int t = 0; t < 2 * kHsyncWindow; t++) {
+            acc += hb[t];
+            if (acc <= kHsyncLevel && i == 2 * kHsyncWindow) i = t;
+        }
+    } else { // window outside the staged heads (sync lost): plain loads
+        for (int t = 0; t < 2 * kHsyncWindow; t++) {
+            acc += __ldg(inp + p0 + t);
+            if (acc <= kHsyncLevel && i == 2 * kHsyncWindow) i = t;
+        }
+    }
+    hs += i - kHsyncWindow;
+    if (hs < 0) hs += kHres; // POSMOD(i + hsync, HRES), |i| <= W
+    else if (hs >= kHres) hs -= kHres;
+    return hs;
+}
 
 __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states,
                                                        LineRec *__restrict__ lines_base,
@@ -57,15 +85,12 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
     LineRec *lines = lines_base + (size_t) m * kLines;
 
     // ---- 1. stage line heads: heads[j][w] = the aligned word at ((j * H - 16) & ~3) + 4w
-    for (int idx = tid; idx < kVres * kHeadWords; idx += kSyncThreads) {
-        const int j = idx / kHeadWords, w = idx - j * kHeadWords;
-        const int p = ((j * kHres - kHeadBefore) & ~3) + 4 * w;
-        heads[idx] = (p >= 0) ? __ldg(reinterpret_cast<const unsigned *>(inp + p)) : 0u;
+    for (int j = warp; j < kVres; j += kSyncThreads / 32) {
+        const int p = ((j * kHres - kHeadBefore) & ~3);
+        for (int w = lane; w < kHeadWords; w += 32)
+            heads[j * kHeadWords + w] = (p + 4 * w >= 0) ? __ldg(reinterpret_cast<const unsigned *>(inp + p) + w) : 0u;
     }
-    if (tid == 0) {
-        sh.ready = 0;
-        sh.generic = force_generic || abs(cfg.brightness - (kBlack + cfg.black_point)) > 4096;
-    }
+    if (tid == 0) sh.generic = force_generic || abs(cfg.brightness - (kBlack + cfg.black_point)) > 4096;
 
     // ---- 2. vsync (crt_core.c:379-396): candidate c = line posmod(vsync + c - W); first crossing wins
     const int vs_in = st->vsync;
@@ -96,6 +121,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
     int field = (jcross > kHres / 2);
     const int ratio = (((cfg.outh << 16) / kLines) + 32768) >> 16; // crt_core.c:404-407
     field *= ratio / 2;
+    const int hs_in = st->hsync;
     for (int k = tid; k < kLines; k += kSyncThreads) { // chain-independent per-line geometry
         SyncLine g;
         int beg = (int) ((unsigned) k * ((unsigned) cfg.outh + cfg.v_fac) / (unsigned) kLines + (unsigned) field);
@@ -108,97 +134,96 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
         g.beg = beg;
         g.end = end;
         sh.ln[k] = g;
+        sh.hs[k] = hs_in; // initial guess of the chain
     }
     __syncthreads();
+    if (tid < kVper) { // decoded lines of each colour row, in order (skipped lines do not touch ccf)
+        int n = 0;
+        for (int k = 0; k < kLines; k++)
+            if (sh.ln[k].beg >= 0 && sh.ln[k].row == tid) sh.rowlist[tid][n++] = (short) k;
+        sh.rowcount[tid] = n;
+    }
+
+    // ---- 3a. hsync chain hs[k] = f_k(hs[k-1]) (crt_core.c:437-450) by verified speculation: every line
+    // is evaluated in parallel from the current guess of its predecessor; a sweep that changes nothing
+    // proves hs[] is the chain's unique solution.  The sync edge recaptures the search from any start
+    // within the window, so this takes a handful of sweeps instead of 240 dependent steps.
+    for (int sweep = 0; sweep <= kLines; sweep++) {
+        int nh[(kLines + kSyncThreads - 1) / kSyncThreads];
+        int changed = 0;
+#pragma unroll
+        for (int q = 0; q < (kLines + kSyncThreads - 1) / kSyncThreads; q++) {
+            const int k = tid + q * kSyncThreads;
+            nh[q] = 0;
+            if (k < kLines) {
+                const int prev = (k == 0) ? hs_in : sh.hs[k - 1];
+                nh[q] = (sh.ln[k].beg >= 0) ? hsync_step(heads, inp, sh.ln[k].jl, prev) : prev; // crt_core.c:431
+                changed |= (nh[q] != sh.hs[k]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < (kLines + kSyncThreads - 1) / kSyncThreads; q++) {
+            const int k = tid + q * kSyncThreads;
+            if (k < kLines) sh.hs[k] = nh[q];
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
 
     if (warp == 0) {
-        // ---- 3a. hsync chain (crt_core.c:437-450), lanes 0..2W-1 hold the window prefix sums
-        int hs = st->hsync;
-        // byte masks: lane j sums window bytes 0..j -> 0x01 in every byte position <= j
-        unsigned mask[4];
+        // ---- 3b. burst lock (crt_core.c:456-467): ccr = ccr * 127 / 128 + sample, 10 samples per phase
+        // per line.  Lane = 4 * row + phase walks its own row's lines; the next line's samples are
+        // fetched while the current line's 10 dependent steps run.
+        const int row = lane >> 2, phase = lane & 3;
+        const bool chain_lane = lane < 4 * kVper;
+        const int t0 = (phase - kCbBeg) & 3; // burst samples of this phase: t0, t0 + 4, ...
+        int x = chain_lane ? st->ccf[row][phase] : 0;
+        const int count = chain_lane ? sh.rowcount[row] : 0;
+        auto fetch = [&](int n, int (&smp)[kBurstLen / 4]) {
+            const int k = sh.rowlist[row][n];
+            const int hs = sh.hs[k], jl = sh.ln[k].jl;
+            const int pb = jl * kHres + (hs & ~3) + kCbBeg + t0; // this phase's first burst sample
+            const int j = (hs > kHres / 2) ? jl + 1 : jl;
+            const int off = pb - ((j * kHres - kHeadBefore) & ~3);
+            if (j < kVres && off >= 0 && off + kBurstLen <= kHeadWords * 4) {
+                const signed char *hb = reinterpret_cast<const signed char *>(heads + j * kHeadWords) + off;
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
-            unsigned v = 0;
+                for (int q = 0; q < kBurstLen / 4; q++) smp[q] = hb[4 * q];
+            } else {
 #pragma unroll
-            for (int b = 0; b < 4; b++)
-                if (4 * w + b <= lane && 4 * w + b < 2 * kHsyncWindow) v |= 1u << (8 * b);
-            mask[w] = v;
-        }
-        for (int k = 0; k < kLines; k++) {
-            if (sh.ln[k].beg >= 0) { // skipped lines leave hsync alone (crt_core.c:431)
-                const int jl = sh.ln[k].jl;
-                const int j = (hs > kHres / 2) ? jl + 1 : jl;             // line whose head holds the window
-                const int p0 = jl * kHres + hs + kSyncBeg - kHsyncWindow; // first window sample
-                const int off = p0 - ((j * kHres - kHeadBefore) & ~3);
-                int prefix;
-                if (j < kVres && off >= 0 && off + 20 <= kHeadWords * 4) {
-                    const unsigned *wp = heads + j * kHeadWords + (off >> 2);
-                    const int shft = 8 * (off & 3);
-                    const unsigned w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
-                    prefix = __dp4a((int) __funnelshift_r(w0, w1, shft), (int) mask[0], 0);
-                    prefix = __dp4a((int) __funnelshift_r(w1, w2, shft), (int) mask[1], prefix);
-                    prefix = __dp4a((int) __funnelshift_r(w2, w3, shft), (int) mask[2], prefix);
-                    prefix = __dp4a((int) __funnelshift_r(w3, w4, shft), (int) mask[3], prefix);
-                } else { // window outside the staged heads: plain loads + scan
-                    int v = 0;
-                    if (lane < 2 * kHsyncWindow) v = __ldg(inp + p0 + lane);
-                    prefix = warp_scan_incl(v, lane);
+                for (int q = 0; q < kBurstLen / 4; q++) smp[q] = __ldg(inp + pb + 4 * q);
+            }
+        };
+        int cur[kBurstLen / 4], nxt[kBurstLen / 4];
+#pragma unroll
+        for (int q = 0; q < kBurstLen / 4; q++) cur[q] = nxt[q] = 0;
+        if (count > 0) fetch(0, cur);
+        for (int n = 0; n < count; n++) {
+            if (n + 1 < count) fetch(n + 1, nxt);
+            // C's x * 127 / 128 truncates towards zero.  While the product cannot wrap it equals
+            // x - ((x + 127) >> 7) for x >= 0 and x - (x >> 7) for x < 0 (ceil / floor of x / 128):
+            // both candidates come straight from x, so a step is 3 dependent instructions.
+            if (abs(x) < (1 << 23)) {
+#pragma unroll
+                for (int q = 0; q < kBurstLen / 4; q++) {
+                    const int up = x - ((x + 127) >> 7) + cur[q], dn = x - (x >> 7) + cur[q];
+                    x = (x >= 0) ? up : dn;
                 }
-                const unsigned hit = __ballot_sync(0xffffffffu, lane < 2 * kHsyncWindow && prefix <= kHsyncLevel);
-                hs += (hit ? __ffs(hit) - 1 : 2 * kHsyncWindow) - kHsyncWindow;
-                if (hs < 0) hs += kHres; // POSMOD(i + hsync, HRES), |i| <= W
-                else if (hs >= kHres) hs -= kHres;
+            } else {
+#pragma unroll
+                for (int q = 0; q < kBurstLen / 4; q++) x = wadd(wmul(x, 127) / 128, cur[q]);
             }
-            if (lane == 0) {
-                sh.hs[k] = hs;
-                __threadfence_block();
-                sh.ready = k + 1;
-            }
+            sh.ccr[sh.rowlist[row][n]][phase] = x;
+#pragma unroll
+            for (int q = 0; q < kBurstLen / 4; q++) cur[q] = nxt[q];
         }
+        if (chain_lane) st->ccf[row][phase] = x;
         if (lane == 0) {
             st->vsync = vs;
-            st->hsync = hs;
+            st->hsync = sh.hs[kLines - 1];
             st->field = field;
             if (!kIsVhs) st->rn = (int) ((unsigned) st->rn * kLcgField.mul + kLcgField.add); // crt_core.c:367
         }
-    } else if (warp == 1) {
-        // ---- 3b. burst lock (crt_core.c:456-467).  Lane = 4 * row + phase; trails the hsync warp.
-        const int row_of_lane = lane >> 2, phase = lane & 3;
-        const bool chain_lane = lane < 4 * kVper;
-        int x = chain_lane ? st->ccf[row_of_lane][phase] : 0;
-        const int t0 = (phase - kCbBeg) & 3; // burst samples of this phase: t0, t0 + 4, ...
-        for (int k = 0; k < kLines; k++) {
-            const SyncLine g = sh.ln[k];
-            if (g.beg < 0) continue;
-            while (sh.ready <= k) { }
-            __threadfence_block();
-            const int hs = sh.hs[k];
-            if (chain_lane && row_of_lane == g.row) {
-                const int pb = g.jl * kHres + (hs & ~3) + kCbBeg + t0; // this phase's first burst sample
-                const int j = (hs > kHres / 2) ? g.jl + 1 : g.jl;
-                const int off = pb - ((j * kHres - kHeadBefore) & ~3);
-                int smp[kBurstLen / 4];
-                if (j < kVres && off >= 0 && off + kBurstLen <= kHeadWords * 4) {
-                    const signed char *hb = reinterpret_cast<const signed char *>(heads + j * kHeadWords) + off;
-#pragma unroll
-                    for (int q = 0; q < kBurstLen / 4; q++) smp[q] = hb[4 * q];
-                } else {
-#pragma unroll
-                    for (int q = 0; q < kBurstLen / 4; q++) smp[q] = __ldg(inp + pb + 4 * q);
-                }
-                // ccr = ccr * 127 / 128 + sample, C division truncating towards zero.  While no product can
-                // wrap, trunc(127 x / 128) == x - ((x + (x > 0 ? 127 : 0)) >> 7), a shorter dependent chain.
-                if (abs(x) < (1 << 23)) {
-#pragma unroll
-                    for (int q = 0; q < kBurstLen / 4; q++) x = x - ((x + (x > 0 ? 127 : 0)) >> 7) + smp[q];
-                } else {
-#pragma unroll
-                    for (int q = 0; q < kBurstLen / 4; q++) x = wadd(wmul(x, 127) / 128, smp[q]);
-                }
-                sh.ccr[k][phase] = x;
-            }
-        }
-        if (chain_lane) st->ccf[row_of_lane][phase] = x;
     }
     __syncthreads();
 
