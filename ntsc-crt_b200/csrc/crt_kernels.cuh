@@ -185,17 +185,34 @@ __global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restri
     const int flip = (field == frame);
 
     (void) kTotal;
-    // 16 bytes per thread per pass where alignment allows would need HRES % 16 == 0; lines start on
-    // even addresses only, so the unit is a byte pair.  The line type is warp-uniform per iteration.
+    // One warp per line; every line is a handful of constant runs (crt_ntsc.c:205-252), written as
+    // warp-wide byte fills -- no per-byte classification.
     const int aberration = s.aberration;
-    for (int n = threadIdx.x >> 5; n < kVres; n += blockDim.x >> 5) { // one warp per line
-        const int extent = (n < kTop) ? kHres : kAvBeg;
-        signed char *line = analog + n * kHres;
-        for (int t = 2 * (threadIdx.x & 31); t < extent; t += 64) {
-            char2 v;
-            v.x = (signed char) skeleton_level(n, t, field, flip, aberration, burst);
-            v.y = (signed char) skeleton_level(n, t + 1, field, flip, aberration, burst);
-            *reinterpret_cast<char2 *>(line + t) = v;
+    const int lane = threadIdx.x & 31;
+    constexpr int H = kHres;
+    for (int n = threadIdx.x >> 5; n < kVres; n += blockDim.x >> 5) {
+        signed char *line = analog + n * H;
+        auto fill = [&](int from, int to, int level) {
+            for (int t = from + lane; t < to; t += 32) line[t] = (signed char) level;
+        };
+        if (n <= 3 || (n >= 7 && n <= 9)) { // equalising pulses
+            fill(0, 4 * H / 100, kSync);
+            fill(4 * H / 100, 50 * H / 100, kBlank);
+            fill(50 * H / 100, 54 * H / 100, kSync);
+            fill(54 * H / 100, H, kBlank);
+        } else if (n >= 4 && n <= 6) { // vertical sync
+            const int first = (field == 1 ? 4 : 46) * H / 100;
+            fill(0, first, kSync);
+            fill(first, 50 * H / 100, kBlank);
+            fill(50 * H / 100, 96 * H / 100, kSync);
+            fill(96 * H / 100, H, kBlank);
+        } else { // video line: porch, sync tip, breezeway, burst, back porch (+ blank picture above TOP)
+            fill(0, kSyncBeg, kBlank);
+            fill(kSyncBeg, kBwBeg, (n < kVres - aberration) ? kSync : kBlank); // crt_ntscvhs.c:234-238
+            fill(kBwBeg, kCbBeg, kBlank);
+            for (int t = kCbBeg + lane; t < kCbBeg + kBurstLen; t += 32)
+                line[t] = (signed char) ((kBlank + burst[(t + flip * 2) & 3] * kBurst) >> 5);
+            fill(kCbBeg + kBurstLen, (n < kTop) ? H : kAvBeg, kBlank);
         }
     }
     if (threadIdx.x < 4) { // prime the burst lock (crt_ntsc.c:325-329 / crt_ntscvhs.c:332-336)
@@ -539,14 +556,26 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
         }
         __syncwarp();
         // coalesced stores: 16 lanes x 2 bytes per line, two lines per pass
-        for (int l2 = 0; l2 < nlines; l2 += 2) {
-            const int l = l2 + (lane >> 4), j = lane & 15;
-            if (l < nlines) {
-                signed char *dst = analog + (c0 + xo) + (y0 + l + yo) * kHres;
-                const unsigned w = obuf[l * kModSOutPitch + (j >> 1)];
-                const unsigned two = (w >> (16 * (j & 1))) & 0xffffu;
-                if (2 * j + 1 < nx) *reinterpret_cast<unsigned short *>(dst + 2 * j) = (unsigned short) two;
-                else if (2 * j < nx) dst[2 * j] = (signed char) (two & 0xff);
+        {
+            const int j = lane & 15;
+            const unsigned short *ob = reinterpret_cast<const unsigned short *>(obuf) + (lane >> 4) * (2 * kModSOutPitch) + j;
+            signed char *dst = analog + (c0 + xo) + (y0 + (lane >> 4) + yo) * kHres + 2 * j;
+            if (nx == kModSChunk) { // full chunk: no edge tests
+#pragma unroll 4
+                for (int l2 = 0; l2 + 1 < nlines; l2 += 2) {
+                    *reinterpret_cast<unsigned short *>(dst) = ob[l2 * (2 * kModSOutPitch)];
+                    dst += 2 * kHres;
+                }
+                if ((nlines & 1) && lane < 16) *reinterpret_cast<unsigned short *>(dst) = ob[(nlines - 1) * (2 * kModSOutPitch)];
+            } else {
+                for (int l2 = 0; l2 < nlines; l2 += 2) {
+                    if (l2 + (lane >> 4) < nlines) {
+                        const unsigned short two = ob[l2 * (2 * kModSOutPitch)];
+                        if (2 * j + 1 < nx) *reinterpret_cast<unsigned short *>(dst) = two;
+                        else if (2 * j < nx) *dst = (signed char) (two & 0xff);
+                    }
+                    dst += 2 * kHres;
+                }
             }
         }
         __syncwarp();

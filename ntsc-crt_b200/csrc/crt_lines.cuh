@@ -222,12 +222,14 @@ __device__ __forceinline__ void flush16_scalar(const unsigned *tile, const Lines
 // Template axes (chosen by the host per launch, so every branch on them is compile-time):
 //   FAST  see eq_step; the other instantiation takes the monitors k_sync flagged as generic
 //   MODE  0: 4-byte pixels, no blend; 1: 4-byte pixels, blend; 2: 3-byte pixels (blend at run time)
+//   FMT   the CRT_PIX_FORMAT of the 4-byte modes (byte order and alpha position become immediates);
+//         ignored (0) for MODE 2
 //
 // Per warp, per 16-sample sub-chunk: (F) one straight-line filter block per sample writes packed
 // Y/I/Q into the lane's own shared-memory row; (P) a uniform loop walks the output pixels whose two
 // source samples are now available, reading slots by a warp-uniform index -- so neither phase has
 // per-sample control flow and the register allocator sees two simple loops.
-template <bool FAST, int MODE>
+template <bool FAST, int MODE, int FMT>
 __global__ void __launch_bounds__(kLinesWarps * 32, FAST ? 2 : 1)
 k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, const LineRec *__restrict__ lines_base,
         const signed char *__restrict__ inp_base, int first, const LinesGeom geo)
@@ -287,14 +289,10 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
     }
 
     // storage byte order of 0x00RRGGBB (+ alpha 0xff) for the 4-byte formats (crt_core.h:62-67)
-    unsigned sel_store, alpha_ff;
-    switch (geo.out_format) {
-        case CRT_PIX_FORMAT_RGBA: sel_store = 0x4012; alpha_ff = 0xff000000u; break;
-        case CRT_PIX_FORMAT_ARGB: sel_store = 0x0124; alpha_ff = 0x000000ffu; break;
-        case CRT_PIX_FORMAT_ABGR: sel_store = 0x2104; alpha_ff = 0x000000ffu; break;
-        default:                  sel_store = 0x4210; alpha_ff = 0xff000000u; break; // BGRA
-    }
-    const unsigned blend_mask = (MODE != 2) ? (0x7f7f7f7fu & ~(alpha_ff >> 1) & ~alpha_ff) : 0x7f7f7fu;
+    constexpr unsigned sel_store = (FMT == CRT_PIX_FORMAT_RGBA) ? 0x4012u : (FMT == CRT_PIX_FORMAT_ARGB) ? 0x0124u
+                                 : (FMT == CRT_PIX_FORMAT_ABGR) ? 0x2104u : 0x4210u;
+    constexpr unsigned alpha_ff = (FMT == CRT_PIX_FORMAT_ARGB || FMT == CRT_PIX_FORMAT_ABGR) ? 0x000000ffu : 0xff000000u;
+    constexpr unsigned blend_mask = (MODE != 2) ? (0x7f7f7f7fu & ~(alpha_ff >> 1) & ~alpha_ff) : 0x7f7f7fu;
 
     const int dx = ((kAvLen - 1) << 12) / geo.outw; // crt_core.c:527
     const int nw0 = wsub(0, rec.wave0), nw1 = wsub(0, rec.wave1);
@@ -334,14 +332,14 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
                 make_uint4((unsigned) wmul(y, 16), (unsigned) ci, (unsigned) cq, 0u);
         }
     };
-    auto get = [&](int slot, int &cy, int &ci, int &cq) {
+    auto get = [&](const unsigned char *p, int &cy, int &ci, int &cq) {
         if (FAST) {
-            const uint2 v = *reinterpret_cast<const uint2 *>(yiq + slot * kEntry);
+            const uint2 v = *reinterpret_cast<const uint2 *>(p);
             cy = (int) v.x;
             ci = (int) (short) (unsigned short) v.y; // sign-extended low half
             cq = ((int) v.y) >> 16;
         } else {
-            const uint4 v = *reinterpret_cast<const uint4 *>(yiq + slot * kEntry);
+            const uint4 v = *reinterpret_cast<const uint4 *>(p);
             cy = (int) v.x;
             ci = (int) v.y;
             cq = (int) v.z;
@@ -388,14 +386,17 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
             }
             // ---- (P) every pixel whose samples (s, s + 1) are both in slots 0..kSub (crt_core.c:555-659)
             const int base = c * kStageSamples + u - 1; // sample index held by slot 0
-            const int last = base + kSub;               // newest sample available
+            // pixel k (position npos = k * dx) is computable once sample (npos >> 12) + 1 <= base + kSub
+            // exists, and exists at all while npos < outw * dx (<= scanR, crt_core.c:529,555)
+            const unsigned lim = min((unsigned) (base + kSub) << 12, (unsigned) geo.outw * (unsigned) dx);
+            const unsigned char *slot0 = yiq - base * kEntry; // slot of sample s is slot0 + s * kEntry
 #pragma unroll 1
-            while (k < geo.outw && (int) (npos >> 12) < last) {
-                const int slot = (int) (npos >> 12) - base;
+            while (npos < lim) {
+                const unsigned char *sp = slot0 + (npos >> 12) * kEntry;
                 const int R = (int) (npos & 0xfffu), L = 0xfff - R;
                 int ay, ai, aq, by, bi, bq;
-                get(slot, ay, ai, aq);
-                get(slot + 1, by, bi, bq);
+                get(sp, ay, ai, aq);
+                get(sp + kEntry, by, bi, bq);
                 unsigned px;
                 if (FAST) {
                     const int y = wadd(wmul(ay, 4 * L), wmul(by, 4 * R));
@@ -405,15 +406,16 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
                     px = yiq_pixel(ay, ai, aq, by, bi, bq, R, L, contrast);
                 }
                 if (MODE != 2) {
-                    px = __byte_perm(px, 0xffu, sel_store);
+                    px = (FMT == CRT_PIX_FORMAT_BGRA) ? (px | alpha_ff) : __byte_perm(px, 0xffu, sel_store);
                     if (MODE == 1) px = ((px >> 1) & blend_mask) | alpha_ff;
                 } else if (geo.blend) {
                     px = (px >> 1) & 0x7f7f7fu;
                 }
-                tile_row[k & 15] = px;
+                const int col = k - kdone; // 0..15: the tile restarts after every drain
+                tile_row[col] = px;
                 k++;
                 npos += (unsigned) dx;
-                if (k - kdone == 16) {
+                if (col == 15) {
                     drain(16);
                     kdone += 16;
                 }

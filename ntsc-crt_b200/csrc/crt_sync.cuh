@@ -23,7 +23,8 @@ namespace crt {
 constexpr int kHeadBefore = 16;                 // staged bytes before each line start
 constexpr int kHeadAfter = ((kCbBeg + kBurstLen + 40 + 15) / 16) * 16; // ... and after it
 constexpr int kHeadWords = (kHeadBefore + kHeadAfter) / 4 + 1;        // +1: start is aligned down to 4
-constexpr int kSyncSmem = kVres * kHeadWords * 4;
+constexpr int kCandWords = (kHres + 3) / 4 + 1;                     // a whole line from a 4-aligned start
+constexpr int kSyncSmem = (kVres * kHeadWords + 2 * kVsyncWindow * kCandWords) * 4;
 constexpr int kSyncThreads = 128;
 
 struct SyncLine { // what depends only on k, vsync and the detected field (not on the chains)
@@ -84,25 +85,52 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
     const signed char *inp = inp_base + (size_t) m * kSignalBytes;
     LineRec *lines = lines_base + (size_t) m * kLines;
 
-    // ---- 1. stage line heads: heads[j][w] = the aligned word at ((j * H - 16) & ~3) + 4w
-    for (int j = warp; j < kVres; j += kSyncThreads / 32) {
-        const int p = ((j * kHres - kHeadBefore) & ~3);
-        for (int w = lane; w < kHeadWords; w += 32)
-            heads[j * kHeadWords + w] = (p + 4 * w >= 0) ? __ldg(reinterpret_cast<const unsigned *>(inp + p) + w) : 0u;
+    // ---- 1. stage line heads (heads[j][w] = the aligned word at ((j * H - 16) & ~3) + 4w) and the 2W
+    // vsync candidate lines in full (cand[c][w] = aligned words covering line posmod(vsync + c - W)).
+    // All loads of a batch are issued before any is stored, so the copy runs at memory-level parallelism
+    // instead of one L2 round trip per word.
+    unsigned *cand = heads + kVres * kHeadWords; // [2W][kCandWords]
+    const int vs_in = st->vsync;
+    {
+        constexpr int kBatch = 8;
+        constexpr int kHeadTotal = kVres * kHeadWords, kCandTotal = 2 * kVsyncWindow * kCandWords;
+        for (int base = 0; base < kHeadTotal + kCandTotal; base += kBatch * kSyncThreads) {
+            unsigned v[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; b++) {
+                const int idx = base + b * kSyncThreads + tid;
+                v[b] = 0u;
+                if (idx < kHeadTotal) {
+                    const int j = idx / kHeadWords, w = idx - j * kHeadWords;
+                    const int p = ((j * kHres - kHeadBefore) & ~3) + 4 * w;
+                    if (p >= 0) v[b] = __ldg(reinterpret_cast<const unsigned *>(inp + p));
+                } else if (idx < kHeadTotal + kCandTotal) {
+                    const int q = idx - kHeadTotal, c = q / kCandWords, w = q - c * kCandWords;
+                    const int p = (posmod(vs_in + c - kVsyncWindow, kVres) * kHres & ~3) + 4 * w;
+                    v[b] = __ldg(reinterpret_cast<const unsigned *>(inp + p));
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; b++) {
+                const int idx = base + b * kSyncThreads + tid;
+                if (idx < kHeadTotal + kCandTotal) heads[idx] = v[b];
+            }
+        }
     }
     if (tid == 0) sh.generic = force_generic || abs(cfg.brightness - (kBlack + cfg.black_point)) > 4096;
+    __syncthreads();
 
     // ---- 2. vsync (crt_core.c:379-396): candidate c = line posmod(vsync + c - W); first crossing wins
-    const int vs_in = st->vsync;
     constexpr int kSeg = (kHres + 31) / 32;
     for (int c = warp; c < 2 * kVsyncWindow; c += kSyncThreads / 32) {
-        const signed char *sig = inp + posmod(vs_in + c - kVsyncWindow, kVres) * kHres;
+        const int lstart = posmod(vs_in + c - kVsyncWindow, kVres) * kHres;
+        const signed char *sig = reinterpret_cast<const signed char *>(cand + c * kCandWords) + (lstart & 3);
         const int b0 = lane * kSeg, b1 = min(kHres, b0 + kSeg);
         int sum = 0;
-        for (int t = b0; t < b1; t++) sum += __ldg(sig + t);
+        for (int t = b0; t < b1; t++) sum += sig[t];
         int acc = warp_scan_incl(sum, lane) - sum, idx = -1;
         for (int t = b0; t < b1; t++) {
-            acc += __ldg(sig + t);
+            acc += sig[t];
             if (idx < 0 && acc <= kVsyncLevel) idx = t;
         }
         const unsigned hit = __ballot_sync(0xffffffffu, idx >= 0);

@@ -56,18 +56,26 @@ static int upload_cfg(crtx_ctx *ctx, cudaStream_t stream)
     return 0;
 }
 
+template <bool FAST, int MODE, int FMT>
+static void launch_lines_one(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
+{
+    k_lines<FAST, MODE, FMT><<<count, kLinesWarps * 32, lines_smem<FAST>(), stream>>>(ctx->d_cfg, ctx->d_state,
+                                                                                      ctx->d_lines, ctx->d_inp, lo, geo);
+}
+
 template <bool FAST>
 static void launch_lines_mode(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
 {
-    const int mode = (geo.bpp == 4) ? (geo.blend ? 1 : 0) : 2;
-    const dim3 block(kLinesWarps * 32);
-    constexpr int smem = lines_smem<FAST>();
-    if (mode == 0)
-        k_lines<FAST, 0><<<count, block, smem, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, lo, geo);
-    else if (mode == 1)
-        k_lines<FAST, 1><<<count, block, smem, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, lo, geo);
-    else
-        k_lines<FAST, 2><<<count, block, smem, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, lo, geo);
+    if (geo.bpp != 4) return launch_lines_one<FAST, 2, 0>(ctx, count, lo, geo, stream);
+#define LL(F)                                                                                     \
+    case F:                                                                                       \
+        if (geo.blend) launch_lines_one<FAST, 1, F>(ctx, count, lo, geo, stream);                 \
+        else launch_lines_one<FAST, 0, F>(ctx, count, lo, geo, stream);                           \
+        break;
+    switch (geo.out_format) {
+        LL(CRT_PIX_FORMAT_ARGB) LL(CRT_PIX_FORMAT_RGBA) LL(CRT_PIX_FORMAT_ABGR) LL(CRT_PIX_FORMAT_BGRA)
+    }
+#undef LL
 }
 
 static void launch_lines(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
@@ -76,18 +84,22 @@ static void launch_lines(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo,
     launch_lines_mode<false>(ctx, count, lo, geo, stream);
 }
 
-template <bool FAST, int MODE>
+template <bool FAST, int MODE, int FMT>
 static cudaError_t lines_attr()
 {
-    return cudaFuncSetAttribute(k_lines<FAST, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lines_smem<FAST>());
+    return cudaFuncSetAttribute(k_lines<FAST, MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                lines_smem<FAST>());
 }
 
 static cudaError_t lines_attr_all()
 {
     cudaError_t e = cudaSuccess;
-#define LA(F, M)                                  \
-    if (e == cudaSuccess) e = lines_attr<F, M>();
-    LA(true, 0) LA(true, 1) LA(true, 2) LA(false, 0) LA(false, 1) LA(false, 2)
+#define LA(F, M, T)                                  \
+    if (e == cudaSuccess) e = lines_attr<F, M, T>();
+#define LF(T) LA(true, 0, T) LA(true, 1, T) LA(false, 0, T) LA(false, 1, T)
+    LF(CRT_PIX_FORMAT_ARGB) LF(CRT_PIX_FORMAT_RGBA) LF(CRT_PIX_FORMAT_ABGR) LF(CRT_PIX_FORMAT_BGRA)
+    LA(true, 2, 0) LA(false, 2, 0)
+#undef LF
 #undef LA
     return e;
 }
