@@ -338,6 +338,26 @@ def run_product(args):
     batch.timing()
     frames_e2e = per * nstreams * e2e_steps
 
+    # ---------------- optional: all_gather of the decoded frames (the exchange north_star mentions for
+    # "a batch of frames presented together"); priced separately, it is NVLink-bound
+    gather = None
+    if args.allgather and world > 1:
+        from ntsc_crt_b200 import sharding
+        g_steps = max(2, min(args.steps, 4))
+        full = sharding.allgather_frames(out)  # warm-up, also allocates
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for k in range(g_steps):
+            step(k)
+            full = sharding.allgather_frames(out)
+        g1.record(stream)
+        barrier()
+        g_ms = sharding.max_over_ranks([g0.elapsed_time(g1)], device=dev)[0]
+        gather = {"value": world * B * g_steps / (g_ms / 1e3), "unit": "frames/s",
+                  "bytes_received_per_rank_per_step": (world - 1) * B * H_OUT * W_OUT * 4, "steps": g_steps}
+        del full
+
     # ---------------- max over ranks
     if world > 1:
         t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -384,6 +404,8 @@ def run_product(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if gather:
+            line["allgather"] = gather
         print(json.dumps(line), flush=True)
     batch.close()
     if world > 1:
@@ -401,6 +423,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=64)
     ap.add_argument("--set", action="append", default=[], help="library option name=value (A/B testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allgather", action="store_true", help="also time steps that all_gather the decoded frames")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup
     if args.impl == "reference":

@@ -403,6 +403,9 @@ __device__ __forceinline__ bool mod_takes(const SrcCfg &s)
     return mod_staged_ok(s, destw) == STAGED;
 }
 
+// FMT / COLOR are launch-uniform (the host groups monitors by them) so byte extraction and the
+// chroma path compile to straight-line code; monitors that do not match return at once.
+template <int FMT, bool COLOR>
 __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg *__restrict__ srcs,
                                                                    const MonCfg *__restrict__ cfgs,
                                                                    signed char *__restrict__ analog_base, int first,
@@ -411,7 +414,7 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SrcCfg s = srcs[blockIdx.x];
-    if (!mod_takes<true>(s)) return;
+    if (!mod_takes<true>(s) || s.format != FMT || (s.as_color != 0) != COLOR) return;
     const MonCfg cfg = cfgs[first + blockIdx.x];
     signed char *analog = analog_base + (size_t) (first + blockIdx.x) * kSignalBytes;
 
@@ -420,7 +423,10 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
     int *coltab = reinterpret_cast<int *>(obuf + 32 * kModSOutPitch);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 8 * kModSWarpSmem) + 2 * warp;
 
-    const int bpp = bpp_of(s.format);
+    constexpr int bpp = (FMT <= 1) ? 3 : 4;
+    constexpr int rp = (FMT == 0 || FMT == 3) ? 0 : (FMT == 2) ? 1 : (FMT == 4) ? 3 : 2; // crt_core.h:62-67
+    constexpr int gp = (FMT == 2 || FMT == 4) ? 2 : 1;
+    constexpr int bp = (FMT == 0 || FMT == 3) ? 2 : (FMT == 2) ? 3 : (FMT == 4) ? 1 : 0;
     int destw = kAvLen, desth = (kLines * 64500) >> 16;
     if (s.raw) { // crt_ntsc.c:163-172
         destw = min(s.w, kAvLen);
@@ -445,10 +451,8 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
     const int yo = kTop + s.yoffset + (kLines - desth) / 2;
     const int white = kWhite * cfg.white_point / 100;
     const int ire0 = kBlack + cfg.black_point;
-    int rp, gp, bp;
-    fmt_positions(s.format, rp, gp, bp);
     const unsigned char *data = static_cast<const unsigned char *>(s.data);
-    const bool color = s.as_color != 0;
+    constexpr bool color = COLOR;
 
     int mI[4], mQ[4]; // ph * ccmodI/Q (crt_ntsc.c:174-188, 314-315)
 #pragma unroll
@@ -521,22 +525,26 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
         const unsigned char *srow = stage + (c & 1) * 32 * kModSRow + lane * kModSRow
                                   + (int) (reinterpret_cast<uintptr_t>(rowp + (size_t) f0 * bpp) & 15);
 #pragma unroll 1
-        for (int x4 = 0; x4 < nx; x4 += 4) {
+        for (int x4 = 0; x4 < nx; x4 += 4) { // kModSChunk is a multiple of 4: coltab[x4 .. x4 + 3] exist
             unsigned packed = 0;
+            int rr[4], gg[4], bb[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int off = coltab[min(x4 + k, kModSChunk - 1)];
-                int r, g, b;
+            for (int k = 0; k < 4; k++) { // all four pixel fetches first, then the dependent arithmetic
+                const int off = coltab[x4 + k];
                 if (bpp == 4) {
                     const unsigned v = *reinterpret_cast<const unsigned *>(srow + off);
-                    r = (v >> (8 * rp)) & 0xff;
-                    g = (v >> (8 * gp)) & 0xff;
-                    b = (v >> (8 * bp)) & 0xff;
+                    rr[k] = (v >> (8 * rp)) & 0xff;
+                    gg[k] = (v >> (8 * gp)) & 0xff;
+                    bb[k] = (v >> (8 * bp)) & 0xff;
                 } else {
-                    r = srow[off + rp];
-                    g = srow[off + gp];
-                    b = srow[off + bp];
+                    rr[k] = srow[off + rp];
+                    gg[k] = srow[off + gp];
+                    bb[k] = srow[off + bp];
                 }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int r = rr[k], g = gg[k], b = bb[k];
                 const int fy = (19595 * r + 38470 * g + 7471 * b) >> 14; // crt_ntsc.c:308-310
                 hy += wmul(fy - hy, kIirY) >> 11; // iirf, crt_ntsc.c:117-126
                 int sum = hy;

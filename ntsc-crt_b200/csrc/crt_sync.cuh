@@ -25,7 +25,7 @@ constexpr int kHeadAfter = ((kCbBeg + kBurstLen + 40 + 15) / 16) * 16; // ... an
 constexpr int kHeadWords = (kHeadBefore + kHeadAfter) / 4 + 1;        // +1: start is aligned down to 4
 constexpr int kCandWords = (kHres + 3) / 4 + 1;                     // a whole line from a 4-aligned start
 constexpr int kSyncSmem = (kVres * kHeadWords + 2 * kVsyncWindow * kCandWords) * 4;
-constexpr int kSyncThreads = 128;
+constexpr int kSyncThreads = 256;
 
 struct SyncLine { // what depends only on k, vsync and the detected field (not on the chains)
     short jl;   // signal line the decoded line reads: posmod(top + k + vsync, vres)
@@ -46,7 +46,8 @@ struct SyncShared {
 
 // hsync search of one decoded line given the hsync it enters with (crt_core.c:437-447):
 // integrate 2W samples starting W before the expected sync edge, stop at the threshold.
-__device__ __forceinline__ int hsync_step(const unsigned *heads, const signed char *inp, int jl, int hs)
+template <typename FetchByte>
+__device__ __forceinline__ int hsync_step(const unsigned *heads, FetchByte fetch_byte, int jl, int hs)
 {
     const int p0 = jl * kHres + hs + kSyncBeg - kHsyncWindow; // first window sample
     const int j = (hs > kHres / 2) ? jl + 1 : jl;             // line whose staged head holds the window
@@ -61,7 +62,7 @@ __device__ __forceinline__ int hsync_step(const unsigned *heads, const signed ch
         }
     } else { // window outside the staged heads (sync lost): plain loads
         for (int t = 0; t < 2 * kHsyncWindow; t++) {
-            acc += __ldg(inp + p0 + t);
+            acc += fetch_byte(p0 + t);
             if (acc <= kHsyncLevel && i == 2 * kHsyncWindow) i = t;
         }
     }
@@ -71,9 +72,43 @@ __device__ __forceinline__ int hsync_step(const unsigned *heads, const signed ch
     return hs;
 }
 
+// Four samples of inp[] starting at the 4-aligned index p, computed from analog[] exactly as the noise
+// pass does (crt_core.c:346-367): sample i uses the LCG state advanced i + 1 steps from the call's seed.
+__device__ __forceinline__ unsigned noisy_word(const signed char *__restrict__ analog, int p, int noise, unsigned rn0,
+                                               const Affine *__restrict__ jump_lo, const Affine *__restrict__ jump_hi)
+{
+    unsigned w = __ldg(reinterpret_cast<const unsigned *>(analog + p));
+    if (noise == 0) {
+        w = __vmaxs4(w, 0x81818181u);
+    } else {
+        const int t = p / kNoiseVec;
+        const Affine lo = jump_lo[t % kJumpLo], hi = jump_hi[t / kJumpLo];
+        unsigned rn = (rn0 * hi.mul + hi.add) * lo.mul + lo.add; // state before sample 16 t
+        for (int k = 0; k < (p % kNoiseVec); k++) rn = rn * kLcgMul + kLcgAdd;
+        unsigned o = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            rn = rn * kLcgMul + kLcgAdd;
+            int v = (int) (signed char) (w >> (8 * b)) + (wmul((int) ((rn >> 16) & 0xff) - 0x7f, noise) >> 8);
+            o |= ((unsigned) clampi(v, -127, 127) & 0xffu) << (8 * b);
+        }
+        w = o;
+    }
+    // beyond inp[] the buffer holds its zero padding, never written by the noise pass
+    if (p + 4 > kInputSize) w = (p >= kInputSize) ? 0u : (w & (0xffffffffu >> (8 * (p + 4 - kInputSize))));
+    return w;
+}
+
+// FUSED (LCG systems): the kernel reads analog[], applies the noise itself to what it stages, and its
+// otherwise idle warps write the whole inp[] while warp 0 runs the burst-lock chain -- the separate noise
+// pass disappears.  !FUSED (VHS, whose noise comes from rand()): inp[] was written by k_noise_terms.
+template <bool FUSED>
 __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states,
                                                        LineRec *__restrict__ lines_base,
-                                                       const signed char *__restrict__ inp_base, int first,
+                                                       const signed char *__restrict__ analog_base,
+                                                       signed char *__restrict__ inp_base,
+                                                       const Affine *__restrict__ jump_lo,
+                                                       const Affine *__restrict__ jump_hi, int first,
                                                        int force_generic)
 {
     extern __shared__ __align__(16) unsigned heads[]; // [kVres][kHeadWords]
@@ -82,8 +117,21 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
     const MonCfg cfg = cfgs[m];
     if (cfg.bpp == 0) return; // crt_core.c:312-315
     MonState *st = &states[m];
-    const signed char *inp = inp_base + (size_t) m * kSignalBytes;
+    const signed char *analog = analog_base + (size_t) m * kSignalBytes;
+    signed char *inp_w = inp_base + (size_t) m * kSignalBytes;
+    const signed char *inp = inp_w; // !FUSED reads; fall-back loads when sync is lost (see below)
     LineRec *lines = lines_base + (size_t) m * kLines;
+    const unsigned rn0 = (unsigned) st->rn;
+    const int noise = cfg.noise;
+    auto fetch = [&](int p) { // one staged word
+        if (p < 0) return 0u;
+        if (FUSED) return noisy_word(analog, p, noise, rn0, jump_lo, jump_hi);
+        return __ldg(reinterpret_cast<const unsigned *>(inp + p));
+    };
+    auto fetch_byte = [&](int p) { // a single sample outside the staged regions (sync lost)
+        const unsigned w = fetch(p & ~3);
+        return (int) (signed char) (w >> (8 * (p & 3)));
+    };
 
     // ---- 1. stage line heads (heads[j][w] = the aligned word at ((j * H - 16) & ~3) + 4w) and the 2W
     // vsync candidate lines in full (cand[c][w] = aligned words covering line posmod(vsync + c - W)).
@@ -92,7 +140,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
     unsigned *cand = heads + kVres * kHeadWords; // [2W][kCandWords]
     const int vs_in = st->vsync;
     {
-        constexpr int kBatch = 8;
+        constexpr int kBatch = FUSED ? 4 : 8;
         constexpr int kHeadTotal = kVres * kHeadWords, kCandTotal = 2 * kVsyncWindow * kCandWords;
         for (int base = 0; base < kHeadTotal + kCandTotal; base += kBatch * kSyncThreads) {
             unsigned v[kBatch];
@@ -103,11 +151,11 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
                 if (idx < kHeadTotal) {
                     const int j = idx / kHeadWords, w = idx - j * kHeadWords;
                     const int p = ((j * kHres - kHeadBefore) & ~3) + 4 * w;
-                    if (p >= 0) v[b] = __ldg(reinterpret_cast<const unsigned *>(inp + p));
+                    v[b] = fetch(p);
                 } else if (idx < kHeadTotal + kCandTotal) {
                     const int q = idx - kHeadTotal, c = q / kCandWords, w = q - c * kCandWords;
                     const int p = (posmod(vs_in + c - kVsyncWindow, kVres) * kHres & ~3) + 4 * w;
-                    v[b] = __ldg(reinterpret_cast<const unsigned *>(inp + p));
+                    v[b] = fetch(p);
                 }
             }
 #pragma unroll
@@ -185,7 +233,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
             nh[q] = 0;
             if (k < kLines) {
                 const int prev = (k == 0) ? hs_in : sh.hs[k - 1];
-                nh[q] = (sh.ln[k].beg >= 0) ? hsync_step(heads, inp, sh.ln[k].jl, prev) : prev; // crt_core.c:431
+                nh[q] = (sh.ln[k].beg >= 0) ? hsync_step(heads, fetch_byte, sh.ln[k].jl, prev) : prev; // crt_core.c:431
                 changed |= (nh[q] != sh.hs[k]);
             }
         }
@@ -219,7 +267,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
                 for (int q = 0; q < kBurstLen / 4; q++) smp[q] = hb[4 * q];
             } else {
 #pragma unroll
-                for (int q = 0; q < kBurstLen / 4; q++) smp[q] = __ldg(inp + pb + 4 * q);
+                for (int q = 0; q < kBurstLen / 4; q++) smp[q] = fetch_byte(pb + 4 * q);
             }
         };
         int cur[kBurstLen / 4], nxt[kBurstLen / 4];
@@ -250,7 +298,38 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
             st->vsync = vs;
             st->hsync = sh.hs[kLines - 1];
             st->field = field;
-            if (!kIsVhs) st->rn = (int) ((unsigned) st->rn * kLcgField.mul + kLcgField.add); // crt_core.c:367
+            if (!kIsVhs) st->rn = (int) (rn0 * kLcgField.mul + kLcgField.add); // crt_core.c:367
+        }
+    } else if (FUSED) {
+        // ---- 3c. the noise pass proper (crt_core.c:346-367), by the 7 warps that would otherwise wait:
+        // analog -> inp, 16 samples per thread per step, 128-bit accesses
+        for (int t = tid - 32; t < kNoiseThreads; t += kSyncThreads - 32) {
+            const int i0 = t * kNoiseVec;
+            const uint4 in = *reinterpret_cast<const uint4 *>(analog + i0);
+            unsigned w[4] = { in.x, in.y, in.z, in.w };
+            if (noise == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) w[k] = __vmaxs4(w[k], 0x81818181u);
+            } else {
+                const Affine lo = jump_lo[t % kJumpLo], hi = jump_hi[t / kJumpLo];
+                unsigned rn = (rn0 * hi.mul + hi.add) * lo.mul + lo.add;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    unsigned o = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        rn = rn * kLcgMul + kLcgAdd;
+                        int v = (int) (signed char) (w[k] >> (8 * b)) + (wmul((int) ((rn >> 16) & 0xff) - 0x7f, noise) >> 8);
+                        o |= ((unsigned) clampi(v, -127, 127) & 0xffu) << (8 * b);
+                    }
+                    w[k] = o;
+                }
+            }
+            if (i0 + kNoiseVec <= kInputSize) {
+                *reinterpret_cast<uint4 *>(inp_w + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+                for (int b = 0; i0 + b < kInputSize; b++) inp_w[i0 + b] = (signed char) (w[b >> 2] >> (8 * (b & 3)));
+            }
         }
     }
     __syncthreads();

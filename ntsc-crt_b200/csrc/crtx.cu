@@ -104,6 +104,31 @@ static cudaError_t lines_attr_all()
     return e;
 }
 
+#if (CRT_SYSTEM != CRT_SYSTEM_NES)
+template <int FMT, bool COLOR>
+static void launch_mod_staged_one(crtx_ctx *ctx, int count, int first, cudaStream_t stream)
+{
+    static bool attr_done = false; // per instantiation; cudaFuncSetAttribute is idempotent
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_mod_picture_rgb_staged<FMT, COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSSmem);
+        attr_done = true;
+    }
+    k_mod_picture_rgb_staged<FMT, COLOR><<<count, 256, kModSSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog,
+                                                                            first, ctx->opt_tma);
+}
+
+static void launch_mod_staged(crtx_ctx *ctx, int format, bool color, int count, int first, cudaStream_t stream)
+{
+#define MS(F)                                                                        \
+    case F:                                                                          \
+        if (color) launch_mod_staged_one<F, true>(ctx, count, first, stream);        \
+        else launch_mod_staged_one<F, false>(ctx, count, first, stream);             \
+        break;
+    switch (format) { MS(0) MS(1) MS(2) MS(3) MS(4) MS(5) default: break; }
+#undef MS
+}
+#endif
+
 // RAII bracket: records start/stop events around one launch when timing is on
 struct LaunchTimer {
     crtx_ctx *ctx;
@@ -151,20 +176,27 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
     }
     ctx->launches += 1;
 #else
+    int extra = 0;
     {
         LaunchTimer lt(ctx, stream, 0);
         k_mod_skeleton_rgb<<<count, 256, 0, stream>>>(ctx->d_src + first, ctx->d_state, ctx->d_analog, first);
     }
     {
         LaunchTimer lt(ctx, stream, 1);
-        if (ctx->opt_mod_staged)
-            k_mod_picture_rgb_staged<<<count, 256, kModSSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog,
-                                                                        first, ctx->opt_tma);
+        if (ctx->opt_mod_staged) { // runs of equal (pixel format, colour) share one instantiation
+            for (int lo = 0; lo < count;) {
+                int hi = lo + 1;
+                while (hi < count && src[hi].format == src[lo].format && (src[hi].as_color != 0) == (src[lo].as_color != 0)) hi++;
+                launch_mod_staged(ctx, src[lo].format, src[lo].as_color != 0, hi - lo, first + lo, stream);
+                extra += 1;
+                lo = hi;
+            }
+        }
         // monitors whose source span does not fit a stage row (or all of them when staging is off)
         k_mod_picture_rgb<<<count, 256, kModSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog, first,
                                                             ctx->opt_mod_staged);
     }
-    ctx->launches += 2 + (ctx->opt_mod_staged ? 1 : 0);
+    ctx->launches += 2 + extra;
 #endif
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -182,20 +214,35 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
         LaunchTimer lt(ctx, stream, 2);
         k_noise_terms<<<tgrid, 256, 0, stream>>>(ctx->d_cfg, ctx->d_analog, ctx->d_inp, d_noise_terms, first);
     }
-#else
-    (void) d_noise_terms;
-    dim3 ngrid(kNoiseBlocks, count);
-    {
-        LaunchTimer lt(ctx, stream, 2);
-        k_noise<<<ngrid, 256, 0, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_analog, ctx->d_inp, ctx->d_jump_lo,
-                                           ctx->d_jump_hi, first);
-    }
-#endif
     {
         LaunchTimer lt(ctx, stream, 3);
-        k_sync<<<count, kSyncThreads, kSyncSmem, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_inp, first,
-                                                           ctx->opt_generic);
+        k_sync<false><<<count, kSyncThreads, kSyncSmem, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_analog,
+                                                                  ctx->d_inp, ctx->d_jump_lo, ctx->d_jump_hi, first,
+                                                                  ctx->opt_generic);
     }
+    const int pre = 2;
+#else
+    (void) d_noise_terms;
+    int pre = 1;
+    if (ctx->opt_fused_noise) { // the noise pass runs inside k_sync (crt_sync.cuh)
+        LaunchTimer lt(ctx, stream, 3);
+        k_sync<true><<<count, kSyncThreads, kSyncSmem, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_analog,
+                                                                 ctx->d_inp, ctx->d_jump_lo, ctx->d_jump_hi, first,
+                                                                 ctx->opt_generic);
+    } else {
+        dim3 ngrid(kNoiseBlocks, count);
+        {
+            LaunchTimer lt(ctx, stream, 2);
+            k_noise<<<ngrid, 256, 0, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_analog, ctx->d_inp, ctx->d_jump_lo,
+                                               ctx->d_jump_hi, first);
+        }
+        LaunchTimer lt(ctx, stream, 3);
+        k_sync<false><<<count, kSyncThreads, kSyncSmem, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_analog,
+                                                                  ctx->d_inp, ctx->d_jump_lo, ctx->d_jump_hi, first,
+                                                                  ctx->opt_generic);
+        pre = 2;
+    }
+#endif
     // The line kernel takes the output geometry as launch-uniform arguments: split the range into
     // runs of monitors that share it (normally one run).
     int launched = 0;
@@ -223,7 +270,7 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
         launched += 2;
         lo = hi;
     }
-    ctx->launches += 2 + launched;
+    ctx->launches += pre + launched;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -320,10 +367,10 @@ int crtx_create(crtx_ctx **out, int n)
         CTX_TRY(cudaMemcpy(ctx->d_jump_hi, hi.data(), sizeof(Affine) * kJumpHi, cudaMemcpyHostToDevice));
     }
     CTX_TRY(lines_attr_all());
-    CTX_TRY(cudaFuncSetAttribute(k_sync, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
+    CTX_TRY(cudaFuncSetAttribute(k_sync<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
+    CTX_TRY(cudaFuncSetAttribute(k_sync<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
 #if (CRT_SYSTEM != CRT_SYSTEM_NES)
     CTX_TRY(cudaFuncSetAttribute(k_mod_picture_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSmem));
-    CTX_TRY(cudaFuncSetAttribute(k_mod_picture_rgb_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSSmem));
 #endif
 #undef CTX_TRY
     *out = ctx;
@@ -547,6 +594,7 @@ int crtx_set_option(crtx_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "generic_eq")) ctx->opt_generic = value;
     else if (!strcmp(name, "timing")) ctx->opt_timing = value;
     else if (!strcmp(name, "mod_staged")) ctx->opt_mod_staged = value;
+    else if (!strcmp(name, "fused_noise")) ctx->opt_fused_noise = value;
     else return fail("crtx_set_option: unknown option '%s'", name);
     return 0;
 }

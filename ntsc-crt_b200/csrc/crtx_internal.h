@@ -31,6 +31,7 @@ struct crtx_ctx {
     int opt_generic = 0;
     int opt_timing = 0;
     int opt_mod_staged = 1;
+    int opt_fused_noise = 1;
     struct Timed {
         int kernel;
         cudaEvent_t start, stop;
