@@ -282,8 +282,18 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
             if (abs(x) < (1 << 23)) {
 #pragma unroll
                 for (int q = 0; q < kBurstLen / 4; q++) {
-                    const int up = x - ((x + 127) >> 7) + cur[q], dn = x - (x >> 7) + cur[q];
-                    x = (x >= 0) ? up : dn;
+                    // both roundings come straight from x, the sign picks one with a predicated subtract:
+                    // 3 dependent instructions per step (add, shift, subtract) instead of 4-5
+                    asm volatile("{\n"
+                                 " .reg .pred p;\n .reg .s32 up, dn, t;\n"
+                                 " setp.ge.s32 p, %0, 0;\n"
+                                 " add.s32 up, %0, 127;\n"
+                                 " add.s32 t, %0, %1;\n"
+                                 " shr.s32 up, up, 7;\n"
+                                 " shr.s32 dn, %0, 7;\n"
+                                 " @p sub.s32 %0, t, up;\n"
+                                 " @!p sub.s32 %0, t, dn;\n"
+                                 "}" : "+r"(x) : "r"(cur[q]));
                 }
             } else {
 #pragma unroll
@@ -303,32 +313,44 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
     } else if (FUSED) {
         // ---- 3c. the noise pass proper (crt_core.c:346-367), by the 7 warps that would otherwise wait:
         // analog -> inp, 16 samples per thread per step, 128-bit accesses
-        for (int t = tid - 32; t < kNoiseThreads; t += kSyncThreads - 32) {
-            const int i0 = t * kNoiseVec;
-            const uint4 in = *reinterpret_cast<const uint4 *>(analog + i0);
-            unsigned w[4] = { in.x, in.y, in.z, in.w };
-            if (noise == 0) {
+        constexpr int kNB = 4; // loads in flight per thread: the 7 warps must cover DRAM latency by themselves
+        for (int tb = tid - 32; tb < kNoiseThreads; tb += kNB * (kSyncThreads - 32)) {
+            uint4 in[kNB];
 #pragma unroll
-                for (int k = 0; k < 4; k++) w[k] = __vmaxs4(w[k], 0x81818181u);
-            } else {
-                const Affine lo = jump_lo[t % kJumpLo], hi = jump_hi[t / kJumpLo];
-                unsigned rn = (rn0 * hi.mul + hi.add) * lo.mul + lo.add;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    unsigned o = 0;
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        rn = rn * kLcgMul + kLcgAdd;
-                        int v = (int) (signed char) (w[k] >> (8 * b)) + (wmul((int) ((rn >> 16) & 0xff) - 0x7f, noise) >> 8);
-                        o |= ((unsigned) clampi(v, -127, 127) & 0xffu) << (8 * b);
-                    }
-                    w[k] = o;
-                }
+            for (int u = 0; u < kNB; u++) {
+                const int t = tb + u * (kSyncThreads - 32);
+                in[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (t < kNoiseThreads) in[u] = *reinterpret_cast<const uint4 *>(analog + t * kNoiseVec);
             }
-            if (i0 + kNoiseVec <= kInputSize) {
-                *reinterpret_cast<uint4 *>(inp_w + i0) = make_uint4(w[0], w[1], w[2], w[3]);
-            } else {
-                for (int b = 0; i0 + b < kInputSize; b++) inp_w[i0 + b] = (signed char) (w[b >> 2] >> (8 * (b & 3)));
+#pragma unroll
+            for (int u = 0; u < kNB; u++) {
+                const int t = tb + u * (kSyncThreads - 32);
+                if (t >= kNoiseThreads) continue;
+                const int i0 = t * kNoiseVec;
+                unsigned w[4] = { in[u].x, in[u].y, in[u].z, in[u].w };
+                if (noise == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) w[k] = __vmaxs4(w[k], 0x81818181u);
+                } else {
+                    const Affine lo = jump_lo[t % kJumpLo], hi = jump_hi[t / kJumpLo];
+                    unsigned rn = (rn0 * hi.mul + hi.add) * lo.mul + lo.add;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        unsigned o = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            rn = rn * kLcgMul + kLcgAdd;
+                            int v = (int) (signed char) (w[k] >> (8 * b)) + (wmul((int) ((rn >> 16) & 0xff) - 0x7f, noise) >> 8);
+                            o |= ((unsigned) clampi(v, -127, 127) & 0xffu) << (8 * b);
+                        }
+                        w[k] = o;
+                    }
+                }
+                if (i0 + kNoiseVec <= kInputSize) {
+                    *reinterpret_cast<uint4 *>(inp_w + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+                } else {
+                    for (int b = 0; i0 + b < kInputSize; b++) inp_w[i0 + b] = (signed char) (w[b >> 2] >> (8 * (b & 3)));
+                }
             }
         }
     }
