@@ -38,6 +38,7 @@ struct SyncShared {
     SyncLine ln[kLines];
     int hs[kLines];     // hsync after each decoded line's search
     int ccr[kLines][4]; // burst-lock accumulator of the line's colour row after its 10 steps
+    signed char burst[kLines][kBurstLen]; // the 40 burst samples each decoded line locks onto
     short rowlist[3][kLines]; // decoded lines of each colour row, in order
     int rowcount[3];
     int vs_found[2 * kVsyncWindow]; // per vsync candidate: crossing index or -1
@@ -246,62 +247,45 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
         if (!__syncthreads_or(changed)) break;
     }
 
+    // ---- 3b. burst lock (crt_core.c:456-467): ccr = ccr * 127 / 128 + sample, 10 samples per phase per line.
+    // First every thread gathers the 40 burst samples of its lines (their position depends on hsync, now
+    // known) into shared memory, so the serial chain below is nothing but the recurrence.
+    for (int idx = tid; idx < kLines * kBurstLen; idx += kSyncThreads) {
+        const int k = idx / kBurstLen, t = idx - k * kBurstLen;
+        int v = 0;
+        if (sh.ln[k].beg >= 0) {
+            const int hs = sh.hs[k], jl = sh.ln[k].jl;
+            const int p = jl * kHres + (hs & ~3) + kCbBeg + t;
+            const int j = (hs > kHres / 2) ? jl + 1 : jl;
+            const int off = p - ((j * kHres - kHeadBefore) & ~3);
+            if (j < kVres && off >= 0 && off < kHeadWords * 4)
+                v = (int) (signed char) (heads[j * kHeadWords + (off >> 2)] >> (8 * (off & 3)));
+            else
+                v = fetch_byte(p);
+        }
+        sh.burst[k][t] = (signed char) v;
+    }
+    __syncthreads();
     if (warp == 0) {
-        // ---- 3b. burst lock (crt_core.c:456-467): ccr = ccr * 127 / 128 + sample, 10 samples per phase
-        // per line.  Lane = 4 * row + phase walks its own row's lines; the next line's samples are
-        // fetched while the current line's 10 dependent steps run.
+        // Lane = 4 * row + phase walks its own colour row's lines.
         const int row = lane >> 2, phase = lane & 3;
         const bool chain_lane = lane < 4 * kVper;
         const int t0 = (phase - kCbBeg) & 3; // burst samples of this phase: t0, t0 + 4, ...
         int x = chain_lane ? st->ccf[row][phase] : 0;
         const int count = chain_lane ? sh.rowcount[row] : 0;
-        auto fetch = [&](int n, int (&smp)[kBurstLen / 4]) {
-            const int k = sh.rowlist[row][n];
-            const int hs = sh.hs[k], jl = sh.ln[k].jl;
-            const int pb = jl * kHres + (hs & ~3) + kCbBeg + t0; // this phase's first burst sample
-            const int j = (hs > kHres / 2) ? jl + 1 : jl;
-            const int off = pb - ((j * kHres - kHeadBefore) & ~3);
-            if (j < kVres && off >= 0 && off + kBurstLen <= kHeadWords * 4) {
-                const signed char *hb = reinterpret_cast<const signed char *>(heads + j * kHeadWords) + off;
-#pragma unroll
-                for (int q = 0; q < kBurstLen / 4; q++) smp[q] = hb[4 * q];
-            } else {
-#pragma unroll
-                for (int q = 0; q < kBurstLen / 4; q++) smp[q] = fetch_byte(pb + 4 * q);
-            }
-        };
-        int cur[kBurstLen / 4], nxt[kBurstLen / 4];
-#pragma unroll
-        for (int q = 0; q < kBurstLen / 4; q++) cur[q] = nxt[q] = 0;
-        if (count > 0) fetch(0, cur);
         for (int n = 0; n < count; n++) {
-            if (n + 1 < count) fetch(n + 1, nxt);
+            const int k = sh.rowlist[row][n];
+            const signed char *bs = &sh.burst[k][t0];
             // C's x * 127 / 128 truncates towards zero.  While the product cannot wrap it equals
-            // x - ((x + 127) >> 7) for x >= 0 and x - (x >> 7) for x < 0 (ceil / floor of x / 128):
-            // both candidates come straight from x, so a step is 3 dependent instructions.
+            // x - ((x + (x >= 0 ? 127 : 0)) >> 7): ceil(x / 128) for x >= 0, floor for x < 0.
             if (abs(x) < (1 << 23)) {
 #pragma unroll
-                for (int q = 0; q < kBurstLen / 4; q++) {
-                    // both roundings come straight from x, the sign picks one with a predicated subtract:
-                    // 3 dependent instructions per step (add, shift, subtract) instead of 4-5
-                    asm volatile("{\n"
-                                 " .reg .pred p;\n .reg .s32 up, dn, t;\n"
-                                 " setp.ge.s32 p, %0, 0;\n"
-                                 " add.s32 up, %0, 127;\n"
-                                 " add.s32 t, %0, %1;\n"
-                                 " shr.s32 up, up, 7;\n"
-                                 " shr.s32 dn, %0, 7;\n"
-                                 " @p sub.s32 %0, t, up;\n"
-                                 " @!p sub.s32 %0, t, dn;\n"
-                                 "}" : "+r"(x) : "r"(cur[q]));
-                }
+                for (int q = 0; q < kBurstLen / 4; q++) x = x - ((x + ((x >= 0) ? 127 : 0)) >> 7) + bs[4 * q];
             } else {
 #pragma unroll
-                for (int q = 0; q < kBurstLen / 4; q++) x = wadd(wmul(x, 127) / 128, cur[q]);
+                for (int q = 0; q < kBurstLen / 4; q++) x = wadd(wmul(x, 127) / 128, bs[4 * q]);
             }
-            sh.ccr[sh.rowlist[row][n]][phase] = x;
-#pragma unroll
-            for (int q = 0; q < kBurstLen / 4; q++) cur[q] = nxt[q];
+            sh.ccr[k][phase] = x;
         }
         if (chain_lane) st->ccf[row][phase] = x;
         if (lane == 0) {
