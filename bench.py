@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.05)
+            self._halt.wait(0.001)
 
     def finish(self):
         self._halt.set()
@@ -378,6 +378,12 @@ def run_product(args):
         per_launch_bytes = B * (demod_bytes(0) + demod_bytes(1)) / 2.0
         achieved = (per_launch_bytes / 1e9) / ((lines_ms / max(1, lines_n)) / 1e3) if lines_n else None
         kernel_share = {k: round(v[0] / ms, 4) for k, v in ktimes.items()}
+        traffic = None
+        try:  # DRAM bytes of the line kernel per launch, from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj["k_lines_dram_bytes_per_frame"] * B
+        except Exception:
+            pass
         cpu = cpu_baseline_single() if (world == 1 and not args.no_cpu_baseline) else None
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -395,7 +401,7 @@ def run_product(args):
             "gpu_launches_e2e": int(launches_e2e),
             "roofline": {"bound": "hbm", "kernel": "k_lines (crt_demodulate line pass, crt_core.c:511-664)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "algorithmic_bytes_per_launch": per_launch_bytes, "launch_ms": lines_ms / max(1, lines_n),
                          "peak_source": peak_src},
             "kernel_ms_per_step": {k: round(v[0] / max(1, args.steps), 4) for k, v in ktimes.items()},
