@@ -141,7 +141,10 @@ def _cpu_init(seed=1):
     eng = make()
     eng.set(blend=1, scanlines=1)
     _WORKER["eng"] = eng
-    _WORKER["img"] = S.rand_image(W_IN, H_IN, seed=seed + os.getpid() % 97)
+    if VARIANT == "ntsc":
+        _WORKER["img"] = S.rand_image(W_IN, H_IN, seed=seed + os.getpid() % 97)
+    else:
+        _WORKER["img"] = S.nes_image(W_IN, H_IN, seed=seed + os.getpid() % 97)
     _WORKER["f"] = 0
 
 
@@ -154,7 +157,10 @@ def _cpu_worker(fields):
     t0 = time.perf_counter()
     for _ in range(fields):
         f = _WORKER["f"]
-        eng.modulate(img, format=layout.PIX_BGRA, as_color=1, field=f & 1, frame=(f >> 1) & 1)
+        if VARIANT == "ntsc":
+            eng.modulate(img, format=layout.PIX_BGRA, as_color=1, field=f & 1, frame=(f >> 1) & 1)
+        else:
+            eng.modulate(img, dot_crawl_offset=f & 1, hue=0)
         eng.demodulate(0)
         _WORKER["f"] = f + 1
     return time.perf_counter() - t0
@@ -237,7 +243,11 @@ def run_product(args):
     B = args.batch
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
     # inputs: one distinct image per monitor, BGRA; far larger than L2 in total (see config)
-    src = torch.randint(0, 256, (B, H_IN, W_IN, 4), dtype=torch.uint8, generator=gen).to(dev)
+    nes = VARIANT != "ntsc"
+    if nes:
+        src = torch.randint(0, 512, (B, H_IN, W_IN), dtype=torch.int16, generator=gen).to(dev)
+    else:
+        src = torch.randint(0, 256, (B, H_IN, W_IN, 4), dtype=torch.uint8, generator=gen).to(dev)
     out = torch.zeros(B, H_OUT, W_OUT, 4, dtype=torch.uint8, device=dev)
     batch = capi.Batch(VARIANT, B)
     batch.set_option("timing", 1)
@@ -256,6 +266,7 @@ def run_product(args):
             s.data = src[i].data_ptr()
             s.format, s.w, s.h = layout.PIX_BGRA, W_IN, H_IN
             s.raw, s.as_color, s.field, s.frame = 0, 1, field, 0
+            s.dot_crawl_offset, s.reinit = field, 0
         tables.append(t)
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
@@ -270,6 +281,12 @@ def run_product(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    if nes:  # first call of a NES stream writes the sync template (crt_nes.c:118-121)
+        t0 = (capi.Source * B)()
+        C.memmove(t0, tables[0], C.sizeof(t0))
+        for i in range(B):
+            t0[i].reinit = 1
+        batch._check(batch.lib.crtx_modulate(batch._ctx, 0, B, t0, sp))
     for k in range(args.warmup):
         step(k)
     barrier()
@@ -292,7 +309,10 @@ def run_product(args):
     Be = min(args.e2e_batch, B)
     nstreams = 4
     per = Be // nstreams
-    h_src = torch.randint(0, 256, (Be, H_IN, W_IN, 4), dtype=torch.uint8, generator=gen).pin_memory()
+    if nes:
+        h_src = torch.randint(0, 512, (Be, H_IN, W_IN), dtype=torch.int16, generator=gen).pin_memory()
+    else:
+        h_src = torch.randint(0, 256, (Be, H_IN, W_IN, 4), dtype=torch.uint8, generator=gen).pin_memory()
     h_out = torch.zeros(Be, H_OUT, W_OUT, 4, dtype=torch.uint8).pin_memory()
     streams = [torch.cuda.Stream(dev) for _ in range(nstreams)]
     htables = []
@@ -375,7 +395,8 @@ def run_product(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         lines_ms, lines_n = ktimes["lines"]
-        per_launch_bytes = B * (demod_bytes(0) + demod_bytes(1)) / 2.0
+        isz = batch.spec.input_size
+        per_launch_bytes = B * (demod_bytes(0, input_size=isz) + demod_bytes(1, input_size=isz)) / 2.0
         achieved = (per_launch_bytes / 1e9) / ((lines_ms / max(1, lines_n)) / 1e3) if lines_n else None
         kernel_share = {k: round(v[0] / ms, 4) for k, v in ktimes.items()}
         traffic = None
@@ -389,11 +410,12 @@ def run_product(args):
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-            "config": {"workload": "NTSC 832x624 BGRA -> 832x624 BGRA, interlaced, colour, noise 0, blend 1, scanlines 1 (BASELINE configs[1])",
+            "config": {"workload": ("NTSC 832x624 BGRA -> 832x624 BGRA, interlaced, colour, noise 0, blend 1, scanlines 1 (BASELINE configs[1])"
+                                    if not nes else "%s 256x240 PPU pixels -> 832x624 BGRA, noise 0, blend 1, scanlines 1 (BASELINE configs[2], informational)" % VARIANT),
                        "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (frames sharded, no collective)" % world,
                        "l2": "inputs larger than L2: %.0f MB of images + signals touched per step per GPU" % (B * 4.63)},
             "e2e": {"value": e2e_value, "unit": "frames/s",
-                    "h2d_bytes_per_step": per * nstreams * W_IN * H_IN * 4,
+                    "h2d_bytes_per_step": per * nstreams * W_IN * H_IN * (2 if nes else 4),
                     "d2h_bytes_per_step": per * nstreams * W_OUT * H_OUT * 4,
                     "batch": per * nstreams, "steps": e2e_steps, "api": "crtx_frames_host, pinned host buffers, %d streams" % nstreams,
                     "wall_s": e2e_wall},
@@ -430,8 +452,14 @@ def main():
     ap.add_argument("--set", action="append", default=[], help="library option name=value (A/B testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--allgather", action="store_true", help="also time steps that all_gather the decoded frames")
+    ap.add_argument("--variant", default="ntsc", choices=["ntsc", "nes", "nes_p0"],
+                    help="informational runs of the other systems (the contract metric is the default, ntsc)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup
+    global VARIANT, W_IN, H_IN
+    VARIANT = args.variant
+    if VARIANT != "ntsc":
+        W_IN, H_IN = 256, 240  # PPU image (BASELINE configs[2])
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -214,3 +214,36 @@ def test_batch_matches_independent_oracles():
             S.assert_same_state(got, oras[i].state(), "batch monitor %d step %d" % (i, step))
     assert b.launches >= 3 * 5  # modulate 2-3, noise, sync, line kernel per geometry group
     b.close()
+
+
+@pytest.mark.parametrize("outw,outh,fmt,blend,scanlines", [
+    (1920, 1080, layout.PIX_BGRA, 1, 1),   # > 2 pixels per sample
+    (3200, 300, layout.PIX_RGBA, 0, 0),    # > 4 pixels per sample (dx < 1024)
+    (100, 80, layout.PIX_ARGB, 1, 0),      # heavy decimation, fewer rows than lines (lines skipped / shared)
+    (333, 250, layout.PIX_BGRA, 1, 1),     # width not a multiple of 4: scalar flush path
+    (641, 479, layout.PIX_BGR, 1, 1),      # 3-byte pixels, odd geometry, blend
+    (832, 624, layout.PIX_ABGR, 0, 1),
+])
+def test_dropin_ntsc_output_geometries(outw, outh, fmt, blend, scanlines):
+    """Output sizes / formats that take the other flush paths and many-pixels-per-sample resampling."""
+    img = S.rand_image(400, 300, seed=outw)
+    gpu, ora, ref = trio("ntsc", outw, outh, fmt)
+    run_all((gpu, ora, ref), lambda e: e.set(blend=blend, scanlines=scanlines))
+    for it in range(3):
+        run_all((gpu, ora, ref), lambda e: e.modulate(img, format=layout.PIX_BGRA, as_color=1, field=it & 1, frame=0))
+        run_all((gpu, ora, ref), lambda e: e.demodulate(2 * it))
+        check(gpu, ora, ref, "geometry %dx%d fmt %d call %d" % (outw, outh, fmt, it))
+
+
+@pytest.mark.parametrize("w,h,fmt", [(1920, 1080, layout.PIX_BGRA), (3000, 200, layout.PIX_RGB), (97, 61, layout.PIX_RGBA),
+                                     (753, 236, layout.PIX_ARGB)])
+def test_dropin_ntsc_source_geometries(w, h, fmt):
+    """Source sizes on both sides of the staged encoder's span limit (wide sources take the gather kernel)."""
+    img = S.pack_rgb(S.rand_image(w, h, bpp=3, seed=w), fmt)
+    gpu, ora, ref = trio("ntsc", 640, 480)
+    run_all((gpu, ora, ref), lambda e: e.set(blend=0, scanlines=1))
+    for it in range(2):
+        run_all((gpu, ora, ref), lambda e: e.modulate(img, format=fmt, as_color=1, field=it & 1, frame=it))
+        check(gpu, ora, ref, "source %dx%d mod %d" % (w, h, it))
+        run_all((gpu, ora, ref), lambda e: e.demodulate(0))
+        check(gpu, ora, ref, "source %dx%d demod %d" % (w, h, it))
