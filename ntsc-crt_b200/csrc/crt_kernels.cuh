@@ -610,57 +610,63 @@ __device__ __forceinline__ int nes_square(int p, int phase) // crt_nes.c:21-61
     return c_nes_level[high * 8 + emph * 4 + ((p >> 4) & 3)];
 }
 
-// grid (ceil(H / 256), 262, n): one thread per sample of the field; each byte is written at most
-// once with its final value (skeleton < burst < picture precedence of crt_nes.c:81-201).
+// One CTA per monitor.  The composite level of a picture sample depends only on the 9-bit PPU pixel
+// and the chroma phase modulo 12 (square_sample is periodic in phase: (hue + phase) % 12 and
+// (phase >> 1) % 6), plus the monitor's black / white points -- so the CTA first tabulates all 512 x 12
+// finished sample bytes in shared memory (crt_nes.c:21-61, 182-190), after which a sample is an index
+// computation and one table read, written with coalesced byte stores.
 __global__ void __launch_bounds__(256) k_mod_nes(const SrcCfg *__restrict__ srcs, const MonCfg *__restrict__ cfgs,
                                                  MonState *__restrict__ states,
                                                  signed char *__restrict__ analog_base, int first)
 {
-    const int t = blockIdx.x * 256 + threadIdx.x, n = blockIdx.y, m = blockIdx.z;
+    __shared__ signed char tab[512 * 12];
+    __shared__ signed char burst[3][4];
+    const int m = blockIdx.x, tid = threadIdx.x;
     const SrcCfg s = srcs[m];
     const MonCfg cfg = cfgs[first + m];
     signed char *analog = analog_base + (size_t) (first + m) * kSignalBytes;
     const int xo = (kAvBeg + s.xoffset) & ~3, yo = kTop + s.yoffset;
 
-    if (n == 0 && blockIdx.x == 0 && threadIdx.x < 12) { // prime the burst lock (crt_nes.c:196-200)
-        int row = threadIdx.x >> 2, x = threadIdx.x & 3, sn, cs;
-        int deg = (s.hue + x * 90 + (row + s.dot_crawl_offset) * 120 + 33) % 360;
-        sincos14_d(sn, cs, deg * 8192 / 180);
-        // iccf[n % 3][t & 3] holds the last burst sample written for that (row, phase)
-        states[first + m].ccf[row][x] = ((int) (signed char) ((kBlank + (sn >> 10) * kBurst) >> 5)) * 128;
-    }
-    if (t >= kHres) return;
-    const int y = n - yo;
-    const bool pic_line = (y >= 0 && y < kLines);
-    int v = 0;
-    bool write = false;
-    if (s.reinit) { // setup_field, crt_nes.c:81-104
-        int sync_end = (n >= 259) ? kNesVsyncEnd : kBwBeg;
-        v = (t >= kSyncBeg && t < sync_end) ? kSync : kBlank;
-        write = true;
-    }
-    if (pic_line && t >= kCbBeg && t < kCbBeg + kBurstLen) { // crt_nes.c:174-178
-        int sn, cs;
-        int deg = (s.hue + (t & 3) * 90 + ((n % 3) + s.dot_crawl_offset) * 120 + 33) % 360;
-        sincos14_d(sn, cs, deg * 8192 / 180);
-        v = (int) (signed char) ((kBlank + (sn >> 10) * kBurst) >> 5);
-        write = true;
-    }
-    if (pic_line && t >= xo && t < xo + kAvLen) { // crt_nes.c:180-193
-        const int x = t - xo;
-        int row = (y * s.h) / kLines;
-        if (row >= s.h) row = s.h - 1; // reference reads one row past the image here (undefined)
-        if (row < 0) row = 0;
-        const unsigned short *data = static_cast<const unsigned short *>(s.data);
-        int p = __ldg(data + ((x * s.w) / kAvLen) + row * s.w);
-        int phase = ((y + yo + s.dot_crawl_offset) % 3) * 4 + 3 * x;
+    for (int e = tid; e < 512 * 12; e += 256) {
+        const int p = e / 12, phase = e - p * 12;
         int ire = kBlack + cfg.black_point;
-        ire += nes_square(p, phase) + nes_square(p, phase + 1) + nes_square(p, phase + 2)
-             + nes_square(p, phase + 3);
-        v = (int) (signed char) ((wmul(ire, cfg.white_point) / 100) >> 12);
-        write = true;
+        ire += nes_square(p, phase) + nes_square(p, phase + 1) + nes_square(p, phase + 2) + nes_square(p, phase + 3);
+        tab[e] = (signed char) ((wmul(ire, cfg.white_point) / 100) >> 12);
     }
-    if (write) analog[n * kHres + t] = (signed char) v;
+    if (tid < 12) { // burst rows (crt_nes.c:123-130) and the primed burst lock (crt_nes.c:196-200)
+        const int row = tid >> 2, x = tid & 3;
+        int sn, cs;
+        const int deg = (s.hue + x * 90 + (row + s.dot_crawl_offset) * 120 + 33) % 360;
+        sincos14_d(sn, cs, deg * 8192 / 180);
+        const signed char v = (signed char) ((kBlank + (sn >> 10) * kBurst) >> 5);
+        burst[row][x] = v;
+        states[first + m].ccf[row][x] = (int) v * 128;
+    }
+    __syncthreads();
+
+    if (s.reinit) { // setup_field, crt_nes.c:81-104: every line whole
+        for (int e = tid; e < kVres * kHres; e += 256) {
+            const int n = e / kHres, t = e - n * kHres;
+            const int sync_end = (n >= 259) ? kNesVsyncEnd : kBwBeg;
+            analog[e] = (signed char) ((t >= kSyncBeg && t < sync_end) ? kSync : kBlank);
+        }
+        __syncthreads(); // the picture below overwrites parts of what was just written
+    }
+    for (int e = tid; e < kLines * kBurstLen; e += 256) { // crt_nes.c:174-178
+        const int y = e / kBurstLen, t = kCbBeg + (e - y * kBurstLen);
+        const int n = y + yo;
+        analog[n * kHres + t] = burst[n % 3][t & 3];
+    }
+    const unsigned short *data = static_cast<const unsigned short *>(s.data);
+    for (int e = tid; e < kLines * kAvLen; e += 256) { // crt_nes.c:180-193
+        const int y = e / kAvLen, x = e - y * kAvLen;
+        int row = (y * s.h) / kLines;
+        if (row >= s.h) row = s.h - 1; // the reference reads one row past the image here (undefined)
+        if (row < 0) row = 0;
+        const int p = __ldg(data + ((x * s.w) / kAvLen) + row * s.w) & 0x1ff;
+        const int phase = (((y + yo + s.dot_crawl_offset) % 3) * 4 + 3 * x) % 12;
+        analog[(y + yo) * kHres + xo + x] = tab[p * 12 + phase];
+    }
 }
 
 #endif // NES

@@ -134,6 +134,7 @@ constexpr int kMaxOutw = 8192;
 struct LinesGeom { // uniform over a launch: host groups monitors by these (crtx.cu)
     int outw, out_format, bpp, blend;
     int use_tma;
+    int pass; // -1: every line; -2: only the last line of each shared-row run; >= 0: lines at this run position
     int rnd; // 32768, passed as an argument so that it lives in a register (see pole())
 };
 
@@ -261,7 +262,8 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
     LineRec rec;
     rec.pos = 0; rec.wave0 = rec.wave1 = 0; rec.beg = -1; rec.end = -1; rec.hsync = 0;
     if (kline < kLines) rec = lines_base[(size_t) m * kLines + kline];
-    const bool active = (kline < kLines) && rec.beg >= 0;
+    const bool active = (kline < kLines) && rec.beg >= 0
+                     && (geo.pass == -1 || (geo.pass == -2 ? rec.pad1 != 0 : rec.pad0 == geo.pass));
     const unsigned active_mask = __ballot_sync(0xffffffffu, active);
     if (active_mask == 0) return;
     const unsigned nactive = __popc(active_mask);

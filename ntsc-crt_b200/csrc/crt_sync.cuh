@@ -352,7 +352,14 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
         const SyncLine g = sh.ln[k];
         const int hs = sh.hs[k];
         LineRec rec;
-        rec.pad0 = rec.pad1 = 0;
+        // When the output has fewer rows than there are decoded lines, consecutive lines land on the same
+        // row and the reference applies them in order (each one blending onto, or overwriting, its
+        // predecessor).  pad0 = position of this line within its run, pad1 = 1 for the run's last line;
+        // the host then launches the line kernel once per position (crtx.cu).
+        int rank = 0;
+        for (int j = k - 1; j >= 0 && g.beg >= 0 && sh.ln[j].beg == g.beg; j--) rank++;
+        rec.pad0 = rank;
+        rec.pad1 = (k == kLines - 1 || sh.ln[k + 1].beg != g.beg) ? 1 : 0;
         rec.hsync = hs;
         rec.beg = g.beg;
         rec.end = g.end;

@@ -169,10 +169,9 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
     if (upload_cfg(ctx, stream)) return 1;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_src + first, src, sizeof(SrcCfg) * count, cudaMemcpyHostToDevice, stream));
 #if (CRT_SYSTEM == CRT_SYSTEM_NES)
-    dim3 grid((kHres + 255) / 256, kVres, count);
     {
         LaunchTimer lt(ctx, stream, 0);
-        k_mod_nes<<<grid, 256, 0, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_state, ctx->d_analog, first);
+        k_mod_nes<<<count, 256, 0, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_state, ctx->d_analog, first);
     }
     ctx->launches += 1;
 #else
@@ -251,7 +250,9 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
         int hi = lo + 1;
         while (hi < first + count) {
             const MonCfg &c = ctx->h_cfg[hi];
-            if (c.outw != c0.outw || c.out_format != c0.out_format || c.blend != c0.blend) break;
+            if (c.outw != c0.outw || c.out_format != c0.out_format || c.blend != c0.blend || c.outh != c0.outh
+                || c.v_fac != c0.v_fac)
+                break;
             hi++;
         }
         LinesGeom geo;
@@ -265,7 +266,25 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
             LaunchTimer lt(ctx, stream, 4);
             // the second launch takes the monitors whose signal left the fast equaliser's exact range
             // (flagged by k_sync); it is an empty pass otherwise
-            launch_lines(ctx, hi - lo, lo, geo, stream);
+            // Fewer output rows than decoded lines: several lines share a row and must be applied in
+            // order (crt_core.c:409-664 is a sequential loop).  Without blend only the last line of a run
+            // survives; with blend one launch per run position keeps the order.
+            const long long rows = (long long) c0.outh + (long long) c0.v_fac;
+            if (rows >= kLines) {
+                geo.pass = -1;
+                launch_lines(ctx, hi - lo, lo, geo, stream);
+            } else if (!geo.blend) {
+                geo.pass = -2;
+                launch_lines(ctx, hi - lo, lo, geo, stream);
+            } else {
+                const int runs = (int) ((kLines + (rows > 0 ? rows : 1) - 1) / (rows > 0 ? rows : 1)) + 1;
+                for (int p = 0; p < runs; p++) {
+                    geo.pass = p;
+                    launch_lines(ctx, hi - lo, lo, geo, stream);
+                    launched += 2;
+                }
+                launched -= 2;
+            }
         }
         launched += 2;
         lo = hi;

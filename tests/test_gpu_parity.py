@@ -236,7 +236,7 @@ def test_dropin_ntsc_output_geometries(outw, outh, fmt, blend, scanlines):
 
 
 @pytest.mark.parametrize("w,h,fmt", [(1920, 1080, layout.PIX_BGRA), (3000, 200, layout.PIX_RGB), (97, 61, layout.PIX_RGBA),
-                                     (753, 236, layout.PIX_ARGB)])
+                                     (753, 240, layout.PIX_ARGB)])  # h = 236 would read row h in the reference (crt_ntsc.c:263)
 def test_dropin_ntsc_source_geometries(w, h, fmt):
     """Source sizes on both sides of the staged encoder's span limit (wide sources take the gather kernel)."""
     img = S.pack_rgb(S.rand_image(w, h, bpp=3, seed=w), fmt)
