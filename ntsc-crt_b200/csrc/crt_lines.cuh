@@ -37,9 +37,9 @@ __device__ __forceinline__ int pole(int f, int in, int rnd)
 
 // One eqf() step (crt_core.c:205-233).
 // FAST is exact when every Q16 gain of 65536 is an identity and no product wraps, i.e. every band
-// stays below 32768 in magnitude.  k_sync guarantees that per monitor from |wave| <= 65536 (chroma
-// inputs <= 16257; a one-pole stage with 0 < c <= 65536 never leaves the range of its inputs) and
-// |bright| <= 4096 (luma; the hf = 79824 cascade overshoots by at most 1.558^4).  Then for I and Q
+// stays below 32768 in magnitude.  k_sync guarantees that per monitor from max|s| * |wave| >> 9 <= 16382
+// (chroma inputs <= 16383; a one-pole stage with 0 < c <= 65536 never leaves the range of its inputs,
+// so |fH3 - fL3| < 32768) and |bright| <= 4096 (luma; the hf = 79824 cascade overshoots by at most 1.558^4).  Then for I and Q
 // r0 + r1 == fH[3] exactly -- their low cascades cancel and are not evaluated at all -- and Y's
 // middle gain 8192 is an arithmetic shift by 3.
 template <int LF, int HF, int G1, int G2, bool FAST, bool IS_Y>
@@ -104,7 +104,8 @@ constexpr int kSub = 12;                      // samples filtered between two pi
                                               // unrolled block needs no register rotation at all
 constexpr int kStageSamples = 96;             // samples per staged chunk (8 sub-chunks): fewer, larger
                                               // bulk copies -- 32 per warp per stage -- keep the TMA unit ahead
-constexpr int kStageRow = kStageSamples + 16; // bytes per line per stage: a 16-byte aligned superset
+constexpr int kStageRow = ((kStageSamples + 15 + 15) / 16) * 16; // bytes per line per stage: the 16-byte
+                                              // aligned superset of a window at any byte phase
 constexpr int kStageBytes = 32 * kStageRow;   // per warp per stage
 constexpr int kTilePitch = 20;                // words: 16 pixel columns per line, pitch/4 odd
 constexpr int kTileBytes = 32 * kTilePitch * 4;
@@ -113,7 +114,8 @@ constexpr int kTileBytes = 32 * kTilePitch * 4;
 // resampler stops at sample AV_LEN - 1 (crt_core.c:529, 555).
 constexpr int kSamplesPadded = ((kAvLen + kSub - 1) / kSub) * kSub;
 constexpr int kNumStages = (kSamplesPadded + kStageSamples - 1) / kStageSamples;
-static_assert(kStageBytes % 16 == 0 && kStageSamples % kSub == 0 && kSub % 12 == 0, "stage layout");
+static_assert(kStageRow % 16 == 0 && kStageSamples % 16 == 0 && kStageSamples % kSub == 0 && kSub % 12 == 0,
+              "stage layout: TMA source offsets and destinations are multiples of 16");
 
 // Per-lane row of decoded Y/I/Q for the current sub-chunk: slot 0 carries the last sample of the
 // previous sub-chunk, slots 1..kSub the new ones.  FAST packs a sample into 8 bytes (Y | I:Q as

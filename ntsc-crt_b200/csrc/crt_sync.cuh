@@ -43,6 +43,7 @@ struct SyncShared {
     int rowcount[3];
     int vs_found[2 * kVsyncWindow]; // per vsync candidate: crossing index or -1
     int generic;
+    int linemax[kVres + 1]; // FUSED: largest |inp| on each signal line (filled by the noise warps)
 };
 
 // hsync search of one decoded line given the hsync it enters with (crt_core.c:437-447):
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
         }
     }
     if (tid == 0) sh.generic = force_generic || abs(cfg.brightness - (kBlack + cfg.black_point)) > 4096;
+    for (int j = tid; j <= kVres; j += kSyncThreads) sh.linemax[j] = FUSED ? 0 : 127;
     __syncthreads();
 
     // ---- 2. vsync (crt_core.c:379-396): candidate c = line posmod(vsync + c - W); first crossing wins
@@ -335,6 +337,13 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
                 } else {
                     for (int b = 0; i0 + b < kInputSize; b++) inp_w[i0 + b] = (signed char) (w[b >> 2] >> (8 * (b & 3)));
                 }
+                // largest magnitude in this chunk, credited to the (at most two) lines it touches
+                unsigned a4 = __vmaxu4(__vmaxu4(__vabsss4(w[0]), __vabsss4(w[1])), __vmaxu4(__vabsss4(w[2]), __vabsss4(w[3])));
+                a4 = __vmaxu4(a4, a4 >> 16);
+                const int mx = (int) (__vmaxu4(a4, a4 >> 8) & 0xffu);
+                const int l0 = i0 / kHres, l1 = min(i0 + kNoiseVec - 1, kInputSize - 1) / kHres;
+                if (mx > sh.linemax[l0]) atomicMax(&sh.linemax[l0], mx);
+                if (l1 != l0 && mx > sh.linemax[l1]) atomicMax(&sh.linemax[l1], mx);
             }
         }
     }
@@ -372,8 +381,13 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
             rec.pos = posmod(kAvBeg + hs - 3, kHres) + g.ypos * kHres;
             rec.wave0 = wmul(wsub(wmul(dci, huecs), wmul(dcq, huesn)) >> 4, cfg.saturation);
             rec.wave1 = wmul(wadd(wmul(dcq, huecs), wmul(dci, huesn)) >> 4, cfg.saturation);
-            // the fast equaliser path of k_lines is exact while |wave| <= 65536 (crt_lines.cuh)
-            if (abs(rec.wave0) > 65536 || abs(rec.wave1) > 65536) sh.generic = 1;
+            // The fast equaliser path of k_lines is exact while every chroma input (s * wave) >> 9 stays
+            // within +-16383 (crt_lines.cuh).  |s| is bounded by the largest sample of the one or two
+            // signal lines the decode window covers -- measured by the noise warps when the noise pass is
+            // fused, 127 (the clamp of crt_core.c:363-364) otherwise.
+            const int smax = max(sh.linemax[g.ypos], sh.linemax[min(g.ypos + 1, kVres)]);
+            const long long wmax = max(llabs((long long) rec.wave0), llabs((long long) rec.wave1));
+            if (((smax * wmax) >> 9) + 1 > 16383) sh.generic = 1;
         }
         lines[k] = rec;
     }
