@@ -185,6 +185,11 @@ class Batch:
     def set_state(self, states, first=0, stream=0):
         self._check(self.lib.crtx_set_state(self._ctx, first, len(states), states, stream))
 
+    def seed(self, seed, first=0, count=None):
+        """VHS: put the monitors' rand() replica in the state srand(seed) leaves glibc in."""
+        count = self.n - first if count is None else count
+        self._check(self.lib.crtx_seed(self._ctx, first, count, seed))
+
     def get_lines(self, i, stream=0):
         t = (Line * self.spec.lines)()
         self._check(self.lib.crtx_get_lines(self._ctx, i, t, stream))

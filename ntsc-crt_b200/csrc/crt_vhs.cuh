@@ -1,0 +1,244 @@
+// crt_vhs.cuh -- the VHS variant's noise pass in the batch interface (crt_core.c:343-367).
+//
+// The reference draws its VHS noise from libc rand(): one draw per call for the wobble, then per
+// sample one draw for the noise value, one for the first bound of the "bottom of frame" band and --
+// short-circuit && -- a third only when the first test passed.  The drop-in calls (crt_dropin.cu) keep
+// drawing from the process's libc on the host; the batch interface carries, per monitor, a replica of
+// glibc's TYPE_3 generator (o[n] = o[n-31] + o[n-3] mod 2^32, output o[n] >> 1; glibc 2.39
+// stdlib/random_r.c) seeded by crtx_seed, and this kernel reproduces the reference's draw order exactly:
+//
+//   bulk   samples [0, kVhsBulk): the first test can never pass there (it needs i > INPUT_SIZE - 25 lines),
+//          so every sample costs exactly two draws.  256 threads each own a contiguous run of samples; the
+//          generator state at the start of every run comes from jump-ahead matrices (powers of the
+//          31 x 31 transition matrix, doubling tree), then each thread steps the recurrence in registers.
+//   tail   the last ~26.5 lines, where the draw count is data dependent.  The raw stream for the whole
+//          tail is generated in parallel the same way; the walk "sample -> position of its first draw" is
+//          then resolved per signal line by pointer jumping (within a line the tests' thresholds are
+//          constant, so next(p) = p + 2 + [test1(raw[p + 1])] is a function of p alone): 10 doubling
+//          rounds give every sample its position, after which all samples of the line are evaluated in
+//          parallel with the reference's literal expressions.
+#pragma once
+
+#include "crt_kernels.cuh"
+
+#if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
+
+namespace crt {
+
+constexpr int kVhsThreads = 256;
+constexpr int kVhsRun = 31 * 27;                      // samples per thread in the bulk region (2 draws each)
+constexpr int kVhsBulk = kVhsThreads * kVhsRun;       // 214 272 <= INPUT_SIZE - 25 lines
+constexpr int kVhsTailSamples = kInputSize - kVhsBulk;
+constexpr int kVhsTailRun = 310;                      // raw values per thread for the tail (10 x 31)
+constexpr int kVhsTailRaw = kVhsThreads * kVhsTailRun; // 79 360 >= 3 draws x tail samples
+constexpr int kVhsWin = 2752;                         // raw values visible to one line's walk (>= 3 * 910 + 3)
+constexpr int kVhsLevels = 8;                         // doubling levels: 2^8 = 256 runs
+static_assert(kVhsBulk <= kInputSize - 25 * kHres, "bulk region must stay clear of the data-dependent band");
+static_assert(kVhsTailRaw >= 3 * kVhsTailSamples + 64 && kVhsWin >= 3 * kHres + 8, "tail stream sizes");
+
+struct VhsRand { // generator state: the last 31 raw values, oldest first
+    unsigned hist[31];
+    unsigned pad;
+};
+
+struct VhsJump { // powers of the transition matrix, [level][row][col], applied as new = A * old
+    unsigned bulk[kVhsLevels][31][31]; // (M^(2 * kVhsRun))^(2^level)
+    unsigned tail[kVhsLevels][31][31]; // (M^kVhsTailRun)^(2^level)
+};
+
+// one draw on a chronological state held in shared/global memory (used for the odd single draws)
+__device__ __forceinline__ unsigned vhs_draw_mem(unsigned *h)
+{
+    const unsigned v = h[0] + h[28];
+    for (int j = 0; j < 30; j++) h[j] = h[j + 1];
+    h[30] = v;
+    return v >> 1;
+}
+
+// states[t + 2^k] = A_k * states[t] for t < 2^k, k = 0 .. kVhsLevels - 1: after it states[0 .. 256]
+// hold the generator state at the start of every run (and, at [256], after the last one).
+__device__ __forceinline__ void vhs_spread_states(unsigned (*states)[32], const unsigned (*A)[31][31], int tid)
+{
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int k = 0; k <= kVhsLevels; k++) {
+        const int half = 1 << k; // states [0, half) known; fill [half, 2 * half) (level 8 fills only [256])
+        const unsigned (*Ak)[31] = A[k < kVhsLevels ? k : kVhsLevels - 1];
+        const int todo = (k < kVhsLevels) ? half : 1;
+        for (int t = warp; t < todo; t += kVhsThreads / 32) {
+            const int from = (k < kVhsLevels) ? t : 128, to = (k < kVhsLevels) ? t + half : 256;
+            if (lane < 31) {
+                unsigned acc = 0;
+                for (int j = 0; j < 31; j++) acc += Ak[lane][j] * states[from][j];
+                states[to][lane] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// the reference's literal tests (crt_core.c:350-351) for sample i given the two draws
+__device__ __forceinline__ bool vhs_test1(int i, unsigned a) { return i > (kInputSize - kHres * (16 + ((int) (a % 20u) - 10))); }
+__device__ __forceinline__ bool vhs_test2(int i, unsigned b) { return i < (kInputSize - kHres * (5 + ((int) (b % 8u) - 4))); }
+
+__global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states_mon,
+                                                           VhsRand *__restrict__ rands,
+                                                           const VhsJump *__restrict__ jump,
+                                                           unsigned *__restrict__ raw_base,
+                                                           const signed char *__restrict__ analog_base,
+                                                           signed char *__restrict__ inp_base, int first)
+{
+    extern __shared__ __align__(16) unsigned char vsm[];
+    unsigned (*states)[32] = reinterpret_cast<unsigned (*)[32]>(vsm);                 // [257][32]
+    short *terms = reinterpret_cast<short *>(vsm + 257 * 32 * 4);                       // [256][32]
+    unsigned *win = reinterpret_cast<unsigned *>(vsm + 257 * 32 * 4);                   // tail: [kVhsWin + 8]
+    unsigned short *jt = reinterpret_cast<unsigned short *>(win + kVhsWin + 8);         // tail: [10][kVhsWin + 8]
+    __shared__ int s_wobble, s_adv, s_start;
+    const int m = first + blockIdx.x, tid = threadIdx.x;
+    if (cfgs[m].bpp == 0) return; // crt_core.c:312-315
+    const int noise = cfgs[m].noise;
+    const signed char *analog = analog_base + (size_t) m * kSignalBytes;
+    signed char *inp = inp_base + (size_t) m * kSignalBytes;
+    unsigned *raw = raw_base + (size_t) blockIdx.x * kVhsTailRaw;
+    VhsRand *rs = &rands[m];
+
+    // ---- the wobble draw (crt_core.c:344), then the run start states
+    if (tid == 0) {
+        unsigned h[31];
+        for (int j = 0; j < 31; j++) h[j] = rs->hist[j];
+        s_wobble = ((int) (vhs_draw_mem(h) % 8u) - 4) + 14;
+        for (int j = 0; j < 31; j++) states[0][j] = h[j];
+    }
+    __syncthreads();
+    vhs_spread_states(states, jump->bulk, tid);
+
+    // ---- bulk: thread t owns samples [t * kVhsRun, (t + 1) * kVhsRun), two draws each
+    {
+        unsigned h[31];
+#pragma unroll
+        for (int j = 0; j < 31; j++) h[j] = states[tid][j];
+        for (int it = 0; it < kVhsRun / 31; it++) {
+#pragma unroll
+            for (int d = 0; d < 62; d++) { // draw d of the block uses slot d % 31 (31-periodic alignment)
+                const int slot = d % 31;
+                h[slot] += h[(slot + 28) % 31];
+                if ((d & 1) == 0) { // the noise draw; the odd draw feeds the never-true first test
+                    const int rn = (int) (h[slot] >> 1);
+                    int t = wmul(((rn >> 16) & 0xff) - 0x7f, noise) >> 8;
+                    t = clampi(t, -255, 255); // analog is within [-128, 127]: beyond +-255 the sum saturates anyway
+                    terms[tid * 32 + (d >> 1)] = (short) t;
+                }
+            }
+            __syncthreads();
+            // apply, coalesced over the 31 samples of each thread's slice
+            for (int u = tid >> 5; u < kVhsThreads; u += kVhsThreads / 32) {
+                const int j = tid & 31;
+                if (j < 31) {
+                    const int i = u * kVhsRun + it * 31 + j;
+                    inp[i] = (signed char) clampi(analog[i] + terms[u * 32 + j], -127, 127);
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- tail raw stream: kVhsTailRaw values continuing after the bulk, to global scratch
+    if (tid < 31) states[0][tid] = states[256][tid];
+    __syncthreads();
+    vhs_spread_states(states, jump->tail, tid);
+    {
+        unsigned h[31];
+#pragma unroll
+        for (int j = 0; j < 31; j++) h[j] = states[tid][j];
+        for (int it = 0; it < kVhsTailRun / 31; it++) {
+#pragma unroll
+            for (int d = 0; d < 31; d++) {
+                h[d] += h[(d + 28) % 31];
+                raw[tid * kVhsTailRun + it * 31 + d] = h[d];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- tail walk, one signal line (or the partial first one) at a time
+    const int wobble = s_wobble;
+    int D = 0;            // raw values consumed so far in the tail
+    int last_rn = 0;
+    for (int i0 = kVhsBulk; i0 < kInputSize;) {
+        const int line = i0 / kHres, xa = i0 - line * kHres, nx = kHres - xa; // samples xa .. 909 of this line
+        for (int q = tid; q < kVhsWin + 8; q += kVhsThreads) win[q] = (D + q < kVhsTailRaw) ? raw[D + q] : 0u;
+        __syncthreads();
+        // Within a line the first test is the same function of its draw for every sample except x == 0
+        // (its bound is a multiple of the line length), so x == 0 is stepped on its own.
+        if (tid == 0) {
+            int p = 0;
+            if (xa == 0) p = 2 + (vhs_test1(i0, win[1] >> 1) ? 1 : 0);
+            s_start = p; // position of the first "regular" sample
+        }
+        const int irep = line * kHres + 1;
+        for (int p = tid; p < kVhsWin + 8; p += kVhsThreads)
+            jt[p] = (unsigned short) ((p + 3 < kVhsWin) ? p + 2 + (vhs_test1(irep, win[p + 1] >> 1) ? 1 : 0) : kVhsWin);
+        __syncthreads();
+        for (int k = 1; k < 10; k++) { // jt[k][p] = 2^k-th successor
+            unsigned short *prev = jt + (k - 1) * (kVhsWin + 8), *cur = jt + k * (kVhsWin + 8);
+            for (int p = tid; p < kVhsWin + 8; p += kVhsThreads) cur[p] = prev[min((int) prev[p], kVhsWin)];
+            __syncthreads();
+        }
+        const int x0 = (xa == 0) ? 1 : xa; // first regular sample
+        for (int x = xa + tid; x < kHres; x += kVhsThreads) {
+            int P = 0;
+            if (!(xa == 0 && x == 0)) {
+                P = s_start;
+                const int e = x - x0;
+                for (int k = 0; k < 10; k++)
+                    if ((e >> k) & 1) P = jt[k * (kVhsWin + 8) + min(P, kVhsWin)];
+            }
+            const int i = line * kHres + x;
+            const int rn = (int) (win[P] >> 1);
+            int gain = noise, used = 2;
+            if (vhs_test1(i, win[P + 1] >> 1)) { // crt_core.c:350-357
+                used = 3;
+                if (vhs_test2(i, win[P + 2] >> 1)) {
+                    int sn, cs;
+                    sincos14_d(sn, cs, ((i * wobble) / kHres) * 8192 / 180);
+                    gain = cs >> 8;
+                }
+            }
+            const int s = analog[i] + (wmul(((rn >> 16) & 0xff) - 0x7f, gain) >> 8);
+            inp[i] = (signed char) clampi(s, -127, 127);
+            if (x == kHres - 1) { // the line's last sample closes the walk
+                s_adv = P + used;
+                last_rn = rn;
+                if (i == kInputSize - 1) states_mon[m].rn = rn; // crt_core.c:367
+            }
+        }
+        __syncthreads();
+        D += s_adv;
+        i0 += nx;
+        __syncthreads();
+    }
+    (void) last_rn;
+    // ---- the generator state after the call: the last 31 raw values consumed
+    if (tid < 31) {
+        // total draws: 1 + 2 * kVhsBulk + D; D >= 31 always (the tail spans > 24 000 samples)
+        rs->hist[tid] = raw[D - 31 + tid];
+    }
+}
+
+// the aberration draw of crt_modulate (crt_ntscvhs.c:205-207), one thread per monitor
+__global__ void k_vhs_aberration(SrcCfg *__restrict__ srcs, const int *__restrict__ wants, VhsRand *__restrict__ rands,
+                                 int first, int count)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    int ab = 0;
+    if (wants[k]) ab = ((int) (vhs_draw_mem(rands[first + k].hist) % 12u) - 8) + 14;
+    srcs[first + k].aberration = ab;
+}
+
+constexpr int kVhsSmem = 257 * 32 * 4 + ((256 * 32 * 2 > (kVhsWin + 8) * 4 + 10 * (kVhsWin + 8) * 2)
+                                             ? 256 * 32 * 2
+                                             : (kVhsWin + 8) * 4 + 10 * (kVhsWin + 8) * 2);
+
+} // namespace crt
+
+#endif

@@ -129,6 +129,75 @@ static void launch_mod_staged(crtx_ctx *ctx, int format, bool color, int count, 
 }
 #endif
 
+#if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
+// ---- glibc TYPE_3 rand() replica, host side (glibc 2.39 stdlib/random_r.c: srandom_r, random_r)
+typedef std::vector<uint32_t> Mat; // 31 x 31, row major, arithmetic mod 2^32
+
+static Mat mat_mul(const Mat &a, const Mat &b)
+{
+    Mat c(31 * 31, 0u);
+    for (int i = 0; i < 31; i++)
+        for (int k = 0; k < 31; k++) {
+            const uint32_t aik = a[i * 31 + k];
+            if (!aik) continue;
+            for (int j = 0; j < 31; j++) c[i * 31 + j] += aik * b[k * 31 + j];
+        }
+    return c;
+}
+
+static Mat mat_pow(Mat base, unsigned e)
+{
+    Mat r(31 * 31, 0u);
+    for (int i = 0; i < 31; i++) r[i * 31 + i] = 1u;
+    while (e) {
+        if (e & 1u) r = mat_mul(base, r);
+        base = mat_mul(base, base);
+        e >>= 1;
+    }
+    return r;
+}
+
+static void vhs_build_jump(VhsJump *out)
+{
+    // one draw on the chronological state (oldest first): new[j] = old[j + 1], new[30] = old[0] + old[28]
+    Mat m(31 * 31, 0u);
+    for (int j = 0; j < 30; j++) m[j * 31 + j + 1] = 1u;
+    m[30 * 31 + 0] = 1u;
+    m[30 * 31 + 28] = 1u;
+    Mat b = mat_pow(m, 2u * kVhsRun), t = mat_pow(m, (unsigned) kVhsTailRun);
+    for (int k = 0; k < kVhsLevels; k++) {
+        memcpy(out->bulk[k], b.data(), sizeof(out->bulk[k]));
+        memcpy(out->tail[k], t.data(), sizeof(out->tail[k]));
+        b = mat_mul(b, b);
+        t = mat_mul(t, t);
+    }
+}
+
+static void vhs_seed_state(unsigned seed, VhsRand *st)
+{
+    int32_t r[31];
+    if (seed == 0) seed = 1;
+    int32_t word = (int32_t) seed;
+    r[0] = word;
+    for (int i = 1; i < 31; i++) {
+        const int32_t hi = word / 127773, lo = word % 127773;
+        word = 16807 * lo - 2836 * hi;
+        if (word < 0) word += 2147483647;
+        r[i] = word;
+    }
+    // fptr = &r[3], rptr = &r[0]: the first draw is r[3] + r[0], so chronologically r[3] is the oldest
+    uint32_t h[31];
+    for (int j = 0; j < 31; j++) h[j] = (uint32_t) r[(j + 3) % 31];
+    for (int k = 0; k < 310; k++) { // srandom_r discards 10 * 31 outputs
+        const uint32_t v = h[0] + h[28];
+        memmove(h, h + 1, 30 * sizeof(uint32_t));
+        h[30] = v;
+    }
+    memcpy(st->hist, h, sizeof(h));
+    st->pad = 0;
+}
+#endif
+
 // RAII bracket: records start/stop events around one launch when timing is on
 struct LaunchTimer {
     crtx_ctx *ctx;
@@ -168,6 +237,14 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
     if (count == 0) return 0;
     if (upload_cfg(ctx, stream)) return 1;
     CUDA_TRY(cudaMemcpyAsync(ctx->d_src + first, src, sizeof(SrcCfg) * count, cudaMemcpyHostToDevice, stream));
+#if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
+    if (ctx->vhs_draw_aberration) { // batch interface: draw on the device (crt_ntscvhs.c:205-207)
+        k_vhs_aberration<<<(count + 63) / 64, 64, 0, stream>>>(ctx->d_src, ctx->d_vhs_wants + first,
+                                                               static_cast<VhsRand *>(ctx->d_vhs_rand), first, count);
+        ctx->vhs_draw_aberration = 0;
+        ctx->launches += 1;
+    }
+#endif
 #if (CRT_SYSTEM == CRT_SYSTEM_NES)
     {
         LaunchTimer lt(ctx, stream, 0);
@@ -207,11 +284,16 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
     if (count == 0) return 0;
     if (upload_cfg(ctx, stream)) return 1;
 #if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
-    if (!d_noise_terms) return fail("VHS demodulate needs host-drawn noise terms (device rand() replica not built yet)");
-    dim3 tgrid((kInputSize + 255) / 256, count);
-    {
+    if (d_noise_terms) { // drop-in path: the terms were drawn from the process's libc on the host
+        dim3 tgrid((kInputSize + 255) / 256, count);
         LaunchTimer lt(ctx, stream, 2);
         k_noise_terms<<<tgrid, 256, 0, stream>>>(ctx->d_cfg, ctx->d_analog, ctx->d_inp, d_noise_terms, first);
+    } else { // batch path: the per-monitor rand() replica (crt_vhs.cuh)
+        LaunchTimer lt(ctx, stream, 2);
+        k_noise_vhs<<<count, kVhsThreads, kVhsSmem, stream>>>(ctx->d_cfg, ctx->d_state, static_cast<VhsRand *>(ctx->d_vhs_rand),
+                                                              static_cast<const VhsJump *>(ctx->d_vhs_jump),
+                                                              ctx->d_vhs_raw + (size_t) first * kVhsTailRaw, ctx->d_analog,
+                                                              ctx->d_inp, first);
     }
     {
         LaunchTimer lt(ctx, stream, 3);
@@ -385,6 +467,21 @@ int crtx_create(crtx_ctx **out, int n)
         CTX_TRY(cudaMemcpy(ctx->d_jump_lo, lo.data(), sizeof(Affine) * kJumpLo, cudaMemcpyHostToDevice));
         CTX_TRY(cudaMemcpy(ctx->d_jump_hi, hi.data(), sizeof(Affine) * kJumpHi, cudaMemcpyHostToDevice));
     }
+#if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
+    {
+        CTX_TRY(cudaMalloc(&ctx->d_vhs_rand, sizeof(VhsRand) * n));
+        CTX_TRY(cudaMalloc(&ctx->d_vhs_jump, sizeof(VhsJump)));
+        CTX_TRY(cudaMalloc(&ctx->d_vhs_raw, sizeof(unsigned) * (size_t) kVhsTailRaw * n));
+        CTX_TRY(cudaMalloc(&ctx->d_vhs_wants, sizeof(int) * n));
+        std::vector<VhsJump> j(1);
+        vhs_build_jump(&j[0]);
+        CTX_TRY(cudaMemcpy(ctx->d_vhs_jump, j.data(), sizeof(VhsJump), cudaMemcpyHostToDevice));
+        std::vector<VhsRand> r(n);
+        for (int i = 0; i < n; i++) vhs_seed_state(1u, &r[i]); // libc's default seed
+        CTX_TRY(cudaMemcpy(ctx->d_vhs_rand, r.data(), sizeof(VhsRand) * n, cudaMemcpyHostToDevice));
+        CTX_TRY(cudaFuncSetAttribute(k_noise_vhs, cudaFuncAttributeMaxDynamicSharedMemorySize, kVhsSmem));
+    }
+#endif
     CTX_TRY(lines_attr_all());
     CTX_TRY(cudaFuncSetAttribute(k_sync<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
     CTX_TRY(cudaFuncSetAttribute(k_sync<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
@@ -408,6 +505,10 @@ void crtx_destroy(crtx_ctx *ctx)
     cudaFree(ctx->d_jump_lo);
     cudaFree(ctx->d_jump_hi);
     cudaFree(ctx->d_src_img);
+    cudaFree(ctx->d_vhs_rand);
+    cudaFree(ctx->d_vhs_jump);
+    cudaFree(ctx->d_vhs_raw);
+    cudaFree(ctx->d_vhs_wants);
     for (size_t i = 0; i < ctx->timed.size(); i++) {
         cudaEventDestroy(ctx->timed[i].start);
         cudaEventDestroy(ctx->timed[i].stop);
@@ -483,9 +584,16 @@ int crtx_get_state(crtx_ctx *ctx, int first, int count, crtx_state *s, void *str
 int crtx_seed(crtx_ctx *ctx, int first, int count, unsigned seed)
 {
     if (check_range(ctx, first, count)) return 1;
-    (void) seed;
-    if (!kIsVhs) return 0; // only the VHS variant draws from rand()
-    return fail("crtx_seed: the device rand() replica is not built yet in this variant");
+#if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
+    std::vector<VhsRand> r(count);
+    for (int i = 0; i < count; i++) vhs_seed_state(seed, &r[i]); // what srand(seed) leaves in glibc
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(static_cast<VhsRand *>(ctx->d_vhs_rand) + first, r.data(), sizeof(VhsRand) * count,
+                        cudaMemcpyHostToDevice));
+#else
+    (void) seed; // only the VHS variant draws from rand()
+#endif
+    return 0;
 }
 
 signed char *crtx_analog(crtx_ctx *ctx, int i)
@@ -523,18 +631,22 @@ int crtx_write_signal(crtx_ctx *ctx, int i, int which, const signed char *host, 
 int crtx_modulate(crtx_ctx *ctx, int first, int count, const crtx_source *src, void *stream)
 {
     if (check_range(ctx, first, count)) return 1;
-    if (kIsVhs) {
-        for (int i = 0; i < count; i++)
-            if (src[i].do_aberration) return fail("crtx_modulate: do_aberration needs the device rand() replica (not built yet)");
-    }
     ctx->scratch_src.resize(count);
     for (int i = 0; i < count; i++) fill_src(&ctx->scratch_src[i], &src[i]);
+#if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
+    { // the aberration draw happens on the device, from the monitor's rand() replica
+        std::vector<int> wants(count);
+        for (int i = 0; i < count; i++) wants[i] = src[i].do_aberration ? 1 : 0;
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_vhs_wants + first, wants.data(), sizeof(int) * count, cudaMemcpyHostToDevice,
+                                 static_cast<cudaStream_t>(stream)));
+        ctx->vhs_draw_aberration = 1;
+    }
+#endif
     return modulate_launch(ctx, first, count, ctx->scratch_src.data(), static_cast<cudaStream_t>(stream));
 }
 
 int crtx_demodulate(crtx_ctx *ctx, int first, int count, void *stream)
 {
-    if (kIsVhs) return fail("crtx_demodulate: the VHS noise pass needs the device rand() replica (not built yet)");
     return demodulate_launch(ctx, first, count, static_cast<cudaStream_t>(stream), NULL);
 }
 

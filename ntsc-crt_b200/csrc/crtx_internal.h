@@ -21,6 +21,12 @@ struct crtx_ctx {
     signed char *d_inp = nullptr;
     crt::Affine *d_jump_lo = nullptr;
     crt::Affine *d_jump_hi = nullptr;
+    void *d_vhs_rand = nullptr;   // VHS: VhsRand[n], glibc rand() replica per monitor
+    void *d_vhs_jump = nullptr;   // VHS: jump-ahead matrices
+    unsigned *d_vhs_raw = nullptr; // VHS: tail raw-stream scratch
+    int *d_vhs_wants = nullptr;   // VHS: do_aberration flags of the current modulate
+    bool vhs_seeded = false;
+    int vhs_draw_aberration = 0;
     unsigned char *d_src_img = nullptr; // crtx_frames_host staging, src_slot bytes per monitor
     size_t src_slot = 0;
     std::vector<crt::MonCfg> h_cfg;

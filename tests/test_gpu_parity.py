@@ -247,3 +247,44 @@ def test_dropin_ntsc_source_geometries(w, h, fmt):
         check(gpu, ora, ref, "source %dx%d mod %d" % (w, h, it))
         run_all((gpu, ora, ref), lambda e: e.demodulate(0))
         check(gpu, ora, ref, "source %dx%d demod %d" % (w, h, it))
+
+
+def test_batch_vhs_device_rand_replica_matches_glibc_stream():
+    """config 5 in the batch interface: noise and aberration draws come from the per-monitor replica of
+    glibc's rand() (crtx_seed), in the reference's draw order -- compared with the oracle driven by the
+    same seeds (which tests/test_oracle_vs_ref.py pins against the real libc stream)."""
+    import torch
+    from ntsc_crt_b200 import capi
+    n = 3
+    seeds = [1, 42, 2024]
+    img = S.bars_image(832, 624)
+    dimg = torch.from_numpy(img).cuda()
+    b = capi.Batch("vhs", n)
+    outs = [torch.zeros(624, 832, 4, dtype=torch.uint8, device="cuda") for _ in range(n)]
+    oras = []
+    for i in range(n):
+        b.set_monitor(i, outs[i], noise=24, blend=1, scanlines=1)
+        b.seed(seeds[i], first=i, count=1)
+        o = S.OracleEngine("vhs", 832, 624, seed=seeds[i])
+        o.set(blend=1, scanlines=1)
+        oras.append(o)
+    b.commit_monitors()
+    for step in range(4):
+        aberr = 1 if step == 2 else 0
+        for i in range(n):
+            b.set_source(i, dimg, format=layout.PIX_BGRA, as_color=1 - (i & 1), field=step & 1, frame=(step >> 1) & 1,
+                         do_aberration=aberr)
+            oras[i].modulate(img, format=layout.PIX_BGRA, as_color=1 - (i & 1), field=step & 1, frame=(step >> 1) & 1,
+                             do_aberration=aberr)
+        b.modulate()
+        b.demodulate()
+        for i in range(n):
+            oras[i].demodulate(24)
+        torch.cuda.synchronize()
+        st = b.get_state()
+        for i in range(n):
+            got = dict(analog=b.signal(i, "analog"), inp=b.signal(i, "inp"), out=outs[i].cpu().numpy(),
+                       ccf=np.array([[st[i].ccf[0][x] for x in range(4)]]),
+                       hsync=st[i].hsync, vsync=st[i].vsync, rn=st[i].rn)
+            S.assert_same_state(got, oras[i].state(), "vhs batch monitor %d step %d" % (i, step))
+    b.close()
