@@ -610,23 +610,22 @@ __device__ __forceinline__ int nes_square(int p, int phase) // crt_nes.c:21-61
     return c_nes_level[high * 8 + emph * 4 + ((p >> 4) & 3)];
 }
 
-// One CTA per monitor.  The composite level of a picture sample depends only on the 9-bit PPU pixel
-// and the chroma phase modulo 12 (square_sample is periodic in phase: (hue + phase) % 12 and
-// (phase >> 1) % 6), plus the monitor's black / white points -- so the CTA first tabulates all 512 x 12
-// finished sample bytes in shared memory (crt_nes.c:21-61, 182-190), after which a sample is an index
-// computation and one table read, written with coalesced byte stores.
-__global__ void __launch_bounds__(256) k_mod_nes(const SrcCfg *__restrict__ srcs, const MonCfg *__restrict__ cfgs,
-                                                 MonState *__restrict__ states,
-                                                 signed char *__restrict__ analog_base, int first)
+// The composite level of a picture sample depends only on the 9-bit PPU pixel and the chroma phase
+// modulo 12 (square_sample is periodic in phase: (hue + phase) % 12 and (phase >> 1) % 6), plus the
+// monitor's black / white points.  k_nes_table tabulates all 512 x 12 finished sample bytes per monitor
+// (crt_nes.c:21-61, 182-190) together with the burst rows; k_mod_nes then turns every sample into an
+// index computation and one table read, written with coalesced byte stores.
+constexpr int kNesTabBytes = 512 * 12 + 16; // + 12 burst bytes (3 rows x 4 phases) + pad
+constexpr int kNesParts = 8;               // CTAs per monitor in k_mod_nes
+
+__global__ void __launch_bounds__(256) k_nes_table(const SrcCfg *__restrict__ srcs, const MonCfg *__restrict__ cfgs,
+                                                   MonState *__restrict__ states, signed char *__restrict__ tabs,
+                                                   int first)
 {
-    __shared__ signed char tab[512 * 12];
-    __shared__ signed char burst[3][4];
     const int m = blockIdx.x, tid = threadIdx.x;
     const SrcCfg s = srcs[m];
     const MonCfg cfg = cfgs[first + m];
-    signed char *analog = analog_base + (size_t) (first + m) * kSignalBytes;
-    const int xo = (kAvBeg + s.xoffset) & ~3, yo = kTop + s.yoffset;
-
+    signed char *tab = tabs + (size_t) (first + m) * kNesTabBytes;
     for (int e = tid; e < 512 * 12; e += 256) {
         const int p = e / 12, phase = e - p * 12;
         int ire = kBlack + cfg.black_point;
@@ -639,33 +638,59 @@ __global__ void __launch_bounds__(256) k_mod_nes(const SrcCfg *__restrict__ srcs
         const int deg = (s.hue + x * 90 + (row + s.dot_crawl_offset) * 120 + 33) % 360;
         sincos14_d(sn, cs, deg * 8192 / 180);
         const signed char v = (signed char) ((kBlank + (sn >> 10) * kBurst) >> 5);
-        burst[row][x] = v;
+        tab[512 * 12 + tid] = v;
         states[first + m].ccf[row][x] = (int) v * 128;
     }
-    __syncthreads();
+}
 
-    if (s.reinit) { // setup_field, crt_nes.c:81-104: every line whole
-        for (int e = tid; e < kVres * kHres; e += 256) {
-            const int n = e / kHres, t = e - n * kHres;
-            const int sync_end = (n >= 259) ? kNesVsyncEnd : kBwBeg;
-            analog[e] = (signed char) ((t >= kSyncBeg && t < sync_end) ? kSync : kBlank);
-        }
-        __syncthreads(); // the picture below overwrites parts of what was just written
+// grid (kNesParts, n): each CTA takes every kNesParts-th chunk of the monitor's work
+__global__ void __launch_bounds__(256) k_mod_nes(const SrcCfg *__restrict__ srcs, const signed char *__restrict__ tabs,
+                                                 signed char *__restrict__ analog_base, int first)
+{
+    __shared__ __align__(16) signed char tab[kNesTabBytes];
+    const int m = blockIdx.y, part = blockIdx.x, tid = threadIdx.x;
+    const SrcCfg s = srcs[m];
+    signed char *analog = analog_base + (size_t) (first + m) * kSignalBytes;
+    const int xo = (kAvBeg + s.xoffset) & ~3, yo = kTop + s.yoffset;
+    {
+        const uint4 *src4 = reinterpret_cast<const uint4 *>(tabs + (size_t) (first + m) * kNesTabBytes);
+        for (int e = tid; e < kNesTabBytes / 16; e += 256) reinterpret_cast<uint4 *>(tab)[e] = __ldg(src4 + e);
     }
-    for (int e = tid; e < kLines * kBurstLen; e += 256) { // crt_nes.c:174-178
-        const int y = e / kBurstLen, t = kCbBeg + (e - y * kBurstLen);
-        const int n = y + yo;
-        analog[n * kHres + t] = burst[n % 3][t & 3];
+    __syncthreads();
+    const signed char *burst = tab + 512 * 12;
+
+    // this CTA's share: lines n with n % kNesParts == part (skeleton), picture lines y likewise
+    if (s.reinit) { // setup_field, crt_nes.c:81-104: every line whole; picture lines are done below
+        for (int n = part; n < kVres; n += kNesParts) {
+            if (n >= yo && n < yo + kLines) continue; // written (skeleton first) by the CTA that owns the line
+            const int sync_end = (n >= 259) ? kNesVsyncEnd : kBwBeg;
+            for (int t = tid; t < kHres; t += 256)
+                analog[n * kHres + t] = (signed char) ((t >= kSyncBeg && t < sync_end) ? kSync : kBlank);
+        }
     }
     const unsigned short *data = static_cast<const unsigned short *>(s.data);
-    for (int e = tid; e < kLines * kAvLen; e += 256) { // crt_nes.c:180-193
-        const int y = e / kAvLen, x = e - y * kAvLen;
+    for (int y = part; y < kLines; y += kNesParts) {
+        const int n = y + yo;
+        // every byte of a picture line is written by this one CTA, in order: skeleton, burst, picture
+        if (s.reinit) {
+            const int sync_end = (n >= 259) ? kNesVsyncEnd : kBwBeg;
+            for (int t = tid; t < kHres; t += 256)
+                analog[n * kHres + t] = (signed char) ((t >= kSyncBeg && t < sync_end) ? kSync : kBlank);
+            __syncthreads();
+        }
+        if (tid < kBurstLen) { // crt_nes.c:174-178
+            const int t = kCbBeg + tid;
+            analog[n * kHres + t] = burst[(n % 3) * 4 + (t & 3)];
+        }
         int row = (y * s.h) / kLines;
         if (row >= s.h) row = s.h - 1; // the reference reads one row past the image here (undefined)
         if (row < 0) row = 0;
-        const int p = __ldg(data + ((x * s.w) / kAvLen) + row * s.w) & 0x1ff;
-        const int phase = (((y + yo + s.dot_crawl_offset) % 3) * 4 + 3 * x) % 12;
-        analog[(y + yo) * kHres + xo + x] = tab[p * 12 + phase];
+        const unsigned short *src_row = data + row * s.w;
+        const int phase0 = ((y + yo + s.dot_crawl_offset) % 3) * 4;
+        for (int x = tid; x < kAvLen; x += 256) { // crt_nes.c:180-193
+            const int p = __ldg(src_row + (x * s.w) / kAvLen) & 0x1ff;
+            analog[n * kHres + xo + x] = tab[p * 12 + (phase0 + 3 * x) % 12];
+        }
     }
 }
 

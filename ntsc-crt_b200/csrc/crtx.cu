@@ -248,9 +248,10 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
 #if (CRT_SYSTEM == CRT_SYSTEM_NES)
     {
         LaunchTimer lt(ctx, stream, 0);
-        k_mod_nes<<<count, 256, 0, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_state, ctx->d_analog, first);
+        k_nes_table<<<count, 256, 0, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_state, ctx->d_nes_tab, first);
+        k_mod_nes<<<dim3(kNesParts, count), 256, 0, stream>>>(ctx->d_src + first, ctx->d_nes_tab, ctx->d_analog, first);
     }
-    ctx->launches += 1;
+    ctx->launches += 2;
 #else
     int extra = 0;
     {
@@ -467,6 +468,9 @@ int crtx_create(crtx_ctx **out, int n)
         CTX_TRY(cudaMemcpy(ctx->d_jump_lo, lo.data(), sizeof(Affine) * kJumpLo, cudaMemcpyHostToDevice));
         CTX_TRY(cudaMemcpy(ctx->d_jump_hi, hi.data(), sizeof(Affine) * kJumpHi, cudaMemcpyHostToDevice));
     }
+#if (CRT_SYSTEM == CRT_SYSTEM_NES)
+    CTX_TRY(cudaMalloc(&ctx->d_nes_tab, (size_t) kNesTabBytes * n));
+#endif
 #if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
     {
         CTX_TRY(cudaMalloc(&ctx->d_vhs_rand, sizeof(VhsRand) * n));
@@ -505,6 +509,7 @@ void crtx_destroy(crtx_ctx *ctx)
     cudaFree(ctx->d_jump_lo);
     cudaFree(ctx->d_jump_hi);
     cudaFree(ctx->d_src_img);
+    cudaFree(ctx->d_nes_tab);
     cudaFree(ctx->d_vhs_rand);
     cudaFree(ctx->d_vhs_jump);
     cudaFree(ctx->d_vhs_raw);
