@@ -57,18 +57,24 @@ __device__ __forceinline__ unsigned vhs_draw_mem(unsigned *h)
 
 // states[t + 2^k] = A_k * states[t] for t < 2^k, k = 0 .. kVhsLevels - 1: after it states[0 .. 256]
 // hold the generator state at the start of every run (and, at [256], after the last one).
-__device__ __forceinline__ void vhs_spread_states(unsigned (*states)[32], const unsigned (*A)[31][31], int tid)
+__device__ __forceinline__ void vhs_spread_states(unsigned (*states)[32], const unsigned (*A)[31][31], int tid,
+                                                  unsigned *Am /* shared, 31 * 31 words */)
 {
     const int warp = tid >> 5, lane = tid & 31;
     for (int k = 0; k <= kVhsLevels; k++) {
         const int half = 1 << k; // states [0, half) known; fill [half, 2 * half) (level 8 fills only [256])
-        const unsigned (*Ak)[31] = A[k < kVhsLevels ? k : kVhsLevels - 1];
+        if (k < kVhsLevels) { // this level's matrix into shared memory (row stride 31: conflict-free rows)
+            const unsigned *src = &A[k][0][0];
+            for (int e = tid; e < 31 * 31; e += kVhsThreads) Am[e] = __ldg(src + e);
+            __syncthreads();
+        } // level 8 reuses A^(128), still resident
         const int todo = (k < kVhsLevels) ? half : 1;
         for (int t = warp; t < todo; t += kVhsThreads / 32) {
             const int from = (k < kVhsLevels) ? t : 128, to = (k < kVhsLevels) ? t + half : 256;
             if (lane < 31) {
                 unsigned acc = 0;
-                for (int j = 0; j < 31; j++) acc += Ak[lane][j] * states[from][j];
+#pragma unroll
+                for (int j = 0; j < 31; j++) acc += Am[lane * 31 + j] * states[from][j];
                 states[to][lane] = acc;
             }
         }
@@ -93,6 +99,7 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
     unsigned *win = reinterpret_cast<unsigned *>(vsm + 257 * 32 * 4);                   // tail: [kVhsWin + 8]
     unsigned short *jt = reinterpret_cast<unsigned short *>(win + kVhsWin + 8);         // tail: [10][kVhsWin + 8]
     __shared__ int s_wobble, s_adv, s_start;
+    __shared__ unsigned s_mat[31 * 31];
     const int m = first + blockIdx.x, tid = threadIdx.x;
     if (cfgs[m].bpp == 0) return; // crt_core.c:312-315
     const int noise = cfgs[m].noise;
@@ -109,7 +116,7 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
         for (int j = 0; j < 31; j++) states[0][j] = h[j];
     }
     __syncthreads();
-    vhs_spread_states(states, jump->bulk, tid);
+    vhs_spread_states(states, jump->bulk, tid, s_mat);
 
     // ---- bulk: thread t owns samples [t * kVhsRun, (t + 1) * kVhsRun), two draws each
     {
@@ -144,7 +151,7 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
     // ---- tail raw stream: kVhsTailRaw values continuing after the bulk, to global scratch
     if (tid < 31) states[0][tid] = states[256][tid];
     __syncthreads();
-    vhs_spread_states(states, jump->tail, tid);
+    vhs_spread_states(states, jump->tail, tid, s_mat);
     {
         unsigned h[31];
 #pragma unroll
@@ -165,7 +172,20 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
     int last_rn = 0;
     for (int i0 = kVhsBulk; i0 < kInputSize;) {
         const int line = i0 / kHres, xa = i0 - line * kHres, nx = kHres - xa; // samples xa .. 909 of this line
-        for (int q = tid; q < kVhsWin + 8; q += kVhsThreads) win[q] = (D + q < kVhsTailRaw) ? raw[D + q] : 0u;
+        { // all of a thread's window loads in flight together
+            constexpr int kPer = (kVhsWin + 8 + kVhsThreads - 1) / kVhsThreads;
+            unsigned v[kPer];
+#pragma unroll
+            for (int u = 0; u < kPer; u++) {
+                const int q = tid + u * kVhsThreads;
+                v[u] = (q < kVhsWin + 8 && D + q < kVhsTailRaw) ? raw[D + q] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kPer; u++) {
+                const int q = tid + u * kVhsThreads;
+                if (q < kVhsWin + 8) win[q] = v[u];
+            }
+        }
         __syncthreads();
         // Within a line the first test is the same function of its draw for every sample except x == 0
         // (its bound is a multiple of the line length), so x == 0 is stepped on its own.
@@ -180,6 +200,7 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
         __syncthreads();
         for (int k = 1; k < 10; k++) { // jt[k][p] = 2^k-th successor
             unsigned short *prev = jt + (k - 1) * (kVhsWin + 8), *cur = jt + k * (kVhsWin + 8);
+#pragma unroll 4
             for (int p = tid; p < kVhsWin + 8; p += kVhsThreads) cur[p] = prev[min((int) prev[p], kVhsWin)];
             __syncthreads();
         }
