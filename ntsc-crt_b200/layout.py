@@ -27,7 +27,7 @@ def bpp4fmt(fmt):
 
 @dataclass(frozen=True)
 class SystemSpec:
-    name: str          # library suffix: ntsc | vhs | nes | nes_p0
+    name: str          # library suffix: ntsc | ntsc_conv | vhs | nes | nes_p0
     system: int        # CRT_SYSTEM
     pattern: int       # CRT_CHROMA_PATTERN
     hres: int
@@ -77,6 +77,8 @@ def _nes_spec(name, pattern):
 
 SPECS = {
     "ntsc": _rgb_spec("ntsc", SYS_NTSC),
+    # the USE_CONVOLUTION 1 build of crt_core.c (line 85): same layouts and timing, FIR decoder filters
+    "ntsc_conv": _rgb_spec("ntsc_conv", SYS_NTSC),
     "vhs": _rgb_spec("vhs", SYS_VHS),
     "nes": _nes_spec("nes", 2),
     "nes_p0": _nes_spec("nes_p0", 0),
@@ -85,6 +87,11 @@ SPECS = {
 
 def system_spec(name):
     return SPECS[name]
+
+
+def uses_convolution(name):
+    """True for variants built from the reference's USE_CONVOLUTION 1 decoder (crt_core.c:85-147)."""
+    return name.endswith("_conv")
 
 
 _crt_cache = {}

@@ -257,6 +257,23 @@ ocrt_system(int system, int chroma_pattern)
     return NULL;
 }
 
+const ocrt_sys *
+ocrt_system_conv(int system, int chroma_pattern)
+{
+    static ocrt_sys table[5];
+    static int ready[5];
+    const ocrt_sys *base = ocrt_system(system, chroma_pattern);
+    int slot;
+    if (!base) return NULL;
+    slot = (system == OCRT_SYS_NTSC) ? 0 : (system == OCRT_SYS_VHS) ? 1 : 2 + chroma_pattern;
+    if (!ready[slot]) {
+        table[slot] = *base;
+        table[slot].conv = 1;
+        ready[slot] = 1;
+    }
+    return &table[slot];
+}
+
 /* ------------------------------------------------------------------------- */
 /* monitor state (crt_core.c:241-289)                                         */
 /* ------------------------------------------------------------------------- */
@@ -624,6 +641,23 @@ eq_step(eq_state *f, const int *c, i32 s)
     return wadd(wadd(r0, r1), r2);
 }
 
+/* eqf() of the USE_CONVOLUTION build (crt_core.c:96-147, USE_7_SAMPLE_KERNEL): a 7-deep history,
+ * zero at the start of every line (reset_eq, crt_core.c:117-121), newest sample in h[0] */
+typedef struct fir_state {
+    i32 h[7];
+} fir_state;
+
+static i32
+fir_step(fir_state *f, i32 s)
+{
+    i32 k;
+    for (k = 6; k > 0; k--) f->h[k] = f->h[k - 1];
+    f->h[0] = s;
+    /* index : 0 1 2 3 4 5 6   weight: 1 4 7 8 7 4 1 */
+    return wadd(wadd(wadd(wadd(s, f->h[6]), wmul(wadd(f->h[1], f->h[5]), 4)), wmul(wadd(f->h[2], f->h[4]), 7)),
+                wmul(f->h[3], 8)) >> 5;
+}
+
 /* filter + resample + YIQ->RGB for decoded lines [first, first+count)
  * (crt_core.c:511-664) */
 void
@@ -645,6 +679,7 @@ ocrt_line_pass(const ocrt_sys *sys, ocrt_monitor *m, const ocrt_line *table, int
         const ocrt_line *rec = &table[k];
         const signed char *sig = m->inp + rec->pos;
         eq_state ey, ei, eq;
+        fir_state fy, fi, fq;
         unsigned char *px, *row_end;
         u32 pos;
         i32 i, row;
@@ -652,7 +687,15 @@ ocrt_line_pass(const ocrt_sys *sys, ocrt_monitor *m, const ocrt_line *table, int
         memset(&ey, 0, sizeof(ey));
         memset(&ei, 0, sizeof(ei));
         memset(&eq, 0, sizeof(eq));
-        for (i = 0; i < L; i++) { /* crt_core.c:538-543 */
+        memset(&fy, 0, sizeof(fy));
+        memset(&fi, 0, sizeof(fi));
+        memset(&fq, 0, sizeof(fq));
+        for (i = 0; sys->conv && i < L; i++) { /* crt_core.c:538-543 with the FIR eqf */
+            yy[i] = wmul(fir_step(&fy, sig[i] + bright), 16);
+            ii[i] = fir_step(&fi, wmul(sig[i], rec->wave[i & 3]) >> 9) >> 3;
+            qq[i] = fir_step(&fq, wmul(sig[i], rec->wave[(i + 3) & 3]) >> 9) >> 3;
+        }
+        for (i = 0; !sys->conv && i < L; i++) { /* crt_core.c:538-543 */
             yy[i] = eq_step(&ey, sys->eq[0], sig[i] + bright) * 16;
             ii[i] = eq_step(&ei, sys->eq[1], wmul(sig[i], rec->wave[i & 3]) >> 9) >> 3;
             qq[i] = eq_step(&eq, sys->eq[2], wmul(sig[i], rec->wave[(i + 3) & 3]) >> 9) >> 3;

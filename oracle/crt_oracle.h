@@ -48,6 +48,9 @@ typedef struct ocrt_sys {
     int eq[3][5];
     /* encoder band-limit coefficients c for Y, I, Q (crt_ntsc.c:142-146) */
     int iir_c[3];
+    /* 1: the USE_CONVOLUTION build of the decoder (crt_core.c:85, 96-147): eqf() is the 7-tap
+     * [1 4 7 8 7 4 1] >> 5 kernel instead of the three-band equaliser */
+    int conv;
 } ocrt_sys;
 
 /* Mirrors the caller-visible part of struct CRT (crt_core.h:74-92). */
@@ -96,6 +99,8 @@ typedef struct ocrt_line {
 } ocrt_line;
 
 const ocrt_sys *ocrt_system(int system, int chroma_pattern);
+/* the same system with the reference's USE_CONVOLUTION 1 decoder (crt_core.c:85) */
+const ocrt_sys *ocrt_system_conv(int system, int chroma_pattern);
 
 void ocrt_sincos14(int *s, int *c, int n);
 int  ocrt_bpp(int format);

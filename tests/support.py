@@ -189,7 +189,7 @@ class _OSys(C.Structure):
         "cc_vper", "hsync_window", "vsync_window", "hsync_thresh", "vsync_thresh",
         "sync_beg", "bw_beg", "cb_beg", "av_beg", "av_len", "burst_len",
         "white_level", "burst_level", "black_level", "blank_level", "sync_level",
-        "vhs_noise", "nes_vsync_end")] + [("eq", (C.c_int * 5) * 3), ("iir_c", C.c_int * 3)]
+        "vhs_noise", "nes_vsync_end")] + [("eq", (C.c_int * 5) * 3), ("iir_c", C.c_int * 3), ("conv", C.c_int)]
 
 
 class _OMonitor(C.Structure):
@@ -233,6 +233,8 @@ def oracle_lib():
         lib = C.CDLL(os.path.join(ORACLE_DIR, "libcrt_oracle.so"))
         lib.ocrt_system.restype = C.POINTER(_OSys)
         lib.ocrt_system.argtypes = [C.c_int, C.c_int]
+        lib.ocrt_system_conv.restype = C.POINTER(_OSys)
+        lib.ocrt_system_conv.argtypes = [C.c_int, C.c_int]
         lib.ocrt_monitor_create.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.c_int,
                                             C.c_int, C.c_int, C.c_void_p]
         lib.ocrt_monitor_create.restype = C.c_int
@@ -265,7 +267,8 @@ class OracleEngine:
     def __init__(self, variant, outw, outh, fmt=layout.PIX_BGRA, out=None, seed=1):
         self.spec = layout.system_spec(variant)
         self.lib = oracle_lib()
-        self.sys = self.lib.ocrt_system(self.spec.system, self.spec.pattern)
+        get = self.lib.ocrt_system_conv if layout.uses_convolution(variant) else self.lib.ocrt_system
+        self.sys = get(self.spec.system, self.spec.pattern)
         assert self.sys, "unknown system"
         self.mon = _OMonitor()
         bpp = max(1, layout.bpp4fmt(fmt))

@@ -32,7 +32,7 @@ def check(ref, ora, what):
 
 
 def test_struct_layout_matches_reference():
-    for variant in ("ntsc", "vhs", "nes", "nes_p0"):
+    for variant in ("ntsc", "ntsc_conv", "vhs", "nes", "nes_p0"):
         spec = layout.system_spec(variant)
         lib = C.CDLL(S.ref_path(variant))
         assert lib.ref_sizeof_crt() == C.sizeof(layout.crt_struct(spec)), variant
@@ -164,6 +164,33 @@ def test_ntsc_unknown_format_is_silent_noop():
     ref, ora = pair("ntsc", 128, 96)
     both(ref, ora, lambda e: e.modulate(img, format=17, as_color=1))
     check(ref, ora, "bad in format")
+
+
+@pytest.mark.parametrize("outw,outh,blend,scanlines", [(832, 624, 1, 1), (640, 480, 0, 1), (256, 240, 1, 0),
+                                                       (300, 100, 1, 0)])
+def test_ntsc_conv_variant(outw, outh, blend, scanlines):
+    """a11: the USE_CONVOLUTION 1 build (crt_core.c:85-147, 7-tap kernel) against the oracle's FIR eqf."""
+    img = S.rand_image(333, 250, seed=outw)
+    ref, ora = pair("ntsc_conv", outw, outh)
+    both(ref, ora, lambda e: e.set(blend=blend, scanlines=scanlines, hue=15, brightness=-7, contrast=190,
+                                   saturation=12))
+    for it in range(5):
+        both(ref, ora, lambda e: e.modulate(img, format=layout.PIX_BGRA, as_color=1, field=it & 1,
+                                            frame=(it >> 1) & 1))
+        both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 17))
+        check(ref, ora, "conv %dx%d call %d" % (outw, outh, it))
+
+
+def test_ntsc_conv_extreme_knobs_and_formats():
+    for fmt in range(6):
+        rgb = S.rand_image(200, 120, bpp=3, seed=40 + fmt)
+        img = S.pack_rgb(rgb, fmt)
+        ref, ora = pair("ntsc_conv", 400, 300, fmt)
+        both(ref, ora, lambda e: e.set(blend=fmt & 1, scanlines=1, saturation=4000, contrast=900, brightness=5000))
+        for it in range(2):
+            both(ref, ora, lambda e: e.modulate(img, format=fmt, as_color=1, field=it, frame=0))
+            both(ref, ora, lambda e: e.demodulate(30))
+            check(ref, ora, "conv extreme fmt %d call %d" % (fmt, it))
 
 
 @pytest.mark.parametrize("variant", ["nes", "nes_p0"])
