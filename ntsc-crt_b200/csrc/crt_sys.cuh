@@ -23,6 +23,12 @@ constexpr int kSystem = CRT_SYSTEM;
 constexpr int kPattern = CRT_CHROMA_PATTERN;
 constexpr bool kIsNes = (CRT_SYSTEM == CRT_SYSTEM_NES);
 constexpr bool kIsVhs = (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS);
+// -DCRTX_CONV=1 builds the decoder of the reference's USE_CONVOLUTION 1 configuration (an unguarded
+// #define at crt_core.c:85, so a separate library like every other compile-time choice there)
+#ifndef CRTX_CONV
+#define CRTX_CONV 0
+#endif
+constexpr bool kConv = (CRTX_CONV != 0);
 
 constexpr int kHres = CRT_HRES;
 constexpr int kVres = CRT_VRES;

@@ -59,6 +59,12 @@ static int upload_cfg(crtx_ctx *ctx, cudaStream_t stream)
 template <bool FAST, int MODE, int FMT>
 static void launch_lines_one(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
 {
+    if (kConv) { // USE_CONVOLUTION build: one warp per decoded line (crt_lines_fir.cuh)
+        const dim3 grid((kLines + kFirWarps - 1) / kFirWarps, count);
+        k_lines_fir<FAST, MODE, FMT><<<grid, kFirWarps * 32, fir_smem<FAST>(), stream>>>(ctx->d_cfg, ctx->d_state,
+                                                                                         ctx->d_lines, ctx->d_inp, lo, geo);
+        return;
+    }
     k_lines<FAST, MODE, FMT><<<count, kLinesWarps * 32, lines_smem<FAST>(), stream>>>(ctx->d_cfg, ctx->d_state,
                                                                                       ctx->d_lines, ctx->d_inp, lo, geo);
 }
@@ -87,6 +93,9 @@ static void launch_lines(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo,
 template <bool FAST, int MODE, int FMT>
 static cudaError_t lines_attr()
 {
+    if (kConv)
+        return cudaFuncSetAttribute(k_lines_fir<FAST, MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    fir_smem<FAST>());
     return cudaFuncSetAttribute(k_lines<FAST, MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 lines_smem<FAST>());
 }
