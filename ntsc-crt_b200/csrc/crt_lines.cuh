@@ -83,9 +83,9 @@ __device__ __forceinline__ unsigned yiq_to_rgb(int y, int i, int q, int contrast
     int r = wmul(wadd(wadd(y, wmul(3879, i)), wmul(2556, q)) >> 12, contrast) >> 8;
     int g = wmul(wsub(wsub(y, wmul(1126, i)), wmul(2605, q)) >> 12, contrast) >> 8;
     int b = wmul(wadd(wsub(y, wmul(4530, i)), wmul(7021, q)) >> 12, contrast) >> 8;
-    r = clampi(r, 0, 255);
-    g = clampi(g, 0, 255);
-    b = clampi(b, 0, 255);
+    r = __vimin_s32_relu(r, 255); // max(min(r, 255), 0) in one VIMNMX.RELU
+    g = __vimin_s32_relu(g, 255);
+    b = __vimin_s32_relu(b, 255);
     return (unsigned) (r << 16 | g << 8 | b);
 }
 

@@ -60,7 +60,7 @@ template <bool FAST, int MODE, int FMT>
 static void launch_lines_one(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
 {
     if (kConv) { // USE_CONVOLUTION build: one warp per decoded line (crt_lines_fir.cuh)
-        const dim3 grid((kLines + kFirWarps - 1) / kFirWarps, count);
+        const dim3 grid(FAST ? kFirGroups : 3, count); // see k_lines_fir: the generic pass is normally empty
         k_lines_fir<FAST, MODE, FMT><<<grid, kFirWarps * 32, fir_smem<FAST>(), stream>>>(ctx->d_cfg, ctx->d_state,
                                                                                          ctx->d_lines, ctx->d_inp, lo, geo);
         return;
