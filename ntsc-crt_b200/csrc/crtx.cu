@@ -60,7 +60,11 @@ template <bool FAST, int MODE, int FMT>
 static void launch_lines_one(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
 {
     if (kConv) { // USE_CONVOLUTION build: one warp per decoded line (crt_lines_fir.cuh)
-        const dim3 grid(FAST ? kFirGroups : 3, count); // see k_lines_fir: the generic pass is normally empty
+        // about two waves of resident CTAs (2 per SM) over the whole launch, see k_lines_fir; the generic
+        // pass is normally empty and gets the smallest grid
+        int gx = FAST ? (4 * ctx->sm_count + count - 1) / count : 1;
+        gx = gx < 1 ? 1 : (gx > kFirGroups ? kFirGroups : gx);
+        const dim3 grid(gx, count);
         k_lines_fir<FAST, MODE, FMT><<<grid, kFirWarps * 32, fir_smem<FAST>(), stream>>>(ctx->d_cfg, ctx->d_state,
                                                                                          ctx->d_lines, ctx->d_inp, lo, geo);
         return;
@@ -436,6 +440,7 @@ int crtx_create(crtx_ctx **out, int n)
     crtx_ctx *ctx = new crtx_ctx();
     ctx->n = n;
     ctx->device = dev;
+    ctx->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     ctx->h_cfg.assign(n, MonCfg());
     memset(ctx->h_cfg.data(), 0, sizeof(MonCfg) * n);
     ctx->cfg_dirty_lo = 0;

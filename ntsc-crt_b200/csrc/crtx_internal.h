@@ -13,6 +13,7 @@
 struct crtx_ctx {
     int n = 0;
     int device = 0;
+    int sm_count = 148;
     crt::MonCfg *d_cfg = nullptr;
     crt::MonState *d_state = nullptr;
     crt::SrcCfg *d_src = nullptr;
