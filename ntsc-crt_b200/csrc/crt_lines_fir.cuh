@@ -30,6 +30,7 @@ constexpr int kFirSamples = 32 * kFirChunk;        // 768 >= AV_LEN of every sys
 constexpr int kFirHalo = 6;                        // taps - 1
 constexpr int kFirStage = ((kFirSamples + 15 + 15) / 16) * 16; // staged bytes per line
 constexpr int kFirSeg = 832;                       // output pixels staged per bulk load / store
+constexpr int kFirIter = kFirSeg / 32;               // pixels per lane and segment
 constexpr int kFirGroups = (kLines + kFirWarps - 1) / kFirWarps;
 static_assert(kFirSamples >= kAvLen, "one warp covers a whole line");
 static_assert(kFirChunk % 8 == 0 && kFirChunk % 4 == 0, "slot padding and carrier phase are per-lane constants");
@@ -63,6 +64,17 @@ template <int PENDING> __device__ __forceinline__ void tma_store_wait_read()
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Row element at a shared-memory ADDRESS (+ constant byte offset), sign-extended.  The resampler keeps
+// absolute shared addresses in registers; going through ld.shared directly keeps the address arithmetic
+// out of the pixel loop (a generic pointer would be re-derived from the shared window base every time).
+template <typename Elem, int OFF> __device__ __forceinline__ int lds_elem(unsigned addr)
+{
+    int v;
+    if (sizeof(Elem) == 2) asm volatile("ld.shared.s16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    else asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+
 // one channel of the factored kernel: [1 1] three times, then a 4-wide box as two pair sums
 struct FirChan {
     int a, b, c, d, p1, p2;
@@ -95,7 +107,7 @@ struct FirLine {
 // resident CTAs.  While line n is being decoded the record of line n + 2, the signal window of line
 // n + 1 and (from the middle of line n on) the previous image's row of line n + 1 are on their way.
 template <bool FAST, int MODE, int FMT>
-__global__ void __launch_bounds__(kFirWarps * 32)
+__global__ void __launch_bounds__(kFirWarps * 32, FAST ? 2 : 1)
 k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, const LineRec *__restrict__ lines_base,
             const signed char *__restrict__ inp_base, int first, const LinesGeom geo)
 {
@@ -160,6 +172,7 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
                                  : (FMT == CRT_PIX_FORMAT_ABGR) ? 0x2104u : 0x4210u;
     constexpr unsigned alpha_ff = (FMT == CRT_PIX_FORMAT_ARGB || FMT == CRT_PIX_FORMAT_ABGR) ? 0x000000ffu : 0xff000000u;
     constexpr unsigned blend_mask = 0x7f7f7f7fu & ~(alpha_ff >> 1) & ~alpha_ff;
+    constexpr unsigned blend_even = 0xfefefefeu & ~alpha_ff; // (x & blend_even) >> 1 == (x >> 1) & blend_mask
     int rp = 0, gp = 0, bp = 0;
     if (MODE == 2) fmt_positions(geo.out_format, rp, gp, bp);
 
@@ -171,6 +184,25 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
         mbar_expect_tx(&bars[2 + buf], cnt * 4);
         tma_load_1d(orow + buf * kFirSeg, out + (size_t) l.beg * pitch + (size_t) k0 * 4, cnt * 4, &bars[2 + buf]);
     };
+
+    // Where output pixel k0 + 32 u + lane reads its samples and with which weight depends only on the
+    // output width: every lane keeps that for its (at most kFirIter) pixels of a segment in registers.
+    int tab_slot[kFirIter], tab_r4[kFirIter];
+    int tab_k0 = -1;
+    auto build_table = [&](int k0) {
+#pragma unroll
+        for (int u = 0; u < kFirIter; u++) {
+            const unsigned pos = (unsigned) (k0 + u * 32 + lane) * dx;
+            const unsigned sidx = pos >> 12;
+            // shared address of the sample's Y slot (clamped for pixels past outw)
+            tab_slot[u] = (int) smem_u32(yrow + 1 + min(sidx + (sidx >> 3), (unsigned) (FirRow<FAST>::kSlots - 3)));
+            tab_r4[u] = (int) ((pos & 0xfffu) << 2);
+        }
+    };
+    if (bulk) {
+        build_table(0);
+        tab_k0 = 0;
+    }
 
     if (geo.use_tma && lane == 0 && cur.active) {
         request_signal(cur, 0);
@@ -252,23 +284,28 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
 
             // ---- (P) pixels (crt_core.c:555-659), 32 consecutive ones per step
             const Elem *slot1 = yrow + 1; // slot of sample 0
-            auto pixel = [&](int px) -> unsigned { // 0x00RRGGBB of output pixel px
-                const unsigned pos = (unsigned) px * dx;
-                const unsigned s = pos >> 12;
-                const Elem *sp = slot1 + (s + (s >> 3));
-                const int ay = sp[0], by = sp[1];
-                const int ai = sp[kComp], bi = sp[kComp + 1];
-                const int aq = sp[2 * kComp], bq = sp[2 * kComp + 1];
+            // 0x00RRGGBB from the two samples at `sp` and the 4x interpolation weight of the second one
+            auto shade = [&](unsigned sp, int R4) -> unsigned { // sp: shared address of the first sample's Y
+                constexpr int E = (int) sizeof(Elem), C = FirRow<FAST>::kCompBytes;
+                const int ay = lds_elem<Elem, 0>(sp), by = lds_elem<Elem, E>(sp);
+                const int ai = lds_elem<Elem, C>(sp), bi = lds_elem<Elem, C + E>(sp);
+                const int aq = lds_elem<Elem, 2 * C>(sp), bq = lds_elem<Elem, 2 * C + E>(sp);
                 if (FAST) {
-                    const int R4 = (int) ((pos & 0xfffu) << 2), L4 = 0x3ffc - R4; // 4 * R, 4 * L
+                    const int L4 = 0x3ffc - R4; // 4 * L
                     const int y = wadd(wmul(ay, L4), wmul(by, R4));
-                    // (v * 4L) >> 16 == (v * L) >> 14: the two dropped bits are zeros
+                    // (v * 4L) >> 16 == (v * L) >> 14: the two dropped bits are zeros.  (One IMAD.HI per term instead
+                    // of multiply + shift was measured 3 % SLOWER on B200: IMAD.HI is a multi-pass instruction.)
                     return yiq_to_rgb(y, wadd(wmul(ai, L4) >> 16, wmul(bi, R4) >> 16),
                                       wadd(wmul(aq, L4) >> 16, wmul(bq, R4) >> 16), contrast);
                 } else {
-                    const int R = (int) (pos & 0xfffu), L = 0xfff - R;
+                    const int R = R4 >> 2, L = 0xfff - R;
                     return yiq_pixel(ay, ai, aq, by, bi, bq, R, L, contrast);
                 }
+            };
+            auto pixel = [&](int px) -> unsigned { // 0x00RRGGBB of output pixel px
+                const unsigned pos = (unsigned) px * dx;
+                const unsigned s = pos >> 12;
+                return shade(smem_u32(slot1 + (s + (s >> 3))), (int) ((pos & 0xfffu) << 2));
             };
 
             if (bulk) {
@@ -284,17 +321,34 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
                         }
                         __syncwarp();
                     }
+                    if (k0 != tab_k0) { // (only images wider than one segment ever rebuild the table)
+                        build_table(k0);
+                        tab_k0 = k0;
+                    }
                     if (MODE == 1) {
                         mbar_wait(&bars[2 + buf], (ph_old >> buf) & 1);
                         ph_old ^= 1u << buf;
                     }
-#pragma unroll 2
-                    for (int j = lane; j < cnt; j += 32) {
-                        const unsigned rgb = pixel(k0 + j);
-                        unsigned v = (FMT == CRT_PIX_FORMAT_BGRA) ? (rgb | alpha_ff) : __byte_perm(rgb, 0xffu, sel_store);
-                        if (MODE == 1) v = (((v >> 1) & blend_mask) | alpha_ff) + ((ob[j] >> 1) & blend_mask); // crt_core.c:608
+#pragma unroll
+                    const int steps = (cnt + 31) >> 5; // lanes (and one whole step) past cnt compute into the unused tail
+                    auto emit = [&](int u) {
+                        const int j = u * 32 + lane;
+                        const unsigned rgb = shade((unsigned) tab_slot[u], tab_r4[u]);
+                        unsigned v = (FMT == CRT_PIX_FORMAT_BGRA) ? rgb : __byte_perm(rgb, 0u, sel_store);
+                        if (MODE == 1) // crt_core.c:608 on whole words; the alpha byte is masked out and set
+                            v = alpha_ff + ((v & blend_even) >> 1) + ((ob[j] & blend_even) >> 1);
+                        else
+                            v |= alpha_ff;
                         ob[j] = v;
+                    };
+#pragma unroll
+                    for (int u = 0; u + 1 < kFirIter; u += 2) {
+                        if (u < steps) {
+                            emit(u);
+                            emit(u + 1);
+                        }
                     }
+                    if ((kFirIter & 1) && kFirIter - 1 < steps) emit(kFirIter - 1);
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
