@@ -112,6 +112,12 @@ int crtx_get_timing(crtx_ctx *ctx, float *ms /* [CRTX_NUM_KERNELS] */, long *lau
 /* diagnostics */
 int crtx_get_lines(crtx_ctx *ctx, int i, crtx_line *table /* crtx_lines() entries */, void *stream);
 long crtx_launch_count(crtx_ctx *ctx); /* kernels launched through this context so far */
+/* options: "tma", "generic_eq", "timing", "mod_staged", "fused_noise" (0/1 switches), and
+ * "line_lo" / "line_hi": crtx_demodulate's line pass only decodes scanlines [line_lo, line_hi) of every
+ * field (sync search and noise still cover the whole field).  This is the scanline-block partition of
+ * ONE image across GPUs (fields of one image depend on each other through the blend, crt_core.c:584-608,
+ * so they cannot be spread over ranks): every rank runs the same calls with its own block and owns the
+ * output rows those lines write; see ntsc-crt_b200/sharding.py. */
 int crtx_set_option(crtx_ctx *ctx, const char *name, int value);
 const char *crtx_last_error(void);
 

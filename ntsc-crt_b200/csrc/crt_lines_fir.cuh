@@ -127,7 +127,7 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
         if (kl < kLines) {
             const LineRec r = recs[kl];
             l.pos = r.pos; l.wave0 = r.wave0; l.wave1 = r.wave1; l.beg = r.beg; l.end = r.end;
-            l.active = r.beg >= 0 && (geo.pass == -1 || (geo.pass == -2 ? r.pad1 != 0 : r.pad0 == geo.pass));
+            l.active = r.beg >= 0 && kl >= geo.line_lo && kl < geo.line_hi && (geo.pass == -1 || (geo.pass == -2 ? r.pad1 != 0 : r.pad0 == geo.pass));
         }
         return l;
     };

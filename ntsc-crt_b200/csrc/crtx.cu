@@ -358,6 +358,8 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
         geo.blend = c0.blend ? 1 : 0;
         geo.use_tma = ctx->opt_tma;
         geo.rnd = 32768;
+        geo.line_lo = ctx->opt_line_lo;
+        geo.line_hi = ctx->opt_line_hi;
         {
             LaunchTimer lt(ctx, stream, 4);
             // the second launch takes the monitors whose signal left the fast equaliser's exact range
@@ -745,6 +747,8 @@ int crtx_set_option(crtx_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "timing")) ctx->opt_timing = value;
     else if (!strcmp(name, "mod_staged")) ctx->opt_mod_staged = value;
     else if (!strcmp(name, "fused_noise")) ctx->opt_fused_noise = value;
+    else if (!strcmp(name, "line_lo")) ctx->opt_line_lo = value;
+    else if (!strcmp(name, "line_hi")) ctx->opt_line_hi = value;
     else return fail("crtx_set_option: unknown option '%s'", name);
     return 0;
 }

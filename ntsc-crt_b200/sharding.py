@@ -43,3 +43,99 @@ def allgather_frames(local, group=None):
     out = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out.view(-1), local.contiguous().view(-1), group=group)
     return out.view((world * local.shape[0],) + tuple(local.shape[1:]))
+
+
+# ---------------------------------------------------------------------------------------------
+# One image over several GPUs: scanline blocks
+# ---------------------------------------------------------------------------------------------
+# The fields of ONE image are sequentially dependent through the blend (crt_core.c:584-608), so a single
+# image cannot be spread over ranks by field.  Its decoded scanlines can: after the sync pre-pass every
+# line is independent (crt_core.c:409-664), and line k of a field only touches output rows
+#     beg = k * (outh + v_fac) / CRT_LINES + field  ..  end = (k + 1) * (outh + v_fac) / CRT_LINES + field
+# (crt_core.c:428-432, rows beg .. end - scanlines - 1 are written).  Every rank runs the SAME calls --
+# modulate, noise, sync search are replicated, they are a small part of the work -- with the line pass
+# restricted to its block (crtx_set_option "line_lo"/"line_hi") and keeps the accumulation of its own rows
+# across the fields; one all_gather of row blocks at the end gives every rank the whole image.
+#
+# The one coupling between blocks: in an odd field every line is shifted down by field * (ratio / 2) rows
+# (crt_core.c:400-407), so the last line of a block may write (duplicate into) the first rows of the
+# NEXT block -- rows the next even field of that block blends with.  `exchange_spill_rows` hands those
+# few rows to the neighbour after each field.
+
+def line_block(rank, world, lines):
+    """Decoded scanlines [lo, hi) of `rank` (contiguous, sizes differ by at most one)."""
+    return shard_range(lines, rank, world)
+
+
+def block_rows(lo, hi, outh, lines, v_fac=0):
+    """Output rows [r0, r1) owned by the rank decoding lines [lo, hi): the rows its lines start on in an
+    even field (crt_core.c:428), clipped to the image."""
+    span = outh + v_fac
+    return min(outh, lo * span // lines), min(outh, hi * span // lines)
+
+
+class ImageSharder:
+    """Row ownership and the two exchanges of the scanline-block partition of one image.
+
+    image: this rank's (outh, outw, bpp) uint8 tensor (any device the process group supports)."""
+
+    def __init__(self, image, lines, rank=None, world=None, v_fac=0, group=None):
+        import torch.distributed as dist
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.world = world if world is not None else (dist.get_world_size(group) if on else 1)
+        self.rank = rank if rank is not None else (dist.get_rank(group) if on else 0)
+        self.image, self.lines, self.v_fac = image, lines, v_fac
+        self.outh = image.shape[0]
+        self.lo, self.hi = line_block(self.rank, self.world, lines)
+        self.blocks = [block_rows(*line_block(r, self.world, lines), self.outh, lines, v_fac)
+                       for r in range(self.world)]
+        self.r0, self.r1 = self.blocks[self.rank]
+
+    def apply(self, batch):
+        """Restrict a capi.Batch's line pass to this rank's block."""
+        batch.set_option("line_lo", self.lo)
+        batch.set_option("line_hi", self.hi)
+
+    def max_spill(self):
+        """Most rows a block can spill into its successor: ratio / 2 of crt_core.c:400-407."""
+        ratio = ((((self.outh + self.v_fac) << 16) // self.lines) + 32768) >> 16
+        return max(1, ratio // 2)
+
+    def exchange_spill_rows(self, written_end):
+        """After a field.  written_end: one past the last output row this rank's LAST line wrote in this
+        field (`end - scanlines` of line hi - 1 from the sync table, or anything <= r1 if it was skipped).
+        Rows [r1, written_end) belong to the next rank, which takes them into its image.  One small
+        all_gather (a few rows per rank)."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        cap = self.max_spill()
+        cnt = max(0, min(int(written_end), self.outh, self.r1 + cap) - self.r1) if self.rank + 1 < self.world else 0
+        mine = torch.zeros((cap + 1,) + tuple(self.image.shape[1:]), dtype=self.image.dtype, device=self.image.device)
+        if cnt:
+            mine[:cnt].copy_(self.image[self.r1:self.r1 + cnt])
+        mine[cap].view(-1)[0] = cnt  # (cap rows of pixels, then the count in the first byte of a spare row)
+        rows = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(rows, mine, group=self.group)
+        if self.rank > 0 and self.blocks[self.rank - 1][1] == self.r0:
+            got = int(rows[self.rank - 1][cap].view(-1)[0])
+            if got:
+                self.image[self.r0:self.r0 + got].copy_(rows[self.rank - 1][:got])
+
+    def gather(self):
+        """Every rank's own rows -> the complete image on every rank (blocks padded to equal height)."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return self.image
+        tall = max(b - a for a, b in self.blocks)
+        mine = torch.zeros((tall,) + tuple(self.image.shape[1:]), dtype=self.image.dtype, device=self.image.device)
+        mine[:self.r1 - self.r0].copy_(self.image[self.r0:self.r1])
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        full = self.image.clone()
+        for r, (a, b) in enumerate(self.blocks):
+            full[a:b].copy_(parts[r][:b - a])
+        return full

@@ -64,3 +64,79 @@ def test_world_size_2_gloo():
     for rank, allf, ms in results:
         assert np.array_equal(allf, want)
         assert ms == [11.0, 5.0]
+
+
+# ---------------------------------------------------------------------------------------------
+# scanline-block partition of ONE image: the host logic, with the oracle's staged decode
+# standing in for the kernels (noise + sync replicated, line pass restricted to the rank's block)
+# ---------------------------------------------------------------------------------------------
+def test_line_blocks_and_row_ownership():
+    for world in (1, 2, 3, 8):
+        for outh in (624, 480, 240, 100, 1080):
+            blocks = [sharding.block_rows(*sharding.line_block(r, world, 240), outh, 240) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == outh
+            for (a, b), (c, d) in zip(blocks, blocks[1:]):
+                assert b == c and a <= b
+    assert sharding.block_rows(0, 30, 624, 240) == (0, 78)  # 30 lines <-> 78 rows at 832x624
+
+
+def _image_worker(rank, world, port, q, cfg):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import pkgload as pl
+    pl.load()
+    import support as S
+    from ntsc_crt_b200 import layout, sharding as sh
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        outw, outh, scanlines, blend, progressive, noise = cfg
+        img = S.rand_image(200, 150, seed=5)
+        eng = S.OracleEngine("ntsc", outw, outh)
+        eng.set(blend=blend, scanlines=scanlines)
+        image = torch.from_numpy(eng.out)  # shares memory with the monitor's output buffer
+        part = sh.ImageSharder(image, eng.spec.lines)
+        for it in range(6):
+            field = 0 if progressive else it & 1
+            eng.modulate(img, format=layout.PIX_BGRA, as_color=1, field=field, frame=(it >> 1) & 1)
+            eng.noise_pass(noise)
+            _, table = eng.sync_pass()
+            eng.line_pass(table, part.lo, part.hi - part.lo)
+            last = table[part.hi - 1]
+            part.exchange_spill_rows(0 if last.skip else max(last.beg + 1, last.end - scanlines))
+        q.put((rank, part.gather().numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,cfg", [
+    (2, (832, 624, 1, 1, False, 0)),   # config 2's knobs: blocks are independent
+    (2, (640, 480, 0, 1, False, 7)),   # scanlines 0 + blend + interlaced: the spill row must travel
+    (3, (333, 250, 0, 1, False, 0)),   # uneven blocks
+    (2, (256, 240, 0, 0, True, 3)),
+    (2, (400, 1080, 0, 1, False, 0)),  # ratio 4.5: two spill rows per odd field
+])
+def test_one_image_over_ranks_matches_the_sequential_decode(world, cfg):
+    import support as S
+    from ntsc_crt_b200 import layout
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_image_worker, args=(r, world, port, q, cfg)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    outw, outh, scanlines, blend, progressive, noise = cfg
+    img = S.rand_image(200, 150, seed=5)
+    ref = S.OracleEngine("ntsc", outw, outh)
+    ref.set(blend=blend, scanlines=scanlines)
+    for it in range(6):
+        field = 0 if progressive else it & 1
+        ref.modulate(img, format=layout.PIX_BGRA, as_color=1, field=field, frame=(it >> 1) & 1)
+        ref.demodulate(noise)
+    for rank, full in results:
+        assert np.array_equal(full, ref.out), "rank %d: %s" % (rank, S.diff_report("image", full, ref.out))
