@@ -102,6 +102,17 @@ int crtx_demodulate(crtx_ctx *ctx, int first, int count, void *stream);
 int crtx_frames_host(crtx_ctx *ctx, int first, int count, const crtx_source *src,
                      void *const *out_host, void *stream);
 
+/* Memory and stream helpers, so that a plain C89 caller (tools/crtx_video.c) needs no CUDA header:
+ * device images, pinned host buffers, copies ordered on `stream` (0 = the default stream), and a
+ * stream / device synchronise.  crtx_memcpy's kind: 0 host -> device, 1 device -> host, 2 device -> device. */
+void *crtx_device_alloc(size_t bytes);   /* zero-filled; NULL on failure */
+void  crtx_device_free(void *p);
+void *crtx_host_alloc(size_t bytes);     /* page-locked; NULL on failure */
+void  crtx_host_free(void *p);
+int   crtx_memcpy(void *dst, const void *src, size_t bytes, int kind, void *stream);
+int   crtx_memcmp_device(const void *a, const void *b, size_t bytes, int *differ, void *stream); /* synchronises */
+int   crtx_sync(void *stream);
+
 /* per-kernel device timing.  After crtx_set_option(ctx, "timing", 1) every launch is bracketed by
  * CUDA events on its stream; crtx_get_timing synchronises, then reports the summed milliseconds and
  * the launch count of each kernel since the last call.  Index: 0 modulate skeleton (or the single

@@ -392,6 +392,19 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
     return 0;
 }
 
+// any 16-byte word of a differs from b -> *flag = 1 (crtx_memcmp_device)
+__global__ void k_differs(const uint4 *__restrict__ a, const uint4 *__restrict__ b, size_t words, const unsigned char *ta,
+                          const unsigned char *tb, int tail, int *flag)
+{
+    bool diff = false;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t) gridDim.x * blockDim.x) {
+        const uint4 x = a[i], y = b[i];
+        diff |= (x.x != y.x) | (x.y != y.y) | (x.z != y.z) | (x.w != y.w);
+    }
+    if (blockIdx.x == 0 && (int) threadIdx.x < tail) diff |= ta[threadIdx.x] != tb[threadIdx.x];
+    if (diff) *flag = 1;
+}
+
 void fill_src(SrcCfg *d, const crtx_source *s)
 {
     memset(d, 0, sizeof(*d));
@@ -736,6 +749,60 @@ int crtx_get_timing(crtx_ctx *ctx, float *ms, long *launches)
         ctx->event_pool.push_back(t.stop);
     }
     ctx->timed.clear();
+    return 0;
+}
+
+void *crtx_device_alloc(size_t bytes)
+{
+    void *p = NULL;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return NULL;
+    if (cudaMemset(p, 0, bytes) != cudaSuccess) {
+        cudaFree(p);
+        return NULL;
+    }
+    return p;
+}
+
+void crtx_device_free(void *p) { if (p) cudaFree(p); }
+
+void *crtx_host_alloc(size_t bytes)
+{
+    void *p = NULL;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return NULL;
+    return p;
+}
+
+void crtx_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int crtx_memcpy(void *dst, const void *src, size_t bytes, int kind, void *stream)
+{
+    const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (kind < 0 || kind > 2) return fail("crtx_memcpy: kind %d", kind);
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, k, (cudaStream_t) stream));
+    return 0;
+}
+
+int crtx_memcmp_device(const void *a, const void *b, size_t bytes, int *differ, void *stream)
+{
+    if (!differ) return fail("crtx_memcmp_device: null result");
+    if (((uintptr_t) a | (uintptr_t) b) & 15) return fail("crtx_memcmp_device: pointers must be 16-byte aligned");
+    int *flag = NULL;
+    CUDA_TRY(cudaMalloc(&flag, sizeof(int)));
+    cudaMemsetAsync(flag, 0, sizeof(int), (cudaStream_t) stream);
+    const size_t words = bytes / 16;
+    k_differs<<<296, 256, 0, (cudaStream_t) stream>>>((const uint4 *) a, (const uint4 *) b, words,
+                                                     (const unsigned char *) a + words * 16,
+                                                     (const unsigned char *) b + words * 16, (int) (bytes - words * 16), flag);
+    cudaError_t e = cudaMemcpyAsync(differ, flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t) stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) stream);
+    cudaFree(flag);
+    CUDA_TRY(e);
+    return 0;
+}
+
+int crtx_sync(void *stream)
+{
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t) stream));
     return 0;
 }
 
