@@ -59,6 +59,14 @@ case("mono", "ntsc", 512, 448, layout.PIX_BGRA, dict(blend=0, scanlines=1),
 case("generic_eq_saturation400", "ntsc", 320, 240, layout.PIX_BGRA,
      dict(saturation=400, brightness=5000, blend=0, scanlines=0),
      ("rand", 256, 240, 4, 3), rgb_calls(2, 2))
+# the USE_CONVOLUTION 1 decoder (crt_core.c:85-147), from libref_ntsc_conv.so
+case("conv_cfg2_832x624_interlaced", "ntsc_conv", 832, 624, layout.PIX_BGRA, dict(blend=1, scanlines=1),
+     ("rand", 832, 624, 4, 7), rgb_calls(6, 0))
+case("conv_640x480_noise12_rgb", "ntsc_conv", 640, 480, layout.PIX_RGB, dict(blend=0, scanlines=1),
+     ("bars", 640, 480, 4, 0), rgb_calls(4, 12))
+case("conv_generic_saturation4000", "ntsc_conv", 333, 250, layout.PIX_ARGB,
+     dict(saturation=4000, contrast=900, brightness=5000, blend=1, scanlines=0),
+     ("rand", 256, 240, 4, 3), rgb_calls(3, 9))
 for v in ("nes", "nes_p0"):
     case("cfg3_%s" % v, v, 832, 624, layout.PIX_BGRA, dict(blend=0, scanlines=1),
          ("nes", 256, 240, 0, 5), [(dict(dot_crawl_offset=i % 3, hue=(i * 30) % 360), 4 * i) for i in range(5)])
