@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restric
                 int ci = wmul(hi, mI[k]) >> 4; // (x + xo) & 3 == k: xo and c0 + x4 are multiples of 4
                 int cq = wmul(hq, mQ[k]) >> 4;
                 int ire = ire0 + (wmul(hy + ci + cq, white) >> 10);
-                ire = clampi(ire, 0, 110);
+                ire = __vimin_s32_relu(ire, 110); // clamp to 0..110 in one instruction
                 packed |= (unsigned) ire << (8 * k);
             }
             obuf[lane * kModOutPitch + (x4 >> 2)] = packed;
@@ -380,7 +380,12 @@ __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restric
 // (true of any cudaMalloc / torch allocation; include/crtx_batch.h).
 // ---------------------------------------------------------------------------------------
 constexpr int kModSChunk = 32;                     // samples per chunk
-constexpr int kModSRow = 192;                      // stage bytes per line per chunk
+constexpr int kModSSpan = 192;                     // largest staged span the kernel accepts (incl. alignment slack)
+// Stage bytes per line per chunk.  Every lane reads "its row, same column" at once, and rows start on
+// 16-byte boundaries, so the pitch decides the bank conflicts: 192 B (48 words) put all 32 lanes on 2
+// banks (16-way, measured as the top stall of this kernel); 176 B (44 words) spreads them over 8 (4-way,
+// the best a 16-byte granular pitch can do).  176 is also exactly the largest copy an accepted span needs.
+constexpr int kModSRow = 176;
 constexpr int kModSOutPitch = kModSChunk / 4 + 1;  // words
 constexpr int kModSWarpSmem = 2 * 32 * kModSRow + 32 * kModSOutPitch * 4 + 32 * 4;
 constexpr int kModSSmem = 8 * kModSWarpSmem + 8 * 2 * 8;
@@ -391,7 +396,7 @@ __device__ __forceinline__ bool mod_staged_ok(const SrcCfg &s, int destw)
     if (bpp == 0 || destw <= 0 || s.w <= 0) return false;
     // widest source span of a chunk: ceil(32 * w / destw) + 1 pixels, plus 15 bytes of alignment
     const long long span = ((long long) kModSChunk * s.w + destw - 1) / destw + 1;
-    return span * bpp + 15 + 16 <= kModSRow && s.w <= 65535
+    return span * bpp + 15 + 16 <= kModSSpan && s.w <= 65535
         && (bpp != 4 || (reinterpret_cast<uintptr_t>(s.data) & 3) == 0);
 }
 
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
                     sum += (wmul(hi, mI[k]) >> 4) + (wmul(hq, mQ[k]) >> 4);
                 }
                 int ire = ire0 + (wmul(sum, white) >> 10);
-                ire = clampi(ire, 0, 110);
+                ire = __vimin_s32_relu(ire, 110); // clamp to 0..110 in one instruction
                 packed |= (unsigned) ire << (8 * k);
             }
             obuf[lane * kModSOutPitch + (x4 >> 2)] = packed;
