@@ -272,9 +272,29 @@ def run_product(args):
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
 
+    # --streams 2: the batch advances as two halves on two streams, the second one modulate behind the
+    # first, so that the issue-bound line pass of one half shares the SMs with the latency-bound encoder
+    # and sync search of the other (their register / shared-memory footprints fit side by side).
+    halves = None
+    if args.streams == 2:
+        s2 = torch.cuda.Stream(dev)
+        h0 = B // 2
+        halves = ((0, h0, sp), (h0, B - h0, s2.cuda_stream))
+        stagger = torch.cuda.Event()
+
     def step(k):
-        batch._check(batch.lib.crtx_modulate(batch._ctx, 0, B, tables[k & 1], sp))
-        batch._check(batch.lib.crtx_demodulate(batch._ctx, 0, B, sp))
+        if halves is None:
+            batch._check(batch.lib.crtx_modulate(batch._ctx, 0, B, tables[k & 1], sp))
+            batch._check(batch.lib.crtx_demodulate(batch._ctx, 0, B, sp))
+            return
+        t = tables[k & 1]
+        (f0, n0, p0), (f1, n1, p1) = halves
+        batch._check(batch.lib.crtx_modulate(batch._ctx, f0, n0, C.cast(C.byref(t, f0 * C.sizeof(capi.Source)), C.POINTER(capi.Source)), p0))
+        stagger.record(stream)
+        batch._check(batch.lib.crtx_demodulate(batch._ctx, f0, n0, p0))
+        s2.wait_event(stagger)
+        batch._check(batch.lib.crtx_modulate(batch._ctx, f1, n1, C.cast(C.byref(t, f1 * C.sizeof(capi.Source)), C.POINTER(capi.Source)), p1))
+        batch._check(batch.lib.crtx_demodulate(batch._ctx, f1, n1, p1))
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -299,6 +319,8 @@ def run_product(args):
     ev0.record(stream)
     for k in range(args.steps):
         step(args.warmup + k)
+    if halves is not None:
+        stream.wait_stream(s2)  # the timed region ends when both halves are done
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -413,7 +435,7 @@ def run_product(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
             "config": {"workload": ("NTSC 832x624 BGRA -> 832x624 BGRA, interlaced, colour, noise 0, blend 1, scanlines 1 (BASELINE configs[1])"
                                     if VARIANT == "ntsc" else "%s -> 832x624 BGRA, noise %d, blend 1, scanlines 1 (informational run of another BASELINE config)" % (VARIANT, noise)),
-                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d (frames sharded, no collective)" % world,
+                       "batch_per_gpu": B, "global_batch": B * world, "streams": args.streams, "parallelism": "dp%d (frames sharded, no collective)" % world,
                        "l2": "inputs larger than L2: %.0f MB of images + signals touched per step per GPU" % (B * 4.63)},
             "e2e": {"value": e2e_value, "unit": "frames/s",
                     "h2d_bytes_per_step": per * nstreams * W_IN * H_IN * (2 if nes else 4),
@@ -448,6 +470,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--streams", type=int, default=1, choices=[1, 2],
+                    help="2: advance the batch as two halves on two CUDA streams, staggered (see step())")
     ap.add_argument("--batch", type=int, default=296,
                     help="monitors (frames per step) per GPU; 296 = 2 resident CTAs x 148 SMs of the line kernel")
     ap.add_argument("--e2e-batch", type=int, default=64)

@@ -74,12 +74,12 @@ __device__ __forceinline__ int hsync_step(const unsigned *heads, FetchByte fetch
     return hs;
 }
 
-// Four samples of inp[] starting at the 4-aligned index p, computed from analog[] exactly as the noise
-// pass does (crt_core.c:346-367): sample i uses the LCG state advanced i + 1 steps from the call's seed.
-__device__ __forceinline__ unsigned noisy_word(const signed char *__restrict__ analog, int p, int noise, unsigned rn0,
-                                               const Affine *__restrict__ jump_lo, const Affine *__restrict__ jump_hi)
+// Four samples of inp[] starting at the 4-aligned index p, computed from the word `w` of analog[] exactly
+// as the noise pass does (crt_core.c:346-367): sample i uses the LCG state advanced i + 1 steps from the
+// call's seed.  Kept apart from the load so that callers can issue a batch of loads before touching any.
+__device__ __forceinline__ unsigned noisy_apply(unsigned w, int p, int noise, unsigned rn0,
+                                                const Affine *__restrict__ jump_lo, const Affine *__restrict__ jump_hi)
 {
-    unsigned w = __ldg(reinterpret_cast<const unsigned *>(analog + p));
     if (noise == 0) {
         w = __vmaxs4(w, 0x81818181u);
     } else {
@@ -99,6 +99,12 @@ __device__ __forceinline__ unsigned noisy_word(const signed char *__restrict__ a
     // beyond inp[] the buffer holds its zero padding, never written by the noise pass
     if (p + 4 > kInputSize) w = (p >= kInputSize) ? 0u : (w & (0xffffffffu >> (8 * (p + 4 - kInputSize))));
     return w;
+}
+
+__device__ __forceinline__ unsigned noisy_word(const signed char *__restrict__ analog, int p, int noise, unsigned rn0,
+                                               const Affine *__restrict__ jump_lo, const Affine *__restrict__ jump_hi)
+{
+    return noisy_apply(__ldg(reinterpret_cast<const unsigned *>(analog + p)), p, noise, rn0, jump_lo, jump_hi);
 }
 
 // FUSED (LCG systems): the kernel reads analog[], applies the noise itself to what it stages, and its
@@ -142,27 +148,31 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
     unsigned *cand = heads + kVres * kHeadWords; // [2W][kCandWords]
     const int vs_in = st->vsync;
     {
-        constexpr int kBatch = FUSED ? 4 : 8;
+        constexpr int kBatch = 8;
         constexpr int kHeadTotal = kVres * kHeadWords, kCandTotal = 2 * kVsyncWindow * kCandWords;
+        const signed char *from = FUSED ? analog : inp;
         for (int base = 0; base < kHeadTotal + kCandTotal; base += kBatch * kSyncThreads) {
             unsigned v[kBatch];
+            int pos[kBatch];
 #pragma unroll
-            for (int b = 0; b < kBatch; b++) {
+            for (int b = 0; b < kBatch; b++) { // where each word comes from (-1: nothing to load)
                 const int idx = base + b * kSyncThreads + tid;
-                v[b] = 0u;
+                pos[b] = -1;
                 if (idx < kHeadTotal) {
                     const int j = idx / kHeadWords, w = idx - j * kHeadWords;
-                    const int p = ((j * kHres - kHeadBefore) & ~3) + 4 * w;
-                    v[b] = fetch(p);
+                    pos[b] = ((j * kHres - kHeadBefore) & ~3) + 4 * w;
                 } else if (idx < kHeadTotal + kCandTotal) {
                     const int q = idx - kHeadTotal, c = q / kCandWords, w = q - c * kCandWords;
-                    const int p = (posmod(vs_in + c - kVsyncWindow, kVres) * kHres & ~3) + 4 * w;
-                    v[b] = fetch(p);
+                    pos[b] = (posmod(vs_in + c - kVsyncWindow, kVres) * kHres & ~3) + 4 * w;
                 }
             }
 #pragma unroll
+            for (int b = 0; b < kBatch; b++) // the raw loads, back to back
+                v[b] = (pos[b] >= 0) ? __ldg(reinterpret_cast<const unsigned *>(from + pos[b])) : 0u;
+#pragma unroll
             for (int b = 0; b < kBatch; b++) {
                 const int idx = base + b * kSyncThreads + tid;
+                if (FUSED && pos[b] >= 0) v[b] = noisy_apply(v[b], pos[b], noise, rn0, jump_lo, jump_hi);
                 if (idx < kHeadTotal + kCandTotal) heads[idx] = v[b];
             }
         }
