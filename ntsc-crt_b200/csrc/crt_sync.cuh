@@ -291,8 +291,23 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
             // C's x * 127 / 128 truncates towards zero.  While the product cannot wrap it equals
             // x - ((x + (x >= 0 ? 127 : 0)) >> 7): ceil(x / 128) for x >= 0, floor for x < 0.
             if (abs(x) < (1 << 23)) {
+                // The sign of x almost never changes within a line, so the rounding bias is taken from the
+                // line's first x and the 10 dependent steps are add, shift, add; the sign bits of the
+                // intermediate values are collected off the critical path and the rare line on which one
+                // differs is redone with the per-step bias.
+                const int bias = (x >= 0) ? 127 : 0;
+                int y = x, flips = 0;
 #pragma unroll
-                for (int q = 0; q < kBurstLen / 4; q++) x = x - ((x + ((x >= 0) ? 127 : 0)) >> 7) + bs[4 * q];
+                for (int q = 0; q < kBurstLen / 4; q++) {
+                    flips |= y ^ x;
+                    y = y - ((y + bias) >> 7) + bs[4 * q];
+                }
+                if (flips < 0) {
+#pragma unroll
+                    for (int q = 0; q < kBurstLen / 4; q++) x = x - ((x + ((x >= 0) ? 127 : 0)) >> 7) + bs[4 * q];
+                } else {
+                    x = y;
+                }
             } else {
 #pragma unroll
                 for (int q = 0; q < kBurstLen / 4; q++) x = wadd(wmul(x, 127) / 128, bs[4 * q]);
