@@ -123,7 +123,20 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
         unsigned h[31];
 #pragma unroll
         for (int j = 0; j < 31; j++) h[j] = states[tid][j];
+        constexpr int kApply = kVhsThreads / (kVhsThreads / 32); // slices each warp applies per block (32)
         for (int it = 0; it < kVhsRun / 31; it++) {
+            // The signal bytes this thread will combine with the terms below do not depend on the draws:
+            // request them all now, so the 32 small loads are in flight while the generator runs (issued
+            // after the barrier, one wait per load, they were 37 % of the kernel's time).
+            signed char sig[kApply];
+            {
+                const int j = tid & 31;
+#pragma unroll
+                for (int q = 0; q < kApply; q++) {
+                    const int u = (tid >> 5) + q * (kVhsThreads / 32);
+                    sig[q] = (j < 31) ? analog[u * kVhsRun + it * 31 + j] : (signed char) 0;
+                }
+            }
 #pragma unroll
             for (int d = 0; d < 62; d++) { // draw d of the block uses slot d % 31 (31-periodic alignment)
                 const int slot = d % 31;
@@ -137,11 +150,12 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
             }
             __syncthreads();
             // apply, coalesced over the 31 samples of each thread's slice
-            for (int u = tid >> 5; u < kVhsThreads; u += kVhsThreads / 32) {
+            {
                 const int j = tid & 31;
-                if (j < 31) {
-                    const int i = u * kVhsRun + it * 31 + j;
-                    inp[i] = (signed char) clampi(analog[i] + terms[u * 32 + j], -127, 127);
+#pragma unroll
+                for (int q = 0; q < kApply; q++) {
+                    const int u = (tid >> 5) + q * (kVhsThreads / 32);
+                    if (j < 31) inp[u * kVhsRun + it * 31 + j] = (signed char) clampi(sig[q] + terms[u * 32 + j], -127, 127);
                 }
             }
             __syncthreads();
@@ -206,6 +220,7 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
         }
         const int x0 = (xa == 0) ? 1 : xa; // first regular sample
         for (int x = xa + tid; x < kHres; x += kVhsThreads) {
+            const int sig = analog[line * kHres + x]; // requested before the (dependent) table walk
             int P = 0;
             if (!(xa == 0 && x == 0)) {
                 P = s_start;
@@ -224,7 +239,7 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
                     gain = cs >> 8;
                 }
             }
-            const int s = analog[i] + (wmul(((rn >> 16) & 0xff) - 0x7f, gain) >> 8);
+            const int s = sig + (wmul(((rn >> 16) & 0xff) - 0x7f, gain) >> 8);
             inp[i] = (signed char) clampi(s, -127, 127);
             if (x == kHres - 1) { // the line's last sample closes the walk
                 s_adv = P + used;
