@@ -429,7 +429,7 @@ def run_product(args):
         traffic = None
         try:  # DRAM bytes of the line kernel per launch, from the committed ncu --set full capture
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tj["k_lines_fir_dram_bytes_per_frame" if VARIANT.endswith("_conv") else "k_lines_dram_bytes_per_frame"] * B
+            traffic = tj["k_lines_fir_dram_bytes_per_frame" if ("_conv" in VARIANT) else "k_lines_dram_bytes_per_frame"] * B
         except Exception:
             pass
         cpu = cpu_baseline_single() if (world == 1 and not args.no_cpu_baseline) else None
@@ -449,7 +449,7 @@ def run_product(args):
             "gpu_launches": int(launches),
             "gpu_launches_e2e": int(launches_e2e),
             "roofline": {"bound": "hbm", "kernel": ("k_lines_fir (crt_demodulate line pass of the USE_CONVOLUTION build, crt_core.c:96-147,511-664)"
-                                                     if VARIANT.endswith("_conv") else "k_lines (crt_demodulate line pass, crt_core.c:511-664)"),
+                                                     if ("_conv" in VARIANT) else "k_lines (crt_demodulate line pass, crt_core.c:511-664)"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "algorithmic_bytes_per_launch": per_launch_bytes, "launch_ms": lines_ms / max(1, lines_n),
@@ -482,7 +482,7 @@ def main():
     ap.add_argument("--set", action="append", default=[], help="library option name=value (A/B testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--allgather", action="store_true", help="also time steps that all_gather the decoded frames")
-    ap.add_argument("--variant", default="ntsc", choices=["ntsc", "ntsc_conv", "nes", "nes_p0", "vhs"],
+    ap.add_argument("--variant", default="ntsc", choices=["ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "nes", "nes_p0", "vhs"],
                     help="informational runs of the other systems (the contract metric is the default, ntsc)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup

@@ -1,6 +1,7 @@
 // crt_lines_fir.cuh -- k_lines_fir, the line pass of crt_demodulate for the reference's
 // USE_CONVOLUTION 1 build (crt_core.c:85-147 with crt_core.c:511-664): eqf() is the 7-tap kernel
-// [1 4 7 8 7 4 1] >> 5 over a history that is zero at the start of every line.
+// [1 4 7 8 7 4 1] >> 5 (or, by the reference's other compile-time switches, [1 3 4 4 3 1] >> 4,
+// [1 2 2 2 1] >> 3, [1 1 1 1] >> 2) over a history that is zero at the start of every line.
 //
 // Shape.  Unlike the three-band equaliser (crt_lines.cuh) this filter has no recurrence, so the line
 // itself is data parallel: ONE WARP DECODES ONE SCANLINE.
@@ -27,7 +28,9 @@ namespace crt {
 constexpr int kFirWarps = 8;                       // lines in flight per CTA
 constexpr int kFirChunk = 24;                      // samples per lane: a multiple of 8 (slot padding) and 4 (carrier)
 constexpr int kFirSamples = 32 * kFirChunk;        // 768 >= AV_LEN of every system
-constexpr int kFirHalo = 6;                        // taps - 1
+constexpr int kFirTaps = kConvTaps ? kConvTaps : 7; // (the kernel is only launched in CRTX_CONV builds)
+constexpr int kFirHalo = kFirTaps - 1;             // run-in samples that rebuild the history
+constexpr int kFirShift = kFirTaps - 2;            // log2 of the weights' sum: 5, 4, 3, 2
 constexpr int kFirStage = ((kFirSamples + 15 + 15) / 16) * 16; // staged bytes per line
 constexpr int kFirSeg = 832;                       // output pixels staged per bulk load / store
 constexpr int kFirIter = kFirSeg / 32;               // pixels per lane and segment
@@ -75,22 +78,35 @@ template <typename Elem, int OFF> __device__ __forceinline__ int lds_elem(unsign
     return v;
 }
 
-// one channel of the factored kernel: [1 1] three times, then a 4-wide box as two pair sums
+// One channel of the factored kernel.  All four kernels are cascades of [1 1] stages and one box:
+//   7 taps [1 4 7 8 7 4 1] = [1 1]^3 * [1 1 1 1]      6 taps [1 3 4 4 3 1] = [1 1]^2 * [1 1 1 1]
+//   5 taps [1 2 2 2 1]     = [1 1]   * [1 1 1 1]      4 taps [1 1 1 1]
+// (exact: nothing is rounded before the final shift); the 4-wide box is two pair sums.
 struct FirChan {
     int a, b, c, d, p1, p2;
 };
 __device__ __forceinline__ void fir_reset(FirChan &f) { f.a = f.b = f.c = f.d = f.p1 = f.p2 = 0; }
 __device__ __forceinline__ int fir_push(FirChan &f, int x)
 {
-    const int s1 = wadd(x, f.a);
-    f.a = x;
-    const int s2 = wadd(s1, f.b);
-    f.b = s1;
-    const int s3 = wadd(s2, f.c);
-    f.c = s2;
-    const int p = wadd(s3, f.d); // s3[i] + s3[i-1]
-    f.d = s3;
-    const int out = wadd(p, f.p2); // + s3[i-2] + s3[i-3]
+    int v = x;
+    if (kFirTaps >= 5) { // first [1 1]
+        const int s1 = wadd(v, f.a);
+        f.a = v;
+        v = s1;
+    }
+    if (kFirTaps >= 6) { // second [1 1]
+        const int s2 = wadd(v, f.b);
+        f.b = v;
+        v = s2;
+    }
+    if (kFirTaps == 7) { // third [1 1]
+        const int s3 = wadd(v, f.c);
+        f.c = v;
+        v = s3;
+    }
+    const int p = wadd(v, f.d); // v[i] + v[i-1]
+    f.d = v;
+    const int out = wadd(p, f.p2); // + v[i-2] + v[i-3]
     f.p2 = f.p1;
     f.p1 = p;
     return out;
@@ -235,7 +251,7 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
             const int wi[4] = { cur.wave0, cur.wave1, nw0, nw1 };
             const int wq[4] = { nw1, cur.wave0, cur.wave1, nw0 };
 
-            // ---- (F) samples [24 * lane - 6, 24 * lane + 24); the first six only rebuild the history
+            // ---- (F) samples [24 * lane - halo, 24 * lane + 24); the first ones only rebuild the history
             const int e0 = lane * kFirChunk;
             if (e0 - kFirHalo < kAvLen) {
                 const signed char *sg = reinterpret_cast<const signed char *>(sigbuf) + a + e0;
@@ -246,7 +262,7 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
                 fir_reset(fq);
 #pragma unroll
                 for (int j = 0; j < kFirHalo; j++) {
-                    const int i4 = (j + 2) & 3; // (e0 - 6 + j) & 3, e0 a multiple of 4
+                    const int i4 = (j - kFirHalo) & 3; // (e0 - halo + j) & 3, e0 a multiple of 4
                     const int s = head ? 0 : (int) sg[head ? 0 : j - kFirHalo];
                     (void) fir_push(fy, head ? 0 : wadd(s, bright));
                     (void) fir_push(fi, wmul(s, wi[i4]) >> 9);
@@ -258,10 +274,10 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
                     const int s = sg[t];
                     // FAST keeps Y not yet scaled by 16 (see crt_lines.cuh: the pixel pass folds the scale into its
                     // weights); the generic path keeps Y * 16 verbatim.
-                    const int y5 = fir_push(fy, wadd(s, bright)) >> 5;
+                    const int y5 = fir_push(fy, wadd(s, bright)) >> kFirShift;
                     const Elem y = (Elem) (FAST ? y5 : wmul(y5, 16));
-                    const Elem ci = (Elem) (fir_push(fi, wmul(s, wi[t & 3]) >> 9) >> 8); // (v >> 5) >> 3
-                    const Elem cq = (Elem) (fir_push(fq, wmul(s, wq[t & 3]) >> 9) >> 8);
+                    const Elem ci = (Elem) (fir_push(fi, wmul(s, wi[t & 3]) >> 9) >> (kFirShift + 3)); // (v >> shift) >> 3
+                    const Elem cq = (Elem) (fir_push(fq, wmul(s, wq[t & 3]) >> 9) >> (kFirShift + 3));
                     const int slot = t + (t >> 3);
                     dst[slot] = y;
                     dst[slot + kComp] = ci;

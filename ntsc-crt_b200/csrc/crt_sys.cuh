@@ -29,6 +29,10 @@ constexpr bool kIsVhs = (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS);
 #define CRTX_CONV 0
 #endif
 constexpr bool kConv = (CRTX_CONV != 0);
+// taps of the convolution kernel: -DCRTX_CONV=1 (or 7) is the stock USE_7_SAMPLE_KERNEL, 6 / 5 / 4 the other
+// compile-time choices of crt_core.c:86-88
+constexpr int kConvTaps = (CRTX_CONV == 0) ? 0 : (CRTX_CONV == 1) ? 7 : CRTX_CONV;
+static_assert(kConvTaps == 0 || (kConvTaps >= 4 && kConvTaps <= 7), "CRTX_CONV: 0, 1 or the tap count 4..7");
 
 constexpr int kHres = CRT_HRES;
 constexpr int kVres = CRT_VRES;

@@ -79,6 +79,10 @@ SPECS = {
     "ntsc": _rgb_spec("ntsc", SYS_NTSC),
     # the USE_CONVOLUTION 1 build of crt_core.c (line 85): same layouts and timing, FIR decoder filters
     "ntsc_conv": _rgb_spec("ntsc_conv", SYS_NTSC),
+    # ... and its 6-, 5- and 4-tap kernels (crt_core.c:86-88)
+    "ntsc_conv6": _rgb_spec("ntsc_conv6", SYS_NTSC),
+    "ntsc_conv5": _rgb_spec("ntsc_conv5", SYS_NTSC),
+    "ntsc_conv4": _rgb_spec("ntsc_conv4", SYS_NTSC),
     "vhs": _rgb_spec("vhs", SYS_VHS),
     "nes": _nes_spec("nes", 2),
     "nes_p0": _nes_spec("nes_p0", 0),
@@ -89,9 +93,17 @@ def system_spec(name):
     return SPECS[name]
 
 
+def conv_taps(name):
+    """Taps of the FIR kernel for variants built from the reference's USE_CONVOLUTION 1 decoder
+    (crt_core.c:85-147), 0 for the stock three-band equaliser."""
+    if "_conv" not in name:
+        return 0
+    tail = name.split("_conv")[1]
+    return int(tail) if tail else 7
+
+
 def uses_convolution(name):
-    """True for variants built from the reference's USE_CONVOLUTION 1 decoder (crt_core.c:85-147)."""
-    return name.endswith("_conv")
+    return conv_taps(name) != 0
 
 
 _crt_cache = {}

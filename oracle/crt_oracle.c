@@ -258,20 +258,26 @@ ocrt_system(int system, int chroma_pattern)
 }
 
 const ocrt_sys *
-ocrt_system_conv(int system, int chroma_pattern)
+ocrt_system_conv_taps(int system, int chroma_pattern, int taps)
 {
-    static ocrt_sys table[5];
-    static int ready[5];
+    static ocrt_sys table[4][5];
+    static int ready[4][5];
     const ocrt_sys *base = ocrt_system(system, chroma_pattern);
     int slot;
-    if (!base) return NULL;
+    if (!base || taps < 4 || taps > 7) return NULL;
     slot = (system == OCRT_SYS_NTSC) ? 0 : (system == OCRT_SYS_VHS) ? 1 : 2 + chroma_pattern;
-    if (!ready[slot]) {
-        table[slot] = *base;
-        table[slot].conv = 1;
-        ready[slot] = 1;
+    if (!ready[taps - 4][slot]) {
+        table[taps - 4][slot] = *base;
+        table[taps - 4][slot].conv = taps;
+        ready[taps - 4][slot] = 1;
     }
-    return &table[slot];
+    return &table[taps - 4][slot];
+}
+
+const ocrt_sys *
+ocrt_system_conv(int system, int chroma_pattern)
+{
+    return ocrt_system_conv_taps(system, chroma_pattern, 7); /* USE_7_SAMPLE_KERNEL 1 is the stock setting */
 }
 
 /* ------------------------------------------------------------------------- */
@@ -641,21 +647,27 @@ eq_step(eq_state *f, const int *c, i32 s)
     return wadd(wadd(r0, r1), r2);
 }
 
-/* eqf() of the USE_CONVOLUTION build (crt_core.c:96-147, USE_7_SAMPLE_KERNEL): a 7-deep history,
- * zero at the start of every line (reset_eq, crt_core.c:117-121), newest sample in h[0] */
+/* eqf() of the USE_CONVOLUTION build (crt_core.c:96-147): a 7-deep history, zero at the start of every
+ * line (reset_eq, crt_core.c:117-121), newest sample in h[0]; the kernel is chosen at compile time among
+ * USE_7_SAMPLE_KERNEL (default), USE_6_, USE_5_ and the 4-tap fall-back (crt_core.c:86-88, 130-146) */
 typedef struct fir_state {
     i32 h[7];
 } fir_state;
 
 static i32
-fir_step(fir_state *f, i32 s)
+fir_step(fir_state *f, i32 s, int taps)
 {
     i32 k;
-    for (k = 6; k > 0; k--) f->h[k] = f->h[k - 1];
-    f->h[0] = s;
-    /* index : 0 1 2 3 4 5 6   weight: 1 4 7 8 7 4 1 */
-    return wadd(wadd(wadd(wadd(s, f->h[6]), wmul(wadd(f->h[1], f->h[5]), 4)), wmul(wadd(f->h[2], f->h[4]), 7)),
-                wmul(f->h[3], 8)) >> 5;
+    i32 *h = f->h;
+    for (k = 6; k > 0; k--) h[k] = h[k - 1];
+    h[0] = s;
+    if (taps == 7) /* weights 1 4 7 8 7 4 1 */
+        return wadd(wadd(wadd(wadd(s, h[6]), wmul(wadd(h[1], h[5]), 4)), wmul(wadd(h[2], h[4]), 7)), wmul(h[3], 8)) >> 5;
+    if (taps == 6) /* weights 1 3 4 4 3 1 */
+        return wadd(wadd(wadd(s, h[5]), wmul(3, wadd(h[1], h[4]))), wmul(4, wadd(h[2], h[3]))) >> 4;
+    if (taps == 5) /* weights 1 2 2 2 1 */
+        return wadd(wadd(s, h[4]), wmul(wadd(wadd(h[1], h[2]), h[3]), 2)) >> 3;
+    return wadd(wadd(wadd(s, h[3]), h[1]), h[2]) >> 2; /* weights 1 1 1 1 */
 }
 
 /* filter + resample + YIQ->RGB for decoded lines [first, first+count)
@@ -691,9 +703,9 @@ ocrt_line_pass(const ocrt_sys *sys, ocrt_monitor *m, const ocrt_line *table, int
         memset(&fi, 0, sizeof(fi));
         memset(&fq, 0, sizeof(fq));
         for (i = 0; sys->conv && i < L; i++) { /* crt_core.c:538-543 with the FIR eqf */
-            yy[i] = wmul(fir_step(&fy, sig[i] + bright), 16);
-            ii[i] = fir_step(&fi, wmul(sig[i], rec->wave[i & 3]) >> 9) >> 3;
-            qq[i] = fir_step(&fq, wmul(sig[i], rec->wave[(i + 3) & 3]) >> 9) >> 3;
+            yy[i] = wmul(fir_step(&fy, sig[i] + bright, sys->conv), 16);
+            ii[i] = fir_step(&fi, wmul(sig[i], rec->wave[i & 3]) >> 9, sys->conv) >> 3;
+            qq[i] = fir_step(&fq, wmul(sig[i], rec->wave[(i + 3) & 3]) >> 9, sys->conv) >> 3;
         }
         for (i = 0; !sys->conv && i < L; i++) { /* crt_core.c:538-543 */
             yy[i] = eq_step(&ey, sys->eq[0], sig[i] + bright) * 16;

@@ -48,8 +48,9 @@ typedef struct ocrt_sys {
     int eq[3][5];
     /* encoder band-limit coefficients c for Y, I, Q (crt_ntsc.c:142-146) */
     int iir_c[3];
-    /* 1: the USE_CONVOLUTION build of the decoder (crt_core.c:85, 96-147): eqf() is the 7-tap
-     * [1 4 7 8 7 4 1] >> 5 kernel instead of the three-band equaliser */
+    /* non-zero: the USE_CONVOLUTION build of the decoder (crt_core.c:85, 96-147): eqf() is a FIR kernel of
+     * this many taps (7: [1 4 7 8 7 4 1] >> 5, the stock one; 6, 5, 4: crt_core.c:86-88) instead of the
+     * three-band equaliser */
     int conv;
 } ocrt_sys;
 
@@ -101,6 +102,7 @@ typedef struct ocrt_line {
 const ocrt_sys *ocrt_system(int system, int chroma_pattern);
 /* the same system with the reference's USE_CONVOLUTION 1 decoder (crt_core.c:85) */
 const ocrt_sys *ocrt_system_conv(int system, int chroma_pattern);
+const ocrt_sys *ocrt_system_conv_taps(int system, int chroma_pattern, int taps); /* 4 .. 7 */
 
 void ocrt_sincos14(int *s, int *c, int n);
 int  ocrt_bpp(int format);

@@ -67,6 +67,9 @@ case("conv_640x480_noise12_rgb", "ntsc_conv", 640, 480, layout.PIX_RGB, dict(ble
 case("conv_generic_saturation4000", "ntsc_conv", 333, 250, layout.PIX_ARGB,
      dict(saturation=4000, contrast=900, brightness=5000, blend=1, scanlines=0),
      ("rand", 256, 240, 4, 3), rgb_calls(3, 9))
+for v in ("ntsc_conv6", "ntsc_conv5", "ntsc_conv4"):  # the other kernels of the option (crt_core.c:86-88)
+    case("%s_640x480" % v, v, 640, 480, layout.PIX_BGRA, dict(blend=1, scanlines=1, hue=-20, saturation=13),
+         ("rand", 333, 250, 4, 11), rgb_calls(4, 6))
 for v in ("nes", "nes_p0"):
     case("cfg3_%s" % v, v, 832, 624, layout.PIX_BGRA, dict(blend=0, scanlines=1),
          ("nes", 256, 240, 0, 5), [(dict(dot_crawl_offset=i % 3, hue=(i * 30) % 360), 4 * i) for i in range(5)])

@@ -235,6 +235,8 @@ def oracle_lib():
         lib.ocrt_system.argtypes = [C.c_int, C.c_int]
         lib.ocrt_system_conv.restype = C.POINTER(_OSys)
         lib.ocrt_system_conv.argtypes = [C.c_int, C.c_int]
+        lib.ocrt_system_conv_taps.restype = C.POINTER(_OSys)
+        lib.ocrt_system_conv_taps.argtypes = [C.c_int, C.c_int, C.c_int]
         lib.ocrt_monitor_create.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.c_int,
                                             C.c_int, C.c_int, C.c_void_p]
         lib.ocrt_monitor_create.restype = C.c_int
@@ -267,8 +269,9 @@ class OracleEngine:
     def __init__(self, variant, outw, outh, fmt=layout.PIX_BGRA, out=None, seed=1):
         self.spec = layout.system_spec(variant)
         self.lib = oracle_lib()
-        get = self.lib.ocrt_system_conv if layout.uses_convolution(variant) else self.lib.ocrt_system
-        self.sys = get(self.spec.system, self.spec.pattern)
+        taps = layout.conv_taps(variant)
+        self.sys = (self.lib.ocrt_system_conv_taps(self.spec.system, self.spec.pattern, taps) if taps
+                    else self.lib.ocrt_system(self.spec.system, self.spec.pattern))
         assert self.sys, "unknown system"
         self.mon = _OMonitor()
         bpp = max(1, layout.bpp4fmt(fmt))

@@ -101,6 +101,26 @@ def test_conv_knobs_and_generic_path():
         check(gpu, ora, ref, "conv extreme %d" % it)
 
 
+@pytest.mark.parametrize("variant", ["ntsc_conv6", "ntsc_conv5", "ntsc_conv4"])
+def test_conv_other_kernels(variant):
+    """The 6-, 5- and 4-tap kernels of the same reference build option (crt_core.c:86-88, 136-146)."""
+    img = S.rand_image(333, 250, seed=len(variant))
+    for outw, outh, fmt, blend, scanlines in ((832, 624, layout.PIX_BGRA, 1, 1), (641, 300, layout.PIX_RGB, 1, 0),
+                                               (100, 80, layout.PIX_ARGB, 1, 0)):
+        gpu = S.ProductEngine(variant, outw, outh, fmt)
+        ora = S.OracleEngine(variant, outw, outh, fmt)
+        ref = S.RefEngine(variant, outw, outh, fmt, seed=1) if S.have_ref(variant) else None
+        run_all((gpu, ora, ref), lambda e: e.set(blend=blend, scanlines=scanlines, hue=-20, brightness=11, saturation=13))
+        for it in range(4):
+            run_all((gpu, ora, ref), lambda e: e.modulate(img, format=layout.PIX_BGRA, as_color=1, field=it & 1,
+                                                          frame=(it >> 1) & 1))
+            run_all((gpu, ora, ref), lambda e: e.demodulate(0 if it < 2 else 21))
+            check(gpu, ora, ref, "%s %dx%d call %d" % (variant, outw, outh, it))
+        run_all((gpu, ora, ref), lambda e: e.set(saturation=3000, contrast=700, brightness=-4500))
+        run_all((gpu, ora, ref), lambda e: e.demodulate(9))
+        check(gpu, ora, ref, "%s %dx%d extreme" % (variant, outw, outh))
+
+
 @pytest.mark.parametrize("tma", [1, 0])
 def test_conv_batch_matches_oracle(tma):
     """crtx_* batch interface: independent monitors with different knobs and sources, several fields."""

@@ -32,7 +32,7 @@ def check(ref, ora, what):
 
 
 def test_struct_layout_matches_reference():
-    for variant in ("ntsc", "ntsc_conv", "vhs", "nes", "nes_p0"):
+    for variant in ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0"):
         spec = layout.system_spec(variant)
         lib = C.CDLL(S.ref_path(variant))
         assert lib.ref_sizeof_crt() == C.sizeof(layout.crt_struct(spec)), variant
@@ -179,6 +179,22 @@ def test_ntsc_conv_variant(outw, outh, blend, scanlines):
                                             frame=(it >> 1) & 1))
         both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 17))
         check(ref, ora, "conv %dx%d call %d" % (outw, outh, it))
+
+
+@pytest.mark.parametrize("variant", ["ntsc_conv6", "ntsc_conv5", "ntsc_conv4"])
+def test_ntsc_conv_other_kernels(variant):
+    """the 6-, 5- and 4-tap kernels of the same build option (crt_core.c:86-88, 136-146)"""
+    img = S.rand_image(333, 250, seed=len(variant))
+    ref, ora = pair(variant, 640, 480)
+    both(ref, ora, lambda e: e.set(blend=1, scanlines=1, hue=-20, brightness=11, saturation=13))
+    for it in range(4):
+        both(ref, ora, lambda e: e.modulate(img, format=layout.PIX_BGRA, as_color=1, field=it & 1,
+                                            frame=(it >> 1) & 1))
+        both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 21))
+        check(ref, ora, "%s call %d" % (variant, it))
+    both(ref, ora, lambda e: e.set(saturation=3000, contrast=700, brightness=-4500))
+    both(ref, ora, lambda e: e.demodulate(9))
+    check(ref, ora, "%s extreme" % variant)
 
 
 def test_ntsc_conv_extreme_knobs_and_formats():
