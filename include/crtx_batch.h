@@ -113,6 +113,14 @@ int   crtx_memcpy(void *dst, const void *src, size_t bytes, int kind, void *stre
 int   crtx_memcmp_device(const void *a, const void *b, size_t bytes, int *differ, void *stream); /* synchronises */
 int   crtx_sync(void *stream);
 
+/* BMP wire format on the device (the subset bmp_rw.c reads and writes): `file_pixels` is the pixel array
+ * exactly as it sits in the file after the 54-byte header -- rows bottom-up, each padded to 4 bytes.
+ * unpack: 24 or 32 bits per pixel -> top-down BGRA with alpha 255 for 24-bit input (bmp_rw.c:22-94);
+ * pack: top-down BGRA -> 32-bit bottom-up rows, what bmp_write24 stores (bmp_rw.c:96-146).  All pointers
+ * are DEVICE pointers; asynchronous on `stream`. */
+int crtx_bmp_unpack(void *bgra, const void *file_pixels, int w, int h, int bits, void *stream);
+int crtx_bmp_pack(void *file_pixels, const void *bgra, int w, int h, void *stream);
+
 /* per-kernel device timing.  After crtx_set_option(ctx, "timing", 1) every launch is bracketed by
  * CUDA events on its stream; crtx_get_timing synchronises, then reports the summed milliseconds and
  * the launch count of each kernel since the last call.  Index: 0 modulate skeleton (or the single

@@ -405,6 +405,26 @@ __global__ void k_differs(const uint4 *__restrict__ a, const uint4 *__restrict__
     if (diff) *flag = 1;
 }
 
+// BMP pixel array (bottom-up rows padded to 4 bytes) <-> top-down BGRA (bmp_rw.c:22-146), one thread per pixel
+__global__ void k_bmp_unpack(unsigned *__restrict__ bgra, const unsigned char *__restrict__ file, int w, int h, int bytespp,
+                             int rowbytes)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const unsigned char *p = file + (size_t) (h - 1 - y) * rowbytes + (size_t) x * bytespp;
+    unsigned v;
+    if (bytespp == 4) v = *reinterpret_cast<const unsigned *>(p);
+    else v = (unsigned) p[0] | (unsigned) p[1] << 8 | (unsigned) p[2] << 16 | 0xff000000u; // bmp_rw.c:90
+    bgra[(size_t) y * w + x] = v;
+}
+
+__global__ void k_bmp_pack(unsigned *__restrict__ file, const unsigned *__restrict__ bgra, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    file[(size_t) (h - 1 - y) * w + x] = bgra[(size_t) y * w + x];
+}
+
 void fill_src(SrcCfg *d, const crtx_source *s)
 {
     memset(d, 0, sizeof(*d));
@@ -797,6 +817,27 @@ int crtx_memcmp_device(const void *a, const void *b, size_t bytes, int *differ, 
     if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t) stream);
     cudaFree(flag);
     CUDA_TRY(e);
+    return 0;
+}
+
+int crtx_bmp_unpack(void *bgra, const void *file_pixels, int w, int h, int bits, void *stream)
+{
+    if (!bgra || !file_pixels || w <= 0 || h <= 0 || h > 65535) return fail("crtx_bmp_unpack: bad arguments");
+    if (bits != 24 && bits != 32) return fail("crtx_bmp_unpack: %d bits per pixel (24 or 32)", bits);
+    const int bytespp = bits / 8, rowbytes = (w * bytespp + 3) & ~3;
+    if (bytespp == 4 && (reinterpret_cast<uintptr_t>(file_pixels) & 3)) return fail("crtx_bmp_unpack: unaligned 32-bit pixel array");
+    const dim3 grid((w + 255) / 256, h);
+    k_bmp_unpack<<<grid, 256, 0, (cudaStream_t) stream>>>((unsigned *) bgra, (const unsigned char *) file_pixels, w, h, bytespp, rowbytes);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int crtx_bmp_pack(void *file_pixels, const void *bgra, int w, int h, void *stream)
+{
+    if (!bgra || !file_pixels || w <= 0 || h <= 0 || h > 65535) return fail("crtx_bmp_pack: bad arguments");
+    const dim3 grid((w + 255) / 256, h);
+    k_bmp_pack<<<grid, 256, 0, (cudaStream_t) stream>>>((unsigned *) file_pixels, (const unsigned *) bgra, w, h);
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 

@@ -26,6 +26,14 @@ def write_bmp24(path, bgra):
         f.write(head + rows)
 
 
+def write_bmp32(path, bgra):
+    h, w = bgra.shape[:2]
+    rows = b"".join(bgra[y].tobytes() for y in range(h - 1, -1, -1))
+    head = b"BM" + struct.pack("<IHHI", 54 + len(rows), 0, 0, 54) + struct.pack("<IiiHHIIiiII", 40, w, h, 1, 32, 0, len(rows), 0, 0, 0, 0)
+    with open(path, "wb") as f:
+        f.write(head + rows)
+
+
 def read_bmp32(path):
     raw = open(path, "rb").read()
     w, h = struct.unpack_from("<ii", raw, 18)
@@ -48,15 +56,15 @@ def moving_bars(n, w, h, seed=0):
 
 
 @pytest.mark.skipif(not os.path.exists(DRIVER), reason="tools/crtx_video not built")
-@pytest.mark.parametrize("flags,noise,segments,w", [([], 0, 5, 320), ([], 12, 4, 321), (["-m", "-a"], 5, 23, 320),
-                                                    (["-p"], 0, 3, 320)])
-def test_batch_video_driver_writes_the_sequential_loops_images(tmp_path, flags, noise, segments, w):
+@pytest.mark.parametrize("flags,noise,segments,w,bits", [([], 0, 5, 320, 24), ([], 12, 4, 321, 24), (["-m", "-a"], 5, 23, 320, 24),
+                                                         (["-p"], 0, 3, 320, 24), ([], 3, 6, 323, 32)])
+def test_batch_video_driver_writes_the_sequential_loops_images(tmp_path, flags, noise, segments, w, bits):
     n, h = 23, 240
     frames = moving_bars(n, w, h)
     os.mkdir(tmp_path / "frames")
     os.mkdir(tmp_path / "output")
     for k in range(n):
-        write_bmp24(str(tmp_path / "frames" / ("%06d.bmp" % (k + 1))), frames[k])
+        (write_bmp24 if bits == 24 else write_bmp32)(str(tmp_path / "frames" / ("%06d.bmp" % (k + 1))), frames[k])
     res = subprocess.run([DRIVER] + flags + ["-S", str(segments), str(n + 1), "640", "480", str(noise)],
                          cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
     assert res.returncode == 0, res.stderr.decode()

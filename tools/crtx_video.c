@@ -15,6 +15,8 @@
  *   the output buffer    never cleared, a field rewrites only its own rows: every segment first
  *                        decodes the two images before its own ("halo"); the buffer it then holds
  *                        must equal the preceding segment's last image, which is verified too
+ * File bytes travel as they are stored: the pixel array of each BMP goes to the device unchanged and is
+ * unpacked there (crtx_bmp_unpack), decoded images are packed into the writer's layout on the device too.
  * A segment that fails verification is decoded again, sequentially, from the true state; its
  * files are rewritten.  The result is what the sequential loop writes (tests/test_gpu_video_driver.py).
  *
@@ -47,13 +49,13 @@ le32(const unsigned char *p)
     return (unsigned) p[0] | ((unsigned) p[1] << 8) | ((unsigned) p[2] << 16) | ((unsigned) p[3] << 24);
 }
 
-/* reads `file` into top-down BGRA at dst (capacity cap bytes); returns 0 on failure */
+/* reads the pixel array of `file` (as stored: bottom-up, padded rows) into dst; returns 0 on failure */
 static int
-bmp_load(const char *file, unsigned char *dst, size_t cap, int *w, int *h, unsigned char **scratch, size_t *scratch_cap)
+bmp_load(const char *file, unsigned char *dst, size_t cap, int *w, int *h, int *bits)
 {
     FILE *f = fopen(file, "rb");
     unsigned char header[54];
-    unsigned width, height, bytespp, rowbytes, y, x;
+    unsigned width, height, bytespp, rowbytes;
     size_t need;
     if (f == NULL) return 0;
     if (fread(header, 1, 54, f) != 54) {
@@ -63,52 +65,26 @@ bmp_load(const char *file, unsigned char *dst, size_t cap, int *w, int *h, unsig
     width = le32(header + 18);
     height = le32(header + 22);
     bytespp = (le32(header + 28) & 0xff) / 8;
-    if ((bytespp != 3 && bytespp != 4) || width == 0 || height == 0 || (size_t) width * height * 4 > cap) {
-        fclose(f);
-        return 0;
-    }
     rowbytes = width * bytespp + ((4 - (width * bytespp) % 4) % 4);
     need = (size_t) rowbytes * height;
-    if (need > *scratch_cap) {
-        free(*scratch);
-        *scratch = (unsigned char *) malloc(need);
-        *scratch_cap = *scratch ? need : 0;
-        if (*scratch == NULL) {
-            fclose(f);
-            return 0;
-        }
-    }
-    if (fread(*scratch, 1, need, f) != need) {
+    if ((bytespp != 3 && bytespp != 4) || width == 0 || height == 0 || need > cap || fread(dst, 1, need, f) != need) {
         fclose(f);
         return 0;
     }
     fclose(f);
-    for (y = 0; y < height; y++) {
-        const unsigned char *src = *scratch + (size_t) (height - 1 - y) * rowbytes;
-        unsigned char *row = dst + (size_t) y * width * 4;
-        if (bytespp == 4) {
-            memcpy(row, src, (size_t) width * 4);
-        } else {
-            for (x = 0; x < width; x++) {
-                row[4 * x + 0] = src[3 * x + 0];
-                row[4 * x + 1] = src[3 * x + 1];
-                row[4 * x + 2] = src[3 * x + 2];
-                row[4 * x + 3] = 255;
-            }
-        }
-    }
     *w = (int) width;
     *h = (int) height;
+    *bits = (int) bytespp * 8;
     return 1;
 }
 
+/* writes the 54-byte header bmp_rw.c:96-146 writes, then the (already bottom-up, 32-bit) pixel array */
 static int
-bmp_save(const char *file, const unsigned char *bgra, int w, int h)
+bmp_save(const char *file, const unsigned char *file_pixels, int w, int h)
 {
     FILE *f;
     unsigned char head[54];
     unsigned filesize = 14 + 40 + (unsigned) w * (unsigned) h * 4;
-    int y;
     memset(head, 0, sizeof(head));
     head[0] = 'B';
     head[1] = 'M';
@@ -131,7 +107,7 @@ bmp_save(const char *file, const unsigned char *bgra, int w, int h)
     f = fopen(file, "wb");
     if (f == NULL) return 0;
     fwrite(head, 1, 54, f);
-    for (y = h - 1; y >= 0; y--) fwrite(bgra + (size_t) y * w * 4, 4, (size_t) w, f);
+    fwrite(file_pixels, 4, (size_t) w * (size_t) h, f);
     fclose(f);
     return 1;
 }
@@ -173,9 +149,8 @@ struct job {
     int outw, outh, noise;
     int color, progressive, scanlines;
     int w, h;           /* source size (all images alike) */
-    size_t src_bytes, out_bytes;
-    unsigned char *scratch;
-    size_t scratch_cap;
+    int bits;           /* of the source files: 24 or 32 */
+    size_t src_bytes, out_bytes, file_bytes; /* device image, device output, source pixel array as stored */
 };
 
 static void
@@ -194,10 +169,10 @@ static void
 load_image(struct job *j, int f, unsigned char *host)
 {
     char name[64];
-    int w, h;
+    int w, h, bits;
     sprintf(name, "frames/%06d.bmp", f + 1);
-    if (!bmp_load(name, host, j->src_bytes, &w, &h, &j->scratch, &j->scratch_cap) || w != j->w || h != j->h) {
-        fprintf(stderr, "crtx_video: unable to read image %s (all images must be %dx%d)\n", name, j->w, j->h);
+    if (!bmp_load(name, host, j->file_bytes, &w, &h, &bits) || w != j->w || h != j->h || bits != j->bits) {
+        fprintf(stderr, "crtx_video: unable to read image %s (all images must be %dx%d, %d bits)\n", name, j->w, j->h, j->bits);
         exit(EXIT_FAILURE);
     }
 }
@@ -211,6 +186,23 @@ save_image(const struct job *j, int f, const unsigned char *host)
         fprintf(stderr, "crtx_video: unable to write image %s\n", name);
         exit(EXIT_FAILURE);
     }
+}
+
+/* file -> pinned host (pixel array as stored) -> device -> top-down BGRA on the device; asynchronous */
+static void
+stage_image(struct job *j, int f, unsigned char *host, void *dev_file, void *dev_bgra)
+{
+    load_image(j, f, host);
+    TRY(crtx_memcpy(dev_file, host, j->file_bytes, 0, NULL));
+    TRY(crtx_bmp_unpack(dev_bgra, dev_file, j->w, j->h, j->bits, NULL));
+}
+
+/* decoded device image -> bottom-up 32-bit rows on the device -> pinned host; asynchronous */
+static void
+fetch_image(const struct job *j, const void *dev_bgra, void *dev_file, unsigned char *host)
+{
+    TRY(crtx_bmp_pack(dev_file, dev_bgra, j->outw, j->outh, NULL));
+    TRY(crtx_memcpy(host, dev_file, j->out_bytes, 1, NULL));
 }
 
 static void
@@ -236,7 +228,7 @@ main(int argc, char **argv)
     crtx_source *srcs;
     crtx_state *st, *st_halo, *fin;
     unsigned char **hsrc, **hout;
-    void **dsrc, **work, **halo;
+    void **dsrc, **draw, **dfile, **work, **halo;
     int after_hs[2], after_vs[2], have_after[2];
     unsigned rn0 = 194u; /* crt_init, crt_core.c:269 */
     char name[64];
@@ -288,8 +280,14 @@ main(int argc, char **argv)
         fclose(f);
         j.w = (int) le32(header + 18);
         j.h = (int) le32(header + 22);
+        j.bits = (int) (le32(header + 28) & 0xff);
+        if (j.w <= 0 || j.h <= 0 || (j.bits != 24 && j.bits != 32)) {
+            fprintf(stderr, "crtx_video: %s is not a 24- or 32-bit BMP\n", name);
+            return EXIT_FAILURE;
+        }
     }
     j.src_bytes = (size_t) j.w * j.h * 4;
+    j.file_bytes = (size_t) ((j.w * (j.bits / 8) + 3) & ~3) * j.h;
     j.out_bytes = (size_t) j.outw * j.outh * 4;
 
     S = segments < j.n ? segments : j.n;
@@ -303,21 +301,25 @@ main(int argc, char **argv)
     hsrc = (unsigned char **) calloc(S, sizeof(*hsrc));
     hout = (unsigned char **) calloc(S, sizeof(*hout));
     dsrc = (void **) calloc(S, sizeof(*dsrc));
+    draw = (void **) calloc(S, sizeof(*draw));
+    dfile = (void **) calloc(S, sizeof(*dfile));
     work = (void **) calloc(S, sizeof(*work));
     halo = (void **) calloc(S, sizeof(*halo));
-    if (!lo || !hi || !mons || !srcs || !st || !st_halo || !fin || !hsrc || !hout || !dsrc || !work || !halo) die("out of memory");
+    if (!lo || !hi || !mons || !srcs || !st || !st_halo || !fin || !hsrc || !hout || !dsrc || !draw || !dfile || !work || !halo) die("out of memory");
 
     TRY(crtx_create(&ctx, S));
     longest = 0;
     for (s = 0; s < S; s++) {
         span_of(j.n, s, S, &lo[s], &hi[s]);
         if (hi[s] - lo[s] > longest) longest = hi[s] - lo[s];
-        hsrc[s] = (unsigned char *) crtx_host_alloc(j.src_bytes);
+        hsrc[s] = (unsigned char *) crtx_host_alloc(j.file_bytes);
         hout[s] = (unsigned char *) crtx_host_alloc(j.out_bytes);
         dsrc[s] = crtx_device_alloc(j.src_bytes);
+        draw[s] = crtx_device_alloc(j.file_bytes);
+        dfile[s] = crtx_device_alloc(j.out_bytes);
         work[s] = crtx_device_alloc(j.out_bytes);
         halo[s] = crtx_device_alloc(j.out_bytes);
-        if (!hsrc[s] || !hout[s] || !dsrc[s] || !work[s] || !halo[s]) die("out of memory (device or pinned host)");
+        if (!hsrc[s] || !hout[s] || !dsrc[s] || !draw[s] || !dfile[s] || !work[s] || !halo[s]) die("out of memory (device or pinned host)");
         mons[s].out = work[s];
         mons[s].outw = j.outw;
         mons[s].outh = j.outh;
@@ -346,8 +348,7 @@ main(int argc, char **argv)
         TRY(crtx_create(&probe, 1));
         TRY(crtx_set_monitors(probe, 0, 1, &pm));
         for (f = 0; f < 4 && f < j.n; f++) {
-            load_image(&j, f, hsrc[0]);
-            TRY(crtx_memcpy(dsrc[0], hsrc[0], j.src_bytes, 0, NULL));
+            stage_image(&j, f, hsrc[0], draw[0], dsrc[0]);
             fill_source(&j, &ps, dsrc[0], f);
             TRY(crtx_modulate(probe, 0, 1, &ps, NULL));
             TRY(crtx_demodulate(probe, 0, 1, NULL));
@@ -378,8 +379,7 @@ main(int argc, char **argv)
         for (s = 0; s < S; s++) {
             if (lo[s] >= t) {
                 if (s < first) first = s;
-                load_image(&j, lo[s] - t, hsrc[s]);
-                TRY(crtx_memcpy(dsrc[s], hsrc[s], j.src_bytes, 0, NULL));
+                stage_image(&j, lo[s] - t, hsrc[s], draw[s], dsrc[s]);
                 fill_source(&j, &srcs[s], dsrc[s], lo[s] - t);
             }
         }
@@ -399,14 +399,13 @@ main(int argc, char **argv)
         for (s = 0; s < S; s++) {
             if (lo[s] + t < hi[s]) {
                 count = s + 1;
-                load_image(&j, lo[s] + t, hsrc[s]);
-                TRY(crtx_memcpy(dsrc[s], hsrc[s], j.src_bytes, 0, NULL));
+                stage_image(&j, lo[s] + t, hsrc[s], draw[s], dsrc[s]);
                 fill_source(&j, &srcs[s], dsrc[s], lo[s] + t);
             }
         }
         TRY(crtx_modulate(ctx, 0, count, srcs, NULL));
         TRY(crtx_demodulate(ctx, 0, count, NULL));
-        for (s = 0; s < count; s++) TRY(crtx_memcpy(hout[s], work[s], j.out_bytes, 1, NULL));
+        for (s = 0; s < count; s++) fetch_image(&j, work[s], dfile[s], hout[s]);
         TRY(crtx_sync(NULL));
         for (s = 0; s < count; s++) save_image(&j, lo[s] + t, hout[s]);
         printf("step %d / %d\n", t + 1, longest);
@@ -428,12 +427,11 @@ main(int argc, char **argv)
         TRY(crtx_set_state(ctx, s, 1, &st[s], NULL));
         TRY(crtx_memcpy(work[s], work[s - 1], j.out_bytes, 2, NULL));
         for (f = lo[s]; f < hi[s]; f++) {
-            load_image(&j, f, hsrc[s]);
-            TRY(crtx_memcpy(dsrc[s], hsrc[s], j.src_bytes, 0, NULL));
+            stage_image(&j, f, hsrc[s], draw[s], dsrc[s]);
             fill_source(&j, &srcs[s], dsrc[s], f);
             TRY(crtx_modulate(ctx, s, 1, &srcs[s], NULL));
             TRY(crtx_demodulate(ctx, s, 1, NULL));
-            TRY(crtx_memcpy(hout[s], work[s], j.out_bytes, 1, NULL));
+            fetch_image(&j, work[s], dfile[s], hout[s]);
             TRY(crtx_sync(NULL));
             save_image(&j, f, hout[s]);
         }
@@ -445,10 +443,11 @@ main(int argc, char **argv)
         crtx_host_free(hsrc[s]);
         crtx_host_free(hout[s]);
         crtx_device_free(dsrc[s]);
+        crtx_device_free(draw[s]);
+        crtx_device_free(dfile[s]);
         crtx_device_free(work[s]);
         crtx_device_free(halo[s]);
     }
     crtx_destroy(ctx);
-    free(j.scratch);
     return EXIT_SUCCESS;
 }
