@@ -136,7 +136,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 // =======================================================================================
 // encoder, RGB systems
 // =======================================================================================
-#if (CRT_SYSTEM != CRT_SYSTEM_NES)
+#if CRT_B200_NTSC_FAMILY
 
 // level of sample t of line n in the sync / blanking / burst skeleton (crt_ntsc.c:205-252)
 __device__ __forceinline__ int skeleton_level(int n, int t, int field, int flip, int aberration, const int *burst)
@@ -700,6 +700,119 @@ __global__ void __launch_bounds__(256) k_mod_nes(const SrcCfg *__restrict__ srcs
 }
 
 #endif // NES
+
+// =======================================================================================
+// encoder, SNES (crt_snes.c:125-327): the NTSC encoder's structure on the NES line layout, a burst and
+// carrier phase that walk a 3-line cycle (+ dot_crawl_offset), and NO band-limit (CRT_DO_BANDLIMITING 0,
+// crt_snes.h:84) -- so, unlike crt_ntsc.c, every sample is independent.
+// =======================================================================================
+#if (CRT_SYSTEM == CRT_SYSTEM_SNES)
+
+constexpr int kSnesParts = 8; // CTAs per monitor; CTA p owns signal lines n with n % kSnesParts == p
+
+__global__ void __launch_bounds__(256) k_mod_snes(const SrcCfg *__restrict__ srcs, const MonCfg *__restrict__ cfgs,
+                                                  MonState *__restrict__ states, signed char *__restrict__ analog_base,
+                                                  int first)
+{
+    __shared__ int modI[3][4], modQ[3][4], burst[3][4];
+    const int m = blockIdx.y, part = blockIdx.x, tid = threadIdx.x;
+    const SrcCfg s = srcs[m];
+    const int bpp = bpp_of(s.format);
+    if (bpp == 0) return; // crt_snes.c:189-192
+    const MonCfg cfg = cfgs[first + m];
+    signed char *analog = analog_base + (size_t) (first + m) * kSignalBytes;
+
+    if (tid < 12) { // crt_snes.c:170-187
+        const int row = tid >> 2, x = tid & 3;
+        int bI = 0, bQ = 0, bB = 0;
+        if (s.as_color) {
+            const int step = 360 / 4;
+            const int n = (row + s.dot_crawl_offset) * (360 / kVper) + s.hue + x * step;
+            int sn, cs;
+            sincos14_d(sn, cs, (n - step + 210) * 8192 / 180); // HUE_OFFSET, crt_snes.h:99
+            bB = sn >> 10;
+            sincos14_d(sn, cs, n * 8192 / 180);
+            bI = sn >> 10;
+            sincos14_d(sn, cs, (n - 90) * 8192 / 180); // Q_OFFSET, crt_snes.h:97
+            bQ = sn >> 10;
+        }
+        modI[row][x] = bI;
+        modQ[row][x] = bQ;
+        burst[row][x] = bB;
+        // crt_snes.c:246-248, 322-326: every video line re-primes the lock of its own row with its burst bytes
+        if (part == 0) states[first + m].ccf[row][x] = (int) (signed char) ((kBlank + bB * kBurst) >> 5) * 128;
+    }
+    __syncthreads();
+
+    int destw = kAvLen, desth = (kLines * 64500) >> 16; // crt_snes.c:129-130, 158-168
+    if (s.raw) {
+        destw = min(s.w, kAvLen);
+        desth = min(s.h, desth);
+    }
+    int xo = kAvBeg + s.xoffset + (kAvLen - destw) / 2;
+    const int yo = kTop + s.yoffset + (kLines - desth) / 2;
+    xo = xo - (xo % 4); // crt_snes.c:201
+    const int white = kWhite * cfg.white_point / 100;
+    const int ire0 = kBlack + cfg.black_point;
+    int rp, gp, bp;
+    fmt_positions(s.format, rp, gp, bp);
+    const unsigned char *data = static_cast<const unsigned char *>(s.data);
+    const bool word_pixels = (bpp == 4) && ((reinterpret_cast<uintptr_t>(data) & 3) == 0);
+
+    for (int n = part; n < kVres; n += kSnesParts) {
+        signed char *line = analog + n * kHres;
+        // ---- sync / blank / burst of line n (crt_snes.c:203-250)
+        const bool equ = (n <= 2) || (n >= 7 && n <= 9);
+        const bool vsy = (n >= 3 && n <= 6);
+        for (int t = tid; t < kHres; t += 256) {
+            int v;
+            bool write = true;
+            if (equ) {
+                v = (t < 4 * kHres / 100 || (t >= 50 * kHres / 100 && t < 54 * kHres / 100)) ? kSync : kBlank;
+            } else if (vsy) {
+                v = (t < 46 * kHres / 100 || (t >= 50 * kHres / 100 && t < 96 * kHres / 100)) ? kSync : kBlank;
+            } else {
+                v = (t >= kSyncBeg && t < kBwBeg) ? kSync : kBlank;
+                write = (t < kAvBeg) || (n < kTop);
+                if (t >= kCbBeg && t < kCbBeg + kBurstLen) v = (kBlank + burst[n % kVper][t & 3] * kBurst) >> 5;
+            }
+            if (write) line[t] = (signed char) v;
+        }
+        // ---- picture line y = n - yo, after the line's own template (crt_snes.c:252-320)
+        const int y = n - yo;
+        if (y < 0 || y >= desth || s.h <= 0 || s.w <= 0) continue;
+        __syncthreads(); // (block-uniform condition) the template bytes above are ordered before the picture's
+        int sy = (y * s.h) / desth;
+        if (sy >= s.h) sy = s.h - 1; // (never taken for y < desth; the reference clamps to one row past the image)
+        const unsigned char *src_row = data + (size_t) sy * s.w * bpp;
+        const int ph = n % kVper;
+        for (int x = tid; x < destw; x += 256) {
+            const unsigned char *pix = src_row + (size_t) ((x * s.w) / destw) * bpp;
+            int r, g, b;
+            if (word_pixels) { // one 32-bit load per pixel instead of three byte loads
+                const unsigned v = __ldg(reinterpret_cast<const unsigned *>(pix));
+                r = (v >> (8 * rp)) & 0xff;
+                g = (v >> (8 * gp)) & 0xff;
+                b = (v >> (8 * bp)) & 0xff;
+            } else {
+                r = pix[rp];
+                g = pix[gp];
+                b = pix[bp];
+            }
+            const int fy = (19595 * r + 38470 * g + 7471 * b) >> 14;
+            int fi = (39059 * r - 18022 * g - 21103 * b) >> 14;
+            int fq = (13894 * r - 34275 * g + 20382 * b) >> 14;
+            const int xoff = (x + xo) % 4;
+            fi = wmul(fi, modI[ph][xoff]) >> 4;
+            fq = wmul(fq, modQ[ph][xoff]) >> 4;
+            int ire = ire0 + (wmul(fy + fi + fq, white) >> 10);
+            ire = __vimin_s32_relu(ire, 110);
+            line[x + xo] = (signed char) ire;
+        }
+    }
+}
+
+#endif // SNES
 
 // =======================================================================================
 // noise pass (crt_core.c:346-367), LCG variant.  16 samples per thread, 128-bit accesses;

@@ -20,9 +20,15 @@
 namespace crt {
 
 constexpr int kSystem = CRT_SYSTEM;
+#ifndef CRT_CHROMA_PATTERN /* crt_snes.h has no such switch: 227.3 cycles per line, as NES pattern 2 */
+#define CRT_CHROMA_PATTERN 2
+#endif
 constexpr int kPattern = CRT_CHROMA_PATTERN;
 constexpr bool kIsNes = (CRT_SYSTEM == CRT_SYSTEM_NES);
 constexpr bool kIsVhs = (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS);
+constexpr bool kIsSnes = (CRT_SYSTEM == CRT_SYSTEM_SNES);
+// the systems whose encoder is crt_ntsc.c / crt_ntscvhs.c (band-limited RGB, 227.5 cycles per line)
+#define CRT_B200_NTSC_FAMILY ((CRT_SYSTEM == CRT_SYSTEM_NTSC) || (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS))
 // -DCRTX_CONV=1 builds the decoder of the reference's USE_CONVOLUTION 1 configuration (an unguarded
 // #define at crt_core.c:85, so a separate library like every other compile-time choice there)
 #ifndef CRTX_CONV
@@ -118,11 +124,16 @@ constexpr int kEqQlf = eq_frac(80), kEqQhf = eq_frac(1000);
 // Q {65536, 65536, 0}
 constexpr int kEqYg1 = 8192, kEqYg2 = 9175, kEqIg2 = 1311;
 
-#if (CRT_SYSTEM != CRT_SYSTEM_NES)
+#if CRT_B200_NTSC_FAMILY
 static_assert(kHres == 910 && kAvBeg == 156 && kAvLen == 753 && kCbBeg == 97 && kSyncBeg == 21
               && kBwBeg == 88, "NTSC timing (SURVEY.md 8a)");
 static_assert(kEqYlf == 42156 && kEqYhf == 79824 && kEqIlf == 2252 && kEqIhf == 32636
               && kEqQlf == 2252 && kEqQhf == 28248, "equaliser fractions (SURVEY.md 8a)");
+#endif
+
+#if (CRT_SYSTEM == CRT_SYSTEM_SNES)
+static_assert(kHres == 909 && kAvBeg == 197 && kAvLen == 682 && kCbBeg == 101 && kSyncBeg == 23 && kBwBeg == 90
+              && kInputSize == 238158, "SNES timing (crt_snes.h:20-109, probed from the compiled reference)");
 #endif
 
 // ---------------------------------------------------------------------------------------

@@ -117,7 +117,7 @@ static cudaError_t lines_attr_all()
     return e;
 }
 
-#if (CRT_SYSTEM != CRT_SYSTEM_NES)
+#if CRT_B200_NTSC_FAMILY
 template <int FMT, bool COLOR>
 static void launch_mod_staged_one(crtx_ctx *ctx, int count, int first, cudaStream_t stream)
 {
@@ -265,6 +265,13 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
         k_mod_nes<<<dim3(kNesParts, count), 256, 0, stream>>>(ctx->d_src + first, ctx->d_nes_tab, ctx->d_analog, first);
     }
     ctx->launches += 2;
+#elif (CRT_SYSTEM == CRT_SYSTEM_SNES)
+    {
+        LaunchTimer lt(ctx, stream, 0);
+        k_mod_snes<<<dim3(kSnesParts, count), 256, 0, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_state, ctx->d_analog,
+                                                              first);
+    }
+    ctx->launches += 1;
 #else
     int extra = 0;
     {
@@ -538,7 +545,7 @@ int crtx_create(crtx_ctx **out, int n)
     CTX_TRY(lines_attr_all());
     CTX_TRY(cudaFuncSetAttribute(k_sync<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
     CTX_TRY(cudaFuncSetAttribute(k_sync<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
-#if (CRT_SYSTEM != CRT_SYSTEM_NES)
+#if CRT_B200_NTSC_FAMILY
     CTX_TRY(cudaFuncSetAttribute(k_mod_picture_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSmem));
 #endif
 #undef CTX_TRY

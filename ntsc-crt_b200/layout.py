@@ -13,7 +13,7 @@ from dataclasses import dataclass
 
 PIX_RGB, PIX_BGR, PIX_ARGB, PIX_RGBA, PIX_ABGR, PIX_BGRA = range(6)  # crt_core.h:62-67
 
-SYS_NTSC, SYS_NES, SYS_VHS = 0, 1, 5  # crt_core.h:30-36
+SYS_NTSC, SYS_NES, SYS_SNES, SYS_VHS = 0, 1, 3, 5  # crt_core.h:30-36
 
 
 def bpp4fmt(fmt):
@@ -27,7 +27,7 @@ def bpp4fmt(fmt):
 
 @dataclass(frozen=True)
 class SystemSpec:
-    name: str          # library suffix: ntsc | ntsc_conv | vhs | nes | nes_p0
+    name: str          # library suffix: ntsc | ntsc_conv[6|5|4] | vhs | nes | nes_p0 | snes
     system: int        # CRT_SYSTEM
     pattern: int       # CRT_CHROMA_PATTERN
     hres: int
@@ -75,6 +75,13 @@ def _nes_spec(name, pattern):
                       6, 6, 110, 30, 0, -37)
 
 
+def _snes_spec(name):
+    # crt_snes.h:20-109: the NES line layout (227.3 cycles per line), composite NTSC levels
+    n = _nes_spec(name, 2)
+    return SystemSpec(name, SYS_SNES, 2, n.hres, n.vres, n.top, n.bot, n.vper, n.sync_beg, n.bw_beg, n.cb_beg,
+                      n.av_beg, n.av_len, n.hsync_window, n.vsync_window, 100, 20, 7, -40)
+
+
 SPECS = {
     "ntsc": _rgb_spec("ntsc", SYS_NTSC),
     # the USE_CONVOLUTION 1 build of crt_core.c (line 85): same layouts and timing, FIR decoder filters
@@ -86,6 +93,7 @@ SPECS = {
     "vhs": _rgb_spec("vhs", SYS_VHS),
     "nes": _nes_spec("nes", 2),
     "nes_p0": _nes_spec("nes_p0", 0),
+    "snes": _snes_spec("snes"),
 }
 
 
@@ -154,6 +162,17 @@ class VhsSettings(C.Structure):
     ]
 
 
+class SnesSettings(C.Structure):
+    """struct NTSC_SETTINGS, CRT_SYSTEM_SNES (crt_snes.h:108-124)."""
+    _fields_ = [
+        ("data", C.c_void_p), ("format", C.c_int), ("w", C.c_int), ("h", C.c_int),
+        ("raw", C.c_int), ("as_color", C.c_int), ("field", C.c_int), ("frame", C.c_int),
+        ("hue", C.c_int), ("xoffset", C.c_int), ("yoffset", C.c_int),
+        ("dot_crawl_offset", C.c_int),
+        ("iirs_initialized", C.c_int),
+    ]
+
+
 class NesSettings(C.Structure):
     """struct NTSC_SETTINGS, CRT_SYSTEM_NES (crt_nes.h:132-143)."""
     _fields_ = [
@@ -165,7 +184,7 @@ class NesSettings(C.Structure):
 
 
 def settings_struct(spec):
-    return {SYS_NTSC: RgbSettings, SYS_VHS: VhsSettings, SYS_NES: NesSettings}[spec.system]
+    return {SYS_NTSC: RgbSettings, SYS_VHS: VhsSettings, SYS_NES: NesSettings, SYS_SNES: SnesSettings}[spec.system]
 
 
 def bind_crt_api(lib, spec):

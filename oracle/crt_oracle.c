@@ -237,12 +237,27 @@ make_nes_sys(ocrt_sys *s, int pattern)
     finish_sys(s);
 }
 
+static void
+make_snes_sys(ocrt_sys *s)
+{
+    /* crt_snes.h:20-109: the NES line layout at 227.3 cycles per line, composite NTSC levels */
+    make_nes_sys(s, 2);
+    s->system = OCRT_SYS_SNES;
+    s->nes_vsync_end = 0;
+    s->white_level = 100;
+    s->burst_level = 20;
+    s->black_level = 7;
+    s->blank_level = 0;
+    s->sync_level = -40;
+}
+
 const ocrt_sys *
 ocrt_system(int system, int chroma_pattern)
 {
-    static ocrt_sys table[5];
+    static ocrt_sys table[6];
     static int ready = 0;
     if (!ready) {
+        make_snes_sys(&table[5]);
         make_rgb_sys(&table[0], OCRT_SYS_NTSC);
         make_rgb_sys(&table[1], OCRT_SYS_VHS);
         make_nes_sys(&table[2], 0);
@@ -252,6 +267,7 @@ ocrt_system(int system, int chroma_pattern)
     }
     if (system == OCRT_SYS_NTSC) return &table[0];
     if (system == OCRT_SYS_VHS) return &table[1];
+    if (system == OCRT_SYS_SNES) return &table[5];
     if (system == OCRT_SYS_NES && chroma_pattern >= 0 && chroma_pattern <= 2)
         return &table[2 + chroma_pattern];
     return NULL;
@@ -260,12 +276,12 @@ ocrt_system(int system, int chroma_pattern)
 const ocrt_sys *
 ocrt_system_conv_taps(int system, int chroma_pattern, int taps)
 {
-    static ocrt_sys table[4][5];
-    static int ready[4][5];
+    static ocrt_sys table[4][6];
+    static int ready[4][6];
     const ocrt_sys *base = ocrt_system(system, chroma_pattern);
     int slot;
     if (!base || taps < 4 || taps > 7) return NULL;
-    slot = (system == OCRT_SYS_NTSC) ? 0 : (system == OCRT_SYS_VHS) ? 1 : 2 + chroma_pattern;
+    slot = (system == OCRT_SYS_NTSC) ? 0 : (system == OCRT_SYS_VHS) ? 1 : (system == OCRT_SYS_SNES) ? 5 : 2 + chroma_pattern;
     if (!ready[taps - 4][slot]) {
         table[taps - 4][slot] = *base;
         table[taps - 4][slot].conv = taps;
@@ -430,6 +446,89 @@ ocrt_encode_rgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src, ocrt
     for (n = 0; n < sys->cc_vper; n++) /* crt_ntsc.c:325-329 / crt_ntscvhs.c:332-336 */
         for (x = 0; x < 4; x++)
             m->ccf[n][x] = (sys->system == OCRT_SYS_VHS) ? 0 : primed[x] * 128;
+}
+
+/* ------------------------------------------------------------------------- */
+/* encoder, SNES (crt_snes.c:125-327)                                          */
+/* ------------------------------------------------------------------------- */
+
+void
+ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
+{
+    const i32 H = sys->hres;
+    i32 bpp = ocrt_bpp(src->format);
+    i32 destw = sys->av_len, desth = (sys->lines * 64500) >> 16;
+    i32 modI[3][4], modQ[3][4], burst[3][4], primed[3][4];
+    i32 n, x, y, xo, yo, white;
+
+    if (src->raw) { /* crt_snes.c:158-168 */
+        destw = src->w < sys->av_len ? src->w : sys->av_len;
+        desth = src->h < desth ? src->h : desth;
+    }
+    for (y = 0; y < 3; y++) /* crt_snes.c:170-187 */
+        for (x = 0; x < 4; x++) {
+            i32 step = 360 / 4, deg = (y + src->dot_crawl_offset) * (360 / 3) + src->hue + x * step;
+            burst[y][x] = modI[y][x] = modQ[y][x] = 0;
+            if (src->as_color) {
+                burst[y][x] = sin14((deg - step + 210) * 8192 / 180) >> 10; /* HUE_OFFSET */
+                modI[y][x] = sin14(deg * 8192 / 180) >> 10;
+                modQ[y][x] = sin14((deg - 90) * 8192 / 180) >> 10;          /* Q_OFFSET */
+            }
+        }
+    if (bpp == 0) return; /* crt_snes.c:189-192 */
+    xo = sys->av_beg + src->xoffset + (sys->av_len - destw) / 2;
+    yo = sys->top + src->yoffset + (sys->lines - desth) / 2;
+    src->field &= 1;
+    src->frame &= 1;
+    xo = xo - (xo % 4);
+    memset(primed, 0, sizeof(primed));
+
+    for (n = 0; n < sys->vres; n++) { /* crt_snes.c:203-250 */
+        signed char *line = m->analog + n * H;
+        if (n <= 2 || (n >= 7 && n <= 9)) {
+            fill(line, 0, 4 * H / 100, sys->sync_level);
+            fill(line, 4 * H / 100, 50 * H / 100, sys->blank_level);
+            fill(line, 50 * H / 100, 54 * H / 100, sys->sync_level);
+            fill(line, 54 * H / 100, H, sys->blank_level);
+        } else if (n >= 3 && n <= 6) {
+            fill(line, 0, 46 * H / 100, sys->sync_level);
+            fill(line, 46 * H / 100, 50 * H / 100, sys->blank_level);
+            fill(line, 50 * H / 100, 96 * H / 100, sys->sync_level);
+            fill(line, 96 * H / 100, H, sys->blank_level);
+        } else {
+            i32 t;
+            fill(line, 0, sys->sync_beg, sys->blank_level);
+            fill(line, sys->sync_beg, sys->bw_beg, sys->sync_level);
+            fill(line, sys->bw_beg, sys->av_beg, sys->blank_level);
+            if (n < sys->top) fill(line, sys->av_beg, H, sys->blank_level);
+            for (t = sys->cb_beg; t < sys->cb_beg + sys->burst_len; t++) {
+                line[t] = (signed char) ((sys->blank_level + burst[n % 3][t % 4] * sys->burst_level) >> 5);
+                primed[(n + 3) % 3][t % 4] = line[t];
+            }
+        }
+    }
+
+    white = sys->white_level * m->white_point / 100;
+    for (y = 0; y < desth; y++) { /* crt_snes.c:252-320; CRT_DO_BANDLIMITING 0: iirf() is the identity */
+        i32 row = (y * src->h) / desth, ph = (y + yo) % 3;
+        if (row >= src->h) row = src->h;
+        for (x = 0; x < destw; x++) {
+            const unsigned char *px = src->data + (size_t) (((x * src->w) / destw) + row * src->w) * bpp;
+            i32 r = px[fmt_r[src->format]], gg = px[fmt_g[src->format]], b = px[fmt_b[src->format]];
+            i32 fy = (19595 * r + 38470 * gg + 7471 * b) >> 14;
+            i32 fi = (39059 * r - 18022 * gg - 21103 * b) >> 14;
+            i32 fq = (13894 * r - 34275 * gg + 20382 * b) >> 14;
+            i32 xoff = (x + xo) % 4, ire;
+            fi = wmul(fi, modI[ph][xoff]) >> 4;
+            fq = wmul(fq, modQ[ph][xoff]) >> 4;
+            ire = sys->black_level + m->black_point + (wmul(fy + fi + fq, white) >> 10);
+            if (ire < 0) ire = 0;
+            if (ire > 110) ire = 110;
+            m->analog[(x + xo) + (y + yo) * H] = (signed char) ire;
+        }
+    }
+    for (n = 0; n < 3; n++) /* crt_snes.c:322-326 */
+        for (x = 0; x < 4; x++) m->ccf[n][x] = primed[n][x] * 128;
 }
 
 /* ------------------------------------------------------------------------- */

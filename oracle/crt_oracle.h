@@ -26,6 +26,7 @@ extern "C" {
 
 #define OCRT_SYS_NTSC 0 /* crt_core.h:30 */
 #define OCRT_SYS_NES  1 /* crt_core.h:31 */
+#define OCRT_SYS_SNES 3 /* crt_core.h:33 */
 #define OCRT_SYS_VHS  5 /* crt_core.h:35 */
 
 #define OCRT_MAX_VPER 3
@@ -72,7 +73,8 @@ typedef struct ocrt_monitor {
 typedef struct ocrt_rgb_source {
     const unsigned char *data;
     int format, w, h, raw, as_color, field, frame, hue, xoffset, yoffset;
-    int do_aberration; /* VHS only */
+    int do_aberration;    /* VHS only */
+    int dot_crawl_offset; /* SNES only (crt_snes.h:121) */
 } ocrt_rgb_source;
 
 /* struct NTSC_SETTINGS of the NES system (crt_nes.h:132-143) */
@@ -117,6 +119,7 @@ void ocrt_monitor_reset(ocrt_monitor *m);
 /* crt_modulate */
 void ocrt_encode_rgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src, ocrt_rand *g);
 void ocrt_encode_nes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_nes_source *src);
+void ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src);
 
 /* crt_demodulate, and its three stages on their own */
 void ocrt_decode(const ocrt_sys *sys, ocrt_monitor *m, int noise, ocrt_rand *g);

@@ -14,7 +14,11 @@
 #define OFF(f) ((int) offsetof(struct CRT, f))
 
 int ref_system(void) { return CRT_SYSTEM; }
+#ifdef CRT_CHROMA_PATTERN
 int ref_chroma_pattern(void) { return CRT_CHROMA_PATTERN; }
+#else /* crt_snes.h has no such switch */
+int ref_chroma_pattern(void) { return -1; }
+#endif
 int ref_sizeof_crt(void) { return (int) sizeof(struct CRT); }
 int ref_sizeof_settings(void) { return (int) sizeof(struct NTSC_SETTINGS); }
 

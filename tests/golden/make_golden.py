@@ -70,6 +70,10 @@ case("conv_generic_saturation4000", "ntsc_conv", 333, 250, layout.PIX_ARGB,
 for v in ("ntsc_conv6", "ntsc_conv5", "ntsc_conv4"):  # the other kernels of the option (crt_core.c:86-88)
     case("%s_640x480" % v, v, 640, 480, layout.PIX_BGRA, dict(blend=1, scanlines=1, hue=-20, saturation=13),
          ("rand", 333, 250, 4, 11), rgb_calls(4, 6))
+case("snes_640x480", "snes", 640, 480, layout.PIX_BGRA, dict(blend=1, scanlines=1, saturation=12),
+     ("rand", 300, 230, 4, 21),
+     [(dict(format=layout.PIX_BGRA, as_color=1, raw=0, field=i & 1, frame=0, hue=(i * 50) % 360,
+            dot_crawl_offset=i % 3, xoffset=4 * (i & 1), yoffset=i % 3), 3 * i) for i in range(4)])
 for v in ("nes", "nes_p0"):
     case("cfg3_%s" % v, v, 832, 624, layout.PIX_BGRA, dict(blend=0, scanlines=1),
          ("nes", 256, 240, 0, 5), [(dict(dot_crawl_offset=i % 3, hue=(i * 30) % 360), 4 * i) for i in range(5)])

@@ -207,7 +207,7 @@ class _OMonitor(C.Structure):
 class _ORgb(C.Structure):
     _fields_ = [("data", C.c_void_p)] + [(n, C.c_int) for n in (
         "format", "w", "h", "raw", "as_color", "field", "frame", "hue", "xoffset",
-        "yoffset", "do_aberration")]
+        "yoffset", "do_aberration", "dot_crawl_offset")]
 
 
 class _ONes(C.Structure):
@@ -245,6 +245,7 @@ def oracle_lib():
         lib.ocrt_encode_rgb.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor),
                                         C.POINTER(_ORgb), C.POINTER(_ORand)]
         lib.ocrt_encode_nes.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ONes)]
+        lib.ocrt_encode_snes.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ORgb)]
         lib.ocrt_decode.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.c_int,
                                     C.POINTER(_ORand)]
         lib.ocrt_noise_pass.argtypes = lib.ocrt_decode.argtypes
@@ -317,6 +318,8 @@ class OracleEngine:
             setattr(s, k, v)
         if self.spec.system == layout.SYS_NES:
             self.lib.ocrt_encode_nes(self.sys, C.byref(self.mon), C.byref(s))
+        elif self.spec.system == layout.SYS_SNES:
+            self.lib.ocrt_encode_snes(self.sys, C.byref(self.mon), C.byref(s))
         else:
             self.lib.ocrt_encode_rgb(self.sys, C.byref(self.mon), C.byref(s), C.byref(self.rand))
 

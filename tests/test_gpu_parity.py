@@ -119,6 +119,55 @@ def test_dropin_unknown_format_is_silent_noop():
     check(gpu, ora, ref, "bad in format")
 
 
+@pytest.mark.parametrize("fmt,as_color,raw,outw,outh", [(layout.PIX_BGRA, 1, 0, 832, 624), (layout.PIX_RGB, 1, 0, 640, 480),
+                                                        (layout.PIX_ARGB, 0, 0, 333, 250), (layout.PIX_ABGR, 1, 1, 100, 80)])
+def test_dropin_snes(fmt, as_color, raw, outw, outh):
+    """CRT_SYSTEM_SNES (crt_snes.c:125-327) through the drop-in interface."""
+    rgb = S.rand_image(300 if not raw else 200, 230 if not raw else 180, bpp=3, seed=fmt)
+    img = S.pack_rgb(rgb, fmt)
+    gpu, ora, ref = trio("snes", outw, outh, fmt)
+    run_all((gpu, ora, ref), lambda e: e.set(blend=1, scanlines=1, hue=10, saturation=12, black_point=2, white_point=95))
+    for it in range(5):
+        run_all((gpu, ora, ref), lambda e: e.modulate(img, format=fmt, as_color=as_color, raw=raw, field=it & 1, frame=0,
+                                                      hue=(it * 50) % 360, dot_crawl_offset=it % 3, xoffset=4 * (it & 1),
+                                                      yoffset=it % 3))
+        check(gpu, ora, ref, "snes mod %d" % it)
+        run_all((gpu, ora, ref), lambda e: e.demodulate(0 if it < 2 else 9))
+        check(gpu, ora, ref, "snes demod %d" % it)
+
+
+def test_batch_snes_matches_oracle():
+    import torch
+    from ntsc_crt_b200 import capi
+    n = 3
+    b = capi.Batch("snes", n)
+    outs, oras, imgs = [], [], []
+    for i in range(n):
+        t = torch.zeros(480, 640, 4, dtype=torch.uint8, device="cuda")
+        outs.append(t)
+        b.set_monitor(i, t, fmt=layout.PIX_BGRA, noise=4 * i, blend=i & 1, scanlines=1, saturation=9 + i)
+        o = S.OracleEngine("snes", 640, 480)
+        o.set(blend=i & 1, scanlines=1, saturation=9 + i)
+        oras.append(o)
+        imgs.append(S.rand_image(256 + 32 * i, 224, seed=200 + i))
+    b.commit_monitors()
+    dimgs = [torch.from_numpy(im).cuda() for im in imgs]
+    for it in range(4):
+        for i in range(n):
+            kw = dict(format=layout.PIX_BGRA, as_color=1, hue=15 * i, dot_crawl_offset=(it + i) % 3)
+            b.set_source(i, dimgs[i], **kw)
+            oras[i].modulate(imgs[i], **kw)
+            oras[i].demodulate(4 * i)
+        b.modulate()
+        b.demodulate()
+        torch.cuda.synchronize()
+        for i in range(n):
+            got = outs[i].cpu().numpy()
+            assert np.array_equal(got, oras[i].out), "snes batch monitor %d field %d: %s" % (
+                i, it, S.diff_report("out", got, oras[i].out))
+    b.close()
+
+
 @pytest.mark.parametrize("variant", ["nes", "nes_p0"])
 def test_dropin_nes(variant):
     """config 3: NES PPU pixels incl. CRT_CHROMA_PATTERN 0, dot crawl cycling 0,1,2."""

@@ -32,7 +32,7 @@ def check(ref, ora, what):
 
 
 def test_struct_layout_matches_reference():
-    for variant in ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0"):
+    for variant in ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "snes"):
         spec = layout.system_spec(variant)
         lib = C.CDLL(S.ref_path(variant))
         assert lib.ref_sizeof_crt() == C.sizeof(layout.crt_struct(spec)), variant
@@ -207,6 +207,24 @@ def test_ntsc_conv_extreme_knobs_and_formats():
             both(ref, ora, lambda e: e.modulate(img, format=fmt, as_color=1, field=it, frame=0))
             both(ref, ora, lambda e: e.demodulate(30))
             check(ref, ora, "conv extreme fmt %d call %d" % (fmt, it))
+
+
+@pytest.mark.parametrize("fmt,as_color,raw", [(layout.PIX_BGRA, 1, 0), (layout.PIX_RGB, 1, 0), (layout.PIX_ARGB, 0, 0),
+                                              (layout.PIX_ABGR, 1, 1)])
+def test_snes(fmt, as_color, raw):
+    """CRT_SYSTEM_SNES (crt_snes.c): RGB source on the NES line layout, 3-line chroma cycle with
+    dot crawl, no encoder band-limit."""
+    rgb = S.rand_image(300 if not raw else 200, 230 if not raw else 180, bpp=3, seed=fmt)
+    img = S.pack_rgb(rgb, fmt)
+    ref, ora = pair("snes", 640, 480)
+    both(ref, ora, lambda e: e.set(blend=1, scanlines=1, hue=10, saturation=12, black_point=2, white_point=95))
+    for it in range(5):
+        both(ref, ora, lambda e: e.modulate(img, format=fmt, as_color=as_color, raw=raw, field=it & 1, frame=0,
+                                            hue=(it * 50) % 360, dot_crawl_offset=it % 3, xoffset=4 * (it & 1),
+                                            yoffset=it % 3))
+        check(ref, ora, "snes mod %d" % it)
+        both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 9))
+        check(ref, ora, "snes demod %d" % it)
 
 
 @pytest.mark.parametrize("variant", ["nes", "nes_p0"])
