@@ -781,24 +781,30 @@ __global__ void __launch_bounds__(256) k_mod_snes(const SrcCfg *__restrict__ src
         // ---- picture line y = n - yo, after the line's own template (crt_snes.c:252-320)
         const int y = n - yo;
         if (y < 0 || y >= desth || s.h <= 0 || s.w <= 0) continue;
-        __syncthreads(); // (block-uniform condition) the template bytes above are ordered before the picture's
+        // the picture normally starts at or after AV_BEG on a line whose template stops there; only when the
+        // two overlap (negative offsets, picture above the first active line) must the template land first
+        if (xo < kAvBeg || n < kTop) __syncthreads(); // block-uniform condition
         int sy = (y * s.h) / desth;
         if (sy >= s.h) sy = s.h - 1; // (never taken for y < desth; the reference clamps to one row past the image)
         const unsigned char *src_row = data + (size_t) sy * s.w * bpp;
         const int ph = n % kVper;
-        for (int x = tid; x < destw; x += 256) {
-            const unsigned char *pix = src_row + (size_t) ((x * s.w) / destw) * bpp;
-            int r, g, b;
-            if (word_pixels) { // one 32-bit load per pixel instead of three byte loads
-                const unsigned v = __ldg(reinterpret_cast<const unsigned *>(pix));
-                r = (v >> (8 * rp)) & 0xff;
-                g = (v >> (8 * gp)) & 0xff;
-                b = (v >> (8 * bp)) & 0xff;
-            } else {
-                r = pix[rp];
-                g = pix[gp];
-                b = pix[bp];
+        constexpr int kPer = (kAvLen + 255) / 256; // samples per thread and line
+        unsigned px[kPer];
+#pragma unroll
+        for (int q = 0; q < kPer; q++) { // all of a thread's pixel fetches first
+            const int x = tid + q * 256;
+            px[q] = 0;
+            if (x < destw) {
+                const unsigned char *pix = src_row + (size_t) (((unsigned) x * (unsigned) s.w) / (unsigned) destw) * bpp;
+                if (word_pixels) px[q] = __ldg(reinterpret_cast<const unsigned *>(pix));
+                else px[q] = (unsigned) pix[0] | (unsigned) pix[1] << 8 | (unsigned) pix[2] << 16 | (bpp == 4 ? (unsigned) pix[3] << 24 : 0u);
             }
+        }
+#pragma unroll
+        for (int q = 0; q < kPer; q++) {
+            const int x = tid + q * 256;
+            if (x >= destw) continue;
+            const int r = (px[q] >> (8 * rp)) & 0xff, g = (px[q] >> (8 * gp)) & 0xff, b = (px[q] >> (8 * bp)) & 0xff;
             const int fy = (19595 * r + 38470 * g + 7471 * b) >> 14;
             int fi = (39059 * r - 18022 * g - 21103 * b) >> 14;
             int fq = (13894 * r - 34275 * g + 20382 * b) >> 14;
