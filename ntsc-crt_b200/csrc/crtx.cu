@@ -59,7 +59,7 @@ static int upload_cfg(crtx_ctx *ctx, cudaStream_t stream)
 template <bool FAST, int MODE, int FMT>
 static void launch_lines_one(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
 {
-    if (kConv) { // USE_CONVOLUTION build: one warp per decoded line (crt_lines_fir.cuh)
+    if constexpr (kConv) { // USE_CONVOLUTION build: one warp per decoded line (crt_lines_fir.cuh)
         // about two waves of resident CTAs (2 per SM) over the whole launch, see k_lines_fir; the generic
         // pass is normally empty and gets the smallest grid
         int gx = FAST ? (4 * ctx->sm_count + count - 1) / count : 1;
@@ -67,10 +67,10 @@ static void launch_lines_one(crtx_ctx *ctx, int count, int lo, const LinesGeom &
         const dim3 grid(gx, count);
         k_lines_fir<FAST, MODE, FMT><<<grid, kFirWarps * 32, fir_smem<FAST>(), stream>>>(ctx->d_cfg, ctx->d_state,
                                                                                          ctx->d_lines, ctx->d_inp, lo, geo);
-        return;
+    } else { // (only the kernel a build uses is instantiated)
+        k_lines<FAST, MODE, FMT><<<count, kLinesWarps * 32, lines_smem<FAST>(), stream>>>(ctx->d_cfg, ctx->d_state,
+                                                                                          ctx->d_lines, ctx->d_inp, lo, geo);
     }
-    k_lines<FAST, MODE, FMT><<<count, kLinesWarps * 32, lines_smem<FAST>(), stream>>>(ctx->d_cfg, ctx->d_state,
-                                                                                      ctx->d_lines, ctx->d_inp, lo, geo);
 }
 
 template <bool FAST>
@@ -97,11 +97,12 @@ static void launch_lines(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo,
 template <bool FAST, int MODE, int FMT>
 static cudaError_t lines_attr()
 {
-    if (kConv)
+    if constexpr (kConv)
         return cudaFuncSetAttribute(k_lines_fir<FAST, MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     fir_smem<FAST>());
-    return cudaFuncSetAttribute(k_lines<FAST, MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                lines_smem<FAST>());
+    else
+        return cudaFuncSetAttribute(k_lines<FAST, MODE, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    lines_smem<FAST>());
 }
 
 static cudaError_t lines_attr_all()
