@@ -734,6 +734,17 @@ int crtx_frames_host(crtx_ctx *ctx, int first, int count, const crtx_source *src
     std::vector<crtx_source> dev(src, src + count);
     for (int i = 0; i < count; i++) {
         size_t b = (size_t) src[i].w * src[i].h * (kIsNes ? 2 : bpp_of(src[i].format));
+        if (ctx->opt_host_src) {
+            // "host_src": the encoder reads a page-locked source image in place over PCIe -- a field only
+            // touches the rows of its own parity (crt_ntsc.c:258-266), about 38 % of an 832x624 image, so
+            // less crosses the link than a whole-image copy moves.  Pageable images still take the copy.
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, src[i].data) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+                dev[i].data = at.devicePointer;
+                continue;
+            }
+            (void) cudaGetLastError();
+        }
         unsigned char *slot = ctx->d_src_img + ctx->src_slot * (size_t) (first + i);
         CUDA_TRY(cudaMemcpyAsync(slot, src[i].data, b, cudaMemcpyHostToDevice, st));
         dev[i].data = slot;
@@ -863,6 +874,7 @@ int crtx_set_option(crtx_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "timing")) ctx->opt_timing = value;
     else if (!strcmp(name, "mod_staged")) ctx->opt_mod_staged = value;
     else if (!strcmp(name, "fused_noise")) ctx->opt_fused_noise = value;
+    else if (!strcmp(name, "host_src")) ctx->opt_host_src = value;
     else if (!strcmp(name, "line_lo")) ctx->opt_line_lo = value;
     else if (!strcmp(name, "line_hi")) ctx->opt_line_hi = value;
     else return fail("crtx_set_option: unknown option '%s'", name);
