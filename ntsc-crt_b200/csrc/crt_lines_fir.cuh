@@ -9,10 +9,10 @@
 //        the 16-byte aligned superset of 768 samples at any byte phase), and -- when blending -- so
 //        does the previous image's row; both are requested one line ahead (each warp walks several
 //        lines of its monitor), so the copies fly while the warp filters;
-//   F  : every lane filters 24 consecutive samples (plus a 6-sample run-in that rebuilds the filter
-//        history), the kernel factored as [1 1]^3 * [1 1 1 1] -- five additions per channel and
-//        sample, exact because nothing is rounded before the final shift -- and writes packed Y/I/Q
-//        into the warp's shared-memory row;
+//   F  : every lane filters 24 consecutive samples (plus a taps - 1 sample run-in that rebuilds the filter
+//        history), the kernel factored as [1 1]^(taps - 4) * [1 1 1 1] -- five additions per channel and
+//        sample for 7 taps, exact because nothing is rounded before the final shift -- and writes Y/I/Q
+//        into the warp's shared-memory rows;
 //   P  : lane = output pixel, 32 consecutive pixels per step: resample, YIQ->RGB, contrast, clamp,
 //        blend with the previous image IN PLACE in the staged row, which one lane then sends to every
 //        output row the line covers (crt_core.c:662-664) as bulk stores; two row buffers alternate so
@@ -42,8 +42,10 @@ static_assert(kFirSeg % 32 == 0, "whole warp steps per segment");
 // Y, I and Q rows of one line, one array per component.  Sample e lives in slot 1 + e + (e >> 3): one pad
 // slot after every 8 samples makes the per-lane chunk pitch 27 entries, which spreads "all lanes, same t"
 // stores over the banks; the pad slot after samples 8j..8j+7 holds a COPY of sample 8j+8, so the resampler
-// always finds sample s + 1 in the slot after sample s.  FAST keeps 16-bit entries (all three components
-// provably fit there, see eq_step and k_sync), which the resampler reads with sign-extending loads.
+// always finds sample s + 1 in the slot after sample s.  FAST keeps 16-bit entries, which the resampler
+// reads with sign-extending loads; they fit because the kernels have unit DC gain and k_sync only leaves
+// a monitor on the FAST path when |bright| <= 4096 (|Y| <= 127 + 4096 before the x16 the pixel pass
+// applies) and every chroma input (s * wave) >> 9 is within +-16383 (|I|, |Q| <= 2048 after the >> 3).
 template <bool FAST> struct FirRow {
     using Elem = typename std::conditional<FAST, short, int>::type;
     static constexpr int kSlots = 1 + kFirSamples + kFirSamples / 8;
