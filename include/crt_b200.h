@@ -18,6 +18,7 @@
  *      CRT_SYSTEM 1 (CRT_CHROMA_PATTERN 2)   libcrt_b200_nes.so
  *      CRT_SYSTEM 1, CRT_CHROMA_PATTERN 0    libcrt_b200_nes_p0.so
  *      CRT_SYSTEM 3                          libcrt_b200_snes.so
+ *      CRT_SYSTEM 6                          libcrt_b200_nesrgb.so
  */
 #ifndef CRT_B200_H
 #define CRT_B200_H
@@ -188,8 +189,44 @@ struct NTSC_SETTINGS {
     int iirs_initialized; /* zero the struct before first use */
 };
 
+#elif (CRT_SYSTEM == CRT_SYSTEM_NESRGB)
+/* ---- RGB image with NES timing and artifacts, crt_nesrgb.h ---- */
+#define CRT_CHROMA_PATTERN 2
+#define CRT_CC_LINE  2273
+#define CRT_HRES     (CRT_CC_LINE * CRT_CB_FREQ / 10)
+#define CRT_TOP      15
+#define CRT_BOT      255
+#define CRT_CC_VPER  3
+#define CRT_HSYNC_WINDOW 6
+#define CRT_VSYNC_WINDOW 6
+#define CRT_B200_LINE_UNITS 341 /* PPU pixels */
+#define CRT_B200_POS(u) ((u) * CRT_HRES / CRT_B200_LINE_UNITS)
+#define PPUpx2pos(u) CRT_B200_POS(u)
+#define SYNC_BEG     CRT_B200_POS(9)
+#define BW_BEG       CRT_B200_POS(9 + 25)
+#define CB_BEG       CRT_B200_POS(9 + 25 + 4)
+#define BP_BEG       CRT_B200_POS(9 + 25 + 4 + 15)
+#define LAV_BEG      CRT_B200_POS(9 + 25 + 4 + 15 + 5)
+#define AV_BEG       CRT_B200_POS(9 + 25 + 4 + 15 + 5 + 1 + 15)
+#define AV_LEN       CRT_B200_POS(256)
+#define WHITE_LEVEL  100
+#define BURST_LEVEL  30
+#define BLACK_LEVEL  0
+#define SYNC_LEVEL   (-37)
+
+struct NTSC_SETTINGS {
+    const unsigned char *data; /* image, one of the CRT_PIX_FORMATs */
+    int format;
+    int w, h;
+    int dot_crawl_offset; /* 0, 1, 2 */
+    int hue;
+    int xoffset;
+    int yoffset;
+    int field_initialized; /* zero the struct before first use */
+};
+
 #else
-#error "crt_b200: this library implements CRT_SYSTEM 0 (NTSC), 1 (NES), 3 (SNES) and 5 (NTSCVHS) only"
+#error "crt_b200: this library implements CRT_SYSTEM 0 (NTSC), 1 (NES), 3 (SNES), 5 (NTSCVHS) and 6 (NESRGB) only"
 #endif
 
 #define CRT_INPUT_SIZE (CRT_HRES * CRT_VRES)

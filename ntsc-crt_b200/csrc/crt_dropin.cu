@@ -217,6 +217,19 @@ void crt_modulate(struct CRT *v, struct NTSC_SETTINGS *s)
     src.yoffset = s->yoffset;
     src.dot_crawl_offset = s->dot_crawl_offset;
     const size_t img_bytes = (size_t) s->w * s->h * sizeof(unsigned short);
+#elif (CRT_SYSTEM == CRT_SYSTEM_NESRGB)
+    src.reinit = !s->field_initialized; /* crt_nesrgb.c:63-66: setup_field runs before the format check */
+    s->field_initialized = 1;
+    const int bpp = bpp_of(s->format);
+    if (bpp == 0 && !src.reinit) return; /* crt_nesrgb.c:81-84 */
+    src.format = s->format;
+    src.w = s->w;
+    src.h = s->h;
+    src.hue = s->hue;
+    src.xoffset = s->xoffset;
+    src.yoffset = s->yoffset;
+    src.dot_crawl_offset = s->dot_crawl_offset;
+    const size_t img_bytes = (size_t) s->w * s->h * bpp;
 #else
     s->iirs_initialized = 1; /* crt_ntsc.c:142-147 */
     const int bpp = bpp_of(s->format);

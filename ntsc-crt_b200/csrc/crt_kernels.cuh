@@ -821,6 +821,97 @@ __global__ void __launch_bounds__(256) k_mod_snes(const SrcCfg *__restrict__ src
 #endif // SNES
 
 // =======================================================================================
+// encoder, NES-RGB (crt_nesrgb.c:19-172): the NES sync template (written once per stream) and 3-line burst
+// cycle around an RGB picture encoded like the SNES one (no band-limit: samples are independent).
+// =======================================================================================
+#if (CRT_SYSTEM == CRT_SYSTEM_NESRGB)
+
+constexpr int kNesRgbParts = 8; // CTAs per monitor; CTA p owns signal lines n with n % kNesRgbParts == p
+
+__global__ void __launch_bounds__(256) k_mod_nesrgb(const SrcCfg *__restrict__ srcs, const MonCfg *__restrict__ cfgs,
+                                                    MonState *__restrict__ states, signed char *__restrict__ analog_base,
+                                                    int first)
+{
+    __shared__ int modI[3][4], modQ[3][4], burst[3][4];
+    const int m = blockIdx.y, part = blockIdx.x, tid = threadIdx.x;
+    const SrcCfg s = srcs[m];
+    const int bpp = bpp_of(s.format);
+    const MonCfg cfg = cfgs[first + m];
+    signed char *analog = analog_base + (size_t) (first + m) * kSignalBytes;
+
+    if (tid < 12) { // crt_nesrgb.c:68-79
+        const int row = tid >> 2, x = tid & 3;
+        const int n = (row + s.dot_crawl_offset) * (360 / kVper) + x * (360 / 4);
+        int sn, cs;
+        sincos14_d(sn, cs, (s.hue + 90 + n + 33) * 8192 / 180);
+        burst[row][x] = sn >> 10;
+        sincos14_d(sn, cs, n * 8192 / 180);
+        modI[row][x] = sn >> 10;
+        sincos14_d(sn, cs, (n - 90) * 8192 / 180);
+        modQ[row][x] = sn >> 10;
+        // crt_nesrgb.c:106-110, 166-170: every picture line re-primes the lock of its row with its burst bytes
+        if (part == 0 && bpp != 0) states[first + m].ccf[row][x] = (int) (signed char) ((kBlank + burst[row][x] * kBurst) >> 5) * 128;
+    }
+    __syncthreads();
+
+    const int xo = (kAvBeg + s.xoffset) & ~3, yo = kTop + s.yoffset; // crt_nesrgb.c:86-90
+    const int white = kWhite * cfg.white_point / 100;
+    const int ire0 = kBlack + cfg.black_point;
+    int rp, gp, bp;
+    fmt_positions(s.format, rp, gp, bp);
+    const unsigned char *data = static_cast<const unsigned char *>(s.data);
+    const bool word_pixels = (bpp == 4) && ((reinterpret_cast<uintptr_t>(data) & 3) == 0);
+
+    for (int n = part; n < kVres; n += kNesRgbParts) {
+        signed char *line = analog + n * kHres;
+        if (s.reinit) { // setup_field, crt_nesrgb.c:19-47 -- before the pixel-format check of crt_nesrgb.c:81-84
+            const int sync_end = (n >= 259) ? kNesVsyncEnd : kBwBeg;
+            for (int t = tid; t < kHres; t += 256) line[t] = (signed char) ((t >= kSyncBeg && t < sync_end) ? kSync : kBlank);
+        }
+        const int y = n - yo;
+        if (bpp == 0 || y < 0 || y >= kLines || s.h <= 0 || s.w <= 0) continue;
+        if (s.reinit) __syncthreads(); // (block-uniform) template before burst and picture
+        if (tid < kBurstLen) { // crt_nesrgb.c:104-110
+            const int t = kCbBeg + tid;
+            line[t] = (signed char) ((kBlank + burst[n % kVper][t & 3] * kBurst) >> 5);
+        }
+        int sy = (y * s.h) / kLines;
+        if (sy >= s.h) sy = s.h - 1; // (never taken; the reference clamps to one row past the image)
+        const unsigned char *src_row = data + (size_t) sy * s.w * bpp;
+        const int ph = n % kVper;
+        constexpr int kPer = (kAvLen + 255) / 256;
+        unsigned px[kPer];
+#pragma unroll
+        for (int q = 0; q < kPer; q++) { // all of a thread's pixel fetches first
+            const int x = tid + q * 256;
+            px[q] = 0;
+            if (x < kAvLen) {
+                const unsigned char *pix = src_row + (size_t) (((unsigned) x * (unsigned) s.w) / (unsigned) kAvLen) * bpp;
+                if (word_pixels) px[q] = __ldg(reinterpret_cast<const unsigned *>(pix));
+                else px[q] = (unsigned) pix[0] | (unsigned) pix[1] << 8 | (unsigned) pix[2] << 16 | (bpp == 4 ? (unsigned) pix[3] << 24 : 0u);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kPer; q++) {
+            const int x = tid + q * 256;
+            if (x >= kAvLen) continue;
+            const int r = (px[q] >> (8 * rp)) & 0xff, g = (px[q] >> (8 * gp)) & 0xff, b = (px[q] >> (8 * bp)) & 0xff;
+            const int fy = (19595 * r + 38470 * g + 7471 * b) >> 14;
+            int fi = (39059 * r - 18022 * g - 21103 * b) >> 14;
+            int fq = (13894 * r - 34275 * g + 20382 * b) >> 14;
+            const int xoff = (x + xo) % 4;
+            fi = wmul(fi, modI[ph][xoff]) >> 4;
+            fq = wmul(fq, modQ[ph][xoff]) >> 4;
+            int ire = ire0 + (wmul(fy + fi + fq, white) >> 10);
+            ire = __vimin_s32_relu(ire, 110);
+            line[x + xo] = (signed char) ire;
+        }
+    }
+}
+
+#endif // NES-RGB
+
+// =======================================================================================
 // noise pass (crt_core.c:346-367), LCG variant.  16 samples per thread, 128-bit accesses;
 // the generator state of sample i is rn0 advanced i + 1 steps, reached by two table look-ups.
 // =======================================================================================

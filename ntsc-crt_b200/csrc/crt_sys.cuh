@@ -27,6 +27,7 @@ constexpr int kPattern = CRT_CHROMA_PATTERN;
 constexpr bool kIsNes = (CRT_SYSTEM == CRT_SYSTEM_NES);
 constexpr bool kIsVhs = (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS);
 constexpr bool kIsSnes = (CRT_SYSTEM == CRT_SYSTEM_SNES);
+constexpr bool kIsNesRgb = (CRT_SYSTEM == CRT_SYSTEM_NESRGB);
 // the systems whose encoder is crt_ntsc.c / crt_ntscvhs.c (band-limited RGB, 227.5 cycles per line)
 #define CRT_B200_NTSC_FAMILY ((CRT_SYSTEM == CRT_SYSTEM_NTSC) || (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS))
 // -DCRTX_CONV=1 builds the decoder of the reference's USE_CONVOLUTION 1 configuration (an unguarded
@@ -62,8 +63,8 @@ constexpr int kBurst = BURST_LEVEL;
 constexpr int kBlack = BLACK_LEVEL;
 constexpr int kBlank = BLANK_LEVEL;
 constexpr int kSync = SYNC_LEVEL;
-#if (CRT_SYSTEM == CRT_SYSTEM_NES)
-constexpr int kNesVsyncEnd = PPUpx2pos(327); // crt_nes.c:91
+#if (CRT_SYSTEM == CRT_SYSTEM_NES) || (CRT_SYSTEM == CRT_SYSTEM_NESRGB)
+constexpr int kNesVsyncEnd = PPUpx2pos(327); // crt_nes.c:91, crt_nesrgb.c:33
 #endif
 
 // Slack after each signal buffer: the reference reads its decode windows up to one line past
@@ -131,7 +132,7 @@ static_assert(kEqYlf == 42156 && kEqYhf == 79824 && kEqIlf == 2252 && kEqIhf == 
               && kEqQlf == 2252 && kEqQhf == 28248, "equaliser fractions (SURVEY.md 8a)");
 #endif
 
-#if (CRT_SYSTEM == CRT_SYSTEM_SNES)
+#if (CRT_SYSTEM == CRT_SYSTEM_SNES) || (CRT_SYSTEM == CRT_SYSTEM_NESRGB)
 static_assert(kHres == 909 && kAvBeg == 197 && kAvLen == 682 && kCbBeg == 101 && kSyncBeg == 23 && kBwBeg == 90
               && kInputSize == 238158, "SNES timing (crt_snes.h:20-109, probed from the compiled reference)");
 #endif

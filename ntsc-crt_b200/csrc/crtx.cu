@@ -266,6 +266,13 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
         k_mod_nes<<<dim3(kNesParts, count), 256, 0, stream>>>(ctx->d_src + first, ctx->d_nes_tab, ctx->d_analog, first);
     }
     ctx->launches += 2;
+#elif (CRT_SYSTEM == CRT_SYSTEM_NESRGB)
+    {
+        LaunchTimer lt(ctx, stream, 0);
+        k_mod_nesrgb<<<dim3(kNesRgbParts, count), 256, 0, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_state,
+                                                                  ctx->d_analog, first);
+    }
+    ctx->launches += 1;
 #elif (CRT_SYSTEM == CRT_SYSTEM_SNES)
     {
         LaunchTimer lt(ctx, stream, 0);

@@ -13,7 +13,7 @@ from dataclasses import dataclass
 
 PIX_RGB, PIX_BGR, PIX_ARGB, PIX_RGBA, PIX_ABGR, PIX_BGRA = range(6)  # crt_core.h:62-67
 
-SYS_NTSC, SYS_NES, SYS_SNES, SYS_VHS = 0, 1, 3, 5  # crt_core.h:30-36
+SYS_NTSC, SYS_NES, SYS_SNES, SYS_VHS, SYS_NESRGB = 0, 1, 3, 5, 6  # crt_core.h:30-36
 
 
 def bpp4fmt(fmt):
@@ -82,6 +82,13 @@ def _snes_spec(name):
                       n.av_beg, n.av_len, n.hsync_window, n.vsync_window, 100, 20, 7, -40)
 
 
+def _nesrgb_spec(name):
+    # crt_nesrgb.h: NES layout, sync and burst levels; white at 100
+    n = _nes_spec(name, 2)
+    return SystemSpec(name, SYS_NESRGB, 2, n.hres, n.vres, n.top, n.bot, n.vper, n.sync_beg, n.bw_beg, n.cb_beg,
+                      n.av_beg, n.av_len, n.hsync_window, n.vsync_window, 100, 30, 0, -37)
+
+
 SPECS = {
     "ntsc": _rgb_spec("ntsc", SYS_NTSC),
     # the USE_CONVOLUTION 1 build of crt_core.c (line 85): same layouts and timing, FIR decoder filters
@@ -94,6 +101,7 @@ SPECS = {
     "nes": _nes_spec("nes", 2),
     "nes_p0": _nes_spec("nes_p0", 0),
     "snes": _snes_spec("snes"),
+    "nesrgb": _nesrgb_spec("nesrgb"),
 }
 
 
@@ -173,6 +181,15 @@ class SnesSettings(C.Structure):
     ]
 
 
+class NesRgbSettings(C.Structure):
+    """struct NTSC_SETTINGS, CRT_SYSTEM_NESRGB (crt_nesrgb.h)."""
+    _fields_ = [
+        ("data", C.c_void_p), ("format", C.c_int), ("w", C.c_int), ("h", C.c_int),
+        ("dot_crawl_offset", C.c_int), ("hue", C.c_int), ("xoffset", C.c_int), ("yoffset", C.c_int),
+        ("field_initialized", C.c_int),
+    ]
+
+
 class NesSettings(C.Structure):
     """struct NTSC_SETTINGS, CRT_SYSTEM_NES (crt_nes.h:132-143)."""
     _fields_ = [
@@ -184,7 +201,8 @@ class NesSettings(C.Structure):
 
 
 def settings_struct(spec):
-    return {SYS_NTSC: RgbSettings, SYS_VHS: VhsSettings, SYS_NES: NesSettings, SYS_SNES: SnesSettings}[spec.system]
+    return {SYS_NTSC: RgbSettings, SYS_VHS: VhsSettings, SYS_NES: NesSettings, SYS_SNES: SnesSettings,
+            SYS_NESRGB: NesRgbSettings}[spec.system]
 
 
 def bind_crt_api(lib, spec):

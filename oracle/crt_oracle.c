@@ -251,13 +251,23 @@ make_snes_sys(ocrt_sys *s)
     s->sync_level = -40;
 }
 
+static void
+make_nesrgb_sys(ocrt_sys *s)
+{
+    /* crt_nesrgb.h: the NES layout and sync / burst levels, white at 100 */
+    make_nes_sys(s, 2);
+    s->system = OCRT_SYS_NESRGB;
+    s->white_level = 100;
+}
+
 const ocrt_sys *
 ocrt_system(int system, int chroma_pattern)
 {
-    static ocrt_sys table[6];
+    static ocrt_sys table[7];
     static int ready = 0;
     if (!ready) {
         make_snes_sys(&table[5]);
+        make_nesrgb_sys(&table[6]);
         make_rgb_sys(&table[0], OCRT_SYS_NTSC);
         make_rgb_sys(&table[1], OCRT_SYS_VHS);
         make_nes_sys(&table[2], 0);
@@ -268,6 +278,7 @@ ocrt_system(int system, int chroma_pattern)
     if (system == OCRT_SYS_NTSC) return &table[0];
     if (system == OCRT_SYS_VHS) return &table[1];
     if (system == OCRT_SYS_SNES) return &table[5];
+    if (system == OCRT_SYS_NESRGB) return &table[6];
     if (system == OCRT_SYS_NES && chroma_pattern >= 0 && chroma_pattern <= 2)
         return &table[2 + chroma_pattern];
     return NULL;
@@ -276,12 +287,12 @@ ocrt_system(int system, int chroma_pattern)
 const ocrt_sys *
 ocrt_system_conv_taps(int system, int chroma_pattern, int taps)
 {
-    static ocrt_sys table[4][6];
-    static int ready[4][6];
+    static ocrt_sys table[4][7];
+    static int ready[4][7];
     const ocrt_sys *base = ocrt_system(system, chroma_pattern);
     int slot;
     if (!base || taps < 4 || taps > 7) return NULL;
-    slot = (system == OCRT_SYS_NTSC) ? 0 : (system == OCRT_SYS_VHS) ? 1 : (system == OCRT_SYS_SNES) ? 5 : 2 + chroma_pattern;
+    slot = (system == OCRT_SYS_NTSC) ? 0 : (system == OCRT_SYS_VHS) ? 1 : (system == OCRT_SYS_SNES) ? 5 : (system == OCRT_SYS_NESRGB) ? 6 : 2 + chroma_pattern;
     if (!ready[taps - 4][slot]) {
         table[taps - 4][slot] = *base;
         table[taps - 4][slot].conv = taps;
@@ -528,6 +539,68 @@ ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
         }
     }
     for (n = 0; n < 3; n++) /* crt_snes.c:322-326 */
+        for (x = 0; x < 4; x++) m->ccf[n][x] = primed[n][x] * 128;
+}
+
+/* ------------------------------------------------------------------------- */
+/* encoder, NES-RGB (crt_nesrgb.c:19-172)                                      */
+/* ------------------------------------------------------------------------- */
+
+void
+ocrt_encode_nesrgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_nesrgb_source *src)
+{
+    const i32 H = sys->hres;
+    i32 modI[3][4], modQ[3][4], burst[3][4], primed[3][4];
+    i32 n, x, y, xo, yo, white, bpp;
+
+    memset(primed, 0, sizeof(primed));
+    if (!src->field_initialized) { /* setup_field, crt_nesrgb.c:19-47 */
+        for (n = 0; n < sys->vres; n++) {
+            signed char *line = m->analog + n * H;
+            fill(line, 0, sys->sync_beg, sys->blank_level);
+            fill(line, sys->sync_beg, n >= 259 ? sys->nes_vsync_end : sys->bw_beg, sys->sync_level);
+            fill(line, n >= 259 ? sys->nes_vsync_end : sys->bw_beg, H, sys->blank_level);
+        }
+        src->field_initialized = 1;
+    }
+    for (y = 0; y < 3; y++) /* crt_nesrgb.c:68-79 */
+        for (x = 0; x < 4; x++) {
+            i32 deg = (y + src->dot_crawl_offset) * 120 + x * 90;
+            burst[y][x] = sin14((src->hue + 90 + deg + 33) * 8192 / 180) >> 10;
+            modI[y][x] = sin14(deg * 8192 / 180) >> 10;
+            modQ[y][x] = sin14((deg - 90) * 8192 / 180) >> 10;
+        }
+    bpp = ocrt_bpp(src->format);
+    if (bpp == 0) return; /* crt_nesrgb.c:81-84 */
+    xo = (sys->av_beg + src->xoffset) & ~3;
+    yo = sys->top + src->yoffset;
+    white = sys->white_level * m->white_point / 100;
+
+    for (y = 0; y < sys->lines; y++) { /* crt_nesrgb.c:92-164 */
+        signed char *line = m->analog + (y + yo) * H;
+        i32 row = (y * src->h) / sys->lines, t, ph = (y + yo) % 3;
+        if (row >= src->h) row = src->h;
+        if (row < 0) row = 0;
+        for (t = sys->cb_beg; t < sys->cb_beg + sys->burst_len; t++) {
+            line[t] = (signed char) ((sys->blank_level + burst[ph][t % 4] * sys->burst_level) >> 5);
+            primed[ph][t % 4] = line[t];
+        }
+        for (x = 0; x < sys->av_len; x++) {
+            const unsigned char *px = src->data + (size_t) (((x * src->w) / sys->av_len) + row * src->w) * bpp;
+            i32 r = px[fmt_r[src->format]], gg = px[fmt_g[src->format]], b = px[fmt_b[src->format]];
+            i32 fy = (19595 * r + 38470 * gg + 7471 * b) >> 14;
+            i32 fi = (39059 * r - 18022 * gg - 21103 * b) >> 14;
+            i32 fq = (13894 * r - 34275 * gg + 20382 * b) >> 14;
+            i32 xoff = (x + xo) % 4, ire;
+            fi = wmul(fi, modI[ph][xoff]) >> 4;
+            fq = wmul(fq, modQ[ph][xoff]) >> 4;
+            ire = sys->black_level + m->black_point + (wmul(fy + fi + fq, white) >> 10);
+            if (ire < 0) ire = 0;
+            if (ire > 110) ire = 110;
+            line[x + xo] = (signed char) ire;
+        }
+    }
+    for (n = 0; n < 3; n++) /* crt_nesrgb.c:166-170 */
         for (x = 0; x < 4; x++) m->ccf[n][x] = primed[n][x] * 128;
 }
 

@@ -28,6 +28,7 @@ extern "C" {
 #define OCRT_SYS_NES  1 /* crt_core.h:31 */
 #define OCRT_SYS_SNES 3 /* crt_core.h:33 */
 #define OCRT_SYS_VHS  5 /* crt_core.h:35 */
+#define OCRT_SYS_NESRGB 6 /* crt_core.h:36 */
 
 #define OCRT_MAX_VPER 3
 #define OCRT_PAD      2048 /* slack after analog/inp for the reference's over-reads */
@@ -85,6 +86,14 @@ typedef struct ocrt_nes_source {
     int field_initialized;
 } ocrt_nes_source;
 
+/* struct NTSC_SETTINGS of the NES-RGB system (crt_nesrgb.h) */
+typedef struct ocrt_nesrgb_source {
+    const unsigned char *data;
+    int format, w, h;
+    int dot_crawl_offset, hue, xoffset, yoffset;
+    int field_initialized;
+} ocrt_nesrgb_source;
+
 /* glibc TYPE_3 rand() replica (the VHS variant draws from libc rand(),
  * crt_core.c:344-351, crt_ntscvhs.c:206; glibc 2.39 stdlib/random_r.c) */
 typedef struct ocrt_rand {
@@ -120,6 +129,7 @@ void ocrt_monitor_reset(ocrt_monitor *m);
 void ocrt_encode_rgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src, ocrt_rand *g);
 void ocrt_encode_nes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_nes_source *src);
 void ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src);
+void ocrt_encode_nesrgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_nesrgb_source *src);
 
 /* crt_demodulate, and its three stages on their own */
 void ocrt_decode(const ocrt_sys *sys, ocrt_monitor *m, int noise, ocrt_rand *g);

@@ -74,6 +74,10 @@ case("snes_640x480", "snes", 640, 480, layout.PIX_BGRA, dict(blend=1, scanlines=
      ("rand", 300, 230, 4, 21),
      [(dict(format=layout.PIX_BGRA, as_color=1, raw=0, field=i & 1, frame=0, hue=(i * 50) % 360,
             dot_crawl_offset=i % 3, xoffset=4 * (i & 1), yoffset=i % 3), 3 * i) for i in range(4)])
+case("nesrgb_640x480", "nesrgb", 640, 480, layout.PIX_BGRA, dict(blend=1, scanlines=1, saturation=11),
+     ("rand", 256, 240, 4, 23),
+     [(dict(format=layout.PIX_BGRA, hue=(i * 70) % 360, dot_crawl_offset=i % 3, xoffset=4 * (i & 1), yoffset=i % 2), 2 * i)
+      for i in range(4)])
 for v in ("nes", "nes_p0"):
     case("cfg3_%s" % v, v, 832, 624, layout.PIX_BGRA, dict(blend=0, scanlines=1),
          ("nes", 256, 240, 0, 5), [(dict(dot_crawl_offset=i % 3, hue=(i * 30) % 360), 4 * i) for i in range(5)])

@@ -215,6 +215,11 @@ class _ONes(C.Structure):
         "w", "h", "dot_crawl_offset", "hue", "xoffset", "yoffset", "field_initialized")]
 
 
+class _ONesRgb(C.Structure):
+    _fields_ = [("data", C.c_void_p)] + [(n, C.c_int) for n in (
+        "format", "w", "h", "dot_crawl_offset", "hue", "xoffset", "yoffset", "field_initialized")]
+
+
 class _ORand(C.Structure):
     _fields_ = [("r", C.c_uint * 31), ("f", C.c_int), ("b", C.c_int)]
 
@@ -246,6 +251,7 @@ def oracle_lib():
                                         C.POINTER(_ORgb), C.POINTER(_ORand)]
         lib.ocrt_encode_nes.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ONes)]
         lib.ocrt_encode_snes.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ORgb)]
+        lib.ocrt_encode_nesrgb.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ONesRgb)]
         lib.ocrt_decode.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.c_int,
                                     C.POINTER(_ORand)]
         lib.ocrt_noise_pass.argtypes = lib.ocrt_decode.argtypes
@@ -283,6 +289,7 @@ class OracleEngine:
         self.lib.ocrt_rand_seed(C.byref(self.rand), seed)
         self.rgb = _ORgb()
         self.nes = _ONes()
+        self.nesrgb = _ONesRgb()
         self._img = None
 
     def __del__(self):
@@ -309,6 +316,8 @@ class OracleEngine:
         if self.spec.system == layout.SYS_NES:
             s = self.nes
             kw.pop("border_color", None)
+        elif self.spec.system == layout.SYS_NESRGB:
+            s = self.nesrgb
         else:
             s = self.rgb
             kw.pop("iirs_initialized", None)
@@ -320,6 +329,8 @@ class OracleEngine:
             self.lib.ocrt_encode_nes(self.sys, C.byref(self.mon), C.byref(s))
         elif self.spec.system == layout.SYS_SNES:
             self.lib.ocrt_encode_snes(self.sys, C.byref(self.mon), C.byref(s))
+        elif self.spec.system == layout.SYS_NESRGB:
+            self.lib.ocrt_encode_nesrgb(self.sys, C.byref(self.mon), C.byref(s))
         else:
             self.lib.ocrt_encode_rgb(self.sys, C.byref(self.mon), C.byref(s), C.byref(self.rand))
 

@@ -136,6 +136,22 @@ def test_dropin_snes(fmt, as_color, raw, outw, outh):
         check(gpu, ora, ref, "snes demod %d" % it)
 
 
+@pytest.mark.parametrize("fmt,outw,outh", [(layout.PIX_BGRA, 832, 624), (layout.PIX_RGB, 640, 480), (layout.PIX_ARGB, 333, 250),
+                                           (9, 320, 240)])
+def test_dropin_nesrgb(fmt, outw, outh):
+    """CRT_SYSTEM_NESRGB (crt_nesrgb.c:19-172) through the drop-in interface (format 9: unknown)."""
+    rgb = S.rand_image(256, 240, bpp=3, seed=3)
+    img = S.pack_rgb(rgb, fmt) if fmt != 9 else S.pack_rgb(rgb, layout.PIX_BGRA)
+    gpu, ora, ref = trio("nesrgb", outw, outh)
+    run_all((gpu, ora, ref), lambda e: e.set(blend=1, scanlines=1, saturation=11, black_point=1, white_point=97))
+    for it in range(4):
+        run_all((gpu, ora, ref), lambda e: e.modulate(img, format=fmt, hue=(it * 70) % 360, dot_crawl_offset=it % 3,
+                                                      xoffset=4 * (it & 1), yoffset=it % 2))
+        check(gpu, ora, ref, "nesrgb mod %d" % it)
+        run_all((gpu, ora, ref), lambda e: e.demodulate(0 if it < 2 else 7))
+        check(gpu, ora, ref, "nesrgb demod %d" % it)
+
+
 def test_batch_snes_matches_oracle():
     import torch
     from ntsc_crt_b200 import capi

@@ -32,7 +32,7 @@ def check(ref, ora, what):
 
 
 def test_struct_layout_matches_reference():
-    for variant in ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "snes"):
+    for variant in ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "snes", "nesrgb"):
         spec = layout.system_spec(variant)
         lib = C.CDLL(S.ref_path(variant))
         assert lib.ref_sizeof_crt() == C.sizeof(layout.crt_struct(spec)), variant
@@ -225,6 +225,22 @@ def test_snes(fmt, as_color, raw):
         check(ref, ora, "snes mod %d" % it)
         both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 9))
         check(ref, ora, "snes demod %d" % it)
+
+
+@pytest.mark.parametrize("fmt", [layout.PIX_BGRA, layout.PIX_RGB, layout.PIX_ARGB, 9])
+def test_nesrgb(fmt):
+    """CRT_SYSTEM_NESRGB (crt_nesrgb.c): the NES sync template and burst cycle around an RGB picture.
+    Format 9 is unknown: the first call still writes the template, nothing else happens."""
+    rgb = S.rand_image(256, 240, bpp=3, seed=3)
+    img = S.pack_rgb(rgb, fmt) if fmt != 9 else S.pack_rgb(rgb, layout.PIX_BGRA)
+    ref, ora = pair("nesrgb", 640, 480)
+    both(ref, ora, lambda e: e.set(blend=0, scanlines=1, saturation=11, black_point=1, white_point=97))
+    for it in range(4):
+        both(ref, ora, lambda e: e.modulate(img, format=fmt, hue=(it * 70) % 360, dot_crawl_offset=it % 3,
+                                            xoffset=4 * (it & 1), yoffset=it % 2))
+        check(ref, ora, "nesrgb mod %d" % it)
+        both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 7))
+        check(ref, ora, "nesrgb demod %d" % it)
 
 
 @pytest.mark.parametrize("variant", ["nes", "nes_p0"])
