@@ -24,7 +24,12 @@ constexpr int kHeadBefore = 16;                 // staged bytes before each line
 constexpr int kHeadAfter = ((kCbBeg + kBurstLen + 40 + 15) / 16) * 16; // ... and after it
 constexpr int kHeadWords = (kHeadBefore + kHeadAfter) / 4 + 1;        // +1: start is aligned down to 4
 constexpr int kCandWords = (kHres + 3) / 4 + 1;                     // a whole line from a 4-aligned start
-constexpr int kSyncSmem = (kVres * kHeadWords + 2 * kVsyncWindow * kCandWords) * 4;
+// One head more than there are signal lines: with hsync in the second half of a line (the steady state of the
+// NTSC timing, ~898) the search window of the LAST signal line sits on the start of the line after it.  Those
+// bytes are the padding after inp[] (the reference reads past its array there); staging them keeps that one
+// line off the 16-dependent-loads fall-back, which used to hold every sweep's barrier for ~5 us.
+constexpr int kHeadLines = kVres + 1;
+constexpr int kSyncSmem = (kHeadLines * kHeadWords + 2 * kVsyncWindow * kCandWords) * 4;
 constexpr int kSyncThreads = 256;
 
 struct SyncLine { // what depends only on k, vsync and the detected field (not on the chains)
@@ -55,7 +60,7 @@ __device__ __forceinline__ int hsync_step(const unsigned *heads, FetchByte fetch
     const int j = (hs > kHres / 2) ? jl + 1 : jl;             // line whose staged head holds the window
     const int off = p0 - ((j * kHres - kHeadBefore) & ~3);
     int i = 2 * kHsyncWindow, acc = 0;
-    if (j < kVres && off >= 0 && off + 2 * kHsyncWindow <= kHeadWords * 4) {
+    if (j < kHeadLines && off >= 0 && off + 2 * kHsyncWindow <= kHeadWords * 4) {
         const signed char *hb = reinterpret_cast<const signed char *>(heads + j * kHeadWords) + off;
 #pragma unroll
         for (int t = 0; t < 2 * kHsyncWindow; t++) {
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
                                                        const Affine *__restrict__ jump_hi, int first,
                                                        int force_generic)
 {
-    extern __shared__ __align__(16) unsigned heads[]; // [kVres][kHeadWords]
+    extern __shared__ __align__(16) unsigned heads[]; // [kHeadLines][kHeadWords]
     __shared__ SyncShared sh;
     const int m = first + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const MonCfg cfg = cfgs[m];
@@ -145,11 +150,11 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
     // vsync candidate lines in full (cand[c][w] = aligned words covering line posmod(vsync + c - W)).
     // All loads of a batch are issued before any is stored, so the copy runs at memory-level parallelism
     // instead of one L2 round trip per word.
-    unsigned *cand = heads + kVres * kHeadWords; // [2W][kCandWords]
+    unsigned *cand = heads + kHeadLines * kHeadWords; // [2W][kCandWords]
     const int vs_in = st->vsync;
     {
         constexpr int kBatch = 8;
-        constexpr int kHeadTotal = kVres * kHeadWords, kCandTotal = 2 * kVsyncWindow * kCandWords;
+        constexpr int kHeadTotal = kHeadLines * kHeadWords, kCandTotal = 2 * kVsyncWindow * kCandWords;
         const signed char *from = FUSED ? analog : inp;
         for (int base = 0; base < kHeadTotal + kCandTotal; base += kBatch * kSyncThreads) {
             unsigned v[kBatch];
@@ -270,7 +275,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
             const int p = jl * kHres + (hs & ~3) + kCbBeg + t;
             const int j = (hs > kHres / 2) ? jl + 1 : jl;
             const int off = p - ((j * kHres - kHeadBefore) & ~3);
-            if (j < kVres && off >= 0 && off < kHeadWords * 4)
+            if (j < kHeadLines && off >= 0 && off < kHeadWords * 4)
                 v = (int) (signed char) (heads[j * kHeadWords + (off >> 2)] >> (8 * (off & 3)));
             else
                 v = fetch_byte(p);
