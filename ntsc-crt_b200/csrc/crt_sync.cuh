@@ -231,11 +231,19 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
         sh.hs[k] = hs_in; // initial guess of the chain
     }
     __syncthreads();
-    if (tid < kVper) { // decoded lines of each colour row, in order (skipped lines do not touch ccf)
+    // Decoded lines of each colour row, in order (skipped lines do not touch ccf).  Warp r compacts row r
+    // with ballots, 32 lines per step -- a 240-iteration loop on one thread per row here made every other
+    // thread wait ~13 % of the kernel at the next barrier.
+    if (warp < kVper) {
         int n = 0;
-        for (int k = 0; k < kLines; k++)
-            if (sh.ln[k].beg >= 0 && sh.ln[k].row == tid) sh.rowlist[tid][n++] = (short) k;
-        sh.rowcount[tid] = n;
+        for (int k0 = 0; k0 < kLines; k0 += 32) {
+            const int k = k0 + lane;
+            const bool mine = (k < kLines) && sh.ln[k].beg >= 0 && sh.ln[k].row == warp;
+            const unsigned m = __ballot_sync(0xffffffffu, mine);
+            if (mine) sh.rowlist[warp][n + __popc(m & ((1u << lane) - 1u))] = (short) k;
+            n += __popc(m);
+        }
+        if (lane == 0) sh.rowcount[warp] = n;
     }
 
     // ---- 3a. hsync chain hs[k] = f_k(hs[k-1]) (crt_core.c:437-450) by verified speculation: every line
