@@ -131,7 +131,7 @@ int crtx_get_timing(crtx_ctx *ctx, float *ms /* [CRTX_NUM_KERNELS] */, long *lau
 /* diagnostics */
 int crtx_get_lines(crtx_ctx *ctx, int i, crtx_line *table /* crtx_lines() entries */, void *stream);
 long crtx_launch_count(crtx_ctx *ctx); /* kernels launched through this context so far */
-/* options: "tma", "generic_eq", "timing", "mod_staged", "fused_noise" (0/1 switches), "host_src" (1:
+/* options: "tma", "generic_eq", "timing", "mod_staged", "fused_noise", "mod_bulk" (0/1 switches), "host_src" (1:
  * crtx_frames_host lets the encoder read page-locked source images in place instead of copying them), and
  * "line_lo" / "line_hi": crtx_demodulate's line pass only decodes scanlines [line_lo, line_hi) of every
  * field (sync search and noise still cover the whole field).  This is the scanline-block partition of

@@ -133,6 +133,15 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
         : "memory");
 }
 
+// 16-byte asynchronous copies global -> shared issued per lane (LDGSTS): the right tool when every lane
+// fetches its own small span -- a per-lane bulk copy is a warp-serial instruction (one issue per lane)
+__device__ __forceinline__ void cp_async_16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
 // =======================================================================================
 // encoder, RGB systems
 // =======================================================================================
@@ -441,7 +450,7 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
     const int y0 = warp * 32;
     if (y0 >= desth) return;
     const int nlines = min(32, desth - y0);
-    if (use_tma) {
+    if (use_tma == 1) {
         if (lane == 0) {
             mbar_init(&bars[0], 1);
             mbar_init(&bars[1], 1);
@@ -496,7 +505,14 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
         const int a = (int) (reinterpret_cast<uintptr_t>(p) & 15);
         const unsigned copy = (unsigned) ((a + bytes + 15) & ~15);
         unsigned char *dst = stage + (c & 1) * 32 * kModSRow + lane * kModSRow;
-        if (use_tma) {
+        if (use_tma == 2) { // per-lane 16-byte asynchronous copies, one group per chunk
+            if (active) {
+#pragma unroll
+                for (unsigned q = 0; q < kModSRow / 16; q++)
+                    if (q * 16 < copy) cp_async_16(dst + q * 16, p - a + q * 16);
+            }
+            cp_async_commit();
+        } else if (use_tma) {
             // rows may sit at different 16-byte phases, so the copies differ in size: sum them up
             unsigned total = active ? copy : 0;
 #pragma unroll
@@ -525,7 +541,12 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
         const int nx = min(kModSChunk, destw - c0);
         coltab[lane] = (col_cur - f0) * bpp; // byte offset of sample x's pixel from the chunk's first pixel
         col_cur = col_nxt;
-        if (use_tma) mbar_wait(&bars[c & 1], (c >> 1) & 1);
+        if (use_tma == 2) { // this lane's own row: everything but the chunk just requested has landed
+            if (c + 1 < nchunks) cp_async_wait<1>();
+            else cp_async_wait<0>();
+        } else if (use_tma) {
+            mbar_wait(&bars[c & 1], (c >> 1) & 1);
+        }
         __syncwarp();
         const unsigned char *srow = stage + (c & 1) * 32 * kModSRow + lane * kModSRow
                                   + (int) (reinterpret_cast<uintptr_t>(rowp + (size_t) f0 * bpp) & 15);

@@ -127,8 +127,10 @@ static void launch_mod_staged_one(crtx_ctx *ctx, int count, int first, cudaStrea
         cudaFuncSetAttribute(k_mod_picture_rgb_staged<FMT, COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSSmem);
         attr_done = true;
     }
+    // staging: 1 = per-lane bulk copies (default), 2 = per-lane cp.async copies ("mod_bulk" 0), 0 = plain loads
+    const int staging = ctx->opt_tma ? (ctx->opt_mod_bulk ? 1 : 2) : 0;
     k_mod_picture_rgb_staged<FMT, COLOR><<<count, 256, kModSSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog,
-                                                                            first, ctx->opt_tma);
+                                                                            first, staging);
 }
 
 static void launch_mod_staged(crtx_ctx *ctx, int format, bool color, int count, int first, cudaStream_t stream)
@@ -882,6 +884,7 @@ int crtx_set_option(crtx_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "mod_staged")) ctx->opt_mod_staged = value;
     else if (!strcmp(name, "fused_noise")) ctx->opt_fused_noise = value;
     else if (!strcmp(name, "host_src")) ctx->opt_host_src = value;
+    else if (!strcmp(name, "mod_bulk")) ctx->opt_mod_bulk = value;
     else if (!strcmp(name, "line_lo")) ctx->opt_line_lo = value;
     else if (!strcmp(name, "line_hi")) ctx->opt_line_hi = value;
     else return fail("crtx_set_option: unknown option '%s'", name);

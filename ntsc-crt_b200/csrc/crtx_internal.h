@@ -40,6 +40,7 @@ struct crtx_ctx {
     int opt_timing = 0;
     int opt_mod_staged = 1;
     int opt_fused_noise = 1;
+    int opt_mod_bulk = 1; // encoder staging: 1 = per-lane bulk copies, 0 = per-lane cp.async (A/B switch; measured equal)
     int opt_host_src = 0; // crtx_frames_host: read page-locked source images in place
     int opt_line_lo = 0, opt_line_hi = 1 << 30; // decoded-line window of the line pass (crtx_set_option)
     struct Timed {
