@@ -116,8 +116,7 @@ __device__ __forceinline__ int fir_push(FirChan &f, int x)
 
 // what a warp keeps of a line record
 struct FirLine {
-    int pos, wave0, wave1, beg, end;
-    bool active;
+    int pos, wave0, wave1, beg, end, run_pos, run_last, index;
 };
 
 // Grid: (CTAs per monitor, monitors).  Warp w of CTA x decodes lines (x + n * gridDim.x) * kFirWarps + w,
@@ -137,17 +136,23 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
     const LineRec *recs = lines_base + (size_t) m * kLines;
     const int stride = (int) gridDim.x * kFirWarps;
 
+    // A record is fetched two lines before it is decoded and must not be LOOKED AT before it is needed:
+    // deciding "active" at fetch time made every line wait for this load (5 % of the kernel's samples).
     auto fetch = [&](int kl) -> FirLine { // warp-uniform
         FirLine l;
-        l.pos = l.wave0 = l.wave1 = 0;
+        l.pos = l.wave0 = l.wave1 = l.run_pos = l.run_last = 0;
         l.beg = l.end = -1;
-        l.active = false;
+        l.index = kl;
         if (kl < kLines) {
             const LineRec r = recs[kl];
             l.pos = r.pos; l.wave0 = r.wave0; l.wave1 = r.wave1; l.beg = r.beg; l.end = r.end;
-            l.active = r.beg >= 0 && kl >= geo.line_lo && kl < geo.line_hi && (geo.pass == -1 || (geo.pass == -2 ? r.pad1 != 0 : r.pad0 == geo.pass));
+            l.run_pos = r.pad0; l.run_last = r.pad1;
         }
         return l;
+    };
+    auto is_active = [&](const FirLine &l) -> bool {
+        return l.index < kLines && l.beg >= 0 && l.index >= geo.line_lo && l.index < geo.line_hi
+            && (geo.pass == -1 || (geo.pass == -2 ? l.run_last != 0 : l.run_pos == geo.pass));
     };
 
     // everything the first line needs from global memory, requested together
@@ -222,7 +227,7 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
         tab_k0 = 0;
     }
 
-    if (geo.use_tma && lane == 0 && cur.active) {
+    if (geo.use_tma && lane == 0 && is_active(cur)) {
         request_signal(cur, 0);
         if (prefetch_old) request_old(cur, 0, 0, seg0);
     }
@@ -231,10 +236,11 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
     for (int it = 0; kline < kLines; it++, kline += stride) {
         const int buf = it & 1;
         // line n + 1's signal window and line n + 2's record
-        if (geo.use_tma && lane == 0 && nxt.active) request_signal(nxt, buf ^ 1);
+        const bool nxt_active = is_active(nxt); // (fetched a whole line ago)
+        if (geo.use_tma && lane == 0 && nxt_active) request_signal(nxt, buf ^ 1);
         const FirLine nn = fetch(kline + 2 * stride);
 
-        if (cur.active) {
+        if (is_active(cur)) {
             unsigned char *sigbuf = stage + buf * kFirStage;
             const int a = cur.pos & 15;
             const int nrows = max(1, cur.end - scanlines - cur.beg); // crt_core.c:662-664
@@ -297,7 +303,7 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
             // now receive the previous image's row of the NEXT line, which in turn has the pixel pass to arrive.
             if (bulk && lane == 0) {
                 tma_store_wait_read<0>();
-                if (prefetch_old && nxt.active) request_old(nxt, buf ^ 1, 0, seg0);
+                if (prefetch_old && nxt_active) request_old(nxt, buf ^ 1, 0, seg0);
             }
 
             // ---- (P) pixels (crt_core.c:555-659), 32 consecutive ones per step
@@ -401,7 +407,7 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
                 }
             }
             __syncwarp(); // every lane is done with the Y/I/Q rows before the next line's filter pass rewrites them
-        } else if (prefetch_old && lane == 0 && nxt.active) {
+        } else if (prefetch_old && lane == 0 && nxt_active) {
             // nothing was requested during this (skipped) line: the other row buffer's last reader is the
             // line before it
             tma_store_wait_read<0>();
