@@ -173,18 +173,51 @@ def _cpu_worker(fields):
 
 
 def cpu_baseline_single(seconds=8.0):
-    """Reference C path, ONE thread, on a bounded sample of the same workload."""
+    """Reference C path, ONE thread pinned to one core, on a bounded sample of the same workload:
+    20 warm-up fields, then at least 200 fields; crt_modulate and crt_demodulate are also timed separately
+    (medians, file I/O does not exist here)."""
+    import statistics
     import pkgload
     pkgload.load()
+    from ntsc_crt_b200 import layout
     kind, _ = _cpu_engine()
-    _cpu_worker(4)  # warm-up
-    fields, spent = 0, 0.0
-    while spent < seconds:
-        spent += _cpu_worker(32)
-        fields += 32
+    pinned = None
+    try:  # like `taskset -c`: keep the scheduler from migrating the measurement
+        allowed = sorted(os.sched_getaffinity(0))
+        pinned = allowed[len(allowed) // 2]
+        os.sched_setaffinity(0, {pinned})
+    except (AttributeError, OSError):
+        allowed = None
+    try:
+        _cpu_worker(20)  # warm-up
+        eng, img = _WORKER["eng"], _WORKER["img"]
+        t_mod, t_dem = [], []
+        fields, spent = 0, 0.0
+        while spent < seconds or fields < 200:
+            f = _WORKER["f"]
+            t0 = time.perf_counter()
+            if VARIANT == "nesrgb":
+                eng.modulate(img, format=layout.PIX_BGRA, dot_crawl_offset=f & 1, hue=0)
+            elif not VARIANT.startswith("nes"):
+                eng.modulate(img, format=layout.PIX_BGRA, as_color=1, field=f & 1, frame=(f >> 1) & 1)
+            else:
+                eng.modulate(img, dot_crawl_offset=f & 1, hue=0)
+            t1 = time.perf_counter()
+            eng.demodulate(24 if VARIANT == "vhs" else 0)
+            t2 = time.perf_counter()
+            _WORKER["f"] = f + 1
+            t_mod.append(t1 - t0)
+            t_dem.append(t2 - t1)
+            spent += t2 - t0
+            fields += 1
+    finally:
+        if allowed is not None:
+            os.sched_setaffinity(0, set(allowed))
     return {"value": fields / spent, "unit": "frames/s", "cores": 1, "kind": kind,
-            "sample": "%d fields of the bench workload (832x624 NTSC, noise 0, blend 1), 1 thread, %.1f s"
-                      % (fields, spent), "host_cores": os.cpu_count()}
+            "sample": "%d fields of the bench workload (832x624 NTSC, noise 0, blend 1), 1 thread%s, %.1f s"
+                      % (fields, " pinned to cpu %d" % pinned if pinned is not None else "", spent),
+            "modulate_ms_median": 1e3 * statistics.median(t_mod), "demodulate_ms_median": 1e3 * statistics.median(t_dem),
+            "host_cores": os.cpu_count()}
 
 
 def run_reference(args):
