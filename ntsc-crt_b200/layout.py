@@ -13,7 +13,7 @@ from dataclasses import dataclass
 
 PIX_RGB, PIX_BGR, PIX_ARGB, PIX_RGBA, PIX_ABGR, PIX_BGRA = range(6)  # crt_core.h:62-67
 
-SYS_NTSC, SYS_NES, SYS_SNES, SYS_VHS, SYS_NESRGB = 0, 1, 3, 5, 6  # crt_core.h:30-36
+SYS_NTSC, SYS_NES, SYS_SNES, SYS_TEMP, SYS_VHS, SYS_NESRGB = 0, 1, 3, 4, 5, 6  # crt_core.h:30-36
 
 
 def bpp4fmt(fmt):
@@ -102,6 +102,11 @@ SPECS = {
     "nes_p0": _nes_spec("nes_p0", 0),
     "snes": _snes_spec("snes"),
     "nesrgb": _nesrgb_spec("nesrgb"),
+    # crt_template.h (reference-side only so far: used to pin the oracle ahead of a product library)
+    "template": SystemSpec("template", SYS_TEMP, 1, *(lambda n: (n.hres, n.vres, n.top, n.bot, 2, n.sync_beg, n.bw_beg,
+                                                                  n.cb_beg, n.av_beg, n.av_len, n.hsync_window,
+                                                                  n.vsync_window, n.white, n.burst, n.black, n.sync))(
+        _rgb_spec("template", SYS_NTSC))),
 }
 
 
@@ -201,7 +206,7 @@ class NesSettings(C.Structure):
 
 
 def settings_struct(spec):
-    return {SYS_NTSC: RgbSettings, SYS_VHS: VhsSettings, SYS_NES: NesSettings, SYS_SNES: SnesSettings,
+    return {SYS_NTSC: RgbSettings, SYS_VHS: VhsSettings, SYS_NES: NesSettings, SYS_SNES: SnesSettings, SYS_TEMP: SnesSettings,
             SYS_NESRGB: NesRgbSettings}[spec.system]
 
 

@@ -252,6 +252,16 @@ make_snes_sys(ocrt_sys *s)
 }
 
 static void
+make_template_sys(ocrt_sys *s)
+{
+    /* crt_template.h: the composite NTSC timing and band-limit of crt_ntsc.h with CRT_CC_VPER 2 */
+    make_rgb_sys(s, OCRT_SYS_NTSC);
+    s->system = OCRT_SYS_TEMP;
+    s->chroma_pattern = 1;
+    s->cc_vper = 2;
+}
+
+static void
 make_nesrgb_sys(ocrt_sys *s)
 {
     /* crt_nesrgb.h: the NES layout and sync / burst levels, white at 100 */
@@ -263,11 +273,12 @@ make_nesrgb_sys(ocrt_sys *s)
 const ocrt_sys *
 ocrt_system(int system, int chroma_pattern)
 {
-    static ocrt_sys table[7];
+    static ocrt_sys table[8];
     static int ready = 0;
     if (!ready) {
         make_snes_sys(&table[5]);
         make_nesrgb_sys(&table[6]);
+        make_template_sys(&table[7]);
         make_rgb_sys(&table[0], OCRT_SYS_NTSC);
         make_rgb_sys(&table[1], OCRT_SYS_VHS);
         make_nes_sys(&table[2], 0);
@@ -279,6 +290,7 @@ ocrt_system(int system, int chroma_pattern)
     if (system == OCRT_SYS_VHS) return &table[1];
     if (system == OCRT_SYS_SNES) return &table[5];
     if (system == OCRT_SYS_NESRGB) return &table[6];
+    if (system == OCRT_SYS_TEMP) return &table[7];
     if (system == OCRT_SYS_NES && chroma_pattern >= 0 && chroma_pattern <= 2)
         return &table[2 + chroma_pattern];
     return NULL;
@@ -287,12 +299,12 @@ ocrt_system(int system, int chroma_pattern)
 const ocrt_sys *
 ocrt_system_conv_taps(int system, int chroma_pattern, int taps)
 {
-    static ocrt_sys table[4][7];
-    static int ready[4][7];
+    static ocrt_sys table[4][8];
+    static int ready[4][8];
     const ocrt_sys *base = ocrt_system(system, chroma_pattern);
     int slot;
     if (!base || taps < 4 || taps > 7) return NULL;
-    slot = (system == OCRT_SYS_NTSC) ? 0 : (system == OCRT_SYS_VHS) ? 1 : (system == OCRT_SYS_SNES) ? 5 : (system == OCRT_SYS_NESRGB) ? 6 : 2 + chroma_pattern;
+    slot = (system == OCRT_SYS_NTSC) ? 0 : (system == OCRT_SYS_VHS) ? 1 : (system == OCRT_SYS_SNES) ? 5 : (system == OCRT_SYS_NESRGB) ? 6 : (system == OCRT_SYS_TEMP) ? 7 : 2 + chroma_pattern;
     if (!ready[taps - 4][slot]) {
         table[taps - 4][slot] = *base;
         table[taps - 4][slot].conv = taps;
@@ -463,10 +475,14 @@ ocrt_encode_rgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src, ocrt
 /* encoder, SNES (crt_snes.c:125-327)                                          */
 /* ------------------------------------------------------------------------- */
 
-void
-ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
+/* crt_snes.c and crt_template.c are one encoder with three switches: the burst's hue offset (HUE_OFFSET),
+ * the band-limit (CRT_DO_BANDLIMITING) and whether the field parity shapes the vertical sync and the source
+ * row (crt_template.c:217-225, 252-258). */
+static void
+encode_template_family(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src, i32 hue_offset, int bandlimit,
+                       int fielded)
 {
-    const i32 H = sys->hres;
+    const i32 H = sys->hres, V = sys->cc_vper;
     i32 bpp = ocrt_bpp(src->format);
     i32 destw = sys->av_len, desth = (sys->lines * 64500) >> 16;
     i32 modI[3][4], modQ[3][4], burst[3][4], primed[3][4];
@@ -476,14 +492,14 @@ ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
         destw = src->w < sys->av_len ? src->w : sys->av_len;
         desth = src->h < desth ? src->h : desth;
     }
-    for (y = 0; y < 3; y++) /* crt_snes.c:170-187 */
+    for (y = 0; y < V; y++) /* crt_snes.c:170-187 */
         for (x = 0; x < 4; x++) {
-            i32 step = 360 / 4, deg = (y + src->dot_crawl_offset) * (360 / 3) + src->hue + x * step;
+            i32 step = 360 / 4, deg = (y + src->dot_crawl_offset) * (360 / V) + src->hue + x * step;
             burst[y][x] = modI[y][x] = modQ[y][x] = 0;
             if (src->as_color) {
-                burst[y][x] = sin14((deg - step + 210) * 8192 / 180) >> 10; /* HUE_OFFSET */
+                burst[y][x] = sin14((deg - step + hue_offset) * 8192 / 180) >> 10; /* HUE_OFFSET */
                 modI[y][x] = sin14(deg * 8192 / 180) >> 10;
-                modQ[y][x] = sin14((deg - 90) * 8192 / 180) >> 10;          /* Q_OFFSET */
+                modQ[y][x] = sin14((deg - 90) * 8192 / 180) >> 10;                 /* Q_OFFSET */
             }
         }
     if (bpp == 0) return; /* crt_snes.c:189-192 */
@@ -502,8 +518,9 @@ ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
             fill(line, 50 * H / 100, 54 * H / 100, sys->sync_level);
             fill(line, 54 * H / 100, H, sys->blank_level);
         } else if (n >= 3 && n <= 6) {
-            fill(line, 0, 46 * H / 100, sys->sync_level);
-            fill(line, 46 * H / 100, 50 * H / 100, sys->blank_level);
+            i32 first = (fielded && src->field == 1) ? 4 : 46; /* crt_template.c:220-225 */
+            fill(line, 0, first * H / 100, sys->sync_level);
+            fill(line, first * H / 100, 50 * H / 100, sys->blank_level);
             fill(line, 50 * H / 100, 96 * H / 100, sys->sync_level);
             fill(line, 96 * H / 100, H, sys->blank_level);
         } else {
@@ -513,15 +530,17 @@ ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
             fill(line, sys->bw_beg, sys->av_beg, sys->blank_level);
             if (n < sys->top) fill(line, sys->av_beg, H, sys->blank_level);
             for (t = sys->cb_beg; t < sys->cb_beg + sys->burst_len; t++) {
-                line[t] = (signed char) ((sys->blank_level + burst[n % 3][t % 4] * sys->burst_level) >> 5);
-                primed[(n + 3) % 3][t % 4] = line[t];
+                line[t] = (signed char) ((sys->blank_level + burst[n % V][t % 4] * sys->burst_level) >> 5);
+                primed[(n + 3) % V][t % 4] = line[t];
             }
         }
     }
 
     white = sys->white_level * m->white_point / 100;
-    for (y = 0; y < desth; y++) { /* crt_snes.c:252-320; CRT_DO_BANDLIMITING 0: iirf() is the identity */
-        i32 row = (y * src->h) / desth, ph = (y + yo) % 3;
+    for (y = 0; y < desth; y++) { /* crt_snes.c:252-320 */
+        i32 hy = 0, hi = 0, hq = 0; /* reset_iir per line */
+        i32 row = (y * src->h) / desth, ph = (y + yo) % V;
+        if (fielded) row += (src->field * src->h + desth) / desth / 2; /* crt_template.c:255-258 */
         if (row >= src->h) row = src->h;
         for (x = 0; x < destw; x++) {
             const unsigned char *px = src->data + (size_t) (((x * src->w) / destw) + row * src->w) * bpp;
@@ -530,6 +549,14 @@ ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
             i32 fi = (39059 * r - 18022 * gg - 21103 * b) >> 14;
             i32 fq = (13894 * r - 34275 * gg + 20382 * b) >> 14;
             i32 xoff = (x + xo) % 4, ire;
+            if (bandlimit) { /* iirf, crt_template.c:117-126 (CRT_DO_BANDLIMITING 1) */
+                hy += wmul(fy - hy, sys->iir_c[0]) >> 11;
+                hi += wmul(fi - hi, sys->iir_c[1]) >> 11;
+                hq += wmul(fq - hq, sys->iir_c[2]) >> 11;
+                fy = hy;
+                fi = hi;
+                fq = hq;
+            }
             fi = wmul(fi, modI[ph][xoff]) >> 4;
             fq = wmul(fq, modQ[ph][xoff]) >> 4;
             ire = sys->black_level + m->black_point + (wmul(fy + fi + fq, white) >> 10);
@@ -538,8 +565,22 @@ ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
             m->analog[(x + xo) + (y + yo) * H] = (signed char) ire;
         }
     }
-    for (n = 0; n < 3; n++) /* crt_snes.c:322-326 */
+    for (n = 0; n < V; n++) /* crt_snes.c:322-326 */
         for (x = 0; x < 4; x++) m->ccf[n][x] = primed[n][x] * 128;
+}
+
+void
+ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
+{
+    encode_template_family(sys, m, src, 210, 0, 0); /* crt_snes.h:84, 99 */
+}
+
+/* crt_template.c:125-337: the reference's worked example for new systems -- NTSC timing with a 2-line
+ * chroma cycle, band-limited (crt_template.h:52, 68) */
+void
+ocrt_encode_template(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
+{
+    encode_template_family(sys, m, src, -60, 1, 1);
 }
 
 /* ------------------------------------------------------------------------- */

@@ -27,6 +27,7 @@ extern "C" {
 #define OCRT_SYS_NTSC 0 /* crt_core.h:30 */
 #define OCRT_SYS_NES  1 /* crt_core.h:31 */
 #define OCRT_SYS_SNES 3 /* crt_core.h:33 */
+#define OCRT_SYS_TEMP 4 /* crt_core.h:34 */
 #define OCRT_SYS_VHS  5 /* crt_core.h:35 */
 #define OCRT_SYS_NESRGB 6 /* crt_core.h:36 */
 
@@ -75,7 +76,7 @@ typedef struct ocrt_rgb_source {
     const unsigned char *data;
     int format, w, h, raw, as_color, field, frame, hue, xoffset, yoffset;
     int do_aberration;    /* VHS only */
-    int dot_crawl_offset; /* SNES only (crt_snes.h:121) */
+    int dot_crawl_offset; /* SNES and template systems (crt_snes.h:121, crt_template.h) */
 } ocrt_rgb_source;
 
 /* struct NTSC_SETTINGS of the NES system (crt_nes.h:132-143) */
@@ -129,6 +130,7 @@ void ocrt_monitor_reset(ocrt_monitor *m);
 void ocrt_encode_rgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src, ocrt_rand *g);
 void ocrt_encode_nes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_nes_source *src);
 void ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src);
+void ocrt_encode_template(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src);
 void ocrt_encode_nesrgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_nesrgb_source *src);
 
 /* crt_demodulate, and its three stages on their own */

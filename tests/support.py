@@ -252,6 +252,7 @@ def oracle_lib():
         lib.ocrt_encode_nes.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ONes)]
         lib.ocrt_encode_snes.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ORgb)]
         lib.ocrt_encode_nesrgb.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ONesRgb)]
+        lib.ocrt_encode_template.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ORgb)]
         lib.ocrt_decode.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.c_int,
                                     C.POINTER(_ORand)]
         lib.ocrt_noise_pass.argtypes = lib.ocrt_decode.argtypes
@@ -331,6 +332,8 @@ class OracleEngine:
             self.lib.ocrt_encode_snes(self.sys, C.byref(self.mon), C.byref(s))
         elif self.spec.system == layout.SYS_NESRGB:
             self.lib.ocrt_encode_nesrgb(self.sys, C.byref(self.mon), C.byref(s))
+        elif self.spec.system == layout.SYS_TEMP:
+            self.lib.ocrt_encode_template(self.sys, C.byref(self.mon), C.byref(s))
         else:
             self.lib.ocrt_encode_rgb(self.sys, C.byref(self.mon), C.byref(s), C.byref(self.rand))
 

@@ -32,7 +32,7 @@ def check(ref, ora, what):
 
 
 def test_struct_layout_matches_reference():
-    for variant in ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "snes", "nesrgb"):
+    for variant in ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "snes", "nesrgb", "template"):
         spec = layout.system_spec(variant)
         lib = C.CDLL(S.ref_path(variant))
         assert lib.ref_sizeof_crt() == C.sizeof(layout.crt_struct(spec)), variant
@@ -225,6 +225,25 @@ def test_snes(fmt, as_color, raw):
         check(ref, ora, "snes mod %d" % it)
         both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 9))
         check(ref, ora, "snes demod %d" % it)
+
+
+@pytest.mark.parametrize("fmt,as_color,raw", [(layout.PIX_BGRA, 1, 0), (layout.PIX_BGR, 1, 0), (layout.PIX_RGBA, 0, 0),
+                                              (layout.PIX_ABGR, 1, 1)])
+def test_template_system(fmt, as_color, raw):
+    """CRT_SYSTEM_TEMP (crt_template.c), the reference's worked example for new systems: NTSC timing, 2-line
+    chroma cycle with dot crawl, band-limited, field-dependent sync and source rows.  No product library yet
+    (SURVEY 8f-3): this pins the oracle ahead of it."""
+    rgb = S.rand_image(300 if not raw else 200, 260 if not raw else 180, bpp=3, seed=fmt)
+    img = S.pack_rgb(rgb, fmt)
+    ref, ora = pair("template", 640, 480)
+    both(ref, ora, lambda e: e.set(blend=1, scanlines=1, hue=-15, saturation=12, black_point=2, white_point=95))
+    for it in range(6):
+        both(ref, ora, lambda e: e.modulate(img, format=fmt, as_color=as_color, raw=raw, field=it & 1 if not raw else 0,
+                                            frame=(it >> 1) & 1, hue=(it * 50) % 360, dot_crawl_offset=it % 4,
+                                            xoffset=4 * (it & 1), yoffset=it % 3))
+        check(ref, ora, "template mod %d" % it)
+        both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 9))
+        check(ref, ora, "template demod %d" % it)
 
 
 @pytest.mark.parametrize("fmt", [layout.PIX_BGRA, layout.PIX_RGB, layout.PIX_ARGB, 9])
