@@ -57,9 +57,13 @@ def frame_parity(f, progressive=False):
 
 class VideoConverter:
     def __init__(self, variant="ntsc", outw=640, outh=480, noise=12, scanlines=1, as_color=1,
-                 progressive=False, segments=64, fmt=layout.PIX_BGRA, saturation=10):
+                 progressive=False, segments=64, fmt=layout.PIX_BGRA, saturation=10, batch_factory=None):
+        """batch_factory(variant, n) -> an object with capi.Batch's interface (default: capi.Batch itself, the CUDA
+        library).  The CPU test-suite injects an oracle-backed stand-in to exercise the scheduling logic below
+        (tests/mock_batch.py); nothing else ever should."""
         import torch
         self.torch = torch
+        self._factory = batch_factory if batch_factory is not None else capi.Batch
         self.variant, self.spec = variant, layout.system_spec(variant)
         if self.spec.system != layout.SYS_NTSC:
             raise ValueError("the video path covers CRT_SYSTEM_NTSC (what video_convert.c is built for)")
@@ -90,7 +94,7 @@ class VideoConverter:
         bpp = layout.bpp4fmt(self.fmt)
         S = max(1, min(self.segments, n))
         spans = [sharding.shard_range(n, s, S) for s in range(S)]  # local frame indices
-        b = capi.Batch(self.variant, S)
+        b = self._factory(self.variant, S)
         self._work = [torch.zeros(self.outh, self.outw, bpp, dtype=torch.uint8, device=dev) for _ in range(S)]
         for s in range(S):
             b.set_monitor(s, self._work[s], fmt=self.fmt, noise=self.noise, **self.knobs)
@@ -114,7 +118,7 @@ class VideoConverter:
             return frames[lf] if lf >= 0 else prev_in[2 + lf]
 
         # ---- speculated sync state: what a steady decode holds after a field of each parity (4 probe fields)
-        probe = capi.Batch(self.variant, 1)
+        probe = self._factory(self.variant, 1)
         scratch = torch.zeros(self.outh, self.outw, bpp, dtype=torch.uint8, device=dev)
         probe.set_monitor(0, scratch, fmt=self.fmt, noise=0, **self.knobs)
         probe.commit_monitors()
@@ -168,37 +172,59 @@ class VideoConverter:
                 outputs[spans[s][0] + t].copy_(self._work[s])
         finals = [(x.hsync, x.vsync) for x in b.get_state()]
 
-        # ---- verification in sequence order, repairing what the speculation got wrong
-        prev_final, prev_last = None, None
-        if world > 1:
+        # ---- verification in sequence order, repairing what the speculation got wrong.  Segment s is exact
+        # relative to (pf, pl) = its predecessor's final sync state and last image.  Inside a rank the
+        # predecessor is the previous local segment; the first segment of rank r > 0 depends on rank r - 1,
+        # whose last segment may itself be repaired -- so ranks repeat "exchange, re-check what the new data
+        # invalidates" until a round changes nothing anywhere (at most `world` rounds; one on a single GPU).
+        def exchange():
             t_state = torch.tensor([[finals[-1][0], finals[-1][1]]], dtype=torch.int64, device=dev)
             all_state = sharding.allgather_frames(t_state, group)
             all_last = sharding.allgather_frames(outputs[n - 1:n].contiguous(), group)
-            if rank > 0:
-                prev_final = (int(all_state[rank - 1][0]), int(all_state[rank - 1][1]))
-                prev_last = all_last[rank - 1]
+            if rank == 0:
+                return None, None
+            return (int(all_state[rank - 1][0]), int(all_state[rank - 1][1])), all_last[rank - 1]
+
         self.recomputed = 0
-        for s in range(S):
-            if starts[s] == 0:
-                continue  # began from the true initial state: exact by construction
-            pf = finals[s - 1] if s > 0 else prev_final
-            pl = outputs[spans[s - 1][1] - 1] if s > 0 else prev_last
-            if pf is not None and st_halo[s] == pf and bool(torch.equal(halo_img[s], pl)):
-                continue
-            # Speculation failed: redo the segment from the true state and the true image.  (Across ranks a
-            # repaired LAST segment is not re-propagated to the next rank in this version; callers can see
-            # it happened through .recomputed.)
-            self.recomputed += 1
-            if pf is None:
-                continue
-            a, e = spans[s]
-            redo = (capi.State * 1)()
-            redo[0].hsync, redo[0].vsync, redo[0].rn = pf[0], pf[1], rn_before(first_frame + a)
-            b.set_state(redo, first=s)
-            self._work[s].copy_(pl)
-            self._run_sequential(b, s, frames, a, e, outputs, first_frame)
-            x = b.get_state(first=s, count=1)[0]
-            finals[s] = (x.hsync, x.vsync)
-        torch.cuda.synchronize(dev)
+        basis = {}       # world > 1: what each checked segment was found exact against
+        repaired = set()
+        while True:
+            prev_final, prev_last = exchange() if world > 1 else (None, None)
+            changed = False
+            for s in range(S):
+                if starts[s] == 0:
+                    continue  # began from the true initial state: exact by construction
+                pf = finals[s - 1] if s > 0 else prev_final
+                pl = outputs[spans[s - 1][1] - 1] if s > 0 else prev_last
+                if pf is None:
+                    continue
+                if s in basis and basis[s][0] == pf and bool(torch.equal(basis[s][1], pl)):
+                    continue  # already exact against this very predecessor
+                if s not in repaired and st_halo[s] == pf and bool(torch.equal(halo_img[s], pl)):
+                    if world > 1:
+                        basis[s] = (pf, pl.clone())
+                    continue  # the speculation held
+                # redo the segment from the true state and the true image
+                self.recomputed += 1
+                changed = True
+                repaired.add(s)
+                if world > 1:
+                    basis[s] = (pf, pl.clone())
+                a, e = spans[s]
+                redo = (capi.State * 1)()
+                redo[0].hsync, redo[0].vsync, redo[0].rn = pf[0], pf[1], rn_before(first_frame + a)
+                b.set_state(redo, first=s)
+                self._work[s].copy_(pl)
+                self._run_sequential(b, s, frames, a, e, outputs, first_frame)
+                x = b.get_state(first=s, count=1)[0]
+                finals[s] = (x.hsync, x.vsync)
+            if world == 1:
+                break
+            flag = torch.tensor([1 if changed else 0], dtype=torch.int64, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+            if int(flag.item()) == 0:
+                break
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
         b.close()
         return outputs
