@@ -13,7 +13,7 @@ from dataclasses import dataclass
 
 PIX_RGB, PIX_BGR, PIX_ARGB, PIX_RGBA, PIX_ABGR, PIX_BGRA = range(6)  # crt_core.h:62-67
 
-SYS_NTSC, SYS_NES, SYS_SNES, SYS_TEMP, SYS_VHS, SYS_NESRGB = 0, 1, 3, 4, 5, 6  # crt_core.h:30-36
+SYS_NTSC, SYS_NES, SYS_PV1K, SYS_SNES, SYS_TEMP, SYS_VHS, SYS_NESRGB = 0, 1, 2, 3, 4, 5, 6  # crt_core.h:30-36
 
 
 def bpp4fmt(fmt):
@@ -54,6 +54,11 @@ class SystemSpec:
     @property
     def lines(self):
         return self.bot - self.top
+
+    @property
+    def cc_samples(self):
+        """CRT_CC_SAMPLES: 4 everywhere but the PV-1000 (crt_pv1k.h)."""
+        return 5 if self.system == SYS_PV1K else 4
 
 
 def _rgb_spec(name, system):
@@ -102,6 +107,10 @@ SPECS = {
     "nes_p0": _nes_spec("nes_p0", 0),
     "snes": _snes_spec("snes"),
     "nesrgb": _nesrgb_spec("nesrgb"),
+    # crt_pv1k.h (reference-side only so far): 1920 samples per line, 5 samples per chroma period, 5-line cycle
+    "pv1k": (lambda h, u: SystemSpec("pv1k", SYS_PV1K, 0, h, 262, 21, 261, 5, 3 * u * h // (71 * u), 6 * u * h // (71 * u),
+                                     8 * u * h // (71 * u), 16 * u * h // (71 * u), 55 * u * h // (71 * u), 8, 8,
+                                     100, 20, 7, -40))(2304 * 5 // 6, 892),
     # crt_template.h (reference-side only so far: used to pin the oracle ahead of a product library)
     "template": SystemSpec("template", SYS_TEMP, 1, *(lambda n: (n.hres, n.vres, n.top, n.bot, 2, n.sync_beg, n.bw_beg,
                                                                   n.cb_beg, n.av_beg, n.av_len, n.hsync_window,
@@ -132,7 +141,7 @@ _crt_cache = {}
 
 def crt_struct(spec):
     """ctypes view of `struct CRT` for one variant (crt_core.h:74-92)."""
-    key = (spec.input_size, spec.vper)
+    key = (spec.input_size, spec.vper, spec.cc_samples)
     if key not in _crt_cache:
         class CRT(C.Structure):
             _fields_ = [
@@ -145,7 +154,7 @@ def crt_struct(spec):
                 ("black_point", C.c_int), ("white_point", C.c_int),
                 ("scanlines", C.c_int), ("blend", C.c_int),
                 ("v_fac", C.c_uint),
-                ("ccf", (C.c_int * 4) * spec.vper),
+                ("ccf", (C.c_int * spec.cc_samples) * spec.vper),
                 ("hsync", C.c_int), ("vsync", C.c_int),
                 ("rn", C.c_int),
             ]
@@ -206,7 +215,7 @@ class NesSettings(C.Structure):
 
 
 def settings_struct(spec):
-    return {SYS_NTSC: RgbSettings, SYS_VHS: VhsSettings, SYS_NES: NesSettings, SYS_SNES: SnesSettings, SYS_TEMP: SnesSettings,
+    return {SYS_NTSC: RgbSettings, SYS_VHS: VhsSettings, SYS_NES: NesSettings, SYS_SNES: SnesSettings, SYS_TEMP: SnesSettings, SYS_PV1K: SnesSettings,
             SYS_NESRGB: NesRgbSettings}[spec.system]
 
 

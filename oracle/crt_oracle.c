@@ -159,8 +159,10 @@ finish_sys(ocrt_sys *s)
 {
     s->input_size = s->hres * s->vres;
     s->lines = s->bot - s->top;
-    s->burst_len = 10 * 4; /* CB_CYCLES * CRT_CB_FREQ */
-    eq_coeffs(s->eq[0], s->hres, 1500, 3000, 65536, 8192, 9175); /* crt_core.c:278 */
+    if (!s->cc_samples) s->cc_samples = 4;
+    s->burst_len = 10 * s->cc_samples; /* CB_CYCLES * CRT_CB_FREQ (CB_FREQ == CC_SAMPLES in every system) */
+    if (s->cc_samples == 5) eq_coeffs(s->eq[0], s->hres, 1500, 3000, 65536, 12192, 7775); /* crt_core.c:282 */
+    else eq_coeffs(s->eq[0], s->hres, 1500, 3000, 65536, 8192, 9175);                    /* crt_core.c:278 */
     eq_coeffs(s->eq[1], s->hres, 80, 1150, 65536, 65536, 1311);   /* crt_core.c:279 */
     eq_coeffs(s->eq[2], s->hres, 80, 1000, 65536, 65536, 0);      /* crt_core.c:280 */
 }
@@ -262,6 +264,40 @@ make_template_sys(ocrt_sys *s)
 }
 
 static void
+make_pv1k_sys(ocrt_sys *s)
+{
+    /* crt_pv1k.h: 5 samples per chroma period, 1920 samples per line, a 5-line chroma cycle */
+    const i32 u = 892, line_ns = (3 + 3 + 2 + 4 + 4 + 55) * 892;
+    memset(s, 0, sizeof(*s));
+    s->system = OCRT_SYS_PV1K;
+    s->chroma_pattern = 0;
+    s->cc_samples = 5;
+    s->hres = 2304 * 5 / 6;
+    s->vres = 262;
+    s->top = 21;
+    s->bot = 261;
+    s->cc_vper = 5;
+    s->hsync_window = 8;
+    s->vsync_window = 8;
+    s->hsync_thresh = 4;
+    s->vsync_thresh = 94;
+    s->sync_beg = (3 * u) * s->hres / line_ns;
+    s->bw_beg = (6 * u) * s->hres / line_ns;
+    s->cb_beg = (8 * u) * s->hres / line_ns;
+    s->av_beg = (16 * u) * s->hres / line_ns;
+    s->av_len = (55 * u) * s->hres / line_ns;
+    s->white_level = 100;
+    s->burst_level = 20;
+    s->black_level = 7;
+    s->blank_level = 0;
+    s->sync_level = -40;
+    s->iir_c[0] = bandlimit_coeff(420000); /* crt_pv1k.h: the NTSC bandwidths */
+    s->iir_c[1] = bandlimit_coeff(150000);
+    s->iir_c[2] = bandlimit_coeff(55000);
+    finish_sys(s);
+}
+
+static void
 make_nesrgb_sys(ocrt_sys *s)
 {
     /* crt_nesrgb.h: the NES layout and sync / burst levels, white at 100 */
@@ -273,12 +309,13 @@ make_nesrgb_sys(ocrt_sys *s)
 const ocrt_sys *
 ocrt_system(int system, int chroma_pattern)
 {
-    static ocrt_sys table[8];
+    static ocrt_sys table[9];
     static int ready = 0;
     if (!ready) {
         make_snes_sys(&table[5]);
         make_nesrgb_sys(&table[6]);
         make_template_sys(&table[7]);
+        make_pv1k_sys(&table[8]);
         make_rgb_sys(&table[0], OCRT_SYS_NTSC);
         make_rgb_sys(&table[1], OCRT_SYS_VHS);
         make_nes_sys(&table[2], 0);
@@ -291,6 +328,7 @@ ocrt_system(int system, int chroma_pattern)
     if (system == OCRT_SYS_SNES) return &table[5];
     if (system == OCRT_SYS_NESRGB) return &table[6];
     if (system == OCRT_SYS_TEMP) return &table[7];
+    if (system == OCRT_SYS_PV1K) return &table[8];
     if (system == OCRT_SYS_NES && chroma_pattern >= 0 && chroma_pattern <= 2)
         return &table[2 + chroma_pattern];
     return NULL;
@@ -299,12 +337,12 @@ ocrt_system(int system, int chroma_pattern)
 const ocrt_sys *
 ocrt_system_conv_taps(int system, int chroma_pattern, int taps)
 {
-    static ocrt_sys table[4][8];
-    static int ready[4][8];
+    static ocrt_sys table[4][9];
+    static int ready[4][9];
     const ocrt_sys *base = ocrt_system(system, chroma_pattern);
     int slot;
     if (!base || taps < 4 || taps > 7) return NULL;
-    slot = (system == OCRT_SYS_NTSC) ? 0 : (system == OCRT_SYS_VHS) ? 1 : (system == OCRT_SYS_SNES) ? 5 : (system == OCRT_SYS_NESRGB) ? 6 : (system == OCRT_SYS_TEMP) ? 7 : 2 + chroma_pattern;
+    slot = (system == OCRT_SYS_NTSC) ? 0 : (system == OCRT_SYS_VHS) ? 1 : (system == OCRT_SYS_SNES) ? 5 : (system == OCRT_SYS_NESRGB) ? 6 : (system == OCRT_SYS_TEMP) ? 7 : (system == OCRT_SYS_PV1K) ? 8 : 2 + chroma_pattern;
     if (!ready[taps - 4][slot]) {
         table[taps - 4][slot] = *base;
         table[taps - 4][slot].conv = taps;
@@ -475,17 +513,24 @@ ocrt_encode_rgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src, ocrt
 /* encoder, SNES (crt_snes.c:125-327)                                          */
 /* ------------------------------------------------------------------------- */
 
-/* crt_snes.c and crt_template.c are one encoder with three switches: the burst's hue offset (HUE_OFFSET),
- * the band-limit (CRT_DO_BANDLIMITING) and whether the field parity shapes the vertical sync and the source
- * row (crt_template.c:217-225, 252-258). */
+/* crt_snes.c, crt_template.c and crt_pv1k.c are one encoder with a handful of switches */
+typedef struct enc_family {
+    i32 vert_step;  /* degrees per line of the vertical chroma cycle: 360 / VPER, PV-1000 720 / VPER */
+    i32 burst_off;  /* HUE_OFFSET added to the burst angle (crt_snes.h:99, crt_template.h:68; 0 for the PV-1000) */
+    i32 q_off;      /* Q_OFFSET: -90, PV-1000 +90 (crt_pv1k.c:176) */
+    int bandlimit;  /* CRT_DO_BANDLIMITING */
+    int fielded;    /* the field parity shapes the vertical sync and the source row (crt_template.c:217-225, 252-258) */
+    i32 equ_a_lo, equ_a_hi, equ_b_lo, equ_b_hi, sync_lo, sync_hi; /* template line ranges */
+} enc_family;
+
 static void
-encode_template_family(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src, i32 hue_offset, int bandlimit,
-                       int fielded)
+encode_template_family(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src, const enc_family *fam)
 {
-    const i32 H = sys->hres, V = sys->cc_vper;
+    const i32 H = sys->hres, V = sys->cc_vper, CC = sys->cc_samples;
     i32 bpp = ocrt_bpp(src->format);
     i32 destw = sys->av_len, desth = (sys->lines * 64500) >> 16;
-    i32 modI[3][4], modQ[3][4], burst[3][4], primed[3][4];
+    i32 modI[OCRT_MAX_VPER][OCRT_MAX_CC], modQ[OCRT_MAX_VPER][OCRT_MAX_CC], burst[OCRT_MAX_VPER][OCRT_MAX_CC];
+    i32 primed[OCRT_MAX_VPER][OCRT_MAX_CC];
     i32 n, x, y, xo, yo, white;
 
     if (src->raw) { /* crt_snes.c:158-168 */
@@ -493,13 +538,13 @@ encode_template_family(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *sr
         desth = src->h < desth ? src->h : desth;
     }
     for (y = 0; y < V; y++) /* crt_snes.c:170-187 */
-        for (x = 0; x < 4; x++) {
-            i32 step = 360 / 4, deg = (y + src->dot_crawl_offset) * (360 / V) + src->hue + x * step;
+        for (x = 0; x < CC; x++) {
+            i32 step = 360 / CC, deg = (y + src->dot_crawl_offset) * fam->vert_step + src->hue + x * step;
             burst[y][x] = modI[y][x] = modQ[y][x] = 0;
             if (src->as_color) {
-                burst[y][x] = sin14((deg - step + hue_offset) * 8192 / 180) >> 10; /* HUE_OFFSET */
+                burst[y][x] = sin14((deg - step + fam->burst_off) * 8192 / 180) >> 10;
                 modI[y][x] = sin14(deg * 8192 / 180) >> 10;
-                modQ[y][x] = sin14((deg - 90) * 8192 / 180) >> 10;                 /* Q_OFFSET */
+                modQ[y][x] = sin14((deg + fam->q_off) * 8192 / 180) >> 10;
             }
         }
     if (bpp == 0) return; /* crt_snes.c:189-192 */
@@ -507,18 +552,18 @@ encode_template_family(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *sr
     yo = sys->top + src->yoffset + (sys->lines - desth) / 2;
     src->field &= 1;
     src->frame &= 1;
-    xo = xo - (xo % 4);
+    xo = xo - (xo % CC);
     memset(primed, 0, sizeof(primed));
 
     for (n = 0; n < sys->vres; n++) { /* crt_snes.c:203-250 */
         signed char *line = m->analog + n * H;
-        if (n <= 2 || (n >= 7 && n <= 9)) {
+        if ((n >= fam->equ_a_lo && n <= fam->equ_a_hi) || (n >= fam->equ_b_lo && n <= fam->equ_b_hi)) {
             fill(line, 0, 4 * H / 100, sys->sync_level);
             fill(line, 4 * H / 100, 50 * H / 100, sys->blank_level);
             fill(line, 50 * H / 100, 54 * H / 100, sys->sync_level);
             fill(line, 54 * H / 100, H, sys->blank_level);
-        } else if (n >= 3 && n <= 6) {
-            i32 first = (fielded && src->field == 1) ? 4 : 46; /* crt_template.c:220-225 */
+        } else if (n >= fam->sync_lo && n <= fam->sync_hi) {
+            i32 first = (fam->fielded && src->field == 1) ? 4 : 46; /* crt_template.c:220-225 */
             fill(line, 0, first * H / 100, sys->sync_level);
             fill(line, first * H / 100, 50 * H / 100, sys->blank_level);
             fill(line, 50 * H / 100, 96 * H / 100, sys->sync_level);
@@ -530,8 +575,8 @@ encode_template_family(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *sr
             fill(line, sys->bw_beg, sys->av_beg, sys->blank_level);
             if (n < sys->top) fill(line, sys->av_beg, H, sys->blank_level);
             for (t = sys->cb_beg; t < sys->cb_beg + sys->burst_len; t++) {
-                line[t] = (signed char) ((sys->blank_level + burst[n % V][t % 4] * sys->burst_level) >> 5);
-                primed[(n + 3) % V][t % 4] = line[t];
+                line[t] = (signed char) ((sys->blank_level + burst[n % V][t % CC] * sys->burst_level) >> 5);
+                primed[(n + 3) % V][t % CC] = line[t];
             }
         }
     }
@@ -540,7 +585,7 @@ encode_template_family(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *sr
     for (y = 0; y < desth; y++) { /* crt_snes.c:252-320 */
         i32 hy = 0, hi = 0, hq = 0; /* reset_iir per line */
         i32 row = (y * src->h) / desth, ph = (y + yo) % V;
-        if (fielded) row += (src->field * src->h + desth) / desth / 2; /* crt_template.c:255-258 */
+        if (fam->fielded) row += (src->field * src->h + desth) / desth / 2; /* crt_template.c:255-258 */
         if (row >= src->h) row = src->h;
         for (x = 0; x < destw; x++) {
             const unsigned char *px = src->data + (size_t) (((x * src->w) / destw) + row * src->w) * bpp;
@@ -548,8 +593,8 @@ encode_template_family(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *sr
             i32 fy = (19595 * r + 38470 * gg + 7471 * b) >> 14;
             i32 fi = (39059 * r - 18022 * gg - 21103 * b) >> 14;
             i32 fq = (13894 * r - 34275 * gg + 20382 * b) >> 14;
-            i32 xoff = (x + xo) % 4, ire;
-            if (bandlimit) { /* iirf, crt_template.c:117-126 (CRT_DO_BANDLIMITING 1) */
+            i32 xoff = (x + xo) % CC, ire;
+            if (fam->bandlimit) { /* iirf, crt_template.c:117-126 (CRT_DO_BANDLIMITING 1) */
                 hy += wmul(fy - hy, sys->iir_c[0]) >> 11;
                 hi += wmul(fi - hi, sys->iir_c[1]) >> 11;
                 hq += wmul(fq - hq, sys->iir_c[2]) >> 11;
@@ -566,13 +611,14 @@ encode_template_family(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *sr
         }
     }
     for (n = 0; n < V; n++) /* crt_snes.c:322-326 */
-        for (x = 0; x < 4; x++) m->ccf[n][x] = primed[n][x] * 128;
+        for (x = 0; x < CC; x++) m->ccf[n][x] = primed[n][x] * 128;
 }
 
 void
 ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
 {
-    encode_template_family(sys, m, src, 210, 0, 0); /* crt_snes.h:84, 99 */
+    static const enc_family fam = { 360 / 3, 210, -90, 0, 0, 0, 2, 7, 9, 3, 6 }; /* crt_snes.h:84-109 */
+    encode_template_family(sys, m, src, &fam);
 }
 
 /* crt_template.c:125-337: the reference's worked example for new systems -- NTSC timing with a 2-line
@@ -580,7 +626,17 @@ ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
 void
 ocrt_encode_template(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
 {
-    encode_template_family(sys, m, src, -60, 1, 1);
+    static const enc_family fam = { 360 / 2, -60, -90, 1, 1, 0, 2, 7, 9, 3, 6 };
+    encode_template_family(sys, m, src, &fam);
+}
+
+/* crt_pv1k.c:125-321: Casio PV-1000 -- 5 samples per chroma period, 5-line cycle stepping 144 degrees, no
+ * first equalising region, vertical sync on lines 258-260 */
+void
+ocrt_encode_pv1k(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src)
+{
+    static const enc_family fam = { 360 * 2 / 5, 0, 90, 1, 1, 1, 0, 7, 9, 258, 260 };
+    encode_template_family(sys, m, src, &fam);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -819,19 +875,42 @@ locked:
         rec->pos = xpos + ypos * H;
 
         ccr = m->ccf[ypos % sys->cc_vper]; /* crt_core.c:456-467 */
-        sig = m->inp + ln + (m->hsync & ~3);
-        for (i = sys->cb_beg; i < sys->cb_beg + sys->burst_len; i++)
-            ccr[i & 3] = wadd(wmul(ccr[i & 3], 127) / 128, sig[i]);
+        if (sys->cc_samples == 4) {
+            sig = m->inp + ln + (m->hsync & ~3);
+            for (i = sys->cb_beg; i < sys->cb_beg + sys->burst_len; i++)
+                ccr[i & 3] = wadd(wmul(ccr[i & 3], 127) / 128, sig[i]);
 
-        pa = m->hsync & 3; /* crt_core.c:469-479 */
-        dci = wsub(ccr[(pa + 1) & 3], ccr[(pa + 3) & 3]);
-        dcq = wsub(ccr[(pa + 2) & 3], ccr[pa & 3]);
-        w0 = wmul(wsub(wmul(dci, huecs), wmul(dcq, huesn)) >> 4, m->saturation);
-        w1 = wmul(wadd(wmul(dcq, huecs), wmul(dci, huesn)) >> 4, m->saturation);
-        rec->wave[0] = w0;
-        rec->wave[1] = w1;
-        rec->wave[2] = wsub(0, w0);
-        rec->wave[3] = wsub(0, w1);
+            pa = m->hsync & 3; /* crt_core.c:469-479 */
+            dci = wsub(ccr[(pa + 1) & 3], ccr[(pa + 3) & 3]);
+            dcq = wsub(ccr[(pa + 2) & 3], ccr[pa & 3]);
+            w0 = wmul(wsub(wmul(dci, huecs), wmul(dcq, huesn)) >> 4, m->saturation);
+            w1 = wmul(wadd(wmul(dcq, huecs), wmul(dci, huesn)) >> 4, m->saturation);
+            rec->wave[0] = w0;
+            rec->wave[1] = w1;
+            rec->wave[2] = wsub(0, w0);
+            rec->wave[3] = wsub(0, w1);
+        } else { /* CRT_CC_SAMPLES 5, crt_core.c:459-467, 480-509 */
+            const i32 CC = sys->cc_samples;
+            i32 ang = m->hue % 360, peak_a, peak_b;
+            sig = m->inp + ln + (m->hsync - (m->hsync % CC));
+            for (i = sys->cb_beg; i < sys->cb_beg + sys->burst_len; i++)
+                ccr[i % CC] = wadd(wmul(ccr[i % CC], 127) / 128, sig[i]);
+            pa = posmod(m->hsync, CC);
+            peak_a = pa + CC / 4;
+            peak_b = pa;
+            dci = wsub(ccr[peak_a % CC], wadd(ccr[(peak_a + CC / 2) % CC], ccr[(peak_a + CC / 2 + 1) % CC]) / 2);
+            dcq = wsub(ccr[(peak_b + CC / 2) % CC], ccr[peak_b % CC]);
+            for (i = 0; i < CC; i++) {
+                int sn, cs;
+                ocrt_sincos14(&sn, &cs, ang * 8192 / 180);
+                rec->wave_i[i] = wmul(wadd(wmul(dci, cs), wmul(dcq, sn)) >> 15, m->saturation);
+                ocrt_sincos14(&sn, &cs, (ang + 90) * 8192 / 180);
+                rec->wave_q[i] = wmul(wadd(wmul(dci, cs), wmul(dcq, sn)) >> 15, m->saturation);
+                ang += 360 / CC;
+            }
+            (void) w0;
+            (void) w1;
+        }
     }
     return field;
 }
@@ -883,6 +962,11 @@ fir_step(fir_state *f, i32 s, int taps)
     return wadd(wadd(wadd(s, h[3]), h[1]), h[2]) >> 2; /* weights 1 1 1 1 */
 }
 
+/* carrier sample of I / Q at signal sample i: crt_core.c:538-543 (4 samples per period: one table, Q three
+ * samples behind) or 545-549 (5 samples: two tables) */
+#define WAVE_I(i) (sys->cc_samples == 4 ? rec->wave[(i) & 3] : rec->wave_i[(i) % sys->cc_samples])
+#define WAVE_Q(i) (sys->cc_samples == 4 ? rec->wave[((i) + 3) & 3] : rec->wave_q[(i) % sys->cc_samples])
+
 /* filter + resample + YIQ->RGB for decoded lines [first, first+count)
  * (crt_core.c:511-664) */
 void
@@ -917,13 +1001,13 @@ ocrt_line_pass(const ocrt_sys *sys, ocrt_monitor *m, const ocrt_line *table, int
         memset(&fq, 0, sizeof(fq));
         for (i = 0; sys->conv && i < L; i++) { /* crt_core.c:538-543 with the FIR eqf */
             yy[i] = wmul(fir_step(&fy, sig[i] + bright, sys->conv), 16);
-            ii[i] = fir_step(&fi, wmul(sig[i], rec->wave[i & 3]) >> 9, sys->conv) >> 3;
-            qq[i] = fir_step(&fq, wmul(sig[i], rec->wave[(i + 3) & 3]) >> 9, sys->conv) >> 3;
+            ii[i] = fir_step(&fi, wmul(sig[i], WAVE_I(i)) >> 9, sys->conv) >> 3;
+            qq[i] = fir_step(&fq, wmul(sig[i], WAVE_Q(i)) >> 9, sys->conv) >> 3;
         }
         for (i = 0; !sys->conv && i < L; i++) { /* crt_core.c:538-543 */
             yy[i] = eq_step(&ey, sys->eq[0], sig[i] + bright) * 16;
-            ii[i] = eq_step(&ei, sys->eq[1], wmul(sig[i], rec->wave[i & 3]) >> 9) >> 3;
-            qq[i] = eq_step(&eq, sys->eq[2], wmul(sig[i], rec->wave[(i + 3) & 3]) >> 9) >> 3;
+            ii[i] = eq_step(&ei, sys->eq[1], wmul(sig[i], WAVE_I(i)) >> 9) >> 3;
+            qq[i] = eq_step(&eq, sys->eq[2], wmul(sig[i], WAVE_Q(i)) >> 9) >> 3;
         }
         px = m->out + (size_t) rec->beg * pitch;
         row_end = px + pitch;

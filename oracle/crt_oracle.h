@@ -26,12 +26,14 @@ extern "C" {
 
 #define OCRT_SYS_NTSC 0 /* crt_core.h:30 */
 #define OCRT_SYS_NES  1 /* crt_core.h:31 */
+#define OCRT_SYS_PV1K 2 /* crt_core.h:32 */
 #define OCRT_SYS_SNES 3 /* crt_core.h:33 */
 #define OCRT_SYS_TEMP 4 /* crt_core.h:34 */
 #define OCRT_SYS_VHS  5 /* crt_core.h:35 */
 #define OCRT_SYS_NESRGB 6 /* crt_core.h:36 */
 
-#define OCRT_MAX_VPER 3
+#define OCRT_MAX_VPER 5 /* CRT_CC_VPER of the PV-1000 */
+#define OCRT_MAX_CC   5 /* CRT_CC_SAMPLES of the PV-1000 (4 everywhere else) */
 #define OCRT_PAD      2048 /* slack after analog/inp for the reference's over-reads */
 
 /* Everything the reference derives from macros (crt_ntsc.h:25-109, crt_nes.h:30-130,
@@ -55,6 +57,7 @@ typedef struct ocrt_sys {
      * this many taps (7: [1 4 7 8 7 4 1] >> 5, the stock one; 6, 5, 4: crt_core.c:86-88) instead of the
      * three-band equaliser */
     int conv;
+    int cc_samples; /* CRT_CC_SAMPLES: samples per chroma period, 4 (5: PV-1000) */
 } ocrt_sys;
 
 /* Mirrors the caller-visible part of struct CRT (crt_core.h:74-92). */
@@ -67,7 +70,7 @@ typedef struct ocrt_monitor {
     int black_point, white_point;
     int scanlines, blend;
     unsigned v_fac;
-    int ccf[OCRT_MAX_VPER][4];
+    int ccf[OCRT_MAX_VPER][OCRT_MAX_CC];
     int hsync, vsync, rn;
 } ocrt_monitor;
 
@@ -76,7 +79,7 @@ typedef struct ocrt_rgb_source {
     const unsigned char *data;
     int format, w, h, raw, as_color, field, frame, hue, xoffset, yoffset;
     int do_aberration;    /* VHS only */
-    int dot_crawl_offset; /* SNES and template systems (crt_snes.h:121, crt_template.h) */
+    int dot_crawl_offset; /* SNES, template and PV-1000 systems (crt_snes.h:121, crt_template.h, crt_pv1k.h) */
 } ocrt_rgb_source;
 
 /* struct NTSC_SETTINGS of the NES system (crt_nes.h:132-143) */
@@ -108,7 +111,8 @@ typedef struct ocrt_line {
     int beg, end;   /* output rows, crt_core.c:428-432 */
     int hsync;      /* after this line's search, crt_core.c:446 */
     int pos;        /* xpos + ypos * hres, crt_core.c:452-454 */
-    int wave[4];    /* crt_core.c:476-479 */
+    int wave[4];    /* crt_core.c:476-479 (CRT_CC_SAMPLES 4) */
+    int wave_i[OCRT_MAX_CC], wave_q[OCRT_MAX_CC]; /* crt_core.c:480-509 (CRT_CC_SAMPLES 5) */
 } ocrt_line;
 
 const ocrt_sys *ocrt_system(int system, int chroma_pattern);
@@ -130,6 +134,7 @@ void ocrt_monitor_reset(ocrt_monitor *m);
 void ocrt_encode_rgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src, ocrt_rand *g);
 void ocrt_encode_nes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_nes_source *src);
 void ocrt_encode_snes(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src);
+void ocrt_encode_pv1k(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src);
 void ocrt_encode_template(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src);
 void ocrt_encode_nesrgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_nesrgb_source *src);
 

@@ -66,7 +66,11 @@ int crtx_set_state(crtx_ctx *c, int first, int count, const crtx_state *s, void 
     (void) stream;
     for (i = 0; i < count; i++) {
         ocrt_monitor *o = &c->mon[first + i];
-        memcpy(o->ccf, s[i].ccf, sizeof(o->ccf));
+        {
+            int r, x;
+            for (r = 0; r < 3; r++)
+                for (x = 0; x < 4; x++) o->ccf[r][x] = s[i].ccf[r][x];
+        }
         o->hsync = s[i].hsync; o->vsync = s[i].vsync; o->rn = s[i].rn;
     }
     return 0;
@@ -78,7 +82,11 @@ int crtx_get_state(crtx_ctx *c, int first, int count, crtx_state *s, void *strea
     (void) stream;
     for (i = 0; i < count; i++) {
         const ocrt_monitor *o = &c->mon[first + i];
-        memcpy(s[i].ccf, o->ccf, sizeof(o->ccf));
+        {
+            int r, x;
+            for (r = 0; r < 3; r++)
+                for (x = 0; x < 4; x++) s[i].ccf[r][x] = o->ccf[r][x];
+        }
         s[i].hsync = o->hsync; s[i].vsync = o->vsync; s[i].rn = o->rn;
     }
     return 0;

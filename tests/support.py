@@ -156,7 +156,7 @@ class CEngine:
 
     @property
     def ccf(self):
-        return np.array([[self.crt.ccf[n][x] for x in range(4)] for n in range(self.spec.vper)])
+        return np.array([[self.crt.ccf[n][x] for x in range(self.spec.cc_samples)] for n in range(self.spec.vper)])
 
     @property
     def hsync(self):
@@ -189,7 +189,7 @@ class _OSys(C.Structure):
         "cc_vper", "hsync_window", "vsync_window", "hsync_thresh", "vsync_thresh",
         "sync_beg", "bw_beg", "cb_beg", "av_beg", "av_len", "burst_len",
         "white_level", "burst_level", "black_level", "blank_level", "sync_level",
-        "vhs_noise", "nes_vsync_end")] + [("eq", (C.c_int * 5) * 3), ("iir_c", C.c_int * 3), ("conv", C.c_int)]
+        "vhs_noise", "nes_vsync_end")] + [("eq", (C.c_int * 5) * 3), ("iir_c", C.c_int * 3), ("conv", C.c_int), ("cc_samples", C.c_int)]
 
 
 class _OMonitor(C.Structure):
@@ -200,7 +200,7 @@ class _OMonitor(C.Structure):
         ("hue", C.c_int), ("brightness", C.c_int), ("contrast", C.c_int),
         ("saturation", C.c_int), ("black_point", C.c_int), ("white_point", C.c_int),
         ("scanlines", C.c_int), ("blend", C.c_int), ("v_fac", C.c_uint),
-        ("ccf", (C.c_int * 4) * 3), ("hsync", C.c_int), ("vsync", C.c_int), ("rn", C.c_int),
+        ("ccf", (C.c_int * 5) * 5), ("hsync", C.c_int), ("vsync", C.c_int), ("rn", C.c_int),
     ]
 
 
@@ -226,7 +226,7 @@ class _ORand(C.Structure):
 
 class OLine(C.Structure):
     _fields_ = [("skip", C.c_int), ("beg", C.c_int), ("end", C.c_int), ("hsync", C.c_int),
-                ("pos", C.c_int), ("wave", C.c_int * 4)]
+                ("pos", C.c_int), ("wave", C.c_int * 4), ("wave_i", C.c_int * 5), ("wave_q", C.c_int * 5)]
 
 
 _oracle = None
@@ -253,6 +253,7 @@ def oracle_lib():
         lib.ocrt_encode_snes.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ORgb)]
         lib.ocrt_encode_nesrgb.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ONesRgb)]
         lib.ocrt_encode_template.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ORgb)]
+        lib.ocrt_encode_pv1k.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.POINTER(_ORgb)]
         lib.ocrt_decode.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.c_int,
                                     C.POINTER(_ORand)]
         lib.ocrt_noise_pass.argtypes = lib.ocrt_decode.argtypes
@@ -334,6 +335,8 @@ class OracleEngine:
             self.lib.ocrt_encode_nesrgb(self.sys, C.byref(self.mon), C.byref(s))
         elif self.spec.system == layout.SYS_TEMP:
             self.lib.ocrt_encode_template(self.sys, C.byref(self.mon), C.byref(s))
+        elif self.spec.system == layout.SYS_PV1K:
+            self.lib.ocrt_encode_pv1k(self.sys, C.byref(self.mon), C.byref(s))
         else:
             self.lib.ocrt_encode_rgb(self.sys, C.byref(self.mon), C.byref(s), C.byref(self.rand))
 
@@ -363,7 +366,7 @@ class OracleEngine:
 
     @property
     def ccf(self):
-        return np.array([[self.mon.ccf[n][x] for x in range(4)] for n in range(self.spec.vper)])
+        return np.array([[self.mon.ccf[n][x] for x in range(self.spec.cc_samples)] for n in range(self.spec.vper)])
 
     @property
     def hsync(self):

@@ -32,7 +32,7 @@ def check(ref, ora, what):
 
 
 def test_struct_layout_matches_reference():
-    for variant in ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "snes", "nesrgb", "template"):
+    for variant in ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "snes", "nesrgb", "template", "pv1k"):
         spec = layout.system_spec(variant)
         lib = C.CDLL(S.ref_path(variant))
         assert lib.ref_sizeof_crt() == C.sizeof(layout.crt_struct(spec)), variant
@@ -40,7 +40,7 @@ def test_struct_layout_matches_reference():
         g = (C.c_int * 20)()
         lib.ref_geometry(g)
         assert list(g)[:12] == [spec.hres, spec.vres, spec.input_size, spec.top, spec.bot,
-                                spec.vper, 4, spec.sync_beg, spec.bw_beg, spec.cb_beg,
+                                spec.vper, spec.cc_samples, spec.sync_beg, spec.bw_beg, spec.cb_beg,
                                 spec.av_beg, spec.av_len], variant
         o = (C.c_int * 19)()
         lib.ref_crt_offsets(o)
@@ -244,6 +244,25 @@ def test_template_system(fmt, as_color, raw):
         check(ref, ora, "template mod %d" % it)
         both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 9))
         check(ref, ora, "template demod %d" % it)
+
+
+@pytest.mark.parametrize("fmt,as_color,raw,conv", [(layout.PIX_BGRA, 1, 0, False), (layout.PIX_RGB, 1, 0, False),
+                                                   (layout.PIX_ARGB, 0, 0, False), (layout.PIX_ABGR, 1, 1, False)])
+def test_pv1k_system(fmt, as_color, raw, conv):
+    """CRT_SYSTEM_PV1K (crt_pv1k.c and the CRT_CC_SAMPLES == 5 branches of crt_core.c:459-467, 480-509, 545-549):
+    1920 samples per line, 5 samples per chroma period, separate I / Q carrier tables.  No product library yet
+    (SURVEY 8f-3): this pins the oracle ahead of it."""
+    rgb = S.rand_image(300 if not raw else 200, 260 if not raw else 180, bpp=3, seed=fmt)
+    img = S.pack_rgb(rgb, fmt)
+    ref, ora = pair("pv1k", 640, 480)
+    both(ref, ora, lambda e: e.set(blend=1, scanlines=1, hue=25, saturation=12, black_point=2, white_point=95))
+    for it in range(6):
+        both(ref, ora, lambda e: e.modulate(img, format=fmt, as_color=as_color, raw=raw, field=it & 1 if not raw else 0,
+                                            frame=(it >> 1) & 1, hue=(it * 50) % 360, dot_crawl_offset=it % 5,
+                                            xoffset=5 * (it & 1), yoffset=it % 3))
+        check(ref, ora, "pv1k mod %d" % it)
+        both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 9))
+        check(ref, ora, "pv1k demod %d" % it)
 
 
 @pytest.mark.parametrize("fmt", [layout.PIX_BGRA, layout.PIX_RGB, layout.PIX_ARGB, 9])
