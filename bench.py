@@ -483,6 +483,8 @@ def run_product(args):
                     "wall_s": e2e_wall},
             "gpu_launches": int(launches),
             "gpu_launches_e2e": int(launches_e2e),
+            # the CLI accumulates 8 modulate + demodulate pairs per interlaced image (crt_main.c:242-255)
+            "cli_images_per_s": value / 8.0,
             "roofline": {"bound": "hbm", "kernel": ("k_lines_fir (crt_demodulate line pass of the USE_CONVOLUTION build, crt_core.c:96-147,511-664)"
                                                      if ("_conv" in VARIANT) else "k_lines (crt_demodulate line pass, crt_core.c:511-664)"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
