@@ -107,6 +107,8 @@ SPECS = {
     "nes_p0": _nes_spec("nes_p0", 0),
     "snes": _snes_spec("snes"),
     "nesrgb": _nesrgb_spec("nesrgb"),
+    # the NTSC system built with CRT_DO_BLOOM 1 (crt_core.h:70; reference-side only so far)
+    "ntsc_bloom": _rgb_spec("ntsc_bloom", SYS_NTSC),
     # crt_pv1k.h (reference-side only so far): 1920 samples per line, 5 samples per chroma period, 5-line cycle
     "pv1k": (lambda h, u: SystemSpec("pv1k", SYS_PV1K, 0, h, 262, 21, 261, 5, 3 * u * h // (71 * u), 6 * u * h // (71 * u),
                                      8 * u * h // (71 * u), 16 * u * h // (71 * u), 55 * u * h // (71 * u), 8, 8,

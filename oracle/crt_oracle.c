@@ -352,6 +352,24 @@ ocrt_system_conv_taps(int system, int chroma_pattern, int taps)
 }
 
 const ocrt_sys *
+ocrt_system_bloom(int system, int chroma_pattern)
+{
+    static ocrt_sys table[9];
+    static int ready[9];
+    const ocrt_sys *base = ocrt_system(system, chroma_pattern);
+    int slot;
+    if (!base || system == OCRT_SYS_NES || system == OCRT_SYS_NESRGB) return NULL; /* "does not work for NES" */
+    slot = (system == OCRT_SYS_NTSC) ? 0 : (system == OCRT_SYS_VHS) ? 1 : (system == OCRT_SYS_SNES) ? 5
+         : (system == OCRT_SYS_TEMP) ? 7 : 8;
+    if (!ready[slot]) {
+        table[slot] = *base;
+        table[slot].bloom = 1;
+        ready[slot] = 1;
+    }
+    return &table[slot];
+}
+
+const ocrt_sys *
 ocrt_system_conv(int system, int chroma_pattern)
 {
     return ocrt_system_conv_taps(system, chroma_pattern, 7); /* USE_7_SAMPLE_KERNEL 1 is the stock setting */
@@ -409,19 +427,31 @@ fill(signed char *line, i32 from, i32 to, i32 level)
     for (t = from; t < to; t++) line[t] = (signed char) level;
 }
 
+/* size of the encoded picture (crt_ntsc.c:148-172, same block in crt_snes.c / crt_template.c / crt_pv1k.c):
+ * with CRT_DO_BLOOM the picture leaves room for the line to widen */
+static void
+picture_size(const ocrt_sys *sys, const ocrt_rgb_source *src, i32 *destw, i32 *desth)
+{
+    const i32 maxw = sys->bloom ? (sys->av_len * 55500) >> 16 : sys->av_len;
+    const i32 maxh = sys->bloom ? (sys->lines * 63500) >> 16 : (sys->lines * 64500) >> 16;
+    if (src->raw) {
+        *destw = src->w < maxw ? src->w : maxw;
+        *desth = src->h < maxh ? src->h : maxh;
+    } else {
+        *destw = maxw;
+        *desth = maxh;
+    }
+}
+
 void
 ocrt_encode_rgb(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *src, ocrt_rand *g)
 {
     const i32 H = sys->hres;
-    i32 destw = sys->av_len;
-    i32 desth = (sys->lines * 64500) >> 16;
+    i32 destw, desth;
     i32 burst[4], modI[4], modQ[4], primed[4] = { 0, 0, 0, 0 };
     i32 k, n, x, y, xo, yo, flip, ph, bpp, aberration = 0, white;
 
-    if (src->raw) { /* crt_ntsc.c:163-172 */
-        destw = src->w < sys->av_len ? src->w : sys->av_len;
-        if (src->h < desth) desth = src->h;
-    }
+    picture_size(sys, src, &destw, &desth);
     for (k = 0; k < 4; k++) { /* crt_ntsc.c:174-188 */
         if (src->as_color) {
             i32 deg = src->hue + k * 90;
@@ -528,15 +558,12 @@ encode_template_family(const ocrt_sys *sys, ocrt_monitor *m, ocrt_rgb_source *sr
 {
     const i32 H = sys->hres, V = sys->cc_vper, CC = sys->cc_samples;
     i32 bpp = ocrt_bpp(src->format);
-    i32 destw = sys->av_len, desth = (sys->lines * 64500) >> 16;
+    i32 destw, desth;
     i32 modI[OCRT_MAX_VPER][OCRT_MAX_CC], modQ[OCRT_MAX_VPER][OCRT_MAX_CC], burst[OCRT_MAX_VPER][OCRT_MAX_CC];
     i32 primed[OCRT_MAX_VPER][OCRT_MAX_CC];
     i32 n, x, y, xo, yo, white;
 
-    if (src->raw) { /* crt_snes.c:158-168 */
-        destw = src->w < sys->av_len ? src->w : sys->av_len;
-        desth = src->h < desth ? src->h : desth;
-    }
+    picture_size(sys, src, &destw, &desth); /* crt_snes.c:148-168 */
     for (y = 0; y < V; y++) /* crt_snes.c:170-187 */
         for (x = 0; x < CC; x++) {
             i32 step = 360 / CC, deg = (y + src->dot_crawl_offset) * fam->vert_step + src->hue + x * step;
@@ -796,6 +823,7 @@ void
 ocrt_noise_pass(const ocrt_sys *sys, ocrt_monitor *m, int noise, ocrt_rand *g)
 {
     i32 i, rn = m->rn, wobble = 0;
+    m->last_noise = noise;
     if (sys->vhs_noise) wobble = ((ocrt_rand_next(g) % 8) - 4) + 14; /* crt_core.c:344 */
     for (i = 0; i < sys->input_size; i++) {
         i32 gain = noise, s;
@@ -975,6 +1003,9 @@ ocrt_line_pass(const ocrt_sys *sys, ocrt_monitor *m, const ocrt_line *table, int
     const i32 L = sys->av_len;
     i32 bpp = ocrt_bpp(m->out_format), pitch, bright, k, dx;
     i32 *yy, *ii, *qq;
+    /* CRT_DO_BLOOM (crt_core.c:399-402, 512-526): filtered beam energy, carried from line to line of the call */
+    const i32 max_e = (128 + (m->last_noise / 2)) * sys->av_len;
+    i32 prev_e = 16384 / 8, k0 = sys->bloom ? 0 : first;
 
     if (bpp == 0) return;
     pitch = m->outw * bpp;
@@ -984,34 +1015,45 @@ ocrt_line_pass(const ocrt_sys *sys, ocrt_monitor *m, const ocrt_line *table, int
     qq = ii + (L + 1);
     dx = ((L - 1) << 12) / m->outw;
 
-    for (k = first; k < first + count; k++) {
+    for (k = k0; k < first + count; k++) { /* (with bloom the energy chain is walked from the first line) */
         const ocrt_line *rec = &table[k];
         const signed char *sig = m->inp + rec->pos;
         eq_state ey, ei, eq;
         fir_state fy, fi, fq;
         unsigned char *px, *row_end;
-        u32 pos;
-        i32 i, row;
+        u32 pos, scan_l = 0, scan_r = (u32) ((L - 1) << 12);
+        i32 i, row, f_lo = 0, f_hi = L;
         if (rec->skip) continue;
+        if (sys->bloom) {
+            i32 e = 0, line_w;
+            for (i = 0; i < L; i++) e += sig[i];
+            prev_e = (prev_e * 123 / 128) + ((((max_e >> 1) - e) << 10) / max_e);
+            line_w = (L * 112 / 128) + (prev_e >> 9);
+            dx = (line_w << 12) / m->outw;
+            scan_l = (u32) (((L / 2) - (line_w >> 1) + 8) << 12);
+            f_lo = (i32) (scan_l >> 12);
+            f_hi = (i32) (scan_r >> 12);
+            if (k < first) continue;
+        }
         memset(&ey, 0, sizeof(ey));
         memset(&ei, 0, sizeof(ei));
         memset(&eq, 0, sizeof(eq));
         memset(&fy, 0, sizeof(fy));
         memset(&fi, 0, sizeof(fi));
         memset(&fq, 0, sizeof(fq));
-        for (i = 0; sys->conv && i < L; i++) { /* crt_core.c:538-543 with the FIR eqf */
+        for (i = f_lo; sys->conv && i < f_hi; i++) { /* crt_core.c:538-543 with the FIR eqf */
             yy[i] = wmul(fir_step(&fy, sig[i] + bright, sys->conv), 16);
             ii[i] = fir_step(&fi, wmul(sig[i], WAVE_I(i)) >> 9, sys->conv) >> 3;
             qq[i] = fir_step(&fq, wmul(sig[i], WAVE_Q(i)) >> 9, sys->conv) >> 3;
         }
-        for (i = 0; !sys->conv && i < L; i++) { /* crt_core.c:538-543 */
+        for (i = f_lo; !sys->conv && i < f_hi; i++) { /* crt_core.c:538-543 */
             yy[i] = eq_step(&ey, sys->eq[0], sig[i] + bright) * 16;
             ii[i] = eq_step(&ei, sys->eq[1], wmul(sig[i], WAVE_I(i)) >> 9) >> 3;
             qq[i] = eq_step(&eq, sys->eq[2], wmul(sig[i], WAVE_Q(i)) >> 9) >> 3;
         }
         px = m->out + (size_t) rec->beg * pitch;
         row_end = px + pitch;
-        for (pos = 0; pos < (u32) ((L - 1) << 12) && px < row_end; pos += (u32) dx, px += bpp) {
+        for (pos = scan_l; pos < scan_r && px < row_end; pos += (u32) dx, px += bpp) {
             i32 R = pos & 0xfff, Lw = 0xfff - R, s = (i32) (pos >> 12);
             i32 y = (wmul(yy[s], Lw) >> 2) + (wmul(yy[s + 1], R) >> 2); /* crt_core.c:568-570 */
             i32 ci = (wmul(ii[s], Lw) >> 14) + (wmul(ii[s + 1], R) >> 14);

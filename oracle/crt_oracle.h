@@ -58,6 +58,7 @@ typedef struct ocrt_sys {
      * three-band equaliser */
     int conv;
     int cc_samples; /* CRT_CC_SAMPLES: samples per chroma period, 4 (5: PV-1000) */
+    int bloom;      /* CRT_DO_BLOOM (crt_core.h:70): beam-energy dependent line width */
 } ocrt_sys;
 
 /* Mirrors the caller-visible part of struct CRT (crt_core.h:74-92). */
@@ -72,6 +73,7 @@ typedef struct ocrt_monitor {
     unsigned v_fac;
     int ccf[OCRT_MAX_VPER][OCRT_MAX_CC];
     int hsync, vsync, rn;
+    int last_noise; /* `noise` of the crt_demodulate call in progress (the bloom energy scale uses it, crt_core.c:400) */
 } ocrt_monitor;
 
 /* struct NTSC_SETTINGS of the RGB systems (crt_ntsc.h:111-124, crt_ntscvhs.h:133-147) */
@@ -119,6 +121,8 @@ const ocrt_sys *ocrt_system(int system, int chroma_pattern);
 /* the same system with the reference's USE_CONVOLUTION 1 decoder (crt_core.c:85) */
 const ocrt_sys *ocrt_system_conv(int system, int chroma_pattern);
 const ocrt_sys *ocrt_system_conv_taps(int system, int chroma_pattern, int taps); /* 4 .. 7 */
+/* the same system built with CRT_DO_BLOOM 1 (crt_core.h:70; RGB systems) */
+const ocrt_sys *ocrt_system_bloom(int system, int chroma_pattern);
 
 void ocrt_sincos14(int *s, int *c, int n);
 int  ocrt_bpp(int format);

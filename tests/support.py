@@ -189,7 +189,7 @@ class _OSys(C.Structure):
         "cc_vper", "hsync_window", "vsync_window", "hsync_thresh", "vsync_thresh",
         "sync_beg", "bw_beg", "cb_beg", "av_beg", "av_len", "burst_len",
         "white_level", "burst_level", "black_level", "blank_level", "sync_level",
-        "vhs_noise", "nes_vsync_end")] + [("eq", (C.c_int * 5) * 3), ("iir_c", C.c_int * 3), ("conv", C.c_int), ("cc_samples", C.c_int)]
+        "vhs_noise", "nes_vsync_end")] + [("eq", (C.c_int * 5) * 3), ("iir_c", C.c_int * 3), ("conv", C.c_int), ("cc_samples", C.c_int), ("bloom", C.c_int)]
 
 
 class _OMonitor(C.Structure):
@@ -201,6 +201,7 @@ class _OMonitor(C.Structure):
         ("saturation", C.c_int), ("black_point", C.c_int), ("white_point", C.c_int),
         ("scanlines", C.c_int), ("blend", C.c_int), ("v_fac", C.c_uint),
         ("ccf", (C.c_int * 5) * 5), ("hsync", C.c_int), ("vsync", C.c_int), ("rn", C.c_int),
+        ("last_noise", C.c_int),
     ]
 
 
@@ -242,6 +243,8 @@ def oracle_lib():
         lib.ocrt_system_conv.argtypes = [C.c_int, C.c_int]
         lib.ocrt_system_conv_taps.restype = C.POINTER(_OSys)
         lib.ocrt_system_conv_taps.argtypes = [C.c_int, C.c_int, C.c_int]
+        lib.ocrt_system_bloom.restype = C.POINTER(_OSys)
+        lib.ocrt_system_bloom.argtypes = [C.c_int, C.c_int]
         lib.ocrt_monitor_create.argtypes = [C.POINTER(_OSys), C.POINTER(_OMonitor), C.c_int,
                                             C.c_int, C.c_int, C.c_void_p]
         lib.ocrt_monitor_create.restype = C.c_int
@@ -279,8 +282,11 @@ class OracleEngine:
         self.spec = layout.system_spec(variant)
         self.lib = oracle_lib()
         taps = layout.conv_taps(variant)
-        self.sys = (self.lib.ocrt_system_conv_taps(self.spec.system, self.spec.pattern, taps) if taps
-                    else self.lib.ocrt_system(self.spec.system, self.spec.pattern))
+        if variant.endswith("_bloom"):
+            self.sys = self.lib.ocrt_system_bloom(self.spec.system, self.spec.pattern)
+        else:
+            self.sys = (self.lib.ocrt_system_conv_taps(self.spec.system, self.spec.pattern, taps) if taps
+                        else self.lib.ocrt_system(self.spec.system, self.spec.pattern))
         assert self.sys, "unknown system"
         self.mon = _OMonitor()
         bpp = max(1, layout.bpp4fmt(fmt))

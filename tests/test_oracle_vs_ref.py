@@ -32,7 +32,7 @@ def check(ref, ora, what):
 
 
 def test_struct_layout_matches_reference():
-    for variant in ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "snes", "nesrgb", "template", "pv1k"):
+    for variant in ("ntsc", "ntsc_bloom", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "snes", "nesrgb", "template", "pv1k"):
         spec = layout.system_spec(variant)
         lib = C.CDLL(S.ref_path(variant))
         assert lib.ref_sizeof_crt() == C.sizeof(layout.crt_struct(spec)), variant
@@ -263,6 +263,21 @@ def test_pv1k_system(fmt, as_color, raw, conv):
         check(ref, ora, "pv1k mod %d" % it)
         both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 9))
         check(ref, ora, "pv1k demod %d" % it)
+
+
+@pytest.mark.parametrize("outw,outh,raw", [(832, 624, 0), (640, 480, 0), (333, 250, 1)])
+def test_bloom_option(outw, outh, raw):
+    """CRT_DO_BLOOM 1 (crt_core.h:70; crt_core.c:399-402, 512-526; crt_ntsc.c:148-161): a line's width follows the
+    filtered beam energy, carried from line to line.  No product library yet: this pins the oracle."""
+    img = S.bars_image(300, 260) if not raw else S.rand_image(200, 180, seed=5)
+    ref, ora = pair("ntsc_bloom", outw, outh)
+    both(ref, ora, lambda e: e.set(blend=1, scanlines=1, brightness=4, contrast=190))
+    for it in range(5):
+        both(ref, ora, lambda e: e.modulate(img, format=layout.PIX_BGRA, as_color=1, raw=raw, field=it & 1 if not raw else 0,
+                                            frame=(it >> 1) & 1))
+        check(ref, ora, "bloom mod %d" % it)
+        both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 20))
+        check(ref, ora, "bloom demod %d" % it)
 
 
 @pytest.mark.parametrize("fmt", [layout.PIX_BGRA, layout.PIX_RGB, layout.PIX_ARGB, 9])
