@@ -305,6 +305,7 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
                 tma_store_wait_read<0>();
                 if (prefetch_old && nxt_active) request_old(nxt, buf ^ 1, 0, seg0);
             }
+            __syncwarp(); // no lane writes this line's row buffer before the stores that last read it are known done
 
             // ---- (P) pixels (crt_core.c:555-659), 32 consecutive ones per step
             const Elem *slot1 = yrow + 1; // slot of sample 0
