@@ -354,7 +354,6 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
                         mbar_wait(&bars[2 + buf], (ph_old >> buf) & 1);
                         ph_old ^= 1u << buf;
                     }
-#pragma unroll
                     const int steps = (cnt + 31) >> 5; // lanes (and one whole step) past cnt compute into the unused tail
                     auto emit = [&](int u) {
                         const int j = u * 32 + lane;
