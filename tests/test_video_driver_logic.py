@@ -40,7 +40,7 @@ def driver(tmp_path_factory):
     inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "oracle")]
     subprocess.run(["gcc", "-O2", "-fPIC", "-fwrapv", "-shared", "-o", str(lib), os.path.join(ROOT, "tests", "mock_crtx.c"),
                     os.path.join(ROOT, "oracle", "crt_oracle.c")] + inc, check=True)
-    subprocess.run(["gcc", "-std=c89", "-pedantic", "-O2", "-o", str(exe), os.path.join(ROOT, "tools", "crtx_video.c"),
+    subprocess.run(["gcc", "-std=c89", "-pedantic", "-O2", "-pthread", "-o", str(exe), os.path.join(ROOT, "tools", "crtx_video.c"),
                     "-I" + os.path.join(ROOT, "include"), "-L" + str(d), "-lcrt_b200_ntsc", "-Wl,-rpath," + str(d)], check=True)
     return str(exe)
 
@@ -60,6 +60,7 @@ def frames_for(n, w, h, wild):
 
 @pytest.mark.parametrize("flags,noise,segments,n,wild", [
     ([], 0, 4, 14, False),
+    ([], 3, 2, 23, False),           # many steps: the reader / writer threads cycle through both buffer sets
     (["-m"], 9, 14, 14, False),      # one image per segment: every seam is a halo seam
     (["-a"], 255, 5, 16, True),      # noise far beyond what the speculated sync state survives
     (["-p"], 200, 3, 10, True),

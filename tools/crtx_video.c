@@ -17,13 +17,16 @@
  *                        must equal the preceding segment's last image, which is verified too
  * File bytes travel as they are stored: the pixel array of each BMP goes to the device unchanged and is
  * unpacked there (crtx_bmp_unpack), decoded images are packed into the writer's layout on the device too.
+ * File I/O overlaps the device: while step t runs, one thread reads the files of step t + 1 into the other set of
+ * page-locked buffers and another writes the images of step t - 1 (only the main thread talks to the library).
  * A segment that fails verification is decoded again, sequentially, from the true state; its
  * files are rewritten.  The result is what the sequential loop writes (tests/test_gpu_video_driver.py).
  *
- *   cc -std=c89 -O2 -I../include crtx_video.c -L../ntsc-crt_b200/lib -lcrt_b200_ntsc -o crtx_video
+ *   cc -std=c89 -O2 -pthread -I../include crtx_video.c -L../ntsc-crt_b200/lib -lcrt_b200_ntsc -o crtx_video
  *   ./crtx_video [-m] [-p] [-a] [-S segments] num_frames outwidth outheight noise
  * (-m monochrome, -p progressive, -a no scanlines: the letters of video_convert.c's option word.)
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -205,6 +208,45 @@ fetch_image(const struct job *j, const void *dev_bgra, void *dev_file, unsigned 
     TRY(crtx_memcpy(host, dev_file, j->out_bytes, 1, NULL));
 }
 
+/* ---- file I/O of one step on its own thread: `count` images read into / written from page-locked buffers ---- */
+struct io_batch {
+    struct job *j;
+    int count, write, running;
+    int *frame;
+    unsigned char **buf;
+    pthread_t th;
+};
+
+static void *
+io_main(void *arg)
+{
+    struct io_batch *b = (struct io_batch *) arg;
+    int i;
+    for (i = 0; i < b->count; i++) {
+        if (b->write) save_image(b->j, b->frame[i], b->buf[i]);
+        else load_image(b->j, b->frame[i], b->buf[i]);
+    }
+    return NULL;
+}
+
+static void
+io_start(struct io_batch *b)
+{
+    if (b->count == 0) return;
+    if (pthread_create(&b->th, NULL, io_main, b) != 0) { /* no thread: do it here */
+        io_main(b);
+        return;
+    }
+    b->running = 1;
+}
+
+static void
+io_join(struct io_batch *b)
+{
+    if (b->running) pthread_join(b->th, NULL);
+    b->running = 0;
+}
+
 static void
 fill_source(const struct job *j, crtx_source *s, const void *dev, int f)
 {
@@ -227,7 +269,8 @@ main(int argc, char **argv)
     crtx_monitor *mons;
     crtx_source *srcs;
     crtx_state *st, *st_halo, *fin;
-    unsigned char **hsrc, **hout;
+    unsigned char **hsrc, **hout, **hsrc2, **hout2; /* two sets of staging buffers: [s] and [S + s] */
+    struct io_batch rd[2], wr[2];
     void **dsrc, **draw, **dfile, **work, **halo;
     int after_hs[2], after_vs[2], have_after[2];
     unsigned rn0 = 194u; /* crt_init, crt_core.c:269 */
@@ -300,12 +343,14 @@ main(int argc, char **argv)
     fin = (crtx_state *) calloc(S, sizeof(*st));
     hsrc = (unsigned char **) calloc(S, sizeof(*hsrc));
     hout = (unsigned char **) calloc(S, sizeof(*hout));
+    hsrc2 = (unsigned char **) calloc(S, sizeof(*hsrc2));
+    hout2 = (unsigned char **) calloc(S, sizeof(*hout2));
     dsrc = (void **) calloc(S, sizeof(*dsrc));
     draw = (void **) calloc(S, sizeof(*draw));
     dfile = (void **) calloc(S, sizeof(*dfile));
     work = (void **) calloc(S, sizeof(*work));
     halo = (void **) calloc(S, sizeof(*halo));
-    if (!lo || !hi || !mons || !srcs || !st || !st_halo || !fin || !hsrc || !hout || !dsrc || !draw || !dfile || !work || !halo) die("out of memory");
+    if (!lo || !hi || !mons || !srcs || !st || !st_halo || !fin || !hsrc || !hout || !hsrc2 || !hout2 || !dsrc || !draw || !dfile || !work || !halo) die("out of memory");
 
     TRY(crtx_create(&ctx, S));
     longest = 0;
@@ -314,12 +359,14 @@ main(int argc, char **argv)
         if (hi[s] - lo[s] > longest) longest = hi[s] - lo[s];
         hsrc[s] = (unsigned char *) crtx_host_alloc(j.file_bytes);
         hout[s] = (unsigned char *) crtx_host_alloc(j.out_bytes);
+        hsrc2[s] = (unsigned char *) crtx_host_alloc(j.file_bytes);
+        hout2[s] = (unsigned char *) crtx_host_alloc(j.out_bytes);
         dsrc[s] = crtx_device_alloc(j.src_bytes);
         draw[s] = crtx_device_alloc(j.file_bytes);
         dfile[s] = crtx_device_alloc(j.out_bytes);
         work[s] = crtx_device_alloc(j.out_bytes);
         halo[s] = crtx_device_alloc(j.out_bytes);
-        if (!hsrc[s] || !hout[s] || !dsrc[s] || !draw[s] || !dfile[s] || !work[s] || !halo[s]) die("out of memory (device or pinned host)");
+        if (!hsrc[s] || !hout[s] || !hsrc2[s] || !hout2[s] || !dsrc[s] || !draw[s] || !dfile[s] || !work[s] || !halo[s]) die("out of memory (device or pinned host)");
         mons[s].out = work[s];
         mons[s].outw = j.outw;
         mons[s].outh = j.outh;
@@ -393,22 +440,74 @@ main(int argc, char **argv)
     for (s = 1; s < S; s++) TRY(crtx_memcpy(halo[s], work[s], j.out_bytes, 2, NULL));
 
     /* ---- main steps: step t decodes image lo[s] + t of every segment still inside its span; longer
-     * segments come first, so the active ones are 0 .. count - 1 ---- */
+     * segments come first, so the active ones are 0 .. count - 1.  Two sets of page-locked buffers alternate:
+     * the files of step t + 1 are read, and the images of step t - 1 written, by two helper threads while the
+     * device works on step t.  A set is handed to a thread only after the crtx_sync that ends the step which
+     * copied from / into it, and taken back (join) before the next step that uses it issues its copies. ---- */
+    for (t = 0; t < 2; t++) {
+        rd[t].j = wr[t].j = &j;
+        rd[t].write = 0;
+        wr[t].write = 1;
+        rd[t].running = wr[t].running = 0;
+        rd[t].count = wr[t].count = 0;
+        rd[t].frame = (int *) malloc(sizeof(int) * S);
+        wr[t].frame = (int *) malloc(sizeof(int) * S);
+        rd[t].buf = (unsigned char **) malloc(sizeof(unsigned char *) * S);
+        wr[t].buf = (unsigned char **) malloc(sizeof(unsigned char *) * S);
+        if (!rd[t].frame || !wr[t].frame || !rd[t].buf || !wr[t].buf) die("out of memory");
+    }
+#define ACTIVE_AT(step, n) do { (n) = 0; for (s = 0; s < S; s++) if (lo[s] + (step) < hi[s]) (n) = s + 1; } while (0)
+#define SET_OF(step, a, b) (((step) & 1) ? (b) : (a))
+    ACTIVE_AT(0, rd[0].count);
+    for (s = 0; s < rd[0].count; s++) {
+        rd[0].frame[s] = lo[s];
+        rd[0].buf[s] = hsrc[s];
+    }
+    io_start(&rd[0]);
     for (t = 0; t < longest; t++) {
-        int count = 0;
-        for (s = 0; s < S; s++) {
-            if (lo[s] + t < hi[s]) {
-                count = s + 1;
-                stage_image(&j, lo[s] + t, hsrc[s], draw[s], dsrc[s]);
-                fill_source(&j, &srcs[s], dsrc[s], lo[s] + t);
+        const int cur = t & 1;
+        unsigned char **in = SET_OF(t, hsrc, hsrc2), **outb = SET_OF(t, hout, hout2);
+        int count;
+        ACTIVE_AT(t, count);
+        io_join(&rd[cur]); /* the files of this step are in `in` */
+        if (t + 1 < longest) { /* the other input set was last copied from in step t - 1, which has been synced */
+            unsigned char **nin = SET_OF(t + 1, hsrc, hsrc2);
+            ACTIVE_AT(t + 1, rd[cur ^ 1].count);
+            for (s = 0; s < rd[cur ^ 1].count; s++) {
+                rd[cur ^ 1].frame[s] = lo[s] + t + 1;
+                rd[cur ^ 1].buf[s] = nin[s];
             }
+            io_start(&rd[cur ^ 1]);
+        }
+        io_join(&wr[cur]); /* the writer of step t - 2 is done with `outb` */
+        for (s = 0; s < count; s++) {
+            TRY(crtx_memcpy(draw[s], in[s], j.file_bytes, 0, NULL));
+            TRY(crtx_bmp_unpack(dsrc[s], draw[s], j.w, j.h, j.bits, NULL));
+            fill_source(&j, &srcs[s], dsrc[s], lo[s] + t);
         }
         TRY(crtx_modulate(ctx, 0, count, srcs, NULL));
         TRY(crtx_demodulate(ctx, 0, count, NULL));
-        for (s = 0; s < count; s++) fetch_image(&j, work[s], dfile[s], hout[s]);
+        for (s = 0; s < count; s++) fetch_image(&j, work[s], dfile[s], outb[s]);
         TRY(crtx_sync(NULL));
-        for (s = 0; s < count; s++) save_image(&j, lo[s] + t, hout[s]);
+        wr[cur].count = count;
+        for (s = 0; s < count; s++) {
+            wr[cur].frame[s] = lo[s] + t;
+            wr[cur].buf[s] = outb[s];
+        }
+        io_start(&wr[cur]);
         printf("step %d / %d\n", t + 1, longest);
+    }
+    io_join(&wr[0]);
+    io_join(&wr[1]);
+    io_join(&rd[0]);
+    io_join(&rd[1]);
+#undef ACTIVE_AT
+#undef SET_OF
+    for (t = 0; t < 2; t++) {
+        free(rd[t].frame);
+        free(wr[t].frame);
+        free(rd[t].buf);
+        free(wr[t].buf);
     }
     TRY(crtx_get_state(ctx, 0, S, fin, NULL));
 
@@ -442,6 +541,8 @@ main(int argc, char **argv)
     for (s = 0; s < S; s++) {
         crtx_host_free(hsrc[s]);
         crtx_host_free(hout[s]);
+        crtx_host_free(hsrc2[s]);
+        crtx_host_free(hout2[s]);
         crtx_device_free(dsrc[s]);
         crtx_device_free(draw[s]);
         crtx_device_free(dfile[s]);
