@@ -25,6 +25,7 @@
 #include "crt_sys.cuh"
 #include "crtx_batch.h"
 #include "crt_records.h"
+#include "crt_ptx.cuh"
 
 namespace crt {
 
@@ -86,61 +87,6 @@ __device__ __forceinline__ void fmt_positions(int f, int &r, int &g, int &b)
         default:                  r = 2; g = 1; b = 0; break; // BGRA
     }
 }
-
-// ---------------------------------------------------------------------------------------
-// TMA (1-D bulk copy) + mbarrier primitives
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-
-__device__ __forceinline__ void mbar_fence_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
-// global -> shared bulk copy; dst, src and bytes must all be multiples of 16
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-            smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
-// 16-byte asynchronous copies global -> shared issued per lane (LDGSTS): the right tool when every lane
-// fetches its own small span -- a per-lane bulk copy is a warp-serial instruction (one issue per lane)
-__device__ __forceinline__ void cp_async_16(void *dst, const void *src)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int PENDING> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
 // =======================================================================================
 // encoder, RGB systems

@@ -56,30 +56,6 @@ template <bool FAST> struct FirRow {
 template <bool FAST> constexpr int fir_warp_smem() { return 2 * kFirStage + FirRow<FAST>::kBytes + 2 * kFirSeg * 4; }
 template <bool FAST> constexpr int fir_smem() { return kFirWarps * fir_warp_smem<FAST>() + kFirWarps * 4 * 8; }
 
-// shared -> global bulk copy (the mirror of tma_load_1d) and its bookkeeping
-__device__ __forceinline__ void tma_store_1d(void *dst, const void *src, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int PENDING> __device__ __forceinline__ void tma_store_wait_read()
-{
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// Row element at a shared-memory ADDRESS (+ constant byte offset), sign-extended.  The resampler keeps
-// absolute shared addresses in registers; going through ld.shared directly keeps the address arithmetic
-// out of the pixel loop (a generic pointer would be re-derived from the shared window base every time).
-template <typename Elem, int OFF> __device__ __forceinline__ int lds_elem(unsigned addr)
-{
-    int v;
-    if (sizeof(Elem) == 2) asm volatile("ld.shared.s16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
-    else asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
-    return v;
-}
-
 // One channel of the factored kernel.  All four kernels are cascades of [1 1] stages and one box:
 //   7 taps [1 4 7 8 7 4 1] = [1 1]^3 * [1 1 1 1]      6 taps [1 3 4 4 3 1] = [1 1]^2 * [1 1 1 1]
 //   5 taps [1 2 2 2 1]     = [1 1]   * [1 1 1 1]      4 taps [1 1 1 1]

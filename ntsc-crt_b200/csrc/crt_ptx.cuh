@@ -1,0 +1,91 @@
+// crt_ptx.cuh -- every line of inline PTX the kernels use, in one place: shared-memory addresses, mbarriers,
+// 1-D bulk copies (TMA) in both directions, per-lane asynchronous 16-byte copies, shared loads at absolute
+// addresses.  (tests/simt/ substitutes this one header to execute the unchanged kernels on a CPU for debugging;
+// nothing in the product includes or links that.)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace crt {
+
+// ---------------------------------------------------------------------------------------
+// TMA (1-D bulk copy) + mbarrier primitives
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// global -> shared bulk copy; dst, src and bytes must all be multiples of 16
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// 16-byte asynchronous copies global -> shared issued per lane (LDGSTS): the right tool when every lane
+// fetches its own small span -- a per-lane bulk copy is a warp-serial instruction (one issue per lane)
+__device__ __forceinline__ void cp_async_16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+// shared -> global bulk copy (the mirror of tma_load_1d) and its bookkeeping
+__device__ __forceinline__ void tma_store_1d(void *dst, const void *src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int PENDING> __device__ __forceinline__ void tma_store_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Row element at a shared-memory ADDRESS (+ constant byte offset), sign-extended.  The resampler keeps
+// absolute shared addresses in registers; going through ld.shared directly keeps the address arithmetic
+// out of the pixel loop (a generic pointer would be re-derived from the shared window base every time).
+template <typename Elem, int OFF> __device__ __forceinline__ int lds_elem(unsigned addr)
+{
+    int v;
+    if (sizeof(Elem) == 2) asm volatile("ld.shared.s16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    else asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+} // namespace crt

@@ -1,0 +1,76 @@
+"""The GPU parity tests, run on the CPU through the SIMT interpreter (tests/simt/): the product's CUDA sources,
+unchanged, compiled by g++ and executed one CUDA thread per fiber.  This is how kernel logic is checked in a
+container without a GPU -- block / warp synchronisation, shuffles, ballots, mbarriers and deferred bulk copies
+included -- against the same oracle and reference the `-m gpu` tests use.  It says nothing about timing, and the
+`-m gpu` tests on the B200 remain the parity proof of the real binary.
+
+The test bodies are the ones of tests/test_gpu_*.py, re-collected here without the gpu mark; a fixture points the
+loaders at tests/simt/_build/libcrt_simt_<variant>.so and lets "device" tensors be host tensors.
+"""
+import os
+import sys
+
+import pytest
+
+import support as S
+from ntsc_crt_b200 import capi
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
+import build as simt_build  # noqa: E402
+
+import test_gpu_conv as _conv  # noqa: E402
+import test_gpu_fuzz as _fuzz  # noqa: E402
+import test_gpu_lineshard as _lineshard  # noqa: E402
+import test_gpu_parity as _parity  # noqa: E402
+import test_gpu_video as _video  # noqa: E402
+
+
+@pytest.fixture(scope="session")
+def simt_libs():
+    simt_build.build()
+    return simt_build.lib_path
+
+
+@pytest.fixture(autouse=True)
+def simt_backend(simt_libs, monkeypatch):
+    import torch
+    monkeypatch.setattr(capi, "lib_path", simt_libs)
+    monkeypatch.setattr(capi, "_libs", {})
+    real_zeros, real_empty = torch.zeros, torch.empty
+
+    def host_only(fn):
+        def wrapped(*a, **kw):
+            kw.pop("device", None)
+            return fn(*a, **kw)
+        return wrapped
+    monkeypatch.setattr(torch, "zeros", host_only(real_zeros))
+    monkeypatch.setattr(torch, "empty", host_only(real_empty))
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **kw: self)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **kw: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **kw: type("S", (), {"cuda_stream": 0})())
+    yield
+
+
+def _adopt(module, prefix):
+    for name in dir(module):
+        if name.startswith("test_"):
+            globals()["test_%s_%s" % (prefix, name[5:])] = getattr(module, name)
+
+
+_adopt(_parity, "parity")
+_adopt(_conv, "conv")
+_adopt(_fuzz, "fuzz")
+_adopt(_lineshard, "lineshard")
+_adopt(_video, "video")
+
+
+def test_the_interpreter_ran_kernels(simt_libs):
+    """Guard against a silent fall-through: the library under test is the interpreter build and it launches."""
+    import ctypes as C
+    lib = C.CDLL(simt_libs("ntsc"))
+    lib.simt_launches.restype = C.c_long
+    before = lib.simt_launches()
+    e = S.ProductEngine("ntsc", 64, 48)
+    e.modulate(S.rand_image(32, 24), format=5, as_color=1)
+    e.demodulate(0)
+    assert lib.simt_launches() >= before + 4
