@@ -19,6 +19,7 @@
  *      CRT_SYSTEM 1, CRT_CHROMA_PATTERN 0    libcrt_b200_nes_p0.so
  *      CRT_SYSTEM 3                          libcrt_b200_snes.so
  *      CRT_SYSTEM 6                          libcrt_b200_nesrgb.so
+ *      CRT_SYSTEM 4                          libcrt_b200_template.so
  */
 #ifndef CRT_B200_H
 #define CRT_B200_H
@@ -31,7 +32,7 @@ extern "C" {
 #define CRT_MINOR 3
 #define CRT_PATCH 2
 
-/* crt_core.h:30-36 -- only 0, 1 and 5 exist in this library */
+/* crt_core.h:30-36 -- every system but the PV-1000 (2) exists in this library */
 #define CRT_SYSTEM_NTSC    0
 #define CRT_SYSTEM_NES     1
 #define CRT_SYSTEM_PV1K    2
@@ -225,8 +226,50 @@ struct NTSC_SETTINGS {
     int field_initialized; /* zero the struct before first use */
 };
 
+#elif (CRT_SYSTEM == CRT_SYSTEM_TEMP)
+/* ---- the reference's worked example for new systems, crt_template.h:22-175: composite NTSC timing, a 2-line
+ * chroma cycle walked by dot_crawl_offset, band-limited RGB encoder ---- */
+#define CRT_CC_LINE  2275
+#define CRT_HRES     (CRT_CC_LINE * CRT_CB_FREQ / 10)
+#define CRT_TOP      21
+#define CRT_BOT      261
+#define CRT_CC_VPER  2
+#define CRT_HSYNC_WINDOW 8
+#define CRT_VSYNC_WINDOW 8
+#define CRT_B200_LINE_UNITS (1500 + 4700 + 600 + 2500 + 1600 + 52600) /* ns */
+#define CRT_B200_POS(u) ((u) * CRT_HRES / CRT_B200_LINE_UNITS)
+#define ns2pos(u)    CRT_B200_POS(u)
+#define SYNC_BEG     CRT_B200_POS(1500)
+#define BW_BEG       CRT_B200_POS(1500 + 4700)
+#define CB_BEG       CRT_B200_POS(1500 + 4700 + 600)
+#define BP_BEG       CRT_B200_POS(1500 + 4700 + 600 + 2500)
+#define AV_BEG       CRT_B200_POS(1500 + 4700 + 600 + 2500 + 1600)
+#define AV_LEN       CRT_B200_POS(52600)
+#define WHITE_LEVEL  100
+#define BURST_LEVEL  20
+#define BLACK_LEVEL  7
+#define SYNC_LEVEL   (-40)
+#define CRT_DO_BANDLIMITING 1
+#define Q_OFFSET     (-90) /* crt_template.h:139 */
+#define HUE_OFFSET   (-60) /* crt_template.h:142 */
+
+struct NTSC_SETTINGS {
+    const unsigned char *data; /* image, one of the CRT_PIX_FORMATs */
+    int format;
+    int w, h;
+    int raw;      /* 1 = do not scale to the active picture area */
+    int as_color; /* 0 = monochrome */
+    int field;    /* 0 even / 1 odd */
+    int frame;    /* 0 even / 1 odd (unused by this encoder) */
+    int hue;      /* 0..359 */
+    int xoffset;  /* samples */
+    int yoffset;  /* lines */
+    int dot_crawl_offset; /* 0..5 */
+    int iirs_initialized; /* zero the struct before first use */
+};
+
 #else
-#error "crt_b200: this library implements CRT_SYSTEM 0 (NTSC), 1 (NES), 3 (SNES), 5 (NTSCVHS) and 6 (NESRGB) only"
+#error "crt_b200: this library implements CRT_SYSTEM 0 (NTSC), 1 (NES), 3 (SNES), 4 (TEMP), 5 (NTSCVHS) and 6 (NESRGB) only"
 #endif
 
 #define CRT_INPUT_SIZE (CRT_HRES * CRT_VRES)

@@ -249,8 +249,8 @@ void crt_modulate(struct CRT *v, struct NTSC_SETTINGS *s)
 #if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
     if (s->do_aberration) src.aberration = ((rand() % 12) - 8) + 14; /* crt_ntscvhs.c:205-207 */
 #endif
-#if (CRT_SYSTEM == CRT_SYSTEM_SNES)
-    src.dot_crawl_offset = s->dot_crawl_offset; /* crt_snes.c:172 */
+#if (CRT_SYSTEM == CRT_SYSTEM_SNES) || (CRT_SYSTEM == CRT_SYSTEM_TEMP)
+    src.dot_crawl_offset = s->dot_crawl_offset; /* crt_snes.c:172, crt_template.c:168 */
 #endif
     const size_t img_bytes = (size_t) s->w * s->h * bpp;
 #endif

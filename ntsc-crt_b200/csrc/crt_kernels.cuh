@@ -93,15 +93,47 @@ __device__ __forceinline__ void fmt_positions(int f, int &r, int &g, int &b)
 // =======================================================================================
 #if CRT_B200_NTSC_FAMILY
 
+// Burst and carrier tables of the encoder, entry x of colour row `row`: sin() >> 10 of
+//   NTSC / VHS (crt_ntsc.c:174-188): burst hue + 90x + 33, I hue + 90x, Q hue + 90x - 90 (one row);
+//   template   (crt_template.c:166-183): with n = (row + dot_crawl_offset) * 180 + hue + 90x:
+//              burst n - 90 + HUE_OFFSET, I n, Q n + Q_OFFSET (rows 0 and 1).
+__device__ __forceinline__ void enc_tables(const SrcCfg &s, int row, int x, int &burst, int &modI, int &modQ)
+{
+    burst = modI = modQ = 0;
+    if (!s.as_color) return;
+    int sn, cs;
+    if (kIsTemp) {
+        const int step = 360 / 4;
+        const int n = (row + s.dot_crawl_offset) * (360 / kVper) + s.hue + x * step;
+        sincos14_d(sn, cs, (n - step + (-60)) * 8192 / 180); // HUE_OFFSET, crt_template.h:142
+        burst = sn >> 10;
+        sincos14_d(sn, cs, n * 8192 / 180);
+        modI = sn >> 10;
+        sincos14_d(sn, cs, (n + (-90)) * 8192 / 180); // Q_OFFSET, crt_template.h:139
+        modQ = sn >> 10;
+    } else {
+        const int n = s.hue + x * 90;
+        sincos14_d(sn, cs, (n + 33) * 8192 / 180);
+        burst = sn >> 10;
+        sincos14_d(sn, cs, n * 8192 / 180);
+        modI = sn >> 10;
+        sincos14_d(sn, cs, (n - 90) * 8192 / 180);
+        modQ = sn >> 10;
+    }
+}
+
+// first / last line of the equalising and vertical-sync groups (crt_ntsc.c:214,222; crt_template.h:149-156)
+constexpr int kEquAHi = kIsTemp ? 2 : 3, kVsyncLo = kIsTemp ? 3 : 4, kVsyncHi = 6, kEquBLo = 7, kEquBHi = 9;
+
 // level of sample t of line n in the sync / blanking / burst skeleton (crt_ntsc.c:205-252)
 __device__ __forceinline__ int skeleton_level(int n, int t, int field, int flip, int aberration, const int *burst)
 {
     constexpr int H = kHres;
-    if (n <= 3 || (n >= 7 && n <= 9)) {
+    if (n <= kEquAHi || (n >= kEquBLo && n <= kEquBHi)) {
         bool sync = (t < 4 * H / 100) || (t >= 50 * H / 100 && t < 54 * H / 100);
         return sync ? kSync : kBlank;
     }
-    if (n >= 4 && n <= 6) {
+    if (n >= kVsyncLo && n <= kVsyncHi) {
         int first = (field == 1 ? 4 : 46) * H / 100;
         bool sync = (t < first) || (t >= 50 * H / 100 && t < 96 * H / 100);
         return sync ? kSync : kBlank;
@@ -123,21 +155,17 @@ __global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restri
     constexpr int kTotal = kTop * kFullPairs + (kVres - kTop) * kHeadPairs;
     const SrcCfg s = srcs[blockIdx.x];
     signed char *analog = analog_base + (size_t) (first + blockIdx.x) * kSignalBytes;
-    __shared__ int burst[4];
+    __shared__ int burst[kVper][4];
 
     if (bpp_of(s.format) == 0) return; // crt_ntsc.c:190-193
-    if (threadIdx.x < 4) {
-        int v = 0;
-        if (s.as_color) { // crt_ntsc.c:174-188
-            int sn, cs;
-            sincos14_d(sn, cs, (s.hue + (int) threadIdx.x * 90 + 33) * 8192 / 180);
-            v = sn >> 10;
-        }
-        burst[threadIdx.x] = v;
+    if (threadIdx.x < 4 * kVper) {
+        int b, mi, mq;
+        enc_tables(s, (int) threadIdx.x >> 2, (int) threadIdx.x & 3, b, mi, mq);
+        burst[threadIdx.x >> 2][threadIdx.x & 3] = b;
     }
     __syncthreads();
     const int field = s.field & 1, frame = s.frame & 1;
-    const int flip = (field == frame);
+    const int flip = kIsTemp ? 0 : (field == frame); // the template system has no phase inversion
 
     (void) kTotal;
     // One warp per line; every line is a handful of constant runs (crt_ntsc.c:205-252), written as
@@ -150,12 +178,12 @@ __global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restri
         auto fill = [&](int from, int to, int level) {
             for (int t = from + lane; t < to; t += 32) line[t] = (signed char) level;
         };
-        if (n <= 3 || (n >= 7 && n <= 9)) { // equalising pulses
+        if (n <= kEquAHi || (n >= kEquBLo && n <= kEquBHi)) { // equalising pulses
             fill(0, 4 * H / 100, kSync);
             fill(4 * H / 100, 50 * H / 100, kBlank);
             fill(50 * H / 100, 54 * H / 100, kSync);
             fill(54 * H / 100, H, kBlank);
-        } else if (n >= 4 && n <= 6) { // vertical sync
+        } else if (n >= kVsyncLo && n <= kVsyncHi) { // vertical sync
             const int first = (field == 1 ? 4 : 46) * H / 100;
             fill(0, first, kSync);
             fill(first, 50 * H / 100, kBlank);
@@ -165,15 +193,19 @@ __global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restri
             fill(0, kSyncBeg, kBlank);
             fill(kSyncBeg, kBwBeg, (n < kVres - aberration) ? kSync : kBlank); // crt_ntscvhs.c:234-238
             fill(kBwBeg, kCbBeg, kBlank);
-            for (int t = kCbBeg + lane; t < kCbBeg + kBurstLen; t += 32)
-                line[t] = (signed char) ((kBlank + burst[(t + flip * 2) & 3] * kBurst) >> 5);
+            for (int t = kCbBeg + lane; t < kCbBeg + kBurstLen; t += 32) // crt_ntsc.c:236-246, crt_template.c:236-240
+                line[t] = (signed char) ((kBlank + burst[n % kVper][(t + flip * 2) & 3] * kBurst) >> 5);
             fill(kCbBeg + kBurstLen, (n < kTop) ? H : kAvBeg, kBlank);
         }
     }
-    if (threadIdx.x < 4) { // prime the burst lock (crt_ntsc.c:325-329 / crt_ntscvhs.c:332-336)
+    if (threadIdx.x < 4 * kVper) { // prime the burst lock (crt_ntsc.c:325-329 / crt_ntscvhs.c:332-336)
         MonState *st = &states[first + blockIdx.x];
-        int p = (int) (signed char) ((kBlank + burst[(threadIdx.x + flip * 2) & 3] * kBurst) >> 5);
-        st->ccf[0][threadIdx.x] = kIsVhs ? 0 : p * 128;
+        const int row = threadIdx.x >> 2, x = threadIdx.x & 3;
+        // template (crt_template.c:239, 331-335): every video line n stores its burst bytes in row (n + 3) % 2, so
+        // row r ends up with the bytes of the lines of the OTHER parity
+        const int from = kIsTemp ? (row + 1) % kVper : 0;
+        int p = (int) (signed char) ((kBlank + burst[from][(x + flip * 2) & 3] * kBurst) >> 5);
+        st->ccf[row][x] = kIsVhs ? 0 : p * 128;
         if (kIsVhs && threadIdx.x == 0) st->hsync = 0; // crt_ntscvhs.c:258-259
     }
 }
@@ -232,8 +264,9 @@ __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restric
     if (destw <= 0 || desth <= 0 || s.w <= 0 || s.h <= 0) return;
     const int field = s.field & 1, frame = s.frame & 1;
     const int flip = (field == frame);
-    const int ph = flip ? -1 : 1;
-    const int xo = (kAvBeg + s.xoffset + (kAvLen - destw) / 2) & ~3;
+    const int ph = kIsTemp ? 1 : (flip ? -1 : 1); // the template system walks colour rows instead (below)
+    const int xo_raw = kAvBeg + s.xoffset + (kAvLen - destw) / 2;
+    const int xo = kIsTemp ? xo_raw - (xo_raw % 4) : (xo_raw & ~3); // crt_template.c:199 / crt_ntsc.c:203
     const int yo = kTop + s.yoffset + (kLines - desth) / 2;
     const int white = kWhite * cfg.white_point / 100;
     const int ire0 = kBlack + cfg.black_point;
@@ -242,22 +275,19 @@ __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restric
     const unsigned char *data = static_cast<const unsigned char *>(s.data);
     const bool aligned4 = ((reinterpret_cast<uintptr_t>(data) & 3) == 0);
 
-    int mI[4], mQ[4]; // ph * ccmodI/Q (crt_ntsc.c:174-188, 314-315)
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        mI[k] = mQ[k] = 0;
-        if (s.as_color) {
-            int sn, cs, deg = s.hue + k * 90;
-            sincos14_d(sn, cs, deg * 8192 / 180);
-            mI[k] = ph * (sn >> 10);
-            sincos14_d(sn, cs, (deg - 90) * 8192 / 180);
-            mQ[k] = ph * (sn >> 10);
-        }
-    }
-
     const int y = warp * 32 + lane; // this lane's picture line
     const int y0 = warp * 32;
     if (y0 >= desth) return;
+    // ph * ccmodI/Q (crt_ntsc.c:174-188, 314-315); template: the tables of this lane's colour row (crt_template.c:266)
+    int mI[4], mQ[4];
+    const int crow = kIsTemp ? posmod(y + yo, kVper) : 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int b;
+        enc_tables(s, crow, k, b, mI[k], mQ[k]);
+        mI[k] *= ph;
+        mQ[k] *= ph;
+    }
     const int nlines = min(32, desth - y0);
     // source row of this lane's line (crt_ntsc.c:258-266).  The reference lets row == h read one
     // row past the image (undefined); we clamp to the last row instead.
@@ -406,29 +436,30 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
     }
     const int field = s.field & 1, frame = s.frame & 1;
     const int flip = (field == frame);
-    const int ph = flip ? -1 : 1;
-    const int xo = (kAvBeg + s.xoffset + (kAvLen - destw) / 2) & ~3;
+    const int ph = kIsTemp ? 1 : (flip ? -1 : 1); // the template system walks colour rows instead (below)
+    const int xo_raw = kAvBeg + s.xoffset + (kAvLen - destw) / 2;
+    const int xo = kIsTemp ? xo_raw - (xo_raw % 4) : (xo_raw & ~3); // crt_template.c:199 / crt_ntsc.c:203
     const int yo = kTop + s.yoffset + (kLines - desth) / 2;
     const int white = kWhite * cfg.white_point / 100;
     const int ire0 = kBlack + cfg.black_point;
     const unsigned char *data = static_cast<const unsigned char *>(s.data);
     constexpr bool color = COLOR;
 
-    int mI[4], mQ[4]; // ph * ccmodI/Q (crt_ntsc.c:174-188, 314-315)
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        mI[k] = mQ[k] = 0;
-        if (color) {
-            int sn, cs, deg = s.hue + k * 90;
-            sincos14_d(sn, cs, deg * 8192 / 180);
-            mI[k] = ph * (sn >> 10);
-            sincos14_d(sn, cs, (deg - 90) * 8192 / 180);
-            mQ[k] = ph * (sn >> 10);
-        }
-    }
-
     const bool active = lane < nlines;
     const int y = y0 + min(lane, nlines - 1);
+    // ph * ccmodI/Q (crt_ntsc.c:174-188, 314-315); template: the tables of this lane's colour row (crt_template.c:266)
+    int mI[4], mQ[4];
+    const int crow = kIsTemp ? posmod(y + yo, kVper) : 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int b;
+        mI[k] = mQ[k] = 0;
+        if (color) {
+            enc_tables(s, crow, k, b, mI[k], mQ[k]);
+            mI[k] *= ph;
+            mQ[k] *= ph;
+        }
+    }
     // source row of this lane's line (crt_ntsc.c:258-266); row == h (one past the image, undefined in
     // the reference) is clamped to the last row
     int row = (int) (((long long) y * s.h) / desth) + (field * s.h + desth) / desth / 2;

@@ -20,16 +20,23 @@
 namespace crt {
 
 constexpr int kSystem = CRT_SYSTEM;
-#ifndef CRT_CHROMA_PATTERN /* crt_snes.h has no such switch: 227.3 cycles per line, as NES pattern 2 */
+#ifndef CRT_CHROMA_PATTERN /* crt_snes.h has no such switch: 227.3 cycles per line, as NES pattern 2; */
+#if (CRT_SYSTEM == CRT_SYSTEM_TEMP) /* nor has crt_template.h: 227.5 cycles per line, as NTSC's pattern 1 */
+#define CRT_CHROMA_PATTERN 1
+#else
 #define CRT_CHROMA_PATTERN 2
+#endif
 #endif
 constexpr int kPattern = CRT_CHROMA_PATTERN;
 constexpr bool kIsNes = (CRT_SYSTEM == CRT_SYSTEM_NES);
 constexpr bool kIsVhs = (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS);
 constexpr bool kIsSnes = (CRT_SYSTEM == CRT_SYSTEM_SNES);
 constexpr bool kIsNesRgb = (CRT_SYSTEM == CRT_SYSTEM_NESRGB);
-// the systems whose encoder is crt_ntsc.c / crt_ntscvhs.c (band-limited RGB, 227.5 cycles per line)
-#define CRT_B200_NTSC_FAMILY ((CRT_SYSTEM == CRT_SYSTEM_NTSC) || (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS))
+constexpr bool kIsTemp = (CRT_SYSTEM == CRT_SYSTEM_TEMP);
+// the systems whose encoder is crt_ntsc.c / crt_ntscvhs.c / crt_template.c (band-limited RGB on the NTSC line
+// layout, 227.5 cycles per line); the template system walks a 2-line chroma cycle instead of flipping the phase
+#define CRT_B200_NTSC_FAMILY \
+    ((CRT_SYSTEM == CRT_SYSTEM_NTSC) || (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS) || (CRT_SYSTEM == CRT_SYSTEM_TEMP))
 // -DCRTX_CONV=1 builds the decoder of the reference's USE_CONVOLUTION 1 configuration (an unguarded
 // #define at crt_core.c:85, so a separate library like every other compile-time choice there)
 #ifndef CRTX_CONV
@@ -161,7 +168,7 @@ constexpr int bandlimit_c(int limit)
     return 2048 - exp_q11_c(-((6434 << 9) / ((1431818 << 9) / limit)));
 }
 
-#if (CRT_SYSTEM == CRT_SYSTEM_NTSC)
+#if (CRT_SYSTEM == CRT_SYSTEM_NTSC) || (CRT_SYSTEM == CRT_SYSTEM_TEMP) // crt_ntsc.h:86-90, crt_template.h:117-121
 constexpr int kIirY = bandlimit_c(420000), kIirI = bandlimit_c(150000), kIirQ = bandlimit_c(55000);
 static_assert(kIirY == 1233 && kIirI == 574 && kIirQ == 232, "NTSC band-limit (SURVEY.md 8a)");
 #elif (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)

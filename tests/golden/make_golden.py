@@ -78,6 +78,15 @@ case("nesrgb_640x480", "nesrgb", 640, 480, layout.PIX_BGRA, dict(blend=1, scanli
      ("rand", 256, 240, 4, 23),
      [(dict(format=layout.PIX_BGRA, hue=(i * 70) % 360, dot_crawl_offset=i % 3, xoffset=4 * (i & 1), yoffset=i % 2), 2 * i)
       for i in range(4)])
+# CRT_SYSTEM_TEMP (crt_template.c), from libref_template.so
+case("template_640x480", "template", 640, 480, layout.PIX_BGRA, dict(blend=1, scanlines=1, hue=-15, saturation=12),
+     ("rand", 300, 260, 4, 25),
+     [(dict(format=layout.PIX_BGRA, as_color=1, raw=0, field=i & 1, frame=(i >> 1) & 1, hue=(i * 50) % 360,
+            dot_crawl_offset=i % 4, xoffset=4 * (i & 1), yoffset=i % 3), 3 * i) for i in range(6)])
+case("template_wide_mono_rgb", "template", 333, 250, layout.PIX_RGB, dict(blend=0, scanlines=0, white_point=90),
+     ("rand", 1920, 400, 4, 26),
+     [(dict(format=layout.PIX_BGRA, as_color=i & 1, raw=0, field=i & 1, frame=0, hue=0, dot_crawl_offset=i, xoffset=0,
+            yoffset=0), 7) for i in range(3)])
 for v in ("nes", "nes_p0"):
     case("cfg3_%s" % v, v, 832, 624, layout.PIX_BGRA, dict(blend=0, scanlines=1),
          ("nes", 256, 240, 0, 5), [(dict(dot_crawl_offset=i % 3, hue=(i * 30) % 360), 4 * i) for i in range(5)])

@@ -22,6 +22,7 @@ import test_gpu_conv as _conv  # noqa: E402
 import test_gpu_fuzz as _fuzz  # noqa: E402
 import test_gpu_lineshard as _lineshard  # noqa: E402
 import test_gpu_parity as _parity  # noqa: E402
+import test_gpu_template as _template  # noqa: E402
 import test_gpu_video as _video  # noqa: E402
 
 
@@ -62,6 +63,18 @@ _adopt(_conv, "conv")
 _adopt(_fuzz, "fuzz")
 _adopt(_lineshard, "lineshard")
 _adopt(_video, "video")
+_adopt(_template, "template")
+
+
+import test_golden as _golden  # noqa: E402
+
+
+@pytest.mark.parametrize("name", [c["name"] for c in _golden.G.CASES])
+def test_golden_vectors_through_the_interpreter(name):
+    """the committed digests of the compiled reference (tests/golden/), reproduced by the interpreted kernels"""
+    import ctypes as C
+    C.CDLL(None).srand(1)  # the VHS drop-in draws from libc rand() like the reference
+    _golden.check(name, lambda v, w, h, f: S.ProductEngine(v, w, h, f))
 
 
 def test_the_interpreter_ran_kernels(simt_libs):
