@@ -20,6 +20,7 @@
  *      CRT_SYSTEM 3                          libcrt_b200_snes.so
  *      CRT_SYSTEM 6                          libcrt_b200_nesrgb.so
  *      CRT_SYSTEM 4                          libcrt_b200_template.so
+ *      CRT_SYSTEM 2                          libcrt_b200_pv1k.so
  */
 #ifndef CRT_B200_H
 #define CRT_B200_H
@@ -32,7 +33,7 @@ extern "C" {
 #define CRT_MINOR 3
 #define CRT_PATCH 2
 
-/* crt_core.h:30-36 -- every system but the PV-1000 (2) exists in this library */
+/* crt_core.h:30-36 */
 #define CRT_SYSTEM_NTSC    0
 #define CRT_SYSTEM_NES     1
 #define CRT_SYSTEM_PV1K    2
@@ -53,8 +54,13 @@ extern "C" {
 #define CRT_PIX_FORMAT_ABGR 4
 #define CRT_PIX_FORMAT_BGRA 5
 
+#if (CRT_SYSTEM == CRT_SYSTEM_PV1K)
+#define CRT_CB_FREQ    5 /* crt_pv1k.h:41,49: five samples per chroma period */
+#define CRT_CC_SAMPLES 5
+#else
 #define CRT_CB_FREQ    4
 #define CRT_CC_SAMPLES 4
+#endif
 #define CRT_VRES       262
 #define CB_CYCLES      10
 #define L_FREQ         1431818
@@ -268,8 +274,49 @@ struct NTSC_SETTINGS {
     int iirs_initialized; /* zero the struct before first use */
 };
 
+#elif (CRT_SYSTEM == CRT_SYSTEM_PV1K)
+/* ---- Casio PV-1000, crt_pv1k.h:36-151: 1920 samples per line, FIVE samples per chroma period, a 5-line chroma
+ * cycle walked by dot_crawl_offset, band-limited RGB encoder ---- */
+#define CRT_CC_LINE  2304
+#define CRT_HRES     (CRT_CC_LINE * CRT_CB_FREQ / 6)
+#define CRT_TOP      21
+#define CRT_BOT      261
+#define CRT_CC_VPER  5
+#define CRT_HSYNC_WINDOW 8
+#define CRT_VSYNC_WINDOW 8
+#define DOT_ns       223
+#define DOTx4_ns     892
+#define CRT_B200_LINE_UNITS ((3 + 3 + 2 + 4 + 4 + 55) * DOTx4_ns) /* ns */
+#define CRT_B200_POS(u) ((u) * CRT_HRES / CRT_B200_LINE_UNITS)
+#define ns2pos(u)    CRT_B200_POS(u)
+#define SYNC_BEG     CRT_B200_POS(3 * DOTx4_ns)
+#define BW_BEG       CRT_B200_POS((3 + 3) * DOTx4_ns)
+#define CB_BEG       CRT_B200_POS((3 + 3 + 2) * DOTx4_ns)
+#define BP_BEG       CRT_B200_POS((3 + 3 + 2 + 4) * DOTx4_ns)
+#define AV_BEG       CRT_B200_POS((3 + 3 + 2 + 4 + 4) * DOTx4_ns)
+#define AV_LEN       CRT_B200_POS(55 * DOTx4_ns)
+#define WHITE_LEVEL  100
+#define BURST_LEVEL  20
+#define BLACK_LEVEL  7
+#define SYNC_LEVEL   (-40)
+
+struct NTSC_SETTINGS {
+    const unsigned char *data; /* image, one of the CRT_PIX_FORMATs */
+    int format;
+    int w, h;
+    int raw;      /* 1 = do not scale to the active picture area */
+    int as_color; /* 0 = monochrome */
+    int field;    /* 0 even / 1 odd */
+    int frame;    /* 0 even / 1 odd (unused by this encoder) */
+    int hue;      /* 0..359 */
+    int xoffset;  /* samples */
+    int yoffset;  /* lines */
+    int dot_crawl_offset; /* 0..5 */
+    int iirs_initialized; /* zero the struct before first use */
+};
+
 #else
-#error "crt_b200: this library implements CRT_SYSTEM 0 (NTSC), 1 (NES), 3 (SNES), 4 (TEMP), 5 (NTSCVHS) and 6 (NESRGB) only"
+#error "crt_b200: unknown CRT_SYSTEM (0 NTSC, 1 NES, 2 PV1K, 3 SNES, 4 TEMP, 5 NTSCVHS, 6 NESRGB)"
 #endif
 
 #define CRT_INPUT_SIZE (CRT_HRES * CRT_VRES)

@@ -45,13 +45,13 @@ typedef struct crtx_source {
     int raw, as_color, field, frame;
     int hue, xoffset, yoffset;
     int do_aberration;    /* CRT_SYSTEM_NTSCVHS */
-    int dot_crawl_offset; /* CRT_SYSTEM_NES */
+    int dot_crawl_offset; /* CRT_SYSTEM_NES, _NESRGB, _SNES, _TEMP, _PV1K */
     int reinit;           /* CRT_SYSTEM_NES: settings.field_initialized was 0 */
 } crtx_source;
 
 /* the persistent decoder state of struct CRT */
 typedef struct crtx_state {
-    int ccf[3][4];
+    int ccf[5][5]; /* ccf[CRT_CC_VPER][CRT_CC_SAMPLES] of the variant in the top-left corner (5 x 5: the PV-1000) */
     int hsync, vsync;
     int rn;
 } crtx_state;
@@ -59,7 +59,7 @@ typedef struct crtx_state {
 /* what the sync pre-pass decided for one decoded scanline (diagnostics / tests) */
 typedef struct crtx_line {
     int pos;        /* start of the 1-line decode window in inp[] (crt_core.c:452-454) */
-    int wave0, wave1; /* hue-rotated carrier (crt_core.c:476-477) */
+    int wave0, wave1; /* hue-rotated carrier (crt_core.c:476-477); PV-1000: dci and dcq (crt_core.c:494-495) */
     int beg;        /* first output row, or -1 when the line is skipped (crt_core.c:431) */
     int end;        /* one past the last output row (crt_core.c:429,432) */
     int hsync;      /* after this line's search (crt_core.c:446) */

@@ -14,7 +14,7 @@ import os
 from . import LIB_DIR
 from . import layout
 
-VARIANTS = ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "snes", "nesrgb", "template")
+VARIANTS = ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "snes", "nesrgb", "template", "pv1k")
 
 
 def lib_path(variant):
@@ -36,7 +36,7 @@ class Source(C.Structure):  # crtx_source
 
 
 class State(C.Structure):  # crtx_state
-    _fields_ = [("ccf", (C.c_int * 4) * 3), ("hsync", C.c_int), ("vsync", C.c_int), ("rn", C.c_int)]
+    _fields_ = [("ccf", (C.c_int * 5) * 5), ("hsync", C.c_int), ("vsync", C.c_int), ("rn", C.c_int)]
 
 
 class Line(C.Structure):  # crtx_line

@@ -120,7 +120,7 @@ void push_state(Shadow *sh, const struct CRT *v)
     crtx_state s;
     memset(&s, 0, sizeof(s));
     for (int n = 0; n < CRT_CC_VPER; n++)
-        for (int x = 0; x < 4; x++) s.ccf[n][x] = v->ccf[n][x];
+        for (int x = 0; x < CRT_CC_SAMPLES; x++) s.ccf[n][x] = v->ccf[n][x];
     s.hsync = v->hsync;
     s.vsync = v->vsync;
     s.rn = v->rn;
@@ -132,7 +132,7 @@ void pull_state(Shadow *sh, struct CRT *v)
     crtx_state s;
     if (crtx_get_state(sh->ctx, 0, 1, &s, sh->stream)) die("crtx_get_state");
     for (int n = 0; n < CRT_CC_VPER; n++)
-        for (int x = 0; x < 4; x++) v->ccf[n][x] = s.ccf[n][x];
+        for (int x = 0; x < CRT_CC_SAMPLES; x++) v->ccf[n][x] = s.ccf[n][x];
     v->hsync = s.hsync;
     v->vsync = s.vsync;
     v->rn = s.rn;
@@ -249,8 +249,8 @@ void crt_modulate(struct CRT *v, struct NTSC_SETTINGS *s)
 #if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
     if (s->do_aberration) src.aberration = ((rand() % 12) - 8) + 14; /* crt_ntscvhs.c:205-207 */
 #endif
-#if (CRT_SYSTEM == CRT_SYSTEM_SNES) || (CRT_SYSTEM == CRT_SYSTEM_TEMP)
-    src.dot_crawl_offset = s->dot_crawl_offset; /* crt_snes.c:172, crt_template.c:168 */
+#if (CRT_SYSTEM == CRT_SYSTEM_SNES) || (CRT_SYSTEM == CRT_SYSTEM_TEMP) || (CRT_SYSTEM == CRT_SYSTEM_PV1K)
+    src.dot_crawl_offset = s->dot_crawl_offset; /* crt_snes.c:172, crt_template.c:168, crt_pv1k.c:168 */
 #endif
     const size_t img_bytes = (size_t) s->w * s->h * bpp;
 #endif

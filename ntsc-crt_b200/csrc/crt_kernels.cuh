@@ -91,18 +91,29 @@ __device__ __forceinline__ void fmt_positions(int f, int &r, int &g, int &b)
 // =======================================================================================
 // encoder, RGB systems
 // =======================================================================================
-#if CRT_B200_NTSC_FAMILY
+#if CRT_B200_BANDLIMITED
 
 // Burst and carrier tables of the encoder, entry x of colour row `row`: sin() >> 10 of
 //   NTSC / VHS (crt_ntsc.c:174-188): burst hue + 90x + 33, I hue + 90x, Q hue + 90x - 90 (one row);
 //   template   (crt_template.c:166-183): with n = (row + dot_crawl_offset) * 180 + hue + 90x:
-//              burst n - 90 + HUE_OFFSET, I n, Q n + Q_OFFSET (rows 0 and 1).
+//              burst n - 90 + HUE_OFFSET, I n, Q n + Q_OFFSET (rows 0 and 1);
+//   PV-1000    (crt_pv1k.c:166-181): with n = (row + dot_crawl_offset) * 144 + hue + 72x (x < 5):
+//              burst n - 72, I n, Q n + 90 (rows 0..4).
 __device__ __forceinline__ void enc_tables(const SrcCfg &s, int row, int x, int &burst, int &modI, int &modQ)
 {
     burst = modI = modQ = 0;
     if (!s.as_color) return;
     int sn, cs;
-    if (kIsTemp) {
+    if (kIsPv1k) {
+        const int step = 360 / 5;
+        const int n = (row + s.dot_crawl_offset) * (360 * 2 / kVper) + s.hue + x * step;
+        sincos14_d(sn, cs, (n - step) * 8192 / 180);
+        burst = sn >> 10;
+        sincos14_d(sn, cs, n * 8192 / 180);
+        modI = sn >> 10;
+        sincos14_d(sn, cs, (n + 90) * 8192 / 180);
+        modQ = sn >> 10;
+    } else if (kIsTemp) {
         const int step = 360 / 4;
         const int n = (row + s.dot_crawl_offset) * (360 / kVper) + s.hue + x * step;
         sincos14_d(sn, cs, (n - step + (-60)) * 8192 / 180); // HUE_OFFSET, crt_template.h:142
@@ -122,8 +133,10 @@ __device__ __forceinline__ void enc_tables(const SrcCfg &s, int row, int x, int 
     }
 }
 
-// first / last line of the equalising and vertical-sync groups (crt_ntsc.c:214,222; crt_template.h:149-156)
-constexpr int kEquAHi = kIsTemp ? 2 : 3, kVsyncLo = kIsTemp ? 3 : 4, kVsyncHi = 6, kEquBLo = 7, kEquBHi = 9;
+// first / last line of the equalising and vertical-sync groups (crt_ntsc.c:214,222; crt_template.h:149-156; the
+// PV-1000 has one equalising group and syncs at the bottom of the field, crt_pv1k.c:208,214)
+constexpr int kEquAHi = kIsPv1k ? -1 : kIsTemp ? 2 : 3, kEquBLo = 7, kEquBHi = 9;
+constexpr int kVsyncLo = kIsPv1k ? 258 : kIsTemp ? 3 : 4, kVsyncHi = kIsPv1k ? 260 : 6;
 
 // level of sample t of line n in the sync / blanking / burst skeleton (crt_ntsc.c:205-252)
 __device__ __forceinline__ int skeleton_level(int n, int t, int field, int flip, int aberration, const int *burst)
@@ -155,17 +168,17 @@ __global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restri
     constexpr int kTotal = kTop * kFullPairs + (kVres - kTop) * kHeadPairs;
     const SrcCfg s = srcs[blockIdx.x];
     signed char *analog = analog_base + (size_t) (first + blockIdx.x) * kSignalBytes;
-    __shared__ int burst[kVper][4];
+    __shared__ int burst[kVper][kCc];
 
     if (bpp_of(s.format) == 0) return; // crt_ntsc.c:190-193
-    if (threadIdx.x < 4 * kVper) {
+    if (threadIdx.x < kCc * kVper) {
         int b, mi, mq;
-        enc_tables(s, (int) threadIdx.x >> 2, (int) threadIdx.x & 3, b, mi, mq);
-        burst[threadIdx.x >> 2][threadIdx.x & 3] = b;
+        enc_tables(s, (int) threadIdx.x / kCc, (int) threadIdx.x % kCc, b, mi, mq);
+        burst[threadIdx.x / kCc][threadIdx.x % kCc] = b;
     }
     __syncthreads();
     const int field = s.field & 1, frame = s.frame & 1;
-    const int flip = kIsTemp ? 0 : (field == frame); // the template system has no phase inversion
+    const int flip = kRowCarrier ? 0 : (field == frame); // the template system and the PV-1000 have no phase inversion
 
     (void) kTotal;
     // One warp per line; every line is a handful of constant runs (crt_ntsc.c:205-252), written as
@@ -194,17 +207,17 @@ __global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restri
             fill(kSyncBeg, kBwBeg, (n < kVres - aberration) ? kSync : kBlank); // crt_ntscvhs.c:234-238
             fill(kBwBeg, kCbBeg, kBlank);
             for (int t = kCbBeg + lane; t < kCbBeg + kBurstLen; t += 32) // crt_ntsc.c:236-246, crt_template.c:236-240
-                line[t] = (signed char) ((kBlank + burst[n % kVper][(t + flip * 2) & 3] * kBurst) >> 5);
+                line[t] = (signed char) ((kBlank + burst[n % kVper][(t + flip * 2) % kCc] * kBurst) >> 5);
             fill(kCbBeg + kBurstLen, (n < kTop) ? H : kAvBeg, kBlank);
         }
     }
-    if (threadIdx.x < 4 * kVper) { // prime the burst lock (crt_ntsc.c:325-329 / crt_ntscvhs.c:332-336)
+    if (threadIdx.x < kCc * kVper) { // prime the burst lock (crt_ntsc.c:325-329 / crt_ntscvhs.c:332-336)
         MonState *st = &states[first + blockIdx.x];
-        const int row = threadIdx.x >> 2, x = threadIdx.x & 3;
-        // template (crt_template.c:239, 331-335): every video line n stores its burst bytes in row (n + 3) % 2, so
-        // row r ends up with the bytes of the lines of the OTHER parity
-        const int from = kIsTemp ? (row + 1) % kVper : 0;
-        int p = (int) (signed char) ((kBlank + burst[from][(x + flip * 2) & 3] * kBurst) >> 5);
+        const int row = threadIdx.x / kCc, x = threadIdx.x % kCc;
+        // template / PV-1000 (crt_template.c:239, 331-335; crt_pv1k.c:236, 326-330): every video line n stores its
+        // burst bytes in row (n + 3) % VPER, so row r ends up with the bytes of the lines with n % VPER == r - 3
+        const int from = kRowCarrier ? posmod(row - 3, kVper) : 0;
+        int p = (int) (signed char) ((kBlank + burst[from][(x + flip * 2) % kCc] * kBurst) >> 5);
         st->ccf[row][x] = kIsVhs ? 0 : p * 128;
         if (kIsVhs && threadIdx.x == 0) st->hsync = 0; // crt_ntscvhs.c:258-259
     }
@@ -264,9 +277,9 @@ __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restric
     if (destw <= 0 || desth <= 0 || s.w <= 0 || s.h <= 0) return;
     const int field = s.field & 1, frame = s.frame & 1;
     const int flip = (field == frame);
-    const int ph = kIsTemp ? 1 : (flip ? -1 : 1); // the template system walks colour rows instead (below)
+    const int ph = kRowCarrier ? 1 : (flip ? -1 : 1); // the template system and the PV-1000 walk colour rows instead (below)
     const int xo_raw = kAvBeg + s.xoffset + (kAvLen - destw) / 2;
-    const int xo = kIsTemp ? xo_raw - (xo_raw % 4) : (xo_raw & ~3); // crt_template.c:199 / crt_ntsc.c:203
+    const int xo = kRowCarrier ? xo_raw - (xo_raw % kCc) : (xo_raw & ~3); // crt_template.c:199, crt_pv1k.c:197 / crt_ntsc.c:203
     const int yo = kTop + s.yoffset + (kLines - desth) / 2;
     const int white = kWhite * cfg.white_point / 100;
     const int ire0 = kBlack + cfg.black_point;
@@ -275,12 +288,23 @@ __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restric
     const unsigned char *data = static_cast<const unsigned char *>(s.data);
     const bool aligned4 = ((reinterpret_cast<uintptr_t>(data) & 3) == 0);
 
+    // five carrier phases (PV-1000): the phase of a sample is not a compile-time constant of the 4-sample inner
+    // step, so the tables live in shared memory, [I | Q][colour row][phase]
+    __shared__ int mtab[2][kVper][kCc];
+    if (kCc == 5) {
+        if (threadIdx.x < kCc * kVper) {
+            int b;
+            enc_tables(s, (int) threadIdx.x / kCc, (int) threadIdx.x % kCc, b, mtab[0][threadIdx.x / kCc][threadIdx.x % kCc],
+                       mtab[1][threadIdx.x / kCc][threadIdx.x % kCc]);
+        }
+        __syncthreads(); // (every return above is block-uniform)
+    }
     const int y = warp * 32 + lane; // this lane's picture line
     const int y0 = warp * 32;
     if (y0 >= desth) return;
     // ph * ccmodI/Q (crt_ntsc.c:174-188, 314-315); template: the tables of this lane's colour row (crt_template.c:266)
     int mI[4], mQ[4];
-    const int crow = kIsTemp ? posmod(y + yo, kVper) : 0;
+    const int crow = kRowCarrier ? posmod(y + yo, kVper) : 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         int b;
@@ -328,8 +352,10 @@ __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restric
                 hy += wmul(fy - hy, kIirY) >> 11; // iirf, crt_ntsc.c:117-126
                 hi += wmul(fi - hi, kIirI) >> 11;
                 hq += wmul(fq - hq, kIirQ) >> 11;
-                int ci = wmul(hi, mI[k]) >> 4; // (x + xo) & 3 == k: xo and c0 + x4 are multiples of 4
-                int cq = wmul(hq, mQ[k]) >> 4;
+                // (x + xo) & 3 == k: xo and c0 + x4 are multiples of 4; with five phases (x + xo) % 5 == x % 5
+                const int p5 = (c0 + x4 + k) % kCc;
+                int ci = wmul(hi, kCc == 5 ? mtab[0][crow][p5] : mI[k]) >> 4;
+                int cq = wmul(hq, kCc == 5 ? mtab[1][crow][p5] : mQ[k]) >> 4;
                 int ire = ire0 + (wmul(hy + ci + cq, white) >> 10);
                 ire = __vimin_s32_relu(ire, 110); // clamp to 0..110 in one instruction
                 packed |= (unsigned) ire << (8 * k);
@@ -378,7 +404,7 @@ constexpr int kModSSmem = 8 * kModSWarpSmem + 8 * 2 * 8;
 __device__ __forceinline__ bool mod_staged_ok(const SrcCfg &s, int destw)
 {
     const int bpp = bpp_of(s.format);
-    if (bpp == 0 || destw <= 0 || s.w <= 0) return false;
+    if (bpp == 0 || destw <= 0 || s.w <= 0 || kCc != 4) return false; // (four samples per carrier period only)
     // widest source span of a chunk: ceil(32 * w / destw) + 1 pixels, plus 15 bytes of alignment
     const long long span = ((long long) kModSChunk * s.w + destw - 1) / destw + 1;
     return span * bpp + 15 + 16 <= kModSSpan && s.w <= 65535
@@ -436,9 +462,9 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
     }
     const int field = s.field & 1, frame = s.frame & 1;
     const int flip = (field == frame);
-    const int ph = kIsTemp ? 1 : (flip ? -1 : 1); // the template system walks colour rows instead (below)
+    const int ph = kRowCarrier ? 1 : (flip ? -1 : 1); // the template system and the PV-1000 walk colour rows instead (below)
     const int xo_raw = kAvBeg + s.xoffset + (kAvLen - destw) / 2;
-    const int xo = kIsTemp ? xo_raw - (xo_raw % 4) : (xo_raw & ~3); // crt_template.c:199 / crt_ntsc.c:203
+    const int xo = kRowCarrier ? xo_raw - (xo_raw % kCc) : (xo_raw & ~3); // crt_template.c:199, crt_pv1k.c:197 / crt_ntsc.c:203
     const int yo = kTop + s.yoffset + (kLines - desth) / 2;
     const int white = kWhite * cfg.white_point / 100;
     const int ire0 = kBlack + cfg.black_point;
@@ -449,7 +475,7 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
     const int y = y0 + min(lane, nlines - 1);
     // ph * ccmodI/Q (crt_ntsc.c:174-188, 314-315); template: the tables of this lane's colour row (crt_template.c:266)
     int mI[4], mQ[4];
-    const int crow = kIsTemp ? posmod(y + yo, kVper) : 0;
+    const int crow = kRowCarrier ? posmod(y + yo, kVper) : 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         int b;

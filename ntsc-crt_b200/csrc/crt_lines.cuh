@@ -59,8 +59,10 @@ __device__ __forceinline__ int eq_step(Eq &f, int s, int rnd)
         f.l2 = pole<LF>(f.l2, f.l1, rnd);
         f.l3 = pole<LF>(f.l3, f.l2, rnd);
         if (FAST) {
-            static_assert(!FAST || !IS_Y || G1 == 8192, "fast Y path assumes the 8192 mid gain");
-            r = wadd(wadd(f.l3, wsub(f.h3, f.l3) >> 3), wmul(wsub(f.s3, f.h3), G2) >> 16);
+            // the middle band: gain 8192 is an arithmetic shift; the PV-1000's 12192 (crt_core.c:282) a product that
+            // cannot wrap inside the fast path's range (|fH3 - fL3| * 12192 < 2^31)
+            const int mid = (G1 == 8192) ? (wsub(f.h3, f.l3) >> 3) : (wmul(wsub(f.h3, f.l3), G1) >> 16);
+            r = wadd(wadd(f.l3, mid), wmul(wsub(f.s3, f.h3), G2) >> 16);
         } else {
             const int r0 = wmul(f.l3, 65536) >> 16;
             const int r1 = wmul(wsub(f.h3, f.l3), G1) >> 16;
@@ -99,10 +101,10 @@ __device__ __forceinline__ unsigned yiq_pixel(int ay, int ai, int aq, int by, in
 }
 
 constexpr int kLinesWarps = 8;                // 256 lane-lines per CTA = one monitor
-constexpr int kSub = 12;                      // samples filtered between two pixel passes: a multiple of
-                                              // 4 (carrier phase) and 3 (equaliser history), so the
-                                              // unrolled block needs no register rotation at all
-constexpr int kStageSamples = 96;             // samples per staged chunk (8 sub-chunks): fewer, larger
+constexpr int kSub = 3 * kCc;                 // samples filtered between two pixel passes: a multiple of
+                                              // 4 (carrier phase; 5 for the PV-1000) and 3 (equaliser history), so
+                                              // the unrolled block needs no register rotation at all
+constexpr int kStageSamples = (kCc == 4) ? 96 : 240; // samples per staged chunk (8 / 16 sub-chunks): fewer, larger
                                               // bulk copies -- 32 per warp per stage -- keep the TMA unit ahead
 constexpr int kStageRow = ((kStageSamples + 15 + 15) / 16) * 16; // bytes per line per stage: the 16-byte
                                               // aligned superset of a window at any byte phase
@@ -114,8 +116,8 @@ constexpr int kTileBytes = 32 * kTilePitch * 4;
 // resampler stops at sample AV_LEN - 1 (crt_core.c:529, 555).
 constexpr int kSamplesPadded = ((kAvLen + kSub - 1) / kSub) * kSub;
 constexpr int kNumStages = (kSamplesPadded + kStageSamples - 1) / kStageSamples;
-static_assert(kStageRow % 16 == 0 && kStageSamples % 16 == 0 && kStageSamples % kSub == 0 && kSub % 12 == 0,
-              "stage layout: TMA source offsets and destinations are multiples of 16");
+static_assert(kStageRow % 16 == 0 && kStageSamples % 16 == 0 && kStageSamples % kSub == 0 && kSub % kCc == 0 && kSub % 3 == 0,
+              "stage layout: TMA source offsets and destinations are multiples of 16; carrier phase == t % kCc");
 
 // Per-lane row of decoded Y/I/Q for the current sub-chunk: slot 0 carries the last sample of the
 // previous sub-chunk, slots 1..kSub the new ones.  FAST packs a sample into 8 bytes (Y | I:Q as
@@ -123,7 +125,7 @@ static_assert(kStageRow % 16 == 0 && kStageSamples % 16 == 0 && kStageSamples % 
 // An odd pitch in entries makes "all lanes, same slot" accesses bank-conflict free.
 template <bool FAST> struct YiqRow {
     static constexpr int kEntryBytes = FAST ? 8 : 16;
-    static constexpr int kPitch = kSub + 1; // entries, odd
+    static constexpr int kPitch = (kSub + 1) | 1; // entries, odd
     static constexpr int kBytes = 32 * kPitch * kEntryBytes;
 };
 template <bool FAST> constexpr int lines_warp_smem() { return 2 * kStageBytes + kTileBytes + YiqRow<FAST>::kBytes; }
@@ -236,7 +238,7 @@ __device__ __forceinline__ void flush16_scalar(const unsigned *tile, const Lines
 // source samples are now available, reading slots by a warp-uniform index -- so neither phase has
 // per-sample control flow and the register allocator sees two simple loops.
 template <bool FAST, int MODE, int FMT>
-__global__ void __launch_bounds__(kLinesWarps * 32, FAST ? 2 : 1)
+__global__ void __launch_bounds__(kLinesWarps * 32, (FAST && kCc == 4) ? 2 : 1) // (the PV-1000 stages fill shared memory: one CTA per SM)
 k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, const LineRec *__restrict__ lines_base,
         const signed char *__restrict__ inp_base, int first, const LinesGeom geo)
 {
@@ -302,10 +304,15 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
     constexpr unsigned blend_mask = (MODE != 2) ? (0x7f7f7f7fu & ~(alpha_ff >> 1) & ~alpha_ff) : 0x7f7f7fu;
 
     const int dx = ((kAvLen - 1) << 12) / geo.outw; // crt_core.c:527
-    const int nw0 = wsub(0, rec.wave0), nw1 = wsub(0, rec.wave1);
-    // wave[(i + 0) & 3] feeds I, wave[(i + 3) & 3] feeds Q (crt_core.c:538-543)
-    const int wi[4] = { rec.wave0, rec.wave1, nw0, nw1 };
-    const int wq[4] = { nw1, rec.wave0, rec.wave1, nw0 };
+    // carrier value that multiplies sample i for I and for Q, by i % kCc
+    int wi[5], wq[5];
+    if (kCc == 4) { // wave[(i + 0) & 3] feeds I, wave[(i + 3) & 3] feeds Q (crt_core.c:538-543)
+        const int nw0 = wsub(0, rec.wave0), nw1 = wsub(0, rec.wave1);
+        wi[0] = rec.wave0; wi[1] = rec.wave1; wi[2] = nw0; wi[3] = nw1; wi[4] = 0;
+        wq[0] = nw1; wq[1] = rec.wave0; wq[2] = rec.wave1; wq[3] = nw0; wq[4] = 0;
+    } else { // waveI[i % 5], waveQ[i % 5] from the record's dci / dcq (crt_core.c:497-508, 545-549)
+        pv1k_waves(rec.wave0, rec.wave1, cfg->hue, cfg->saturation, wi, wq);
+    }
     const int rnd = geo.rnd;
 
     const signed char *inp = inp_base + (size_t) m * kSignalBytes;
@@ -383,14 +390,14 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
         const int ns = min(kStageSamples, kSamplesPadded - c * kStageSamples); // a multiple of kSub
 #pragma unroll 1
         for (int u = 0; u < ns; u += kSub) {
-            // ---- (F) filter kSub samples, straight line; sample index i = c * 48 + u + t -> slot t + 1
+            // ---- (F) filter kSub samples, straight line; sample index i = c * kStageSamples + u + t -> slot t + 1
             const signed char *rp = row + u;
 #pragma unroll
             for (int t = 0; t < kSub; t++) {
                 const int s = rp[t];
                 const int y = eq_step<kEqYlf, kEqYhf, kEqYg1, kEqYg2, FAST, true>(ey, s + bright, rnd);
-                const int ci = eq_step<kEqIlf, kEqIhf, 65536, kEqIg2, FAST, false>(ei, wmul(s, wi[t & 3]) >> 9, rnd) >> 3;
-                const int cq = eq_step<kEqQlf, kEqQhf, 65536, 0, FAST, false>(eq, wmul(s, wq[t & 3]) >> 9, rnd) >> 3;
+                const int ci = eq_step<kEqIlf, kEqIhf, 65536, kEqIg2, FAST, false>(ei, wmul(s, wi[t % kCc]) >> 9, rnd) >> 3;
+                const int cq = eq_step<kEqQlf, kEqQhf, 65536, 0, FAST, false>(eq, wmul(s, wq[t % kCc]) >> 9, rnd) >> 3;
                 put(t + 1, y, ci, cq);
             }
             // ---- (P) every pixel whose samples (s, s + 1) are both in slots 0..kSub (crt_core.c:555-659)

@@ -35,7 +35,7 @@ constexpr int kFirStage = ((kFirSamples + 15 + 15) / 16) * 16; // staged bytes p
 constexpr int kFirSeg = 832;                       // output pixels staged per bulk load / store
 constexpr int kFirIter = kFirSeg / 32;               // pixels per lane and segment
 constexpr int kFirGroups = (kLines + kFirWarps - 1) / kFirWarps;
-static_assert(kFirSamples >= kAvLen, "one warp covers a whole line");
+static_assert(!kConv || kFirSamples >= kAvLen, "one warp covers a whole line");
 static_assert(kFirChunk % 8 == 0 && kFirChunk % 4 == 0, "slot padding and carrier phase are per-lane constants");
 static_assert(kFirSeg % 32 == 0, "whole warp steps per segment");
 

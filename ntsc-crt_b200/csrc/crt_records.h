@@ -1,6 +1,7 @@
 // crt_records.h -- the small records host code and kernels exchange.
 #pragma once
 
+#include "crt_b200.h"
 #include "crtx_batch.h"
 
 namespace crt {
@@ -19,7 +20,7 @@ struct MonCfg { // host -> device, the caller-settable part of struct CRT
 };
 
 struct MonState { // device resident, the persistent decoder state of struct CRT
-    int ccf[3][4];
+    int ccf[CRT_CC_VPER > 3 ? CRT_CC_VPER : 3][CRT_CC_SAMPLES]; // [3][4] everywhere but the PV-1000 ([5][5])
     int hsync, vsync, rn;
     int field;   // detected field * (ratio / 2) of the last demodulate (crt_core.c:398-407)
     int generic; // last sync pass: some line needs the wrap-exact (generic) equaliser path

@@ -32,6 +32,21 @@ constexpr int kHeadLines = kVres + 1;
 constexpr int kSyncSmem = (kHeadLines * kHeadWords + 2 * kVsyncWindow * kCandWords) * 4;
 constexpr int kSyncThreads = 256;
 
+// CRT_CC_SAMPLES == 5 (crt_core.c:497-508): carrier tables rotated by the hue knob, one I and one Q value per phase
+__device__ __forceinline__ void pv1k_waves(int dci, int dcq, int hue, int saturation, int (&wi)[5], int (&wq)[5])
+{
+    int ang = hue % 360;
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        int sn, cs;
+        sincos14_d(sn, cs, ang * 8192 / 180);
+        wi[i] = wmul(wadd(wmul(dci, cs), wmul(dcq, sn)) >> 15, saturation);
+        sincos14_d(sn, cs, (ang + 90) * 8192 / 180);
+        wq[i] = wmul(wadd(wmul(dci, cs), wmul(dcq, sn)) >> 15, saturation);
+        ang += 360 / 5;
+    }
+}
+
 struct SyncLine { // what depends only on k, vsync and the detected field (not on the chains)
     short jl;   // signal line the decoded line reads: posmod(top + k + vsync, vres)
     short row;  // colour row: ypos % CC_VPER
@@ -42,10 +57,10 @@ struct SyncLine { // what depends only on k, vsync and the detected field (not o
 struct SyncShared {
     SyncLine ln[kLines];
     int hs[kLines];     // hsync after each decoded line's search
-    int ccr[kLines][4]; // burst-lock accumulator of the line's colour row after its 10 steps
-    signed char burst[kLines][kBurstLen]; // the 40 burst samples each decoded line locks onto
-    short rowlist[3][kLines]; // decoded lines of each colour row, in order
-    int rowcount[3];
+    int ccr[kLines][kCc]; // burst-lock accumulator of the line's colour row after its 10 steps
+    signed char burst[kLines][kBurstLen]; // the 40 (PV-1000: 50) burst samples each decoded line locks onto
+    short rowlist[kVper > 3 ? kVper : 3][kLines]; // decoded lines of each colour row, in order
+    int rowcount[kVper > 3 ? kVper : 3];
     int vs_found[2 * kVsyncWindow]; // per vsync candidate: crossing index or -1
     int generic;
     int linemax[kVres + 1]; // FUSED: largest |inp| on each signal line (filled by the noise warps)
@@ -79,12 +94,35 @@ __device__ __forceinline__ int hsync_step(const unsigned *heads, FetchByte fetch
     return hs;
 }
 
+// In the reference inp[] is followed, inside struct CRT, by outw, outh, out_format and four bytes of padding
+// (crt_core.h:74-92; crt_init zeroes the struct).  A sync search or decode window that runs a few samples past the
+// end of inp[] -- the PV-1000 does that in ordinary operation: its picture ends one sample before the end of the
+// line and hsync settles above 4 -- reads those bytes.  They are deterministic, so they are reproduced: 16 bytes
+// behind each signal buffer (the kernels stage from analog[] when the noise pass is fused, from inp[] otherwise).
+// What follows them in the reference is the `out` pointer; windows that reach it are outside the parity domain.
+__global__ void __launch_bounds__(64) k_struct_tail(const MonCfg *__restrict__ cfgs, signed char *__restrict__ analog_base,
+                                                    signed char *__restrict__ inp_base, int first, int count)
+{
+    const int i = blockIdx.x * 64 + threadIdx.x;
+    if (i >= count) return;
+    const MonCfg c = cfgs[first + i];
+    const int v[4] = { c.outw, c.outh, c.out_format, 0 };
+    signed char *a = analog_base + (size_t) (first + i) * kSignalBytes + kInputSize;
+    signed char *b = inp_base + (size_t) (first + i) * kSignalBytes + kInputSize;
+    for (int k = 0; k < 16; k++) { // (byte stores: CRT_INPUT_SIZE is not a multiple of 4 in every system)
+        const signed char byte = (signed char) ((unsigned) v[k >> 2] >> (8 * (k & 3)));
+        a[k] = byte;
+        b[k] = byte;
+    }
+}
+
 // Four samples of inp[] starting at the 4-aligned index p, computed from the word `w` of analog[] exactly
 // as the noise pass does (crt_core.c:346-367): sample i uses the LCG state advanced i + 1 steps from the
 // call's seed.  Kept apart from the load so that callers can issue a batch of loads before touching any.
 __device__ __forceinline__ unsigned noisy_apply(unsigned w, int p, int noise, unsigned rn0,
                                                 const Affine *__restrict__ jump_lo, const Affine *__restrict__ jump_hi)
 {
+    const unsigned raw = w;
     if (noise == 0) {
         w = __vmaxs4(w, 0x81818181u);
     } else {
@@ -101,8 +139,12 @@ __device__ __forceinline__ unsigned noisy_apply(unsigned w, int p, int noise, un
         }
         w = o;
     }
-    // beyond inp[] the buffer holds its zero padding, never written by the noise pass
-    if (p + 4 > kInputSize) w = (p >= kInputSize) ? 0u : (w & (0xffffffffu >> (8 * (p + 4 - kInputSize))));
+    // beyond inp[] lie the bytes k_struct_tail put there (what follows inp[] inside the reference's struct CRT),
+    // identical after analog[] and after inp[], and never touched by the noise pass: keep them raw
+    if (p + 4 > kInputSize) {
+        const unsigned keep = (p >= kInputSize) ? 0u : (0xffffffffu >> (8 * (p + 4 - kInputSize))); // bytes still inside inp[]
+        w = (w & keep) | (raw & ~keep);
+    }
     return w;
 }
 
@@ -182,7 +224,9 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
             }
         }
     }
-    if (tid == 0) sh.generic = force_generic || abs(cfg.brightness - (kBlack + cfg.black_point)) > 4096;
+    // |bright| bound of the fast equaliser path (crt_lines.cuh); halved for the PV-1000, whose luma cascade
+    // (hf = 80024) is only proven wrap-free up to there
+    if (tid == 0) sh.generic = force_generic || abs(cfg.brightness - (kBlack + cfg.black_point)) > (kCc == 5 ? 2048 : 4096);
     for (int j = tid; j <= kVres; j += kSyncThreads) sh.linemax[j] = FUSED ? 0 : 127;
     __syncthreads();
 
@@ -280,7 +324,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
         int v = 0;
         if (sh.ln[k].beg >= 0) {
             const int hs = sh.hs[k], jl = sh.ln[k].jl;
-            const int p = jl * kHres + (hs & ~3) + kCbBeg + t;
+            const int p = jl * kHres + (hs - hs % kCc) + kCbBeg + t; // crt_core.c:458-462 (hs >= 0: "& ~3" when kCc == 4)
             const int j = (hs > kHres / 2) ? jl + 1 : jl;
             const int off = p - ((j * kHres - kHeadBefore) & ~3);
             if (j < kHeadLines && off >= 0 && off < kHeadWords * 4)
@@ -292,10 +336,11 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
     }
     __syncthreads();
     if (warp == 0) {
-        // Lane = 4 * row + phase walks its own colour row's lines.
-        const int row = lane >> 2, phase = lane & 3;
-        const bool chain_lane = lane < 4 * kVper;
-        const int t0 = (phase - kCbBeg) & 3; // burst samples of this phase: t0, t0 + 4, ...
+        // Lane = kCc * row + phase walks its own colour row's lines (at most 5 x 5 = 25 lanes).
+        static_assert(kCc * kVper <= 32, "one lane per (colour row, phase)");
+        const int row = lane / kCc, phase = lane % kCc;
+        const bool chain_lane = lane < kCc * kVper;
+        const int t0 = posmod(phase - kCbBeg, kCc); // burst samples of this phase: t0, t0 + kCc, ...
         int x = chain_lane ? st->ccf[row][phase] : 0;
         const int count = chain_lane ? sh.rowcount[row] : 0;
         for (int n = 0; n < count; n++) {
@@ -311,19 +356,19 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
                 const int bias = (x >= 0) ? 127 : 0;
                 int y = x, flips = 0;
 #pragma unroll
-                for (int q = 0; q < kBurstLen / 4; q++) {
+                for (int q = 0; q < kBurstLen / kCc; q++) {
                     flips |= y ^ x;
-                    y = y - ((y + bias) >> 7) + bs[4 * q];
+                    y = y - ((y + bias) >> 7) + bs[kCc * q];
                 }
                 if (flips < 0) {
 #pragma unroll
-                    for (int q = 0; q < kBurstLen / 4; q++) x = x - ((x + ((x >= 0) ? 127 : 0)) >> 7) + bs[4 * q];
+                    for (int q = 0; q < kBurstLen / kCc; q++) x = x - ((x + ((x >= 0) ? 127 : 0)) >> 7) + bs[kCc * q];
                 } else {
                     x = y;
                 }
             } else {
 #pragma unroll
-                for (int q = 0; q < kBurstLen / 4; q++) x = wadd(wmul(x, 127) / 128, bs[4 * q]);
+                for (int q = 0; q < kBurstLen / kCc; q++) x = wadd(wmul(x, 127) / 128, bs[kCc * q]);
             }
             sh.ccr[k][phase] = x;
         }
@@ -413,18 +458,33 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
         rec.pos = 0;
         rec.wave0 = rec.wave1 = 0;
         if (g.beg >= 0) {
-            const int pa = hs & 3;
-            const int dci = wsub(sh.ccr[k][(pa + 1) & 3], sh.ccr[k][(pa + 3) & 3]);
-            const int dcq = wsub(sh.ccr[k][(pa + 2) & 3], sh.ccr[k][pa]);
             rec.pos = posmod(kAvBeg + hs - 3, kHres) + g.ypos * kHres;
-            rec.wave0 = wmul(wsub(wmul(dci, huecs), wmul(dcq, huesn)) >> 4, cfg.saturation);
-            rec.wave1 = wmul(wadd(wmul(dcq, huecs), wmul(dci, huesn)) >> 4, cfg.saturation);
+            long long wmax;
+            if (kCc == 4) {
+                const int pa = hs & 3;
+                const int dci = wsub(sh.ccr[k][(pa + 1) & 3], sh.ccr[k][(pa + 3) & 3]);
+                const int dcq = wsub(sh.ccr[k][(pa + 2) & 3], sh.ccr[k][pa]);
+                rec.wave0 = wmul(wsub(wmul(dci, huecs), wmul(dcq, huesn)) >> 4, cfg.saturation);
+                rec.wave1 = wmul(wadd(wmul(dcq, huecs), wmul(dci, huesn)) >> 4, cfg.saturation);
+                wmax = max(llabs((long long) rec.wave0), llabs((long long) rec.wave1));
+            } else { // crt_core.c:480-509: the record carries dci / dcq, the line kernel rebuilds the ten carrier values
+                const int pa = hs % kCc, peak = pa + kCc / 4;
+                const int *ccr = sh.ccr[k];
+                const int dci = wsub(ccr[peak % kCc], wadd(ccr[(peak + kCc / 2) % kCc], ccr[(peak + kCc / 2 + 1) % kCc]) / 2);
+                const int dcq = wsub(ccr[(pa + kCc / 2) % kCc], ccr[pa % kCc]);
+                rec.wave0 = dci;
+                rec.wave1 = dcq;
+                int wi[5], wq[5];
+                pv1k_waves(dci, dcq, cfg.hue, cfg.saturation, wi, wq);
+                wmax = 0;
+#pragma unroll
+                for (int i = 0; i < 5; i++) wmax = max(wmax, max(llabs((long long) wi[i]), llabs((long long) wq[i])));
+            }
             // The fast equaliser path of k_lines is exact while every chroma input (s * wave) >> 9 stays
             // within +-16383 (crt_lines.cuh).  |s| is bounded by the largest sample of the one or two
             // signal lines the decode window covers -- measured by the noise warps when the noise pass is
             // fused, 127 (the clamp of crt_core.c:363-364) otherwise.
             const int smax = max(sh.linemax[g.ypos], sh.linemax[min(g.ypos + 1, kVres)]);
-            const long long wmax = max(llabs((long long) rec.wave0), llabs((long long) rec.wave1));
             if (((smax * wmax) >> 9) + 1 > 16383) sh.generic = 1;
         }
         lines[k] = rec;

@@ -23,6 +23,8 @@ constexpr int kSystem = CRT_SYSTEM;
 #ifndef CRT_CHROMA_PATTERN /* crt_snes.h has no such switch: 227.3 cycles per line, as NES pattern 2; */
 #if (CRT_SYSTEM == CRT_SYSTEM_TEMP) /* nor has crt_template.h: 227.5 cycles per line, as NTSC's pattern 1 */
 #define CRT_CHROMA_PATTERN 1
+#elif (CRT_SYSTEM == CRT_SYSTEM_PV1K) /* crt_pv1k.h: 230.4 cycles per line, none of the NES patterns */
+#define CRT_CHROMA_PATTERN 0
 #else
 #define CRT_CHROMA_PATTERN 2
 #endif
@@ -33,10 +35,16 @@ constexpr bool kIsVhs = (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS);
 constexpr bool kIsSnes = (CRT_SYSTEM == CRT_SYSTEM_SNES);
 constexpr bool kIsNesRgb = (CRT_SYSTEM == CRT_SYSTEM_NESRGB);
 constexpr bool kIsTemp = (CRT_SYSTEM == CRT_SYSTEM_TEMP);
+constexpr bool kIsPv1k = (CRT_SYSTEM == CRT_SYSTEM_PV1K);
+constexpr int kCc = CRT_CC_SAMPLES; // samples per chroma period: 4, or 5 for the PV-1000 (crt_pv1k.h:49)
+static_assert(kCc == 4 || kCc == 5, "crt_core.c:286-288");
 // the systems whose encoder is crt_ntsc.c / crt_ntscvhs.c / crt_template.c (band-limited RGB on the NTSC line
 // layout, 227.5 cycles per line); the template system walks a 2-line chroma cycle instead of flipping the phase
 #define CRT_B200_NTSC_FAMILY \
     ((CRT_SYSTEM == CRT_SYSTEM_NTSC) || (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS) || (CRT_SYSTEM == CRT_SYSTEM_TEMP))
+// ... plus the PV-1000 (crt_pv1k.c): the same encoder structure on its own line layout, five carrier phases, a 5-line cycle
+#define CRT_B200_BANDLIMITED (CRT_B200_NTSC_FAMILY || (CRT_SYSTEM == CRT_SYSTEM_PV1K))
+constexpr bool kRowCarrier = kIsTemp || kIsPv1k; // carrier tables per colour row (line % CRT_CC_VPER), no phase flip
 // -DCRTX_CONV=1 builds the decoder of the reference's USE_CONVOLUTION 1 configuration (an unguarded
 // #define at crt_core.c:85, so a separate library like every other compile-time choice there)
 #ifndef CRTX_CONV
@@ -130,7 +138,8 @@ constexpr int kEqIlf = eq_frac(80), kEqIhf = eq_frac(1150);
 constexpr int kEqQlf = eq_frac(80), kEqQhf = eq_frac(1000);
 // band gains, Q16 (crt_core.c:278-280): Y {65536, 8192, 9175}, I {65536, 65536, 1311},
 // Q {65536, 65536, 0}
-constexpr int kEqYg1 = 8192, kEqYg2 = 9175, kEqIg2 = 1311;
+// with five samples per chroma period Y's gains are {65536, 12192, 7775} (crt_core.c:282)
+constexpr int kEqYg1 = (kCc == 5) ? 12192 : 8192, kEqYg2 = (kCc == 5) ? 7775 : 9175, kEqIg2 = 1311;
 
 #if CRT_B200_NTSC_FAMILY
 static_assert(kHres == 910 && kAvBeg == 156 && kAvLen == 753 && kCbBeg == 97 && kSyncBeg == 21
@@ -168,7 +177,14 @@ constexpr int bandlimit_c(int limit)
     return 2048 - exp_q11_c(-((6434 << 9) / ((1431818 << 9) / limit)));
 }
 
-#if (CRT_SYSTEM == CRT_SYSTEM_NTSC) || (CRT_SYSTEM == CRT_SYSTEM_TEMP) // crt_ntsc.h:86-90, crt_template.h:117-121
+#if (CRT_SYSTEM == CRT_SYSTEM_PV1K)
+static_assert(kHres == 1920 && kInputSize == 503040 && kSyncBeg == 81 && kBwBeg == 162 && kCbBeg == 216 && kAvBeg == 432
+              && kAvLen == 1487 && kBurstLen == 50 && kVper == 5, "PV-1000 timing (crt_pv1k.h:36-101)");
+static_assert(kEqYlf == 42252 && kEqYhf == 80024 && kEqIlf == 2104 && kEqIhf == 32636 && kEqQlf == 2104 && kEqQhf == 28444,
+              "PV-1000 equaliser fractions (crt_core.c:171-196 with CRT_HRES 1920; probed from the compiled reference)");
+#endif
+
+#if (CRT_SYSTEM == CRT_SYSTEM_NTSC) || (CRT_SYSTEM == CRT_SYSTEM_TEMP) || (CRT_SYSTEM == CRT_SYSTEM_PV1K) // crt_ntsc.h:86-90, crt_template.h:117-121, crt_pv1k.h:108-112
 constexpr int kIirY = bandlimit_c(420000), kIirI = bandlimit_c(150000), kIirQ = bandlimit_c(55000);
 static_assert(kIirY == 1233 && kIirI == 574 && kIirQ == 232, "NTSC band-limit (SURVEY.md 8a)");
 #elif (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)

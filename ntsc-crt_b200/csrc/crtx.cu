@@ -50,6 +50,9 @@ static int upload_cfg(crtx_ctx *ctx, cudaStream_t stream)
         // pageable source: staged before the call returns, so h_cfg may be edited right after
         CUDA_TRY(cudaMemcpyAsync(ctx->d_cfg + lo, ctx->h_cfg.data() + lo, sizeof(MonCfg) * (hi - lo),
                                  cudaMemcpyHostToDevice, stream));
+        // the bytes that follow inp[] in the reference's struct CRT depend on the output geometry (crt_sync.cuh)
+        k_struct_tail<<<(hi - lo + 63) / 64, 64, 0, stream>>>(ctx->d_cfg, ctx->d_analog, ctx->d_inp, lo, hi - lo);
+        ctx->launches += 1;
         ctx->cfg_dirty_lo = ctx->n;
         ctx->cfg_dirty_hi = 0;
     }
@@ -118,7 +121,7 @@ static cudaError_t lines_attr_all()
     return e;
 }
 
-#if CRT_B200_NTSC_FAMILY
+#if CRT_B200_BANDLIMITED
 template <int FMT, bool COLOR>
 static void launch_mod_staged_one(crtx_ctx *ctx, int count, int first, cudaStream_t stream)
 {
@@ -290,7 +293,9 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
     }
     {
         LaunchTimer lt(ctx, stream, 1);
-        if (ctx->opt_mod_staged) { // runs of equal (pixel format, colour) share one instantiation
+        // (the staged kernel steps four samples per carrier period: not for the PV-1000's five, which takes the gather kernel)
+        const bool staged = ctx->opt_mod_staged && kCc == 4;
+        if (staged) { // runs of equal (pixel format, colour) share one instantiation
             for (int lo = 0; lo < count;) {
                 int hi = lo + 1;
                 while (hi < count && src[hi].format == src[lo].format && (src[hi].as_color != 0) == (src[lo].as_color != 0)) hi++;
@@ -301,7 +306,7 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
         }
         // monitors whose source span does not fit a stage row (or all of them when staging is off)
         k_mod_picture_rgb<<<count, 256, kModSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog, first,
-                                                            ctx->opt_mod_staged);
+                                                            staged ? 1 : 0);
     }
     ctx->launches += 2 + extra;
 #endif
@@ -555,7 +560,7 @@ int crtx_create(crtx_ctx **out, int n)
     CTX_TRY(lines_attr_all());
     CTX_TRY(cudaFuncSetAttribute(k_sync<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
     CTX_TRY(cudaFuncSetAttribute(k_sync<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
-#if CRT_B200_NTSC_FAMILY
+#if CRT_B200_BANDLIMITED
     CTX_TRY(cudaFuncSetAttribute(k_mod_picture_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSmem));
 #endif
 #undef CTX_TRY
@@ -626,7 +631,8 @@ int crtx_set_state(crtx_ctx *ctx, int first, int count, const crtx_state *s, voi
     CUDA_TRY(cudaMemcpyAsync(tmp.data(), ctx->d_state + first, sizeof(MonState) * count, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int i = 0; i < count; i++) {
-        memcpy(tmp[i].ccf, s[i].ccf, sizeof(tmp[i].ccf));
+        for (int r = 0; r < kVper; r++)
+            for (int x = 0; x < kCc; x++) tmp[i].ccf[r][x] = s[i].ccf[r][x];
         tmp[i].hsync = s[i].hsync;
         tmp[i].vsync = s[i].vsync;
         tmp[i].rn = s[i].rn;
@@ -644,7 +650,9 @@ int crtx_get_state(crtx_ctx *ctx, int first, int count, crtx_state *s, void *str
     CUDA_TRY(cudaMemcpyAsync(tmp.data(), ctx->d_state + first, sizeof(MonState) * count, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int i = 0; i < count; i++) {
-        memcpy(s[i].ccf, tmp[i].ccf, sizeof(s[i].ccf));
+        memset(s[i].ccf, 0, sizeof(s[i].ccf));
+        for (int r = 0; r < kVper; r++)
+            for (int x = 0; x < kCc; x++) s[i].ccf[r][x] = tmp[i].ccf[r][x];
         s[i].hsync = tmp[i].hsync;
         s[i].vsync = tmp[i].vsync;
         s[i].rn = tmp[i].rn;

@@ -818,12 +818,28 @@ ocrt_lcg_jump(unsigned n, unsigned *mul, unsigned *add)
     *add = rc;
 }
 
+/* In the reference inp[] is followed, inside struct CRT, by outw, outh, out_format and four bytes of padding
+ * (crt_core.h:74-92; crt_init zeroes the struct): a decode window or sync search that runs a few samples past the
+ * end of inp[] reads those bytes.  They are deterministic, so they are reproduced here (16 bytes); what follows
+ * them is the `out` pointer, which is not (windows that reach it are outside the parity domain). */
+static void
+inp_struct_tail(const ocrt_sys *sys, ocrt_monitor *m)
+{
+    i32 v[4];
+    v[0] = m->outw;
+    v[1] = m->outh;
+    v[2] = m->out_format;
+    v[3] = 0;
+    memcpy(m->inp + sys->input_size, v, sizeof(v));
+}
+
 /* signal + noise -> inp (crt_core.c:343-367) */
 void
 ocrt_noise_pass(const ocrt_sys *sys, ocrt_monitor *m, int noise, ocrt_rand *g)
 {
     i32 i, rn = m->rn, wobble = 0;
     m->last_noise = noise;
+    inp_struct_tail(sys, m);
     if (sys->vhs_noise) wobble = ((ocrt_rand_next(g) % 8) - 4) + 14; /* crt_core.c:344 */
     for (i = 0; i < sys->input_size; i++) {
         i32 gain = noise, s;

@@ -87,6 +87,16 @@ case("template_wide_mono_rgb", "template", 333, 250, layout.PIX_RGB, dict(blend=
      ("rand", 1920, 400, 4, 26),
      [(dict(format=layout.PIX_BGRA, as_color=i & 1, raw=0, field=i & 1, frame=0, hue=0, dot_crawl_offset=i, xoffset=0,
             yoffset=0), 7) for i in range(3)])
+# CRT_SYSTEM_PV1K (crt_pv1k.c, CRT_CC_SAMPLES 5), from libref_pv1k.so.  The 832x624 interlaced case
+# has decode windows that run a few samples past inp[] into outw / outh (crt_core.h:74-92): part of the parity domain.
+case("pv1k_832x624_interlaced", "pv1k", 832, 624, layout.PIX_BGRA, dict(blend=1, scanlines=1, hue=25, saturation=11),
+     ("rand", 300, 260, 4, 27),
+     [(dict(format=layout.PIX_BGRA, as_color=1, raw=0, field=i & 1, frame=(i >> 1) & 1, hue=(i * 50) % 360,
+            dot_crawl_offset=i % 4, xoffset=4 * (i & 1), yoffset=i % 3), 0 if i < 2 else 9) for i in range(6)])
+case("pv1k_333x250_rgb_generic", "pv1k", 333, 250, layout.PIX_RGB, dict(blend=0, scanlines=0, saturation=400, brightness=3000),
+     ("bars", 400, 300, 4, 0),
+     [(dict(format=layout.PIX_BGRA, as_color=1, raw=0, field=i & 1, frame=0, hue=100 * i, dot_crawl_offset=i, xoffset=0,
+            yoffset=0), 4 * i) for i in range(3)])
 for v in ("nes", "nes_p0"):
     case("cfg3_%s" % v, v, 832, 624, layout.PIX_BGRA, dict(blend=0, scanlines=1),
          ("nes", 256, 240, 0, 5), [(dict(dot_crawl_offset=i % 3, hue=(i * 30) % 360), 4 * i) for i in range(5)])

@@ -31,7 +31,7 @@ def draw_case(rng, variant):
 
 @pytest.mark.parametrize("variant,seed", [("ntsc", 1), ("ntsc", 2), ("ntsc", 3), ("ntsc_conv", 4), ("ntsc_conv", 5),
                                           ("nes", 6), ("nes_p0", 7), ("ntsc", 8), ("ntsc_conv", 9), ("snes", 10),
-                                          ("ntsc_conv5", 11), ("template", 12)])
+                                          ("ntsc_conv5", 11), ("template", 12), ("pv1k", 13)])
 def test_random_configurations(variant, seed):
     rng = np.random.default_rng(1000 + seed)
     for case in range(4):
@@ -56,7 +56,7 @@ def test_random_configurations(variant, seed):
                 kw = dict(format=src_fmt, as_color=int(rng.integers(0, 2)), field=field, frame=int(rng.integers(0, 2)),
                           raw=0, hue=int(rng.integers(0, 360)), xoffset=int(rng.integers(0, 4)) * 4,
                           yoffset=int(rng.integers(0, 3)))
-                if variant in ("snes", "template"):
+                if variant in ("snes", "template", "pv1k"):
                     kw["dot_crawl_offset"] = int(rng.integers(0, 4))
             for e in (gpu, ora):
                 e.modulate(img, **kw)

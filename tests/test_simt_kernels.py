@@ -22,6 +22,7 @@ import test_gpu_conv as _conv  # noqa: E402
 import test_gpu_fuzz as _fuzz  # noqa: E402
 import test_gpu_lineshard as _lineshard  # noqa: E402
 import test_gpu_parity as _parity  # noqa: E402
+import test_gpu_pv1k as _pv1k  # noqa: E402
 import test_gpu_template as _template  # noqa: E402
 import test_gpu_video as _video  # noqa: E402
 
@@ -64,6 +65,7 @@ _adopt(_fuzz, "fuzz")
 _adopt(_lineshard, "lineshard")
 _adopt(_video, "video")
 _adopt(_template, "template")
+_adopt(_pv1k, "pv1k")
 
 
 import test_golden as _golden  # noqa: E402
