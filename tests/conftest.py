@@ -25,7 +25,17 @@ def _cuda_ok():
         return False
 
 
+# Library variants written after the round's GPU budget was spent (checked through tests/simt/ only): their GPU
+# tests run after everything that has already been green on a B200, so that with `-x` a first-contact failure there
+# cannot hide the state of the verified variants.  Remove a name once its tests have passed on the GPU.
+NOT_YET_RUN_ON_GPU = ("template", "pv1k")
+
+
 def pytest_collection_modifyitems(config, items):
+    late = [it for it in items if "gpu" in it.keywords and any(n in it.nodeid for n in NOT_YET_RUN_ON_GPU)]
+    if late:
+        ids = set(id(it) for it in late)
+        items[:] = [it for it in items if id(it) not in ids] + late
     if _cuda_ok():
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
