@@ -121,6 +121,18 @@ int   crtx_sync(void *stream);
 int crtx_bmp_unpack(void *bgra, const void *file_pixels, int w, int h, int bits, void *stream);
 int crtx_bmp_pack(void *file_pixels, const void *bgra, int w, int h, void *stream);
 
+/* PPM wire format on the device (what ppm_rw.c reads and writes): `file_pixels` is the P6 pixel data exactly as it
+ * sits in the file after the header -- R, G, B bytes, rows top-down, no padding; `xrgb` are the loaders' int pixels
+ * 0x00RRGGBB (= CRT_PIX_FORMAT_BGRA in memory).  unpack rescales a maximum colour value below 255 like ppm_rw.c:80;
+ * pack drops the top byte (ppm_rw.c:113-118).  DEVICE pointers; asynchronous on `stream`. */
+int crtx_ppm_unpack(void *xrgb, const void *file_pixels, int w, int h, int maxc, void *stream);
+int crtx_ppm_pack(void *file_pixels, const void *xrgb, int w, int h, void *stream);
+
+/* the live driver's phosphor decay (crt_main.c:437-452, run between frames when `fadephos` is on): every int pixel
+ * c becomes (c>>1 & 0x7f7f7f) + (c>>2 & 0x3f3f3f) + (c>>3 & 0x1f1f1f) + (c>>4 & 0x0f0f0f), top byte cleared.
+ * `image` is a DEVICE array of `npix` int pixels; asynchronous on `stream`. */
+int crtx_fade_phosphors(void *image, size_t npix, void *stream);
+
 /* per-kernel device timing.  After crtx_set_option(ctx, "timing", 1) every launch is bracketed by
  * CUDA events on its stream; crtx_get_timing synchronises, then reports the summed milliseconds and
  * the launch count of each kernel since the last call.  Index: 0 modulate skeleton (or the single

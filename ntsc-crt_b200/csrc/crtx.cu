@@ -447,6 +447,91 @@ __global__ void k_bmp_pack(unsigned *__restrict__ file, const unsigned *__restri
     file[(size_t) (h - 1 - y) * w + x] = bgra[(size_t) y * w + x];
 }
 
+// PPM pixel data (P6: R, G, B bytes, row major) <-> the loaders' int pixels 0x00RRGGBB (ppm_rw.c:79-89, 113-118).
+// Four pixels per thread: three 32-bit words of file bytes <-> four int pixels, so both sides move whole words.
+__device__ __forceinline__ unsigned ppm_to8(unsigned x, unsigned maxc) { return (x * 255u + maxc / 2u) / maxc; } // ppm_rw.c:80
+
+__global__ void k_ppm_unpack(unsigned *__restrict__ xrgb, const unsigned char *__restrict__ file, size_t npix, unsigned maxc,
+                             int aligned)
+{
+    const size_t q = (size_t) blockIdx.x * blockDim.x + threadIdx.x; // group of 4 pixels
+    if (q * 4 >= npix) return;
+    unsigned char b[12];
+    const size_t left = npix - q * 4;
+    if (aligned && left >= 4) {
+        const unsigned *w = reinterpret_cast<const unsigned *>(file) + q * 3;
+        const unsigned w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            b[k] = (unsigned char) (w0 >> (8 * k));
+            b[4 + k] = (unsigned char) (w1 >> (8 * k));
+            b[8 + k] = (unsigned char) (w2 >> (8 * k));
+        }
+    } else {
+        for (int k = 0; k < 12; k++) b[k] = ((size_t) k < left * 3) ? file[q * 12 + k] : 0;
+    }
+    unsigned px[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned r = b[3 * k], g = b[3 * k + 1], bl = b[3 * k + 2];
+        if (maxc != 255u) { r = ppm_to8(r, maxc); g = ppm_to8(g, maxc); bl = ppm_to8(bl, maxc); }
+        px[k] = r << 16 | g << 8 | bl;
+    }
+    if (left >= 4 && (reinterpret_cast<uintptr_t>(xrgb) & 15) == 0) {
+        reinterpret_cast<uint4 *>(xrgb)[q] = make_uint4(px[0], px[1], px[2], px[3]);
+    } else {
+        for (int k = 0; k < 4 && (size_t) k < left; k++) xrgb[q * 4 + k] = px[k];
+    }
+}
+
+__global__ void k_ppm_pack(unsigned char *__restrict__ file, const unsigned *__restrict__ xrgb, size_t npix, int aligned)
+{
+    const size_t q = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (q * 4 >= npix) return;
+    const size_t left = npix - q * 4;
+    unsigned px[4] = { 0u, 0u, 0u, 0u };
+    for (int k = 0; k < 4 && (size_t) k < left; k++) px[k] = __ldg(xrgb + q * 4 + k);
+    unsigned char b[12];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { // ppm_rw.c:113-118
+        b[3 * k] = (unsigned char) (px[k] >> 16);
+        b[3 * k + 1] = (unsigned char) (px[k] >> 8);
+        b[3 * k + 2] = (unsigned char) px[k];
+    }
+    if (aligned && left >= 4) {
+        unsigned *w = reinterpret_cast<unsigned *>(file) + q * 3;
+        w[0] = (unsigned) b[0] | (unsigned) b[1] << 8 | (unsigned) b[2] << 16 | (unsigned) b[3] << 24;
+        w[1] = (unsigned) b[4] | (unsigned) b[5] << 8 | (unsigned) b[6] << 16 | (unsigned) b[7] << 24;
+        w[2] = (unsigned) b[8] | (unsigned) b[9] << 8 | (unsigned) b[10] << 16 | (unsigned) b[11] << 24;
+    } else {
+        for (size_t k = 0; k < left * 3 && k < 12; k++) file[q * 12 + k] = b[k];
+    }
+}
+
+// the live driver's phosphor decay between frames (crt_main.c:437-452), on int pixels 0x00RRGGBB
+__device__ __forceinline__ unsigned fade1(unsigned v)
+{
+    const unsigned c = v & 0xffffffu;
+    return ((c >> 1) & 0x7f7f7fu) + ((c >> 2) & 0x3f3f3fu) + ((c >> 3) & 0x1f1f1fu) + ((c >> 4) & 0x0f0f0fu);
+}
+
+__global__ void k_fade_phosphors(unsigned *__restrict__ image, size_t npix)
+{
+    const size_t stride = (size_t) gridDim.x * blockDim.x;
+    const size_t quads = npix / 4;
+    if ((reinterpret_cast<uintptr_t>(image) & 15) == 0) {
+        uint4 *p = reinterpret_cast<uint4 *>(image);
+        for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += stride) {
+            uint4 v = p[i];
+            v.x = fade1(v.x); v.y = fade1(v.y); v.z = fade1(v.z); v.w = fade1(v.w);
+            p[i] = v;
+        }
+        for (size_t i = quads * 4 + (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) image[i] = fade1(image[i]);
+    } else {
+        for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) image[i] = fade1(image[i]);
+    }
+}
+
 void fill_src(SrcCfg *d, const crtx_source *s)
 {
     memset(d, 0, sizeof(*d));
@@ -873,6 +958,43 @@ int crtx_bmp_pack(void *file_pixels, const void *bgra, int w, int h, void *strea
     if (!bgra || !file_pixels || w <= 0 || h <= 0 || h > 65535) return fail("crtx_bmp_pack: bad arguments");
     const dim3 grid((w + 255) / 256, h);
     k_bmp_pack<<<grid, 256, 0, (cudaStream_t) stream>>>((unsigned *) file_pixels, (const unsigned *) bgra, w, h);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int crtx_ppm_unpack(void *xrgb, const void *file_pixels, int w, int h, int maxc, void *stream)
+{
+    if (!xrgb || !file_pixels || w <= 0 || h <= 0) return fail("crtx_ppm_unpack: bad arguments");
+    if (maxc < 1 || maxc > 255) return fail("crtx_ppm_unpack: maximum colour value %d (1..255, ppm_rw.c:57-62)", maxc);
+    if (reinterpret_cast<uintptr_t>(xrgb) & 3) return fail("crtx_ppm_unpack: unaligned pixel array");
+    const size_t npix = (size_t) w * h, groups = (npix + 3) / 4;
+    k_ppm_unpack<<<(unsigned) ((groups + 255) / 256), 256, 0, (cudaStream_t) stream>>>(
+        (unsigned *) xrgb, (const unsigned char *) file_pixels, npix, (unsigned) maxc,
+        (reinterpret_cast<uintptr_t>(file_pixels) & 3) == 0 ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int crtx_ppm_pack(void *file_pixels, const void *xrgb, int w, int h, void *stream)
+{
+    if (!xrgb || !file_pixels || w <= 0 || h <= 0) return fail("crtx_ppm_pack: bad arguments");
+    if (reinterpret_cast<uintptr_t>(xrgb) & 3) return fail("crtx_ppm_pack: unaligned pixel array");
+    const size_t npix = (size_t) w * h, groups = (npix + 3) / 4;
+    k_ppm_pack<<<(unsigned) ((groups + 255) / 256), 256, 0, (cudaStream_t) stream>>>(
+        (unsigned char *) file_pixels, (const unsigned *) xrgb, npix, (reinterpret_cast<uintptr_t>(file_pixels) & 3) == 0 ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int crtx_fade_phosphors(void *image, size_t npix, void *stream)
+{
+    if (!image) return fail("crtx_fade_phosphors: bad arguments");
+    if (reinterpret_cast<uintptr_t>(image) & 3) return fail("crtx_fade_phosphors: unaligned pixel array");
+    if (npix == 0) return 0;
+    size_t blocks = (npix / 4 + 255) / 256;
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 8) blocks = 148 * 8; // a few resident CTAs per SM, grid-stride beyond
+    k_fade_phosphors<<<(unsigned) blocks, 256, 0, (cudaStream_t) stream>>>((unsigned *) image, npix);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

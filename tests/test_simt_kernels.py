@@ -25,6 +25,7 @@ import test_gpu_parity as _parity  # noqa: E402
 import test_gpu_pv1k as _pv1k  # noqa: E402
 import test_gpu_template as _template  # noqa: E402
 import test_gpu_video as _video  # noqa: E402
+import test_gpu_wire as _wire  # noqa: E402
 
 
 @pytest.fixture(scope="session")
@@ -38,7 +39,7 @@ def simt_backend(simt_libs, monkeypatch):
     import torch
     monkeypatch.setattr(capi, "lib_path", simt_libs)
     monkeypatch.setattr(capi, "_libs", {})
-    real_zeros, real_empty = torch.zeros, torch.empty
+    real_zeros, real_empty, real_full = torch.zeros, torch.empty, torch.full
 
     def host_only(fn):
         def wrapped(*a, **kw):
@@ -47,6 +48,7 @@ def simt_backend(simt_libs, monkeypatch):
         return wrapped
     monkeypatch.setattr(torch, "zeros", host_only(real_zeros))
     monkeypatch.setattr(torch, "empty", host_only(real_empty))
+    monkeypatch.setattr(torch, "full", host_only(real_full))
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **kw: self)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **kw: None)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **kw: type("S", (), {"cuda_stream": 0})())
@@ -66,6 +68,7 @@ _adopt(_lineshard, "lineshard")
 _adopt(_video, "video")
 _adopt(_template, "template")
 _adopt(_pv1k, "pv1k")
+_adopt(_wire, "wire")
 
 
 import test_golden as _golden  # noqa: E402
