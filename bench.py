@@ -519,7 +519,7 @@ def main():
     ap.add_argument("--set", action="append", default=[], help="library option name=value (A/B testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--allgather", action="store_true", help="also time steps that all_gather the decoded frames")
-    ap.add_argument("--variant", default="ntsc", choices=["ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "nes", "nes_p0", "snes", "nesrgb", "vhs", "template", "pv1k"],
+    ap.add_argument("--variant", default="ntsc", choices=["ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "nes", "nes_p0", "snes", "nesrgb", "vhs", "template", "pv1k", "ntsc_bloom"],
                     help="informational runs of the other systems (the contract metric is the default, ntsc)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup

@@ -21,6 +21,8 @@
  *      CRT_SYSTEM 6                          libcrt_b200_nesrgb.so
  *      CRT_SYSTEM 4                          libcrt_b200_template.so
  *      CRT_SYSTEM 2                          libcrt_b200_pv1k.so
+ *      CRT_SYSTEM 0, CRT_DO_BLOOM 1          libcrt_b200_ntsc_bloom.so
+ * (and libcrt_b200_ntsc_conv{,6,5,4}.so for the USE_CONVOLUTION builds of crt_core.c:85-88)
  */
 #ifndef CRT_B200_H
 #define CRT_B200_H
@@ -322,7 +324,11 @@ struct NTSC_SETTINGS {
 #define CRT_INPUT_SIZE (CRT_HRES * CRT_VRES)
 #define CRT_LINES      (CRT_BOT - CRT_TOP)
 
+/* crt_core.h:70 (an unguarded #define there): beam-energy dependent line width.  Compile the caller with
+ * -DCRT_DO_BLOOM=1 and link libcrt_b200_ntsc_bloom.so, the build of the library with the option on. */
+#ifndef CRT_DO_BLOOM
 #define CRT_DO_BLOOM 0
+#endif
 #define CRT_DO_VSYNC 1
 #define CRT_DO_HSYNC 1
 

@@ -269,10 +269,10 @@ __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restric
     const int bpp = bpp_of(s.format);
     if (bpp == 0) return;
     if (skip_staged && mod_takes<true>(s)) return; // done by k_mod_picture_rgb_staged
-    int destw = kAvLen, desth = (kLines * 64500) >> 16;
-    if (s.raw) { // crt_ntsc.c:163-172
-        destw = min(s.w, kAvLen);
-        desth = min(s.h, desth);
+    int destw = kDestW, desth = kDestH;
+    if (s.raw) { // crt_ntsc.c:148-172
+        destw = min(s.w, kDestW);
+        desth = min(s.h, kDestH);
     }
     if (destw <= 0 || desth <= 0 || s.w <= 0 || s.h <= 0) return;
     const int field = s.field & 1, frame = s.frame & 1;
@@ -414,8 +414,8 @@ __device__ __forceinline__ bool mod_staged_ok(const SrcCfg &s, int destw)
 template <bool STAGED>
 __device__ __forceinline__ bool mod_takes(const SrcCfg &s)
 {
-    int destw = kAvLen;
-    if (s.raw) destw = min(s.w, kAvLen);
+    int destw = kDestW;
+    if (s.raw) destw = min(s.w, kDestW);
     return mod_staged_ok(s, destw) == STAGED;
 }
 
@@ -443,10 +443,10 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
     constexpr int rp = (FMT == 0 || FMT == 3) ? 0 : (FMT == 2) ? 1 : (FMT == 4) ? 3 : 2; // crt_core.h:62-67
     constexpr int gp = (FMT == 2 || FMT == 4) ? 2 : 1;
     constexpr int bp = (FMT == 0 || FMT == 3) ? 2 : (FMT == 2) ? 3 : (FMT == 4) ? 1 : 0;
-    int destw = kAvLen, desth = (kLines * 64500) >> 16;
-    if (s.raw) { // crt_ntsc.c:163-172
-        destw = min(s.w, kAvLen);
-        desth = min(s.h, desth);
+    int destw = kDestW, desth = kDestH;
+    if (s.raw) { // crt_ntsc.c:148-172
+        destw = min(s.w, kDestW);
+        desth = min(s.h, kDestH);
     }
     if (desth <= 0 || s.h <= 0) return;
     const int y0 = warp * 32;
@@ -1013,4 +1013,5 @@ __global__ void __launch_bounds__(256) k_noise_terms(const MonCfg *__restrict__ 
 #include "crt_sync.cuh"
 #include "crt_lines.cuh"
 #include "crt_lines_fir.cuh"
+#include "crt_bloom.cuh"
 #include "crt_vhs.cuh"

@@ -56,6 +56,10 @@ constexpr bool kConv = (CRTX_CONV != 0);
 constexpr int kConvTaps = (CRTX_CONV == 0) ? 0 : (CRTX_CONV == 1) ? 7 : CRTX_CONV;
 static_assert(kConvTaps == 0 || (kConvTaps >= 4 && kConvTaps <= 7), "CRTX_CONV: 0, 1 or the tap count 4..7");
 
+// CRT_DO_BLOOM 1 (crt_core.h:70): the decoder derives each line's width from a filtered beam energy
+// (crt_core.c:399-402, 512-526) and the encoders shrink the picture (crt_ntsc.c:148-160)
+constexpr bool kBloom = (CRT_DO_BLOOM != 0);
+
 constexpr int kHres = CRT_HRES;
 constexpr int kVres = CRT_VRES;
 constexpr int kInputSize = CRT_INPUT_SIZE;
@@ -73,6 +77,9 @@ constexpr int kCbBeg = CB_BEG;
 constexpr int kAvBeg = AV_BEG;
 constexpr int kAvLen = AV_LEN;
 constexpr int kBurstLen = CB_CYCLES * CRT_CB_FREQ;
+// picture size the RGB encoders scale to (crt_ntsc.c:131-132, 148-172)
+constexpr int kDestW = kBloom ? (kAvLen * 55500) >> 16 : kAvLen;
+constexpr int kDestH = kBloom ? ((CRT_BOT - CRT_TOP) * 63500) >> 16 : ((CRT_BOT - CRT_TOP) * 64500) >> 16;
 constexpr int kWhite = WHITE_LEVEL;
 constexpr int kBurst = BURST_LEVEL;
 constexpr int kBlack = BLACK_LEVEL;

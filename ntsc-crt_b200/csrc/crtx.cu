@@ -93,6 +93,11 @@ static void launch_lines_mode(crtx_ctx *ctx, int count, int lo, const LinesGeom 
 
 static void launch_lines(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
 {
+    if (kBloom) { // CRT_DO_BLOOM build: per-line resampling step, one kernel for every format (crt_bloom.cuh)
+        k_lines_bloom<<<dim3(kBloomGroups, count), kBloomWarps * 32, kBloomSmem, stream>>>(
+            ctx->d_cfg, ctx->d_lines, ctx->d_inp, static_cast<const BloomLine *>(ctx->d_bloom), lo, geo);
+        return;
+    }
     launch_lines_mode<true>(ctx, count, lo, geo, stream);
     launch_lines_mode<false>(ctx, count, lo, geo, stream);
 }
@@ -337,7 +342,7 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
                                                                   ctx->d_inp, ctx->d_jump_lo, ctx->d_jump_hi, first,
                                                                   ctx->opt_generic);
     }
-    const int pre = 2;
+    int pre = 2;
 #else
     (void) d_noise_terms;
     int pre = 1;
@@ -360,6 +365,11 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
         pre = 2;
     }
 #endif
+    if (kBloom) { // line sums and the beam-energy chain: every line's resampling step and first sample
+        LaunchTimer lt(ctx, stream, 3);
+        k_bloom<<<count, 256, 0, stream>>>(ctx->d_cfg, ctx->d_lines, ctx->d_inp, static_cast<BloomLine *>(ctx->d_bloom), first);
+        pre += 1;
+    }
     // The line kernel takes the output geometry as launch-uniform arguments: split the range into
     // runs of monitors that share it (normally one run).
     int launched = 0;
@@ -627,6 +637,11 @@ int crtx_create(crtx_ctx **out, int n)
 #if (CRT_SYSTEM == CRT_SYSTEM_NES)
     CTX_TRY(cudaMalloc(&ctx->d_nes_tab, (size_t) kNesTabBytes * n));
 #endif
+    if (kBloom) {
+        CTX_TRY(cudaMalloc(&ctx->d_bloom, sizeof(BloomLine) * (size_t) n * kLines));
+        CTX_TRY(cudaMemset(ctx->d_bloom, 0, sizeof(BloomLine) * (size_t) n * kLines));
+        CTX_TRY(cudaFuncSetAttribute(k_lines_bloom, cudaFuncAttributeMaxDynamicSharedMemorySize, kBloomSmem));
+    }
 #if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
     {
         CTX_TRY(cudaMalloc(&ctx->d_vhs_rand, sizeof(VhsRand) * n));
@@ -666,6 +681,7 @@ void crtx_destroy(crtx_ctx *ctx)
     cudaFree(ctx->d_jump_hi);
     cudaFree(ctx->d_src_img);
     cudaFree(ctx->d_nes_tab);
+    cudaFree(ctx->d_bloom);
     cudaFree(ctx->d_vhs_rand);
     cudaFree(ctx->d_vhs_jump);
     cudaFree(ctx->d_vhs_raw);

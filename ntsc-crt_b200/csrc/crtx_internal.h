@@ -23,6 +23,7 @@ struct crtx_ctx {
     crt::Affine *d_jump_lo = nullptr;
     crt::Affine *d_jump_hi = nullptr;
     signed char *d_nes_tab = nullptr; // NES: per-monitor 512 x 12 sample table + burst rows
+    void *d_bloom = nullptr;      // CRT_DO_BLOOM build: BloomLine[n][CRT_LINES], each line's resampling step and start
     void *d_vhs_rand = nullptr;   // VHS: VhsRand[n], glibc rand() replica per monitor
     void *d_vhs_jump = nullptr;   // VHS: jump-ahead matrices
     unsigned *d_vhs_raw = nullptr; // VHS: tail raw-stream scratch

@@ -97,6 +97,11 @@ case("pv1k_333x250_rgb_generic", "pv1k", 333, 250, layout.PIX_RGB, dict(blend=0,
      ("bars", 400, 300, 4, 0),
      [(dict(format=layout.PIX_BGRA, as_color=1, raw=0, field=i & 1, frame=0, hue=100 * i, dot_crawl_offset=i, xoffset=0,
             yoffset=0), 4 * i) for i in range(3)])
+# the CRT_DO_BLOOM 1 build (crt_core.h:70), from libref_ntsc_bloom.so
+case("bloom_832x624_interlaced", "ntsc_bloom", 832, 624, layout.PIX_BGRA, dict(blend=1, scanlines=1, brightness=4, contrast=190),
+     ("bars", 300, 260, 4, 0), rgb_calls(5, 20))
+case("bloom_401x300_rgb", "ntsc_bloom", 401, 300, layout.PIX_RGB, dict(blend=1, scanlines=0, saturation=25, hue=77),
+     ("rand", 500, 300, 4, 31), rgb_calls(3, 7))
 for v in ("nes", "nes_p0"):
     case("cfg3_%s" % v, v, 832, 624, layout.PIX_BGRA, dict(blend=0, scanlines=1),
          ("nes", 256, 240, 0, 5), [(dict(dot_crawl_offset=i % 3, hue=(i * 30) % 360), 4 * i) for i in range(5)])

@@ -18,6 +18,7 @@ from ntsc_crt_b200 import capi
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
 import build as simt_build  # noqa: E402
 
+import test_gpu_bloom as _bloom  # noqa: E402
 import test_gpu_conv as _conv  # noqa: E402
 import test_gpu_fuzz as _fuzz  # noqa: E402
 import test_gpu_lineshard as _lineshard  # noqa: E402
@@ -69,6 +70,7 @@ _adopt(_video, "video")
 _adopt(_template, "template")
 _adopt(_pv1k, "pv1k")
 _adopt(_wire, "wire")
+_adopt(_bloom, "bloom")
 
 
 import test_golden as _golden  # noqa: E402
