@@ -318,10 +318,34 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
             f.ctx.uc_link = nullptr;
             makecontext(&f.ctx, (void (*)()) fiber_entry, 0);
         }
+        // Order in which runnable threads are resumed within a round.  Any order is a legal interleaving of a CUDA
+        // block; SIMT_SCHEDULE=reverse or random[:seed] (reshuffled every round) re-runs a test under other ones, which
+        // is how an accidental dependence on "lower threads run first" shows up without a GPU.
+        static int mode = -1;
+        static unsigned long long rng = 0x9e3779b97f4a7c15ull;
+        if (mode < 0) {
+            const char *e = getenv("SIMT_SCHEDULE");
+            mode = 0;
+            if (e && !strncmp(e, "reverse", 7)) mode = 1;
+            if (e && !strncmp(e, "random", 6)) {
+                mode = 2;
+                if (e[6] == ':') rng ^= strtoull(e + 7, nullptr, 10) * 0xd1342543de82ef95ull;
+            }
+        }
+        std::vector<int> order(nthreads);
+        for (int i = 0; i < nthreads; i++) order[i] = (mode == 1) ? nthreads - 1 - i : i;
         int live = nthreads;
         while (live > 0) {
             const unsigned long before = g_progress;
-            for (int i = 0; i < nthreads; i++) {
+            if (mode == 2) {
+                for (int i = nthreads - 1; i > 0; i--) {
+                    rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                    const int j = (int) ((rng >> 33) % (unsigned) (i + 1));
+                    const int t = order[i]; order[i] = order[j]; order[j] = t;
+                }
+            }
+            for (int oi = 0; oi < nthreads; oi++) {
+                const int i = order[oi];
                 Fiber &f = blk.fibers[i];
                 if (f.done) continue;
                 g_fiber = &f;

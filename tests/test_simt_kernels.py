@@ -94,3 +94,18 @@ def test_the_interpreter_ran_kernels(simt_libs):
     e.modulate(S.rand_image(32, 24), format=5, as_color=1)
     e.demodulate(0)
     assert lib.simt_launches() >= before + 4
+
+
+@pytest.mark.skipif(os.environ.get("SIMT_SCHEDULE") is not None, reason="already running under an alternative schedule")
+@pytest.mark.parametrize("schedule", ["reverse", "random:7"])
+def test_other_thread_schedules(schedule):
+    """Any order in which the runnable threads of a block are resumed is a legal interleaving.  The kernels newest to
+    the tree (and a few of the long-standing ones) must give the same bits when the interpreter resumes them in
+    reverse or in a freshly shuffled order every round -- an accidental "lower threads ran first" dependence, which a
+    GPU would expose as a race, fails here."""
+    import subprocess
+    env = dict(os.environ, SIMT_SCHEDULE=schedule)
+    sel = "bloom or pv1k or template or wire or conv_batch or batch_matches_independent or tma_and_plain"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=S.ROOT)
+    assert r.returncode == 0, r.stdout[-3000:]
