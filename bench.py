@@ -249,7 +249,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32",
         "data": "synthetic",
-        "config": {"workload": "NTSC 832x624 BGRA -> 832x624 BGRA, interlaced, colour, noise 0, blend 1, scanlines 1",
+        "config": {"workload": ("NTSC 832x624 BGRA -> 832x624 BGRA, interlaced, colour, noise 0, blend 1, scanlines 1" if VARIANT == "ntsc"
+                                else "%s -> 832x624 BGRA, blend 1, scanlines 1 (informational run of another BASELINE config)" % VARIANT),
                    "batch_per_step": cores * fields_per_worker, "host_processes": cores},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
                          "sample": "%d processes x %d fields per step" % (cores, fields_per_worker)},
