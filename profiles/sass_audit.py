@@ -21,6 +21,9 @@ HOT = {  # variant -> substrings of the kernels worth listing
     "nes_p0": ["k_nes_table", "k_mod_nes"],
     "snes": ["k_mod_snes"],
     "nesrgb": ["k_mod_nesrgb"],
+    "template": ["k_mod_skeleton_rgb", "k_mod_picture_rgb_stagedILi5ELb1", "k_syncILb1"],
+    "pv1k": ["k_mod_skeleton_rgb", "k_mod_picture_rgbEPK", "k_syncILb1", "k_linesILb1ELi1ELi5", "k_linesILb0ELi1ELi5"],
+    "ntsc_bloom": ["k_bloom", "k_lines_bloom"],
 }
 
 FMA = ("IMAD", "FFMA", "FMUL", "FADD", "HFMA2")

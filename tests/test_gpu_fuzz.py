@@ -31,7 +31,8 @@ def draw_case(rng, variant):
 
 @pytest.mark.parametrize("variant,seed", [("ntsc", 1), ("ntsc", 2), ("ntsc", 3), ("ntsc_conv", 4), ("ntsc_conv", 5),
                                           ("nes", 6), ("nes_p0", 7), ("ntsc", 8), ("ntsc_conv", 9), ("snes", 10),
-                                          ("ntsc_conv5", 11), ("template", 12), ("pv1k", 13)])
+                                          ("ntsc_conv5", 11), ("template", 12), ("pv1k", 13), ("ntsc_bloom", 14),
+                                          ("pv1k", 15), ("template", 16), ("ntsc_bloom", 17)])
 def test_random_configurations(variant, seed):
     rng = np.random.default_rng(1000 + seed)
     for case in range(4):

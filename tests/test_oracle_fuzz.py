@@ -17,7 +17,8 @@ _spec.loader.exec_module(gpu_fuzz)
 
 
 @pytest.mark.parametrize("variant,seed", [("ntsc", 1), ("ntsc", 3), ("ntsc_conv", 4), ("nes", 6), ("nes_p0", 7),
-                                          ("snes", 10), ("ntsc_conv5", 11)])
+                                          ("snes", 10), ("ntsc_conv5", 11), ("template", 12), ("pv1k", 13), ("ntsc_bloom", 14),
+                                          ("pv1k", 15), ("template", 16), ("ntsc_bloom", 17)])
 def test_gpu_sweep_cases_are_inside_the_reference_domain(variant, seed):
     if not S.have_ref(variant):
         pytest.skip("oracle/_ref not built")
@@ -44,7 +45,7 @@ def test_gpu_sweep_cases_are_inside_the_reference_domain(variant, seed):
                 kw = dict(format=src_fmt, as_color=int(rng.integers(0, 2)), field=field, frame=int(rng.integers(0, 2)),
                           raw=0, hue=int(rng.integers(0, 360)), xoffset=int(rng.integers(0, 4)) * 4,
                           yoffset=int(rng.integers(0, 3)))
-                if variant == "snes":
+                if variant in ("snes", "template", "pv1k"):
                     kw["dot_crawl_offset"] = int(rng.integers(0, 4))
             for e in (ref, ora):
                 e.modulate(img, **kw)
