@@ -51,10 +51,12 @@ def test_headers_compile_as_c89_and_match_the_reference_layout(variant, defs):
         assert size_crt == lib.ref_sizeof_crt() and size_set == lib.ref_sizeof_settings()
 
 
-def test_batch_video_driver_is_strict_c89():
-    """tools/crtx_video.c must build with -std=c89 -pedantic -Werror against crtx_batch.h alone (no CUDA header)."""
+@pytest.mark.parametrize("prog", ["crtx_video", "crtx_still"])
+def test_batch_drivers_are_strict_c89(prog):
+    """tools/crtx_video.c and tools/crtx_still.c must build with -std=c89 -pedantic -Werror against crtx_batch.h alone
+    (no CUDA header)."""
     with tempfile.TemporaryDirectory() as tmp:
         cmd = ["gcc", "-std=c89", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I" + INC, "-c",
-               os.path.join(ROOT, "tools", "crtx_video.c"), "-o", os.path.join(tmp, "crtx_video.o")]
+               os.path.join(ROOT, "tools", prog + ".c"), "-o", os.path.join(tmp, prog + ".o")]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         assert res.returncode == 0, res.stderr.decode()

@@ -26,6 +26,7 @@ import test_gpu_lineshard as _lineshard  # noqa: E402
 import test_gpu_parity as _parity  # noqa: E402
 import test_gpu_pv1k as _pv1k  # noqa: E402
 import test_gpu_template as _template  # noqa: E402
+import test_gpu_still_cli as _still  # noqa: E402
 import test_gpu_video as _video  # noqa: E402
 import test_gpu_video_driver as _vdriver  # noqa: E402
 import test_gpu_wire as _wire  # noqa: E402
@@ -84,6 +85,7 @@ _adopt(_pv1k, "pv1k")
 _adopt(_wire, "wire")
 _adopt(_bloom, "bloom")
 _adopt(_cli, "cli")
+_adopt(_still, "still")
 
 
 def _bare(fn):
