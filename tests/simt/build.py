@@ -117,7 +117,9 @@ def lib_path(variant):
     return os.path.join(OUT, "libcrt_simt_%s.so" % variant)
 
 
-def build(variants=None, force=False):
+def build(variants=None, force=False, asan=False):
+    """asan=True: AddressSanitizer build into _build/asan/ (run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so),
+    ASAN_OPTIONS=detect_leaks=0 and SIMT_TIGHT_ALLOC=1): out-of-bounds accesses of "device" and "shared" memory."""
     defs = variant_defines()
     variants = list(variants) if variants else sorted(defs)
     srcdir = os.path.join(OUT, "src")
@@ -125,12 +127,16 @@ def build(variants=None, force=False):
     newest = max(os.path.getmtime(os.path.join(d, f)) for d in (CSRC, HERE, os.path.join(ROOT, "include"))
                  for f in os.listdir(d) if os.path.isfile(os.path.join(d, f)))
     procs = []
+    if asan:
+        os.makedirs(os.path.join(OUT, "asan"), exist_ok=True)
     for v in variants:
-        lib = lib_path(v)
+        lib = lib_path(v) if not asan else os.path.join(OUT, "asan", os.path.basename(lib_path(v)))
         if not force and os.path.exists(lib) and os.path.getmtime(lib) >= newest:
             continue
         cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-fwrapv", "-fno-strict-aliasing",
                "-Wno-unknown-pragmas", "-Wno-attributes", "-I" + srcdir, "-I" + os.path.join(ROOT, "include")]
+        if asan:
+            cmd += ["-fsanitize=address", "-fno-omit-frame-pointer"]
         cmd += defs[v] + ["-o", lib] + [os.path.join(srcdir, f) for f in ("crtx.cpp", "crt_dropin.cpp", "simt_runtime.cpp")]
         procs.append((v, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for v, p in procs:
@@ -138,8 +144,9 @@ def build(variants=None, force=False):
         if p.returncode:
             sys.stderr.write(log)
             raise RuntimeError("simt build of %s failed" % v)
-    return [lib_path(v) for v in variants]
+    return [lib_path(v) if not asan else os.path.join(OUT, "asan", os.path.basename(lib_path(v))) for v in variants]
 
 
 if __name__ == "__main__":
-    print("\n".join(build(sys.argv[1:] or None, force=True)))
+    args = [a for a in sys.argv[1:] if a != "--asan"]
+    print("\n".join(build(args or None, force=True, asan="--asan" in sys.argv)))

@@ -265,10 +265,19 @@ void bulk_store_wait_read(int pending)
 // ---- device memory: plain host memory, filled with a pattern (cudaMalloc does not zero either)
 void *dev_alloc(size_t bytes)
 {
+    // cudaMalloc hands out 256-byte granular blocks, and the kernels rely on being allowed to read up to the next
+    // 16-byte boundary past an image (include/crtx_batch.h).  SIMT_TIGHT_ALLOC=1 (with an AddressSanitizer build of
+    // the interpreter, see build.py) grants exactly that and nothing more, so any other over-read is reported.
+    static int tight = -1;
+    if (tight < 0) {
+        const char *e = getenv("SIMT_TIGHT_ALLOC");
+        tight = (e && *e == '1') ? 1 : 0;
+    }
     void *p = nullptr;
-    const size_t n = ((bytes ? bytes : 1) + 255) & ~(size_t) 255;
-    if (posix_memalign(&p, 256, n + 256)) return nullptr; // + slack: kernels may read up to the next 16-byte boundary
-    memset(p, 0xcd, n + 256);
+    const size_t gran = tight ? 16 : 256;
+    const size_t n = ((bytes ? bytes : 1) + gran - 1) & ~(gran - 1);
+    if (posix_memalign(&p, 256, n + (tight ? 0 : 256))) return nullptr;
+    memset(p, 0xcd, n + (tight ? 0 : 256));
     return p;
 }
 void dev_free(void *p) { free(p); }

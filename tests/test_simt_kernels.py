@@ -21,6 +21,7 @@ import build as simt_build  # noqa: E402
 import test_gpu_bloom as _bloom  # noqa: E402
 import test_gpu_conv as _conv  # noqa: E402
 import test_gpu_dropin_cli as _cli  # noqa: E402
+import test_gpu_edges as _edges  # noqa: E402
 import test_gpu_fuzz as _fuzz  # noqa: E402
 import test_gpu_lineshard as _lineshard  # noqa: E402
 import test_gpu_parity as _parity  # noqa: E402
@@ -32,9 +33,17 @@ import test_gpu_video_driver as _vdriver  # noqa: E402
 import test_gpu_wire as _wire  # noqa: E402
 
 
+ASAN = os.environ.get("SIMT_ASAN") == "1"  # see tests/simt/build.py: run with LD_PRELOAD=libasan.so SIMT_TIGHT_ALLOC=1
+
+
+def _lib_path(variant):
+    p = simt_build.lib_path(variant)
+    return os.path.join(simt_build.OUT, "asan", os.path.basename(p)) if ASAN else p
+
+
 @pytest.fixture(scope="session")
 def simt_libs():
-    simt_build.build()
+    simt_build.build(asan=ASAN)
     # The C drivers (the reference's unmodified crt_main.c, tools/crtx_video.c) are linked against
     # libcrt_b200_ntsc.so with a RUNPATH; a directory earlier on LD_LIBRARY_PATH that holds the interpreter build
     # under that name makes the very same binaries run their kernels on the CPU.
@@ -43,8 +52,8 @@ def simt_libs():
     link = os.path.join(stand_in, "libcrt_b200_ntsc.so")
     if os.path.lexists(link):
         os.remove(link)
-    os.symlink(simt_build.lib_path("ntsc"), link)
-    return simt_build.lib_path
+    os.symlink(_lib_path("ntsc"), link)
+    return _lib_path
 
 
 @pytest.fixture(autouse=True)
@@ -95,6 +104,9 @@ def _bare(fn):
     g.__doc__ = fn.__doc__
     return g
 
+
+# extreme geometries: half of the GPU test's variants (~12 s each here)
+test_edges_extreme_geometries = pytest.mark.parametrize("variant", ["ntsc", "pv1k", "ntsc_bloom"])(_bare(_edges.test_extreme_geometries))
 
 # the C89 video driver: two of the five GPU cases (noise that forces repairs; 32-bit files, odd width) -- each costs ~15 s here
 test_vdriver_batch_video_driver = pytest.mark.skipif(not os.path.exists(_vdriver.DRIVER), reason="tools/crtx_video not built")(
