@@ -17,6 +17,7 @@
  *      CRT_SYSTEM 5                          libcrt_b200_vhs.so
  *      CRT_SYSTEM 1 (CRT_CHROMA_PATTERN 2)   libcrt_b200_nes.so
  *      CRT_SYSTEM 1, CRT_CHROMA_PATTERN 0    libcrt_b200_nes_p0.so
+ *      CRT_SYSTEM 1, CRT_CHROMA_PATTERN 1    libcrt_b200_nes_p1.so
  *      CRT_SYSTEM 3                          libcrt_b200_snes.so
  *      CRT_SYSTEM 6                          libcrt_b200_nesrgb.so
  *      CRT_SYSTEM 4                          libcrt_b200_template.so

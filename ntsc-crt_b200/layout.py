@@ -105,6 +105,7 @@ SPECS = {
     "vhs": _rgb_spec("vhs", SYS_VHS),
     "nes": _nes_spec("nes", 2),
     "nes_p0": _nes_spec("nes_p0", 0),
+    "nes_p1": _nes_spec("nes_p1", 1),  # crt_nes.h:33-34: 227.5 cycles per line (the NTSC line length, HRES 910)
     "snes": _snes_spec("snes"),
     "nesrgb": _nesrgb_spec("nesrgb"),
     # the NTSC system built with CRT_DO_BLOOM 1 (crt_core.h:70; reference-side only so far)

@@ -102,7 +102,7 @@ case("bloom_832x624_interlaced", "ntsc_bloom", 832, 624, layout.PIX_BGRA, dict(b
      ("bars", 300, 260, 4, 0), rgb_calls(5, 20))
 case("bloom_401x300_rgb", "ntsc_bloom", 401, 300, layout.PIX_RGB, dict(blend=1, scanlines=0, saturation=25, hue=77),
      ("rand", 500, 300, 4, 31), rgb_calls(3, 7))
-for v in ("nes", "nes_p0"):
+for v in ("nes", "nes_p0", "nes_p1"):
     case("cfg3_%s" % v, v, 832, 624, layout.PIX_BGRA, dict(blend=0, scanlines=1),
          ("nes", 256, 240, 0, 5), [(dict(dot_crawl_offset=i % 3, hue=(i * 30) % 360), 4 * i) for i in range(5)])
 case("cfg5_vhs_colour", "vhs", 832, 624, layout.PIX_BGRA, dict(blend=1, scanlines=1),

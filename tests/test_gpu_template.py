@@ -77,3 +77,16 @@ def test_batch_template_matches_oracle():
             assert [[st[i].ccf[r][x] for x in range(4)] for r in range(2)] == oras[i].ccf.tolist(), (i, it)
             assert (st[i].hsync, st[i].vsync, st[i].rn) == (oras[i].hsync, oras[i].vsync, oras[i].rn), (i, it)
     b.close()
+
+
+def test_dropin_nes_chroma_pattern_1():
+    """CRT_CHROMA_PATTERN 1 of the NES (crt_nes.h:33-34: 227.5 cycles per line, CRT_HRES 910), libcrt_b200_nes_p1.so --
+    the third of the three patterns; same kernels, another line length."""
+    for img in (S.nes_image(seed=5), S.nes_image(rainbow=True)):
+        gpu, ora, ref = trio("nes_p1", 832, 624)
+        run_all((gpu, ora, ref), lambda e: e.set(blend=0, scanlines=1))
+        for it in range(5):
+            run_all((gpu, ora, ref), lambda e: e.modulate(img, dot_crawl_offset=it % 3, hue=(it * 30) % 360))
+            check(gpu, ora, ref, "nes_p1 mod %d" % it)
+            run_all((gpu, ora, ref), lambda e: e.demodulate(it * 4))
+            check(gpu, ora, ref, "nes_p1 demod %d" % it)

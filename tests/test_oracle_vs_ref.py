@@ -32,7 +32,7 @@ def check(ref, ora, what):
 
 
 def test_struct_layout_matches_reference():
-    for variant in ("ntsc", "ntsc_bloom", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "snes", "nesrgb", "template", "pv1k"):
+    for variant in ("ntsc", "ntsc_bloom", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "nes_p1", "snes", "nesrgb", "template", "pv1k"):
         spec = layout.system_spec(variant)
         lib = C.CDLL(S.ref_path(variant))
         assert lib.ref_sizeof_crt() == C.sizeof(layout.crt_struct(spec)), variant
@@ -296,7 +296,7 @@ def test_nesrgb(fmt):
         check(ref, ora, "nesrgb demod %d" % it)
 
 
-@pytest.mark.parametrize("variant", ["nes", "nes_p0"])
+@pytest.mark.parametrize("variant", ["nes", "nes_p0", "nes_p1"])
 def test_nes(variant):
     """config 3: NES PPU pixels, dot crawl cycling 0,1,2 (crt_main.c:471)."""
     for img in (S.nes_image(seed=5), S.nes_image(rainbow=True)):
