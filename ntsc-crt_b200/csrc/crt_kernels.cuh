@@ -138,25 +138,6 @@ __device__ __forceinline__ void enc_tables(const SrcCfg &s, int row, int x, int 
 constexpr int kEquAHi = kIsPv1k ? -1 : kIsTemp ? 2 : 3, kEquBLo = 7, kEquBHi = 9;
 constexpr int kVsyncLo = kIsPv1k ? 258 : kIsTemp ? 3 : 4, kVsyncHi = kIsPv1k ? 260 : 6;
 
-// level of sample t of line n in the sync / blanking / burst skeleton (crt_ntsc.c:205-252)
-__device__ __forceinline__ int skeleton_level(int n, int t, int field, int flip, int aberration, const int *burst)
-{
-    constexpr int H = kHres;
-    if (n <= kEquAHi || (n >= kEquBLo && n <= kEquBHi)) {
-        bool sync = (t < 4 * H / 100) || (t >= 50 * H / 100 && t < 54 * H / 100);
-        return sync ? kSync : kBlank;
-    }
-    if (n >= kVsyncLo && n <= kVsyncHi) {
-        int first = (field == 1 ? 4 : 46) * H / 100;
-        bool sync = (t < first) || (t >= 50 * H / 100 && t < 96 * H / 100);
-        return sync ? kSync : kBlank;
-    }
-    if (t >= kCbBeg && t < kCbBeg + kBurstLen)
-        return (int) (signed char) ((kBlank + burst[(t + flip * 2) & 3] * kBurst) >> 5);
-    if (t >= kSyncBeg && t < kBwBeg && n < kVres - aberration) return kSync; // crt_ntscvhs.c:234-238
-    return kBlank;
-}
-
 // One CTA per monitor.  Lines above CRT_TOP are written whole, active lines only up to AV_BEG
 // (the rest of an active line belongs to the picture pass or keeps its old content).
 __global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restrict__ srcs,
