@@ -22,6 +22,7 @@ import test_gpu_bloom as _bloom  # noqa: E402
 import test_gpu_conv as _conv  # noqa: E402
 import test_gpu_dropin_cli as _cli  # noqa: E402
 import test_gpu_edges as _edges  # noqa: E402
+import test_gpu_fullsize as _fullsize  # noqa: E402
 import test_gpu_fuzz as _fuzz  # noqa: E402
 import test_gpu_lineshard as _lineshard  # noqa: E402
 import test_gpu_parity as _parity  # noqa: E402
@@ -103,6 +104,14 @@ def _bare(fn):
     g = types.FunctionType(fn.__code__, fn.__globals__, fn.__name__, fn.__defaults__, fn.__closure__)
     g.__doc__ = fn.__doc__
     return g
+
+
+def test_fullsize_property_on_a_small_batch(monkeypatch):
+    """tests/test_gpu_fullsize.py with 6 monitors instead of 296 (a field costs ~60 ms per monitor here)"""
+    monkeypatch.setattr(_fullsize, "BATCH", 6)
+    monkeypatch.setattr(_fullsize, "GROUPS", 3)
+    monkeypatch.setattr(_fullsize, "FIELDS", 3)
+    _fullsize.test_full_size_batch_is_consistent_and_matches_the_oracle()
 
 
 # extreme geometries: half of the GPU test's variants (~12 s each here)
