@@ -19,7 +19,8 @@
  *      CRT_SYSTEM 1, CRT_CHROMA_PATTERN 0    libcrt_b200_nes_p0.so
  *      CRT_SYSTEM 1, CRT_CHROMA_PATTERN 1    libcrt_b200_nes_p1.so
  *      CRT_SYSTEM 3                          libcrt_b200_snes.so
- *      CRT_SYSTEM 6                          libcrt_b200_nesrgb.so
+ *      CRT_SYSTEM 6 (CRT_CHROMA_PATTERN 2)   libcrt_b200_nesrgb.so
+ *      CRT_SYSTEM 6, CRT_CHROMA_PATTERN 0 / 1  libcrt_b200_nesrgb_p0.so / libcrt_b200_nesrgb_p1.so
  *      CRT_SYSTEM 4                          libcrt_b200_template.so
  *      CRT_SYSTEM 2                          libcrt_b200_pv1k.so
  *      CRT_SYSTEM 0, CRT_DO_BLOOM 1          libcrt_b200_ntsc_bloom.so
@@ -200,9 +201,17 @@ struct NTSC_SETTINGS {
 };
 
 #elif (CRT_SYSTEM == CRT_SYSTEM_NESRGB)
-/* ---- RGB image with NES timing and artifacts, crt_nesrgb.h ---- */
+/* ---- RGB image with NES timing and artifacts, crt_nesrgb.h (chroma patterns as for the NES, crt_nesrgb.h:27-40) ---- */
+#ifndef CRT_CHROMA_PATTERN
 #define CRT_CHROMA_PATTERN 2
-#define CRT_CC_LINE  2273
+#endif
+#if (CRT_CHROMA_PATTERN == 1)
+#define CRT_CC_LINE 2275
+#elif (CRT_CHROMA_PATTERN == 2)
+#define CRT_CC_LINE 2273
+#else
+#define CRT_CC_LINE 2280
+#endif
 #define CRT_HRES     (CRT_CC_LINE * CRT_CB_FREQ / 10)
 #define CRT_TOP      15
 #define CRT_BOT      255

@@ -14,7 +14,7 @@ import os
 from . import LIB_DIR
 from . import layout
 
-VARIANTS = ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "nes_p1", "snes", "nesrgb", "template", "pv1k", "ntsc_bloom")
+VARIANTS = ("ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "nes_p1", "snes", "nesrgb", "nesrgb_p0", "nesrgb_p1", "template", "pv1k", "ntsc_bloom")
 
 
 def lib_path(variant):

@@ -155,7 +155,7 @@ static_assert(kEqYlf == 42156 && kEqYhf == 79824 && kEqIlf == 2252 && kEqIhf == 
               && kEqQlf == 2252 && kEqQhf == 28248, "equaliser fractions (SURVEY.md 8a)");
 #endif
 
-#if (CRT_SYSTEM == CRT_SYSTEM_SNES) || (CRT_SYSTEM == CRT_SYSTEM_NESRGB)
+#if (CRT_SYSTEM == CRT_SYSTEM_SNES) || ((CRT_SYSTEM == CRT_SYSTEM_NESRGB) && (CRT_CHROMA_PATTERN == 2))
 static_assert(kHres == 909 && kAvBeg == 197 && kAvLen == 682 && kCbBeg == 101 && kSyncBeg == 23 && kBwBeg == 90
               && kInputSize == 238158, "SNES timing (crt_snes.h:20-109, probed from the compiled reference)");
 #endif

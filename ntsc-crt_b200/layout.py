@@ -87,10 +87,10 @@ def _snes_spec(name):
                       n.av_beg, n.av_len, n.hsync_window, n.vsync_window, 100, 20, 7, -40)
 
 
-def _nesrgb_spec(name):
-    # crt_nesrgb.h: NES layout, sync and burst levels; white at 100
-    n = _nes_spec(name, 2)
-    return SystemSpec(name, SYS_NESRGB, 2, n.hres, n.vres, n.top, n.bot, n.vper, n.sync_beg, n.bw_beg, n.cb_beg,
+def _nesrgb_spec(name, pattern=2):
+    # crt_nesrgb.h: NES layout (any of its three chroma patterns), sync and burst levels; white at 100
+    n = _nes_spec(name, pattern)
+    return SystemSpec(name, SYS_NESRGB, pattern, n.hres, n.vres, n.top, n.bot, n.vper, n.sync_beg, n.bw_beg, n.cb_beg,
                       n.av_beg, n.av_len, n.hsync_window, n.vsync_window, 100, 30, 0, -37)
 
 
@@ -108,6 +108,8 @@ SPECS = {
     "nes_p1": _nes_spec("nes_p1", 1),  # crt_nes.h:33-34: 227.5 cycles per line (the NTSC line length, HRES 910)
     "snes": _snes_spec("snes"),
     "nesrgb": _nesrgb_spec("nesrgb"),
+    "nesrgb_p0": _nesrgb_spec("nesrgb_p0", 0),
+    "nesrgb_p1": _nesrgb_spec("nesrgb_p1", 1),
     # the NTSC system built with CRT_DO_BLOOM 1 (crt_core.h:70; reference-side only so far)
     "ntsc_bloom": _rgb_spec("ntsc_bloom", SYS_NTSC),
     # crt_pv1k.h (reference-side only so far): 1920 samples per line, 5 samples per chroma period, 5-line cycle

@@ -298,10 +298,10 @@ make_pv1k_sys(ocrt_sys *s)
 }
 
 static void
-make_nesrgb_sys(ocrt_sys *s)
+make_nesrgb_sys(ocrt_sys *s, int pattern)
 {
-    /* crt_nesrgb.h: the NES layout and sync / burst levels, white at 100 */
-    make_nes_sys(s, 2);
+    /* crt_nesrgb.h: the NES layout (all three chroma patterns, crt_nesrgb.h:27-40) and sync / burst levels, white at 100 */
+    make_nes_sys(s, pattern);
     s->system = OCRT_SYS_NESRGB;
     s->white_level = 100;
 }
@@ -309,11 +309,13 @@ make_nesrgb_sys(ocrt_sys *s)
 const ocrt_sys *
 ocrt_system(int system, int chroma_pattern)
 {
-    static ocrt_sys table[9];
+    static ocrt_sys table[11];
     static int ready = 0;
     if (!ready) {
         make_snes_sys(&table[5]);
-        make_nesrgb_sys(&table[6]);
+        make_nesrgb_sys(&table[6], 2);
+        make_nesrgb_sys(&table[9], 0);
+        make_nesrgb_sys(&table[10], 1);
         make_template_sys(&table[7]);
         make_pv1k_sys(&table[8]);
         make_rgb_sys(&table[0], OCRT_SYS_NTSC);
@@ -326,7 +328,7 @@ ocrt_system(int system, int chroma_pattern)
     if (system == OCRT_SYS_NTSC) return &table[0];
     if (system == OCRT_SYS_VHS) return &table[1];
     if (system == OCRT_SYS_SNES) return &table[5];
-    if (system == OCRT_SYS_NESRGB) return &table[6];
+    if (system == OCRT_SYS_NESRGB) return chroma_pattern == 0 ? &table[9] : chroma_pattern == 1 ? &table[10] : &table[6];
     if (system == OCRT_SYS_TEMP) return &table[7];
     if (system == OCRT_SYS_PV1K) return &table[8];
     if (system == OCRT_SYS_NES && chroma_pattern >= 0 && chroma_pattern <= 2)

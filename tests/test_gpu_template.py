@@ -90,3 +90,17 @@ def test_dropin_nes_chroma_pattern_1():
             check(gpu, ora, ref, "nes_p1 mod %d" % it)
             run_all((gpu, ora, ref), lambda e: e.demodulate(it * 4))
             check(gpu, ora, ref, "nes_p1 demod %d" % it)
+
+
+@pytest.mark.parametrize("variant", ["nesrgb_p0", "nesrgb_p1"])
+def test_dropin_nesrgb_chroma_patterns(variant):
+    """the NES-RGB system with the other two chroma patterns of crt_nesrgb.h:27-40 (912 / 910 samples per line)"""
+    img = S.rand_image(256, 240, seed=8)
+    gpu, ora, ref = trio(variant, 832, 624)
+    run_all((gpu, ora, ref), lambda e: e.set(blend=1, scanlines=1, saturation=12))
+    for it in range(4):
+        run_all((gpu, ora, ref), lambda e: e.modulate(img, format=layout.PIX_BGRA, hue=(it * 70) % 360, dot_crawl_offset=it % 3,
+                                                      xoffset=4 * (it & 1), yoffset=it % 2))
+        check(gpu, ora, ref, "%s mod %d" % (variant, it))
+        run_all((gpu, ora, ref), lambda e: e.demodulate(0 if it < 2 else 7))
+        check(gpu, ora, ref, "%s demod %d" % (variant, it))

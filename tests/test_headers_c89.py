@@ -15,7 +15,8 @@ INC = os.path.join(ROOT, "include")
 
 SYSTEMS = [("ntsc", ["-DCRT_SYSTEM=0"]), ("vhs", ["-DCRT_SYSTEM=5"]), ("nes", ["-DCRT_SYSTEM=1"]),
            ("nes_p0", ["-DCRT_SYSTEM=1", "-DCRT_CHROMA_PATTERN=0"]), ("nes_p1", ["-DCRT_SYSTEM=1", "-DCRT_CHROMA_PATTERN=1"]), ("snes", ["-DCRT_SYSTEM=3"]),
-           ("nesrgb", ["-DCRT_SYSTEM=6"]), ("template", ["-DCRT_SYSTEM=4"]), ("pv1k", ["-DCRT_SYSTEM=2"])]
+           ("nesrgb", ["-DCRT_SYSTEM=6"]), ("nesrgb_p0", ["-DCRT_SYSTEM=6", "-DCRT_CHROMA_PATTERN=0"]),
+           ("nesrgb_p1", ["-DCRT_SYSTEM=6", "-DCRT_CHROMA_PATTERN=1"]), ("template", ["-DCRT_SYSTEM=4"]), ("pv1k", ["-DCRT_SYSTEM=2"])]
 
 PROBE = r"""
 #include <stdio.h>

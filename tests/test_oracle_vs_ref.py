@@ -32,7 +32,7 @@ def check(ref, ora, what):
 
 
 def test_struct_layout_matches_reference():
-    for variant in ("ntsc", "ntsc_bloom", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "nes_p1", "snes", "nesrgb", "template", "pv1k"):
+    for variant in ("ntsc", "ntsc_bloom", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "vhs", "nes", "nes_p0", "nes_p1", "snes", "nesrgb", "nesrgb_p0", "nesrgb_p1", "template", "pv1k"):
         spec = layout.system_spec(variant)
         lib = C.CDLL(S.ref_path(variant))
         assert lib.ref_sizeof_crt() == C.sizeof(layout.crt_struct(spec)), variant
@@ -294,6 +294,20 @@ def test_nesrgb(fmt):
         check(ref, ora, "nesrgb mod %d" % it)
         both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 7))
         check(ref, ora, "nesrgb demod %d" % it)
+
+
+@pytest.mark.parametrize("variant", ["nesrgb_p0", "nesrgb_p1"])
+def test_nesrgb_chroma_patterns(variant):
+    """the NES-RGB system with the other two chroma patterns of crt_nesrgb.h:27-40 (912 / 910 samples per line)"""
+    img = S.rand_image(256, 240, seed=8)
+    ref, ora = pair(variant, 832, 624)
+    both(ref, ora, lambda e: e.set(blend=1, scanlines=1, saturation=12))
+    for it in range(4):
+        both(ref, ora, lambda e: e.modulate(img, format=layout.PIX_BGRA, hue=(it * 70) % 360, dot_crawl_offset=it % 3,
+                                            xoffset=4 * (it & 1), yoffset=it % 2))
+        check(ref, ora, "%s mod %d" % (variant, it))
+        both(ref, ora, lambda e: e.demodulate(0 if it < 2 else 7))
+        check(ref, ora, "%s demod %d" % (variant, it))
 
 
 @pytest.mark.parametrize("variant", ["nes", "nes_p0", "nes_p1"])
