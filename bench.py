@@ -145,7 +145,7 @@ def _cpu_init(seed=1):
     eng = make()
     eng.set(blend=1, scanlines=1)
     _WORKER["eng"] = eng
-    if VARIANT not in ("nes", "nes_p0"):
+    if VARIANT not in ("nes", "nes_p0", "nes_p1"):
         _WORKER["img"] = S.rand_image(W_IN, H_IN, seed=seed + os.getpid() % 97)
     else:
         _WORKER["img"] = S.nes_image(W_IN, H_IN, seed=seed + os.getpid() % 97)
@@ -161,7 +161,7 @@ def _cpu_worker(fields):
     t0 = time.perf_counter()
     for _ in range(fields):
         f = _WORKER["f"]
-        if VARIANT == "nesrgb":
+        if VARIANT.startswith("nesrgb"):
             eng.modulate(img, format=layout.PIX_BGRA, dot_crawl_offset=f & 1, hue=0)
         elif not VARIANT.startswith("nes"):
             eng.modulate(img, format=layout.PIX_BGRA, as_color=1, field=f & 1, frame=(f >> 1) & 1)
@@ -196,7 +196,7 @@ def cpu_baseline_single(seconds=8.0):
         while spent < seconds or fields < 200:
             f = _WORKER["f"]
             t0 = time.perf_counter()
-            if VARIANT == "nesrgb":
+            if VARIANT.startswith("nesrgb"):
                 eng.modulate(img, format=layout.PIX_BGRA, dot_crawl_offset=f & 1, hue=0)
             elif not VARIANT.startswith("nes"):
                 eng.modulate(img, format=layout.PIX_BGRA, as_color=1, field=f & 1, frame=(f >> 1) & 1)
@@ -283,7 +283,7 @@ def run_product(args):
     B = args.batch
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
     # inputs: one distinct image per monitor, BGRA; far larger than L2 in total (see config)
-    nes = VARIANT in ("nes", "nes_p0")
+    nes = VARIANT in ("nes", "nes_p0", "nes_p1")
     noise = 24 if VARIANT == "vhs" else 0  # BASELINE configs[4]: VHS at noise 24
     if nes:
         src = torch.randint(0, 512, (B, H_IN, W_IN), dtype=torch.int16, generator=gen).to(dev)
@@ -342,7 +342,7 @@ def run_product(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    if nes or VARIANT == "nesrgb":  # first call of a NES stream writes the sync template (crt_nes.c:118-121)
+    if nes or VARIANT.startswith("nesrgb"):  # first call of a NES stream writes the sync template (crt_nes.c:118-121)
         t0 = (capi.Source * B)()
         C.memmove(t0, tables[0], C.sizeof(t0))
         for i in range(B):
@@ -520,7 +520,7 @@ def main():
     ap.add_argument("--set", action="append", default=[], help="library option name=value (A/B testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--allgather", action="store_true", help="also time steps that all_gather the decoded frames")
-    ap.add_argument("--variant", default="ntsc", choices=["ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "nes", "nes_p0", "snes", "nesrgb", "vhs", "template", "pv1k", "ntsc_bloom"],
+    ap.add_argument("--variant", default="ntsc", choices=["ntsc", "ntsc_conv", "ntsc_conv6", "ntsc_conv5", "ntsc_conv4", "nes", "nes_p0", "nes_p1", "snes", "nesrgb", "nesrgb_p0", "nesrgb_p1", "vhs", "template", "pv1k", "ntsc_bloom"],
                     help="informational runs of the other systems (the contract metric is the default, ntsc)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup
