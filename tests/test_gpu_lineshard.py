@@ -19,6 +19,18 @@ pytestmark = pytest.mark.gpu
     (400, 1080, 0, 1, 3),  # two spill rows, uneven blocks
 ])
 def test_two_contexts_decode_one_image(variant, outw, outh, scanlines, blend, world):
+    decode_one_image_in_blocks(variant, outw, outh, scanlines, blend, world)
+
+
+@pytest.mark.parametrize("variant,outw,outh,scanlines,blend,world", [("pv1k", 640, 480, 0, 1, 2), ("template", 832, 624, 1, 1, 2),
+                                                                    ("ntsc_bloom", 640, 480, 0, 1, 2), ("ntsc_bloom", 400, 1080, 0, 1, 3)])
+def test_blocks_of_the_newer_variants(variant, outw, outh, scanlines, blend, world):
+    """the line window (line_lo / line_hi) through the PV-1000 line kernel and through k_lines_bloom, whose energy
+    chain still runs over every line of the field on every rank"""
+    decode_one_image_in_blocks(variant, outw, outh, scanlines, blend, world)
+
+
+def decode_one_image_in_blocks(variant, outw, outh, scanlines, blend, world):
     import torch
     from ntsc_crt_b200 import capi
     img = S.rand_image(320, 240, seed=11)
