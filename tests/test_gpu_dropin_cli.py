@@ -36,3 +36,25 @@ def test_unmodified_cli_driver_is_byte_identical(tmp_path, flags, noise, hue):
         outs.append(open(out, "rb").read())
     assert len(outs[0]) > 1000
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("system", ["pv1k", "template", "snes", "vhs"])
+@pytest.mark.parametrize("flags,noise,hue", [("-o", 12, 0), ("-opm", 0, 45), ("-opa", 0, 0)])
+def test_unmodified_cli_driver_other_systems(tmp_path, system, flags, noise, hue):
+    """crt_main.c also builds for the other RGB systems (CRT_SYSTEM 2, 3, 4, 5; it has no NES / NES-RGB build): the same
+    source linked against libcrt_b200_<system>.so through include/compat/crt_core.h writes the all-reference build's
+    bytes.  (VHS draws its noise from libc rand(), never seeded by the driver: same stream in both builds.)"""
+    ref_cli, b200_cli = (os.path.join(S.REF_DIR, "cli_%s_%s" % (k, system)) for k in ("ref", "b200"))
+    if not (os.path.exists(ref_cli) and os.path.exists(b200_cli)):
+        pytest.skip("driver binaries not built")
+    rgb = S.bars_image(320, 240, fmt=S.layout.PIX_RGB)[..., :3].copy()
+    src = tmp_path / "in.ppm"
+    write_ppm(str(src), rgb)
+    outs = []
+    for exe, name in ((ref_cli, "ref.ppm"), (b200_cli, "b200.ppm")):
+        out = tmp_path / name
+        subprocess.run([exe, flags, "640", "480", str(noise), str(hue), str(src), str(out)],
+                       check=True, stdout=subprocess.DEVNULL, timeout=300)
+        outs.append(open(out, "rb").read())
+    assert len(outs[0]) > 1000
+    assert outs[0] == outs[1]

@@ -50,10 +50,11 @@ def simt_libs():
     # under that name makes the very same binaries run their kernels on the CPU.
     stand_in = os.path.join(simt_build.OUT, "stand_in")
     os.makedirs(stand_in, exist_ok=True)
-    link = os.path.join(stand_in, "libcrt_b200_ntsc.so")
-    if os.path.lexists(link):
-        os.remove(link)
-    os.symlink(_lib_path("ntsc"), link)
+    for v in simt_build.variant_defines():
+        link = os.path.join(stand_in, "libcrt_b200_%s.so" % v)
+        if os.path.lexists(link):
+            os.remove(link)
+        os.symlink(_lib_path(v), link)
     return _lib_path
 
 
@@ -94,7 +95,7 @@ _adopt(_template, "template")
 _adopt(_pv1k, "pv1k")
 _adopt(_wire, "wire")
 _adopt(_bloom, "bloom")
-_adopt(_cli, "cli")
+test_cli_unmodified_cli_driver_is_byte_identical = _cli.test_unmodified_cli_driver_is_byte_identical
 _adopt(_still, "still")
 
 
@@ -113,6 +114,10 @@ def test_fullsize_property_on_a_small_batch(monkeypatch):
     monkeypatch.setattr(_fullsize, "FIELDS", 3)
     _fullsize.test_full_size_batch_is_consistent_and_matches_the_oracle()
 
+
+# the unmodified CLI driver built for the other systems: one flag set per system here (the GPU test runs three)
+test_cli_other_systems = pytest.mark.parametrize("system", ["pv1k", "template", "snes", "vhs"])(
+    pytest.mark.parametrize("flags,noise,hue", [("-o", 12, 0)])(_bare(_cli.test_unmodified_cli_driver_other_systems)))
 
 # extreme geometries: half of the GPU test's variants (~12 s each here)
 test_edges_extreme_geometries = pytest.mark.parametrize("variant", ["ntsc", "pv1k", "ntsc_bloom"])(_bare(_edges.test_extreme_geometries))
