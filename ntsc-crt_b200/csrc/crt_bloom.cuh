@@ -15,6 +15,12 @@
 
 namespace crt {
 
+// The option is supported where the encoder takes its picture size (crt_sys.cuh: kDestW, kDestH) and the decoder has
+// four carrier phases: NTSC, VHS and the template system.  (The reference itself notes "does not work for NES",
+// crt_core.h:70.)
+static_assert(!kBloom || (CRT_B200_NTSC_FAMILY && kCc == 4),
+              "CRT_DO_BLOOM=1: supported for CRT_SYSTEM 0 (NTSC), 4 (TEMP) and 5 (NTSCVHS) only");
+
 struct BloomLine { // per decoded line, written by k_bloom
     int dx, scan_l;
 };
