@@ -15,11 +15,11 @@
 
 namespace crt {
 
-// The option is supported where the encoder takes its picture size (crt_sys.cuh: kDestW, kDestH) and the decoder has
-// four carrier phases: NTSC, VHS and the template system.  (The reference itself notes "does not work for NES",
-// crt_core.h:70.)
-static_assert(!kBloom || (CRT_B200_NTSC_FAMILY && kCc == 4),
-              "CRT_DO_BLOOM=1: supported for CRT_SYSTEM 0 (NTSC), 4 (TEMP) and 5 (NTSCVHS) only");
+// The option is supported for the systems whose encoder has the option's branch (crt_ntsc.c:148-160 and the same
+// lines of crt_ntscvhs.c, crt_template.c, crt_pv1k.c, crt_snes.c; crt_sys.cuh: kDestW, kDestH).  The NES and NES-RGB
+// encoders have none (the reference notes "does not work for NES", crt_core.h:70).
+static_assert(!kBloom || CRT_B200_BANDLIMITED || (CRT_SYSTEM == CRT_SYSTEM_SNES),
+              "CRT_DO_BLOOM=1: supported for CRT_SYSTEM 0 (NTSC), 2 (PV1K), 3 (SNES), 4 (TEMP) and 5 (NTSCVHS) only");
 
 struct BloomLine { // per decoded line, written by k_bloom
     int dx, scan_l;
@@ -100,6 +100,13 @@ __global__ void __launch_bounds__(kBloomWarps * 32) k_lines_bloom(const MonCfg *
         const int g2 = lane == 0 ? kEqYg2 : lane == 1 ? kEqIg2 : 0;
         const int bright = cfg.brightness - (kBlack + cfg.black_point);
         const int off = lane == 2 ? 3 : 0; // wave[(i + 0) & 3] feeds I, wave[(i + 3) & 3] feeds Q
+        int w5[5] = { 0, 0, 0, 0, 0 };      // five carrier phases (PV-1000): this lane's table, waveI or waveQ
+        if (kCc == 5) {
+            int wi5[5], wq5[5];
+            pv1k_waves(rec.wave0, rec.wave1, cfg.hue, cfg.saturation, wi5, wq5);
+#pragma unroll
+            for (int q = 0; q < 5; q++) w5[q] = (lane == 2) ? wq5[q] : wi5[q];
+        }
         int l0 = 0, l1 = 0, l2 = 0, l3 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0, s1 = 0, s2 = 0, s3 = 0;
         int *dst = comp + lane * kBloomRow;
         for (int i = f_lo; i < f_hi; i++) {
@@ -107,6 +114,10 @@ __global__ void __launch_bounds__(kBloomWarps * 32) k_lines_bloom(const MonCfg *
             int in;
             if (lane == 0) {
                 in = s + bright;
+            } else if (kCc == 5) { // waveI[i % 5] / waveQ[i % 5] (crt_core.c:545-549)
+                const int ph = i % 5;
+                const int w = ph == 0 ? w5[0] : ph == 1 ? w5[1] : ph == 2 ? w5[2] : ph == 3 ? w5[3] : w5[4];
+                in = wmul(s, w) >> 9;
             } else {
                 const int ph = (i + off) & 3;
                 const int w = (ph & 1) ? rec.wave1 : rec.wave0;

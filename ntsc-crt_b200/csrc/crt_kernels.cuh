@@ -749,10 +749,10 @@ __global__ void __launch_bounds__(256) k_mod_snes(const SrcCfg *__restrict__ src
     }
     __syncthreads();
 
-    int destw = kAvLen, desth = (kLines * 64500) >> 16; // crt_snes.c:129-130, 158-168
+    int destw = kDestW, desth = kDestH; // crt_snes.c:129-130, 144-168
     if (s.raw) {
-        destw = min(s.w, kAvLen);
-        desth = min(s.h, desth);
+        destw = min(s.w, kDestW);
+        desth = min(s.h, kDestH);
     }
     int xo = kAvBeg + s.xoffset + (kAvLen - destw) / 2;
     const int yo = kTop + s.yoffset + (kLines - desth) / 2;
