@@ -55,6 +55,9 @@ constexpr bool kConv = (CRTX_CONV != 0);
 // compile-time choices of crt_core.c:86-88
 constexpr int kConvTaps = (CRTX_CONV == 0) ? 0 : (CRTX_CONV == 1) ? 7 : CRTX_CONV;
 static_assert(kConvTaps == 0 || (kConvTaps >= 4 && kConvTaps <= 7), "CRTX_CONV: 0, 1 or the tap count 4..7");
+// crt_core.c:89-93: "the current convolutions do not filter properly at > 4 samples" -- the reference forces
+// USE_CONVOLUTION back to 0 for the PV-1000, so there is no such configuration to reproduce
+static_assert(!kConv || CRT_CC_SAMPLES == 4, "CRTX_CONV: the reference disables USE_CONVOLUTION when CRT_CC_SAMPLES != 4 (crt_core.c:89-93)");
 
 // CRT_DO_BLOOM 1 (crt_core.h:70): the decoder derives each line's width from a filtered beam energy
 // (crt_core.c:399-402, 512-526) and the encoders shrink the picture (crt_ntsc.c:148-160)

@@ -31,7 +31,7 @@ for name, (base, defs, edits, srcs, sysn) in combos.items():
     for f, reps in edits.items():
         txt = open(os.path.join(T, f)).read()
         for a, b in reps:
-            assert a in txt, (f, a); txt = txt.replace(a, b)
+            assert a in txt, (f, a); txt = txt.replace(a, b, 1)  # the switch itself, not any guard further down
         open(os.path.join(T, f), "w").write(txt)
     reflib = os.path.join(B.OUT, "combo_libref_%s.so" % name)
     subprocess.run(["gcc", "-O3", "-fPIC", "-w", "-shared", "-DCRT_SYSTEM=%d" % sysn, "-I" + T, "-o", reflib] + [os.path.join(T, f) for f in srcs] + ["oracle/ref_shim.c"], check=True)
