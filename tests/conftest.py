@@ -28,7 +28,7 @@ def _cuda_ok():
 # Library variants written after the round's GPU budget was spent (checked through tests/simt/ only): their GPU
 # tests run after everything that has already been green on a B200, so that with `-x` a first-contact failure there
 # cannot hide the state of the verified variants.  Remove a name once its tests have passed on the GPU.
-NOT_YET_RUN_ON_GPU = ("template", "pv1k", "nes_p1", "nesrgb_p", "bloom", "test_gpu_wire", "test_gpu_still_cli", "test_gpu_edges", "test_gpu_fullsize", "newer_variants", "other_systems")
+NOT_YET_RUN_ON_GPU = ("template", "pv1k", "nes_p1", "nesrgb_p", "bloom", "test_gpu_wire", "test_gpu_still_cli", "test_gpu_edges", "test_gpu_fullsize", "newer_variants", "other_systems", "test_gpu_batch_api")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -1,0 +1,84 @@
+"""The additive batch interface's contract around the compute calls (include/crtx_batch.h): argument checking with
+an explanation in crtx_last_error(), empty ranges, option names, the launch counter and the per-kernel timers,
+state round trips, monitor ranges that are configured and advanced independently."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import support as S
+from ntsc_crt_b200 import layout
+
+pytestmark = pytest.mark.gpu
+
+
+def test_argument_errors_are_reported_not_ignored():
+    import torch
+    from ntsc_crt_b200 import capi
+    lib = capi.load("ntsc")
+    ctx = C.c_void_p()
+    assert lib.crtx_create(C.byref(ctx), 0) != 0 and b"crtx_create" in lib.crtx_last_error()
+    b = capi.Batch("ntsc", 2)
+    out = torch.zeros(48, 64, 4, dtype=torch.uint8, device="cuda")
+    with pytest.raises(capi.CrtxError, match="unknown option"):
+        b.set_option("no_such_option", 1)
+    with pytest.raises(capi.CrtxError, match="range"):
+        b.modulate(first=1, count=2)
+    with pytest.raises(capi.CrtxError, match="range"):
+        b.demodulate(first=-1, count=1)
+    b.set_monitor(0, out, fmt=layout.PIX_BGRA)
+    b.monitors[0].outw = 9000  # above the supported maximum
+    with pytest.raises(capi.CrtxError, match="outw"):
+        b.commit_monitors(0, 1)
+    b.monitors[0].outw = 64
+    b.monitors[0].out = out.data_ptr() + 1  # 4-byte pixels need a 4-byte aligned image
+    with pytest.raises(capi.CrtxError, match="aligned"):
+        b.commit_monitors(0, 1)
+    b.close()
+
+
+def test_empty_ranges_counters_timers_and_state_round_trip():
+    import torch
+    from ntsc_crt_b200 import capi
+    n = 3
+    b = capi.Batch("ntsc", n)
+    outs = [torch.zeros(240, 320, 4, dtype=torch.uint8, device="cuda") for _ in range(n)]
+    img = S.rand_image(256, 240, seed=9)
+    dimg = torch.from_numpy(img).cuda()
+    for i in range(n):
+        b.set_monitor(i, outs[i], fmt=layout.PIX_BGRA, noise=3, blend=0, scanlines=0)
+        b.set_source(i, dimg, format=layout.PIX_BGRA, as_color=1, field=0, frame=0)
+    b.commit_monitors()
+    b.set_option("timing", 1)
+    before = b.launches
+    b.modulate(first=0, count=0)   # nothing to do is not an error
+    b.demodulate(first=2, count=0)
+    assert b.launches == before
+    # monitors 0 and 2 advance, monitor 1 stays where crtx_create left it
+    for i in (0, 2):
+        b.modulate(first=i, count=1)
+        b.demodulate(first=i, count=1)
+    torch.cuda.synchronize()
+    assert b.launches > before
+    t = b.timing()
+    assert t["sync"][1] == 2 and t["lines"][1] >= 2 and all(ms >= 0 for ms, _ in t.values())
+    ora = S.OracleEngine("ntsc", 320, 240)
+    ora.set(blend=0, scanlines=0)
+    ora.modulate(img, format=layout.PIX_BGRA, as_color=1, field=0, frame=0)
+    ora.demodulate(3)
+    st = b.get_state()
+    for i in (0, 2):
+        assert np.array_equal(outs[i].cpu().numpy(), ora.out), i
+        assert (st[i].hsync, st[i].vsync, st[i].rn) == (ora.hsync, ora.vsync, ora.rn), i
+    assert not outs[1].any() and (st[1].hsync, st[1].vsync, st[1].rn) == (0, 0, 194)  # crt_init's state (crt_core.c:250-269)
+    assert not b.signal(1, "analog").any()
+    # state written back is what the next call starts from: give monitor 1 monitor 0's state and signal, decode again
+    b.set_state((capi.State * 1)(st[0]), first=1)
+    b.write_signal(1, b.signal(0, "analog"), "analog")
+    b.demodulate(first=1, count=1)
+    ora.demodulate(3)
+    torch.cuda.synchronize()
+    assert np.array_equal(outs[1].cpu().numpy(), ora.out)
+    lines = b.get_lines(1)
+    assert len(lines) == 240 and all(l.beg >= 0 and l.end > l.beg for l in lines)
+    b.close()

@@ -18,6 +18,7 @@ from ntsc_crt_b200 import capi
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
 import build as simt_build  # noqa: E402
 
+import test_gpu_batch_api as _api  # noqa: E402
 import test_gpu_bloom as _bloom  # noqa: E402
 import test_gpu_conv as _conv  # noqa: E402
 import test_gpu_dropin_cli as _cli  # noqa: E402
@@ -95,6 +96,7 @@ _adopt(_template, "template")
 _adopt(_pv1k, "pv1k")
 _adopt(_wire, "wire")
 _adopt(_bloom, "bloom")
+_adopt(_api, "api")
 test_cli_unmodified_cli_driver_is_byte_identical = _cli.test_unmodified_cli_driver_is_byte_identical
 _adopt(_still, "still")
 
