@@ -82,3 +82,45 @@ def test_empty_ranges_counters_timers_and_state_round_trip():
     lines = b.get_lines(1)
     assert len(lines) == 240 and all(l.beg >= 0 and l.end > l.beg for l in lines)
     b.close()
+
+
+@pytest.mark.parametrize("variant", ["ntsc", "nes", "pv1k"])
+def test_frames_host_is_the_same_field_with_host_buffers(variant):
+    """crtx_frames_host (what bench.py's e2e figure goes through): source images and decoded images are HOST buffers,
+    the copies happen inside the call on the caller's stream.  Images of different sizes (the staging slots grow),
+    several fields, outputs compared with the oracle's."""
+    import torch
+    from ntsc_crt_b200 import capi
+    n = 3
+    b = capi.Batch(variant, n)
+    nes = variant == "nes"
+    outs = [torch.zeros(480, 640, 4, dtype=torch.uint8, device="cuda") for _ in range(n)]
+    host_outs = [np.zeros((480, 640, 4), dtype=np.uint8) for _ in range(n)]
+    oras = []
+    for i in range(n):
+        b.set_monitor(i, outs[i], fmt=layout.PIX_BGRA, noise=2 * i, blend=1, scanlines=1)
+        o = S.OracleEngine(variant, 640, 480)
+        o.set(blend=1, scanlines=1)
+        oras.append(o)
+    b.commit_monitors()
+    for it in range(3):
+        imgs = [S.nes_image(seed=40 + i + it) if nes else S.rand_image(200 + 150 * i + 64 * it, 120 + 100 * i, seed=40 + i + it)
+                for i in range(n)]
+        for i in range(n):
+            kw = dict(dot_crawl_offset=it % 3, hue=10 * i) if nes else dict(format=layout.PIX_BGRA, as_color=1, field=it & 1, frame=0,
+                                                                              dot_crawl_offset=it % 3)
+            b.sources[i].reinit = 1 if (nes and it == 0) else 0
+            # a HOST image this time: set_source only records the pointer and the size
+            b.sources[i].data = imgs[i].ctypes.data
+            b.sources[i].h, b.sources[i].w = imgs[i].shape[0], imgs[i].shape[1]
+            for k, v in kw.items():
+                setattr(b.sources[i], k, v)
+            oras[i].modulate(imgs[i], **kw)
+            oras[i].demodulate(2 * i)
+        b.frames_host([h.ctypes.data for h in host_outs])
+        torch.cuda.synchronize()
+        for i in range(n):
+            assert np.array_equal(host_outs[i], oras[i].out), "%s field %d monitor %d: %s" % (
+                variant, it, i, S.diff_report("host image", host_outs[i], oras[i].out))
+            assert np.array_equal(outs[i].cpu().numpy(), oras[i].out)
+    b.close()
