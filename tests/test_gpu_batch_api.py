@@ -124,3 +124,40 @@ def test_frames_host_is_the_same_field_with_host_buffers(variant):
                 variant, it, i, S.diff_report("host image", host_outs[i], oras[i].out))
             assert np.array_equal(outs[i].cpu().numpy(), oras[i].out)
     b.close()
+
+
+@pytest.mark.parametrize("variant", ["ntsc", "ntsc_conv", "template", "pv1k"])
+@pytest.mark.parametrize("option,value", [("generic_eq", 1), ("mod_staged", 0), ("fused_noise", 0), ("mod_bulk", 0), ("tma", 0)])
+def test_every_switch_of_the_library_gives_the_same_bits(variant, option, value):
+    """the A/B switches of crtx_set_option select other code paths (the wrap-exact equaliser on every monitor, the
+    gather encoder, the separate noise kernel, per-lane cp.async staging, plain loads instead of bulk copies): all of
+    them must decode to the oracle's image"""
+    import torch
+    from ntsc_crt_b200 import capi
+    b = capi.Batch(variant, 2)
+    b.set_option(option, value)
+    outs = [torch.zeros(300, 400, 4, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    imgs = [S.rand_image(320, 240, seed=60), S.bars_image(500, 260)]
+    dimgs = [torch.from_numpy(im).cuda() for im in imgs]
+    oras = []
+    for i in range(2):
+        b.set_monitor(i, outs[i], fmt=layout.PIX_BGRA, noise=6 * i, blend=1, scanlines=i, saturation=12)
+        o = S.OracleEngine(variant, 400, 300)
+        o.set(blend=1, scanlines=i, saturation=12)
+        oras.append(o)
+    b.commit_monitors()
+    for it in range(3):
+        for i in range(2):
+            kw = dict(format=layout.PIX_BGRA, as_color=1, field=it & 1, frame=0, dot_crawl_offset=it)
+            b.set_source(i, dimgs[i], **kw)
+            oras[i].modulate(imgs[i], **kw)
+            oras[i].demodulate(6 * i)
+        b.modulate()
+        b.demodulate()
+        torch.cuda.synchronize()
+        for i in range(2):
+            got = outs[i].cpu().numpy()
+            assert np.array_equal(got, oras[i].out), "%s %s=%d field %d monitor %d: %s" % (
+                variant, option, value, it, i, S.diff_report("out", got, oras[i].out))
+            assert np.array_equal(b.signal(i, "analog"), oras[i].analog) and np.array_equal(b.signal(i, "inp"), oras[i].inp)
+    b.close()
