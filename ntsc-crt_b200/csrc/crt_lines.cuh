@@ -95,12 +95,13 @@ __device__ __forceinline__ unsigned yiq_to_rgb(int y, int i, int q, int contrast
 }
 
 // crt_core.c:559-581, literal (wrap-exact) form
+template <bool HALF = false>
 __device__ __forceinline__ unsigned yiq_pixel(int ay, int ai, int aq, int by, int bi, int bq, int R, int L, int contrast)
 {
     const int y = wadd(wmul(ay, L) >> 2, wmul(by, R) >> 2);
     const int i = wadd(wmul(ai, L) >> 14, wmul(bi, R) >> 14);
     const int q = wadd(wmul(aq, L) >> 14, wmul(bq, R) >> 14);
-    return yiq_to_rgb(y, i, q, contrast);
+    return yiq_to_rgb<HALF>(y, i, q, contrast);
 }
 
 constexpr int kLinesWarps = 8;                // 256 lane-lines per CTA = one monitor
@@ -419,13 +420,13 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
                 unsigned px;
                 // when blending, the channels are halved while they are clamped (see yiq_to_rgb) instead of afterwards:
                 // two instructions less per pixel (59 -> 57 in the SASS of this loop)
-                constexpr bool kHalved = MODE == 1 && FAST;
+                constexpr bool kHalved = MODE == 1;
                 if (FAST) {
                     const int y = wadd(wmul(ay, 4 * L), wmul(by, 4 * R));
                     px = yiq_to_rgb<kHalved>(y, wadd(wmul(ai, L) >> 14, wmul(bi, R) >> 14),
                                              wadd(wmul(aq, L) >> 14, wmul(bq, R) >> 14), contrast);
                 } else {
-                    px = yiq_pixel(ay, ai, aq, by, bi, bq, R, L, contrast);
+                    px = yiq_pixel<kHalved>(ay, ai, aq, by, bi, bq, R, L, contrast);
                 }
                 if (MODE != 2) {
                     px = (FMT == CRT_PIX_FORMAT_BGRA) ? (px | alpha_ff) : __byte_perm(px, 0xffu, sel_store);

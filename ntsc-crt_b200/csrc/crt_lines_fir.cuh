@@ -285,7 +285,8 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
 
             // ---- (P) pixels (crt_core.c:555-659), 32 consecutive ones per step
             const Elem *slot1 = yrow + 1; // slot of sample 0
-            // 0x00RRGGBB from the two samples at `sp` and the 4x interpolation weight of the second one
+            // 0x00RRGGBB from the two samples at `sp` and the 4x interpolation weight of the second one; when blending
+            // (MODE 1) every channel comes back already halved (yiq_to_rgb<true>), which is what crt_core.c:608 adds
             auto shade = [&](unsigned sp, int R4) -> unsigned { // sp: shared address of the first sample's Y
                 constexpr int E = (int) sizeof(Elem), C = FirRow<FAST>::kCompBytes;
                 const int ay = lds_elem<Elem, 0>(sp), by = lds_elem<Elem, E>(sp);
@@ -296,11 +297,11 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
                     const int y = wadd(wmul(ay, L4), wmul(by, R4));
                     // (v * 4L) >> 16 == (v * L) >> 14: the two dropped bits are zeros.  (One IMAD.HI per term instead
                     // of multiply + shift was measured 3 % SLOWER on B200: IMAD.HI is a multi-pass instruction.)
-                    return yiq_to_rgb(y, wadd(wmul(ai, L4) >> 16, wmul(bi, R4) >> 16),
-                                      wadd(wmul(aq, L4) >> 16, wmul(bq, R4) >> 16), contrast);
+                    return yiq_to_rgb<MODE == 1>(y, wadd(wmul(ai, L4) >> 16, wmul(bi, R4) >> 16),
+                                                 wadd(wmul(aq, L4) >> 16, wmul(bq, R4) >> 16), contrast);
                 } else {
                     const int R = R4 >> 2, L = 0xfff - R;
-                    return yiq_pixel(ay, ai, aq, by, bi, bq, R, L, contrast);
+                    return yiq_pixel<MODE == 1>(ay, ai, aq, by, bi, bq, R, L, contrast);
                 }
             };
             auto pixel = [&](int px) -> unsigned { // 0x00RRGGBB of output pixel px
@@ -336,7 +337,7 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
                         const unsigned rgb = shade((unsigned) tab_slot[u], tab_r4[u]);
                         unsigned v = (FMT == CRT_PIX_FORMAT_BGRA) ? rgb : __byte_perm(rgb, 0u, sel_store);
                         if (MODE == 1) // crt_core.c:608 on whole words; the alpha byte is masked out and set
-                            v = alpha_ff + ((v & blend_even) >> 1) + ((ob[j] & blend_even) >> 1);
+                            v = alpha_ff + v + ((ob[j] & blend_even) >> 1);
                         else
                             v |= alpha_ff;
                         ob[j] = v;
@@ -364,8 +365,8 @@ k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states
                     if (MODE != 2) {
                         unsigned char *p = row0 + (size_t) px * 4;
                         unsigned v = (FMT == CRT_PIX_FORMAT_BGRA) ? (rgb | alpha_ff) : __byte_perm(rgb, 0xffu, sel_store);
-                        if (MODE == 1)
-                            v = (((v >> 1) & blend_mask) | alpha_ff) + ((__ldcg(reinterpret_cast<const unsigned *>(p)) >> 1) & blend_mask);
+                        if (MODE == 1) // (rgb is already halved, v carries the alpha byte)
+                            v += (__ldcg(reinterpret_cast<const unsigned *>(p)) >> 1) & blend_mask;
                         for (int r = 0; r < nrows; r++) __stcg(reinterpret_cast<unsigned *>(p + (size_t) r * pitch), v);
                     } else {
                         unsigned char *p = row0 + (size_t) px * 3;
