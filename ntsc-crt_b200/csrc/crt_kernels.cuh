@@ -349,10 +349,13 @@ __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restric
             signed char *dst = analog + (c0 + xo) + (y0 + l + yo) * kHres;
             unsigned w = obuf[l * kModOutPitch + (lane >> 1)];
             unsigned two = (w >> (16 * (lane & 1))) & 0xffffu;
-            if (2 * lane + 1 < nx) {
+            // the pair is 2-byte aligned when xo is even: always with four carrier phases (xo is a multiple of 4 and
+            // CRT_HRES is even), not with the PV-1000's five (xo is a multiple of 5)
+            if (2 * lane + 1 < nx && (kCc == 4 || ((c0 + xo) & 1) == 0)) {
                 *reinterpret_cast<unsigned short *>(dst + 2 * lane) = (unsigned short) two;
             } else if (2 * lane < nx) {
                 dst[2 * lane] = (signed char) (two & 0xff);
+                if (2 * lane + 1 < nx) dst[2 * lane + 1] = (signed char) (two >> 8);
             }
         }
         __syncwarp();

@@ -117,7 +117,7 @@ def lib_path(variant):
     return os.path.join(OUT, "libcrt_simt_%s.so" % variant)
 
 
-def build(variants=None, force=False, asan=False):
+def build(variants=None, force=False, asan=False, align=True):
     """asan=True: AddressSanitizer build into _build/asan/ (run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so),
     ASAN_OPTIONS=detect_leaks=0 and SIMT_TIGHT_ALLOC=1): out-of-bounds accesses of "device" and "shared" memory."""
     defs = variant_defines()
@@ -137,6 +137,10 @@ def build(variants=None, force=False, asan=False):
                "-Wno-unknown-pragmas", "-Wno-attributes", "-I" + srcdir, "-I" + os.path.join(ROOT, "include")]
         if asan:
             cmd += ["-fsanitize=address", "-fno-omit-frame-pointer"]
+        if align:  # every dereference is checked against its type's alignment (short 2, uint2 8, uint4 16, as on the GPU,
+            # where a misaligned access is a fatal "misaligned address"); a violation traps (SIGILL).  To see where:
+            # build with -fsanitize=alignment alone and LD_PRELOAD=$(gcc -print-file-name=libubsan.so)
+            cmd += ["-fsanitize=alignment", "-fsanitize-undefined-trap-on-error"]
         cmd += defs[v] + ["-o", lib] + [os.path.join(srcdir, f) for f in ("crtx.cpp", "crt_dropin.cpp", "simt_runtime.cpp")]
         procs.append((v, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for v, p in procs:
@@ -148,5 +152,5 @@ def build(variants=None, force=False, asan=False):
 
 
 if __name__ == "__main__":
-    args = [a for a in sys.argv[1:] if a != "--asan"]
-    print("\n".join(build(args or None, force=True, asan="--asan" in sys.argv)))
+    args = [a for a in sys.argv[1:] if a not in ("--asan", "--no-align")]
+    print("\n".join(build(args or None, force=True, asan="--asan" in sys.argv, align="--no-align" not in sys.argv)))

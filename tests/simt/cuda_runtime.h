@@ -31,7 +31,7 @@
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
 
-struct uint2 { unsigned x, y; };
+struct __attribute__((aligned(8))) uint2 { unsigned x, y; };
 struct uint3 { unsigned x, y, z; };
 struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
 struct dim3 {
