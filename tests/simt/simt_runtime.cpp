@@ -10,6 +10,10 @@
 #include <map>
 #include <vector>
 
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/asan_interface.h>
+#endif
+
 #include "crt_ptx.cuh"
 
 namespace crt { // the kernels' dynamic shared-memory arrays ("extern __shared__ T name[]")
@@ -295,18 +299,39 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()
         if (posix_memalign(&s, 4096, kStack)) fatal("out of memory (fiber stacks)");
         stacks.push_back((unsigned char *) s);
     }
-    for (unsigned bz = 0; bz < grid.z; bz++)
-    for (unsigned by = 0; by < grid.y; by++)
-    for (unsigned bx = 0; bx < grid.x; bx++) {
+    // Blocks of a launch may run in any order, or together: SIMT_BLOCKS=reverse runs them last to first, which turns a
+    // hidden "a later block reads what an earlier one wrote" dependence into a wrong result.
+    static int block_order = -1;
+    if (block_order < 0) {
+        const char *e = getenv("SIMT_BLOCKS");
+        block_order = (e && !strncmp(e, "reverse", 7)) ? 1 : 0;
+    }
+    const unsigned long long nblocks = (unsigned long long) grid.x * grid.y * grid.z;
+    for (unsigned long long bi = 0; bi < nblocks; bi++) {
+        const unsigned long long lin = block_order ? nblocks - 1 - bi : bi;
+        const unsigned bx = (unsigned) (lin % grid.x), by = (unsigned) ((lin / grid.x) % grid.y), bz = (unsigned) (lin / ((unsigned long long) grid.x * grid.y));
         g_blocks++;
         Block blk;
         blk.nthreads = nthreads;
         blk.body = &body;
         blk.fibers.resize(nthreads);
         blk.warps.resize((nthreads + 31) / 32);
+#if defined(__SANITIZE_ADDRESS__)
+        ASAN_UNPOISON_MEMORY_REGION(crt::smem_raw, sizeof(crt::smem_raw));
+        ASAN_UNPOISON_MEMORY_REGION(crt::heads, sizeof(crt::heads));
+        ASAN_UNPOISON_MEMORY_REGION(crt::vsm, sizeof(crt::vsm));
+#endif
         memset(crt::smem_raw, 0xa5, sizeof(crt::smem_raw)); // shared memory starts out as garbage
         memset(crt::heads, 0xa5, sizeof(crt::heads));
         memset(crt::vsm, 0xa5, sizeof(crt::vsm));
+#if defined(__SANITIZE_ADDRESS__)
+        { // only the dynamic shared memory the launch asked for exists (the three arrays are the same window by name)
+            const size_t used = (smem_bytes + 7) & ~(size_t) 7;
+            ASAN_POISON_MEMORY_REGION(crt::smem_raw + used, sizeof(crt::smem_raw) - used);
+            ASAN_POISON_MEMORY_REGION(reinterpret_cast<unsigned char *>(crt::heads) + used, sizeof(crt::heads) - used);
+            ASAN_POISON_MEMORY_REGION(crt::vsm + used, sizeof(crt::vsm) - used);
+        }
+#endif
         g_block = &blk;
         for (int i = 0; i < nthreads; i++) {
             Fiber &f = blk.fibers[i];
