@@ -161,3 +161,45 @@ def test_every_switch_of_the_library_gives_the_same_bits(variant, option, value)
                 variant, option, value, it, i, S.diff_report("out", got, oras[i].out))
             assert np.array_equal(b.signal(i, "analog"), oras[i].analog) and np.array_equal(b.signal(i, "inp"), oras[i].inp)
     b.close()
+
+
+@pytest.mark.parametrize("variant", ["ntsc", "ntsc_conv", "pv1k", "ntsc_bloom"])
+@pytest.mark.parametrize("out_skew,src_skew,src_fmt", [(4, 4, layout.PIX_BGRA), (8, 12, layout.PIX_ARGB), (12, 1, layout.PIX_RGB),
+                                                       (4, 2, layout.PIX_BGR)])
+def test_images_that_are_not_16_byte_aligned(variant, out_skew, src_skew, src_fmt):
+    """Device images handed in at 4-, 8- or 12-byte offsets from a 16-byte boundary (views into larger buffers), 3-byte
+    sources at odd addresses: the vector and bulk-copy paths must step aside for the per-lane ones, with no access that
+    is misaligned for its type (the interpreter traps on those, the GPU faults)."""
+    import torch
+    from ntsc_crt_b200 import capi
+    outw, outh = 400, 300
+    b = capi.Batch(variant, 1)
+    big = torch.zeros(outw * outh * 4 + 64, dtype=torch.uint8, device="cuda")
+    base = (-big.data_ptr()) % 16  # bytes to the next 16-byte boundary
+    out = big[base + out_skew: base + out_skew + outw * outh * 4].view(outh, outw, 4)
+    assert out.data_ptr() % 16 == out_skew
+    rgb = S.rand_image(320, 240, bpp=3, seed=90)
+    img = S.pack_rgb(rgb, src_fmt)
+    bpp = img.shape[2]
+    sbig = torch.zeros(img.size + 64, dtype=torch.uint8, device="cuda")
+    sbase = (-sbig.data_ptr()) % 16
+    dimg = sbig[sbase + src_skew: sbase + src_skew + img.size].view(240, 320, bpp)
+    dimg.copy_(torch.from_numpy(img))
+    assert dimg.data_ptr() % 16 == src_skew % 16
+    b.set_monitor(0, out, fmt=layout.PIX_BGRA, noise=3, blend=1, scanlines=1)
+    b.commit_monitors()
+    ora = S.OracleEngine(variant, outw, outh)
+    ora.set(blend=1, scanlines=1)
+    for it in range(3):
+        kw = dict(format=src_fmt, as_color=1, field=it & 1, frame=0, dot_crawl_offset=it, xoffset=4 * (it & 1))
+        b.set_source(0, dimg, **kw)
+        ora.modulate(img, **kw)
+        ora.demodulate(3)
+        b.modulate()
+        b.demodulate()
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        assert np.array_equal(got, ora.out), "%s field %d: %s" % (variant, it, S.diff_report("out", got, ora.out))
+        assert np.array_equal(b.signal(0, "analog"), ora.analog)
+    assert not big[:base + out_skew].any() and not big[base + out_skew + outw * outh * 4:].any(), "wrote outside the image"
+    b.close()
