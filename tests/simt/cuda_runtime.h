@@ -240,7 +240,7 @@ static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = 0; return cudaS
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
-static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.001f; return cudaSuccess; } /* (no clock here: a token value) */
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *)
 {
     memset(a, 0, sizeof(*a));

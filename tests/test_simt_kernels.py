@@ -166,3 +166,22 @@ def test_other_thread_schedules(schedule):
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=S.ROOT)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("variant", ["ntsc", "pv1k"])
+def test_bench_product_arm_dry_run(variant):
+    """bench.py's product arm, every line of it, against the current libraries (tests/simt/bench_dry_run.py): the JSON
+    line must carry the contract's keys and count the launches of the timed steps"""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(S.ROOT, "tests", "simt", "bench_dry_run.py"), "--variant", variant, "--batch", "4",
+                        "--steps", "2", "--warmup", "1", "--e2e-batch", "8", "--no-cpu-baseline"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=S.ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+        assert key in line, key
+    assert line["steps"] == 2 and line["warmup"] >= 3 and line["gpu_launches"] >= 2 * 4
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
