@@ -18,6 +18,8 @@ Timed numbers
   roofline   the line kernel (k_lines = crt_core.c:511-664): algorithmic bytes / its mean CUDA-event
              launch duration, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the reference C code (oracle/_ref, else the oracle port), 1 thread, bounded sample
+  dropin     informational (SURVEY 8d "drop-in fps"): crt_modulate + crt_demodulate of the reference's own interface on
+             host buffers, one struct CRT, synchronous, wall clock; measured in a child process after the timed regions
 """
 import argparse
 import ctypes as C
@@ -264,6 +266,57 @@ def run_reference(args):
 # product arm
 # --------------------------------------------------------------------------------------------
 
+def dropin_fps(seconds=2.0):
+    """SURVEY 8d "drop-in fps": the reference's own seven-function interface on HOST buffers, exactly what the
+    unmodified drivers call -- crt_modulate + crt_demodulate on one struct CRT, synchronous, strict coherence (the
+    library re-uploads analog[] and the image on every call, crt_dropin.cu).  Wall clock around the calls, like a
+    caller sees it.  Informational: it never touches the contract's `value` / `e2e`, and a failure here is reported
+    in the key instead of costing the line."""
+    try:
+        import support as S
+        from ntsc_crt_b200 import layout
+        eng = S.ProductEngine(VARIANT, W_OUT, H_OUT)
+        eng.set(blend=1, scanlines=1)
+        nes = VARIANT in ("nes", "nes_p0", "nes_p1")
+        img = S.nes_image(W_IN, H_IN, seed=7) if nes else S.rand_image(W_IN, H_IN, seed=7)
+
+        def pair(f):
+            if nes:
+                eng.modulate(img, dot_crawl_offset=f & 1, hue=0)
+            elif VARIANT.startswith("nesrgb"):
+                eng.modulate(img, format=layout.PIX_BGRA, dot_crawl_offset=f & 1, hue=0)
+            else:
+                eng.modulate(img, format=layout.PIX_BGRA, as_color=1, field=f & 1, frame=(f >> 1) & 1)
+            eng.demodulate(24 if VARIANT == "vhs" else 0)
+        for f in range(4):
+            pair(f)
+        n, t0 = 0, time.perf_counter()
+        while True:
+            pair(n)
+            n += 1
+            dt = time.perf_counter() - t0
+            if (dt >= seconds and n >= 8) or n >= 4000:
+                break
+        return {"value": n / dt, "unit": "frames/s", "pairs": n, "wall_s": dt,
+                "api": "crt_modulate + crt_demodulate (crt_core.h:100-139) on host buffers, one struct CRT, synchronous, strict coherence"}
+    except Exception as e:  # informational key: never take the bench line down
+        return {"value": None, "error": "%s: %s" % (type(e).__name__, e)}
+
+
+def dropin_isolated(seconds=2.0):
+    """dropin_fps in a child process (`bench.py --impl dropin`): the drop-in library abort()s when CUDA fails (its
+    signatures have no error channel), and an informational figure must not be able to take this process with it."""
+    import subprocess
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "dropin", "--variant", VARIANT,
+                            "--dropin-seconds", str(seconds)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=180)
+        if r.returncode != 0:
+            return {"value": None, "error": "child exit %d: %s" % (r.returncode, r.stderr.strip()[-200:])}
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"value": None, "error": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_product(args):
     import numpy as np
     import torch
@@ -496,6 +549,8 @@ def run_product(args):
             "kernel_share_of_step": kernel_share,
             "clocks": clocks,
         }
+        if world == 1:
+            line["dropin"] = dropin_isolated(0.3 if args.no_cpu_baseline else 2.0)
         if cpu:
             line["cpu_baseline"] = cpu
         if gather:
@@ -511,7 +566,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--impl", default="product", choices=["product", "reference", "dropin"],
+                    help="dropin: only the informational drop-in figure (used by the product arm in a child process)")
+    ap.add_argument("--dropin-seconds", type=float, default=2.0)
     ap.add_argument("--streams", type=int, default=1, choices=[1, 2],
                     help="2: advance the batch as two halves on two CUDA streams, staggered (see step())")
     ap.add_argument("--batch", type=int, default=296,
@@ -528,7 +585,11 @@ def main():
     VARIANT = args.variant
     if VARIANT.startswith("nes"):
         W_IN, H_IN = 256, 240  # PPU image (BASELINE configs[2])
-    if args.impl == "reference":
+    if args.impl == "dropin":
+        import pkgload
+        pkgload.load()
+        print(json.dumps(dropin_fps(args.dropin_seconds)), flush=True)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_product(args)

@@ -185,3 +185,4 @@ def test_bench_product_arm_dry_run(variant):
     assert line["steps"] == 2 and line["warmup"] >= 3 and line["gpu_launches"] >= 2 * 4
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
+    assert line["dropin"]["value"] > 0 and line["dropin"]["pairs"] >= 8, line["dropin"]
