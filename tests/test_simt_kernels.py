@@ -186,3 +186,19 @@ def test_bench_product_arm_dry_run(variant):
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
     assert line["dropin"]["value"] > 0 and line["dropin"]["pairs"] >= 8, line["dropin"]
+
+
+def test_interpreter_selftest(tmp_path):
+    """tests/simt/selftest.cpp: the interpreter against known answers from the documented semantics of what it stands
+    in for (shuffles with widths, ballots, block barriers with a predicate, the SIMD video intrinsics, byte
+    permutes, three phases on one mbarrier with deferred bulk copies)"""
+    import subprocess
+    here = os.path.join(S.ROOT, "tests", "simt")
+    exe = str(tmp_path / "selftest")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fwrapv", "-fno-strict-aliasing", "-Wno-unknown-pragmas", "-Wno-attributes",
+           "-fsanitize=alignment", "-fsanitize-undefined-trap-on-error", "-I" + here, "-I" + os.path.join(S.ROOT, "include"),
+           "-DCRT_SYSTEM=0", os.path.join(here, "selftest.cpp"), os.path.join(here, "simt_runtime.cpp"), "-o", exe]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "selftest ok" in r.stdout, r.stdout[-2000:]
