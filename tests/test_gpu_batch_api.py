@@ -84,8 +84,8 @@ def test_empty_ranges_counters_timers_and_state_round_trip():
     b.close()
 
 
-@pytest.mark.parametrize("variant", ["ntsc", "nes", "pv1k"])
-def test_frames_host_is_the_same_field_with_host_buffers(variant):
+@pytest.mark.parametrize("variant,host_src", [("ntsc", 0), ("nes", 0), ("pv1k", 0), ("ntsc", 1)])
+def test_frames_host_is_the_same_field_with_host_buffers(variant, host_src):
     """crtx_frames_host (what bench.py's e2e figure goes through): source images and decoded images are HOST buffers,
     the copies happen inside the call on the caller's stream.  Images of different sizes (the staging slots grow),
     several fields, outputs compared with the oracle's."""
@@ -93,9 +93,12 @@ def test_frames_host_is_the_same_field_with_host_buffers(variant):
     from ntsc_crt_b200 import capi
     n = 3
     b = capi.Batch(variant, n)
+    if host_src:  # "host_src": page-locked source images are read in place by the encoder instead of being copied first
+        b.set_option("host_src", 1)
     nes = variant == "nes"
     outs = [torch.zeros(480, 640, 4, dtype=torch.uint8, device="cuda") for _ in range(n)]
     host_outs = [np.zeros((480, 640, 4), dtype=np.uint8) for _ in range(n)]
+    pinned = []  # keeps page-locked copies alive
     oras = []
     for i in range(n):
         b.set_monitor(i, outs[i], fmt=layout.PIX_BGRA, noise=2 * i, blend=1, scanlines=1)
@@ -106,6 +109,10 @@ def test_frames_host_is_the_same_field_with_host_buffers(variant):
     for it in range(3):
         imgs = [S.nes_image(seed=40 + i + it) if nes else S.rand_image(200 + 150 * i + 64 * it, 120 + 100 * i, seed=40 + i + it)
                 for i in range(n)]
+        if host_src:  # the same images in page-locked memory (monitor 1 stays pageable: that one takes the copy)
+            held = [torch.from_numpy(im).pin_memory() if i != 1 else torch.from_numpy(im) for i, im in enumerate(imgs)]
+            pinned.append(held)
+            imgs = [t.numpy() for t in held]
         for i in range(n):
             kw = dict(dot_crawl_offset=it % 3, hue=10 * i) if nes else dict(format=layout.PIX_BGRA, as_color=1, field=it & 1, frame=0,
                                                                               dot_crawl_offset=it % 3)

@@ -76,6 +76,7 @@ def simt_backend(simt_libs, monkeypatch):
     monkeypatch.setattr(torch, "empty", host_only(real_empty))
     monkeypatch.setattr(torch, "full", host_only(real_full))
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **kw: self)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **kw: self)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **kw: None)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **kw: type("S", (), {"cuda_stream": 0})())
     yield
