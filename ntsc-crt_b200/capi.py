@@ -50,7 +50,7 @@ CRTX_EXPORTS = ("crtx_system", "crtx_chroma_pattern", "crtx_hres", "crtx_input_s
                 "crtx_cc_vper", "crtx_create", "crtx_destroy", "crtx_set_monitors", "crtx_set_state",
                 "crtx_get_state", "crtx_seed", "crtx_analog", "crtx_inp", "crtx_read_signal",
                 "crtx_write_signal", "crtx_modulate",
-                "crtx_demodulate", "crtx_frames_host", "crtx_get_lines", "crtx_launch_count",
+                "crtx_demodulate", "crtx_frames_host", "crtx_get_lines", "crtx_launch_count", "crtx_lines2_count",
                 "crtx_set_option", "crtx_get_timing", "crtx_last_error")
 
 _libs = {}
@@ -87,6 +87,8 @@ def load(variant):
     lib.crtx_get_lines.argtypes = [vp, ip, C.POINTER(Line), vp]
     lib.crtx_launch_count.argtypes = [vp]
     lib.crtx_launch_count.restype = C.c_long
+    lib.crtx_lines2_count.argtypes = [vp]
+    lib.crtx_lines2_count.restype = C.c_long
     lib.crtx_set_option.argtypes = [vp, C.c_char_p, ip]
     lib.crtx_get_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_long)]
     lib.crtx_last_error.restype = C.c_char_p
@@ -228,3 +230,8 @@ class Batch:
     @property
     def launches(self):
         return self.lib.crtx_launch_count(self._ctx)
+
+    @property
+    def lines2_launches(self):
+        """line passes so far that took k_lines2 (csrc/crt_lines2.cuh) instead of k_lines"""
+        return self.lib.crtx_lines2_count(self._ctx)

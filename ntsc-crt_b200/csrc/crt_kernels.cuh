@@ -996,6 +996,7 @@ __global__ void __launch_bounds__(256) k_noise_terms(const MonCfg *__restrict__ 
 
 #include "crt_sync.cuh"
 #include "crt_lines.cuh"
+#include "crt_lines2.cuh"
 #include "crt_lines_fir.cuh"
 #include "crt_bloom.cuh"
 #include "crt_vhs.cuh"

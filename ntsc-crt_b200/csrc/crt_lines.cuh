@@ -144,6 +144,7 @@ struct LinesGeom { // uniform over a launch: host groups monitors by these (crtx
     int use_tma;
     int pass; // -1: every line; -2: only the last line of each shared-row run; >= 0: lines at this run position
     int rnd; // 32768, passed as an argument so that it lives in a register (see pole())
+    int dx;  // ((AV_LEN - 1) << 12) / outw (crt_core.c:527), computed by the host: no division in the kernels
     int line_lo, line_hi; // decoded lines [lo, hi) this launch may touch (scanline-block sharding across ranks)
 };
 
@@ -307,7 +308,7 @@ k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, co
     constexpr unsigned alpha_ff = (FMT == CRT_PIX_FORMAT_ARGB || FMT == CRT_PIX_FORMAT_ABGR) ? 0x000000ffu : 0xff000000u;
     constexpr unsigned blend_mask = (MODE != 2) ? (0x7f7f7f7fu & ~(alpha_ff >> 1) & ~alpha_ff) : 0x7f7f7fu;
 
-    const int dx = ((kAvLen - 1) << 12) / geo.outw; // crt_core.c:527
+    const int dx = geo.dx; // crt_core.c:527
     // carrier value that multiplies sample i for I and for Q, by i % kCc
     int wi[5], wq[5];
     if (kCc == 4) { // wave[(i + 0) & 3] feeds I, wave[(i + 3) & 3] feeds Q (crt_core.c:538-543)

@@ -91,6 +91,56 @@ static void launch_lines_mode(crtx_ctx *ctx, int count, int lo, const LinesGeom 
 #undef LL
 }
 
+// k_lines2 (crt_lines2.cuh): two monitors per CTA, tabulated resampler.  Taken when the whole run qualifies: the stock
+// IIR decoder, 4-byte pixels, every line owning its rows, a width the pixel ring covers, 16-byte aligned images.
+#if CRTX_HAS_LINES2
+static bool lines2_eligible(const crtx_ctx *ctx, int count, int lo, const LinesGeom &geo)
+{
+    if (!ctx->opt_lines2) return false;
+    if (geo.bpp != 4 || geo.pass != -1 || !lines2_geometry_ok(geo.outw)) return false;
+    for (int i = lo; i < lo + count; i++)
+        if (reinterpret_cast<uintptr_t>(ctx->h_cfg[i].out) & 15) return false;
+    return true;
+}
+
+template <int MODE, int FMT>
+static void launch_lines2_one(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
+{
+    k_lines2<MODE, FMT><<<(count + 1) / 2, kL2Threads, lines2_smem(geo.outw), stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines,
+                                                                                       ctx->d_inp, lo, count, geo);
+}
+
+static void launch_lines2(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
+{
+#define LL(F)                                                                  \
+    case F:                                                                    \
+        if (geo.blend) launch_lines2_one<1, F>(ctx, count, lo, geo, stream);   \
+        else launch_lines2_one<0, F>(ctx, count, lo, geo, stream);             \
+        break;
+    switch (geo.out_format) {
+        LL(CRT_PIX_FORMAT_ARGB) LL(CRT_PIX_FORMAT_RGBA) LL(CRT_PIX_FORMAT_ABGR) LL(CRT_PIX_FORMAT_BGRA)
+    }
+#undef LL
+}
+
+static cudaError_t lines2_attr_all()
+{
+    cudaError_t e = cudaSuccess;
+#define LA(M, T)                                                                                               \
+    if (e == cudaSuccess)                                                                                      \
+        e = cudaFuncSetAttribute(k_lines2<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, lines2_smem(kL2MaxOutw));
+#define LF(T) LA(0, T) LA(1, T)
+        LF(CRT_PIX_FORMAT_ARGB) LF(CRT_PIX_FORMAT_RGBA) LF(CRT_PIX_FORMAT_ABGR) LF(CRT_PIX_FORMAT_BGRA)
+#undef LF
+#undef LA
+    return e;
+}
+#else
+static bool lines2_eligible(const crtx_ctx *, int, int, const LinesGeom &) { return false; }
+static void launch_lines2(crtx_ctx *, int, int, const LinesGeom &, cudaStream_t) {}
+static cudaError_t lines2_attr_all() { return cudaSuccess; }
+#endif
+
 static void launch_lines(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
 {
     if (kBloom) { // CRT_DO_BLOOM build: per-line resampling step, one kernel for every format (crt_bloom.cuh)
@@ -98,8 +148,13 @@ static void launch_lines(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo,
             ctx->d_cfg, ctx->d_lines, ctx->d_inp, static_cast<const BloomLine *>(ctx->d_bloom), lo, geo);
         return;
     }
-    launch_lines_mode<true>(ctx, count, lo, geo, stream);
-    launch_lines_mode<false>(ctx, count, lo, geo, stream);
+    if (lines2_eligible(ctx, count, lo, geo)) {
+        launch_lines2(ctx, count, lo, geo, stream);
+        ctx->lines2_launches += 1;
+    } else {
+        launch_lines_mode<true>(ctx, count, lo, geo, stream);
+    }
+    launch_lines_mode<false>(ctx, count, lo, geo, stream); // the monitors k_sync flagged for the wrap-exact equaliser
 }
 
 template <bool FAST, int MODE, int FMT>
@@ -390,6 +445,7 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
         geo.blend = c0.blend ? 1 : 0;
         geo.use_tma = ctx->opt_tma;
         geo.rnd = 32768;
+        geo.dx = c0.outw > 0 ? ((kAvLen - 1) << 12) / c0.outw : 0;
         geo.line_lo = ctx->opt_line_lo;
         geo.line_hi = ctx->opt_line_hi;
         {
@@ -658,6 +714,7 @@ int crtx_create(crtx_ctx **out, int n)
     }
 #endif
     CTX_TRY(lines_attr_all());
+    CTX_TRY(lines2_attr_all());
     CTX_TRY(cudaFuncSetAttribute(k_sync<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
     CTX_TRY(cudaFuncSetAttribute(k_sync<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
 #if CRT_B200_BANDLIMITED
@@ -887,6 +944,7 @@ int crtx_get_lines(crtx_ctx *ctx, int i, crtx_line *table, void *stream)
 }
 
 long crtx_launch_count(crtx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+long crtx_lines2_count(crtx_ctx *ctx) { return ctx ? ctx->lines2_launches : 0; }
 
 int crtx_get_timing(crtx_ctx *ctx, float *ms, long *launches)
 {
@@ -1031,6 +1089,7 @@ int crtx_set_option(crtx_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "fused_noise")) ctx->opt_fused_noise = value;
     else if (!strcmp(name, "host_src")) ctx->opt_host_src = value;
     else if (!strcmp(name, "mod_bulk")) ctx->opt_mod_bulk = value;
+    else if (!strcmp(name, "lines2")) ctx->opt_lines2 = value;
     else if (!strcmp(name, "line_lo")) ctx->opt_line_lo = value;
     else if (!strcmp(name, "line_hi")) ctx->opt_line_hi = value;
     else return fail("crtx_set_option: unknown option '%s'", name);

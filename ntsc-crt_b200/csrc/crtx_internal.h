@@ -36,12 +36,14 @@ struct crtx_ctx {
     std::vector<crt::SrcCfg> scratch_src;
     int cfg_dirty_lo = 0, cfg_dirty_hi = 0;
     long launches = 0;
+    long lines2_launches = 0; // line passes that took k_lines2 (crtx_lines2_count)
     int opt_tma = 1;
     int opt_generic = 0;
     int opt_timing = 0;
     int opt_mod_staged = 1;
     int opt_fused_noise = 1;
     int opt_mod_bulk = 1; // encoder staging: 1 = per-lane bulk copies, 0 = per-lane cp.async (A/B switch; measured equal)
+    int opt_lines2 = 1;   // line pass: 1 = k_lines2 where the geometry qualifies (crt_lines2.cuh), 0 = always k_lines (A/B switch)
     int opt_host_src = 0; // crtx_frames_host: read page-locked source images in place
     int opt_line_lo = 0, opt_line_hi = 1 << 30; // decoded-line window of the line pass (crtx_set_option)
     struct Timed {

@@ -21,6 +21,7 @@ static const char *g_err = "";
 const char *crtx_last_error(void) { return g_err; }
 int crtx_input_size(void) { return ocrt_system(OCRT_SYS_NTSC, 1)->input_size; }
 long crtx_launch_count(crtx_ctx *ctx) { return ctx->launches; }
+long crtx_lines2_count(crtx_ctx *ctx) { (void) ctx; return 0; }
 
 int crtx_create(crtx_ctx **out, int n)
 {

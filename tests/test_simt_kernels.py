@@ -25,6 +25,7 @@ import test_gpu_dropin_cli as _cli  # noqa: E402
 import test_gpu_edges as _edges  # noqa: E402
 import test_gpu_fullsize as _fullsize  # noqa: E402
 import test_gpu_fuzz as _fuzz  # noqa: E402
+import test_gpu_lines2 as _lines2  # noqa: E402
 import test_gpu_lineshard as _lineshard  # noqa: E402
 import test_gpu_parity as _parity  # noqa: E402
 import test_gpu_pv1k as _pv1k  # noqa: E402
@@ -92,6 +93,7 @@ _adopt(_parity, "parity")
 _adopt(_conv, "conv")
 _adopt(_fuzz, "fuzz")
 _adopt(_lineshard, "lineshard")
+_adopt(_lines2, "lines2")
 _adopt(_video, "video")
 _adopt(_template, "template")
 _adopt(_pv1k, "pv1k")
