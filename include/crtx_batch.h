@@ -96,9 +96,13 @@ int crtx_write_signal(crtx_ctx *ctx, int i, int which, const signed char *host, 
 int crtx_modulate(crtx_ctx *ctx, int first, int count, const crtx_source *src, void *stream);
 int crtx_demodulate(crtx_ctx *ctx, int first, int count, void *stream);
 
-/* host-buffer convenience: src[i].data and out[i] are HOST pointers (pinned for full speed);
- * copies the images in, runs modulate + demodulate, copies the decoded images out, all on
- * `stream`; the monitors' `out` must have been set to device images of the right size. */
+/* host-buffer entry point: src[i].data and out_host[i] are HOST pointers; moves the images in, runs modulate +
+ * demodulate, moves the decoded images out, all on `stream`; the monitors' `out` must have been set to device images
+ * of the right size.  out_host[i] is the monitor's PERSISTENT host image, like the `out` buffer of the reference's
+ * struct CRT: with page-locked (crtx_host_alloc / cudaHostAlloc) images whose rows are multiples of 16 bytes, only the
+ * source rows the field reads (crt_ntsc.c:258-266) and only the output rows it writes (crt_core.c:428-432, 662-664)
+ * cross PCIe, and every other row of out_host[i] keeps its bytes.  Pageable or odd-sized images, and option
+ * "host_rows" 0, take whole-image copies. */
 int crtx_frames_host(crtx_ctx *ctx, int first, int count, const crtx_source *src,
                      void *const *out_host, void *stream);
 
@@ -146,7 +150,7 @@ long crtx_launch_count(crtx_ctx *ctx); /* kernels launched through this context 
 long crtx_lines2_count(crtx_ctx *ctx); /* of those, line passes taken by k_lines2 (two monitors per CTA, tabulated resampler: the
                                          * stock IIR decoder on 4-byte pixels, 16-byte aligned images, outw a multiple of 4 in about
                                          * [528, 2048]); every other geometry runs k_lines.  For tests and A/B runs (option "lines2"). */
-/* options: "tma", "generic_eq", "timing", "mod_staged", "fused_noise", "mod_bulk", "lines2" (0/1 switches), "host_src" (1:
+/* options: "tma", "generic_eq", "timing", "mod_staged", "fused_noise", "mod_bulk", "lines2", "host_rows" (0/1 switches), "host_src" (1:
  * crtx_frames_host lets the encoder read page-locked source images in place instead of copying them), and
  * "line_lo" / "line_hi": crtx_demodulate's line pass only decodes scanlines [line_lo, line_hi) of every
  * field (sync search and noise still cover the whole field).  This is the scanline-block partition of

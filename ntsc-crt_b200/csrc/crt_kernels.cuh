@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restric
     // row past the image (undefined); we clamp to the last row instead.
     int row = (int) (((long long) min(y, desth - 1) * s.h) / desth) + (field * s.h + desth) / desth / 2;
     if (row >= s.h) row = s.h - 1;
+    if (s.compact) row = min(y, desth - 1); // crtx_frames_host staged exactly those rows, in line order (k_rows_gather)
     const int rowoff = row * s.w;
 
     int hy = 0, hi = 0, hq = 0;
@@ -474,6 +475,7 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
     // the reference) is clamped to the last row
     int row = (int) (((long long) y * s.h) / desth) + (field * s.h + desth) / desth / 2;
     if (row >= s.h) row = s.h - 1;
+    if (s.compact) row = y; // crtx_frames_host staged exactly those rows, in line order (k_rows_gather)
     const unsigned char *rowp = data + (size_t) row * s.w * bpp;
     const int nchunks = (destw + kModSChunk - 1) / kModSChunk;
 

@@ -35,7 +35,7 @@ struct SrcCfg { // host -> device, struct NTSC_SETTINGS
     int aberration; // VHS: already drawn number of sync-less lines (crt_ntscvhs.c:205-207)
     int dot_crawl_offset;
     int reinit;
-    int pad;
+    int compact; // internal (crtx_frames_host): `data` holds only the rows this field reads, picture line y in row y
 };
 
 typedef crtx_line LineRec; // 32 bytes

@@ -598,6 +598,81 @@ __global__ void k_fade_phosphors(unsigned *__restrict__ image, size_t npix)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// crtx_frames_host: only the rows a field touches cross PCIe.
+// A field reads 236 of an image's rows (crt_ntsc.c:258-266: row (y * h) / desth + field offset for each picture line
+// y) and writes, per decoded line, rows beg .. end - scanlines - 1 (crt_core.c:428-432, 662-664): 384 of 624 with the
+// drivers' settings.  The rows are irregularly spaced, so a strided DMA cannot describe them; two copy kernels move
+// them through the page-locked host buffers' device mappings instead, 16 bytes per lane, every load of a thread in
+// flight before its first store:
+//   k_rows_gather   host image -> the monitor's staging slot, picture line y in row y (SrcCfg::compact)
+//   k_rows_scatter  device image -> host image, the rows the line table says this field wrote; every other row
+//                   of the host image keeps its content, exactly as the reference's own `out` buffer does.
+// Pageable, unmapped or unaligned host buffers take the whole-image cudaMemcpyAsync as before.
+// ---------------------------------------------------------------------------------------------------------
+struct RowGather {
+    const unsigned char *src; // device mapping of the page-locked host image, or NULL: not a row job
+    unsigned char *dst;       // staging slot
+    int row_bytes, h, desth, field;
+};
+
+constexpr int kRowWarps = 8;
+
+__device__ __forceinline__ void copy_row16(const uint4 *__restrict__ s, uint4 *__restrict__ d, int n16, int lane)
+{
+    for (int i = lane; i < n16; i += 32 * 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (i + 32 * k < n16) v[k] = s[i + 32 * k];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (i + 32 * k < n16) d[i + 32 * k] = v[k];
+    }
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32) k_rows_gather(const RowGather *__restrict__ jobs, int first)
+{
+    const RowGather j = jobs[first + blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = blockIdx.x * kRowWarps + warp;
+    if (!j.src || y >= j.desth) return;
+    int row = (int) (((long long) y * j.h) / j.desth) + (j.field * j.h + j.desth) / j.desth / 2; // crt_ntsc.c:258-266
+    if (row >= j.h) row = j.h - 1; // (as the encoder kernels: the reference's one-row over-read is not reproduced)
+    copy_row16(reinterpret_cast<const uint4 *>(j.src + (size_t) row * j.row_bytes),
+               reinterpret_cast<uint4 *>(j.dst + (size_t) y * j.row_bytes), j.row_bytes / 16, lane);
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32)
+k_rows_scatter(const MonCfg *__restrict__ cfgs, const LineRec *__restrict__ lines, unsigned char *const *__restrict__ host_out,
+               int first, int line_lo, int line_hi)
+{
+    const int m = first + blockIdx.y;
+    unsigned char *host = host_out[m];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * kRowWarps + warp;
+    if (!host || k >= kLines || k < line_lo || k >= line_hi) return;
+    const LineRec rec = lines[(size_t) m * kLines + k];
+    if (rec.beg < 0) return;
+    const MonCfg cfg = cfgs[m];
+    const int pitch = cfg.outw * cfg.bpp;
+    const int nrows = max(1, rec.end - cfg.scanlines - rec.beg); // crt_core.c:662-664
+    for (int r = 0; r < nrows; r++) {
+        const size_t off = (size_t) (rec.beg + r) * pitch;
+        copy_row16(reinterpret_cast<const uint4 *>(cfg.out + off), reinterpret_cast<uint4 *>(host + off), pitch / 16, lane);
+    }
+}
+
+// device mapping of a page-locked host buffer (NULL if `p` is pageable or not mapped)
+static void *host_mapping(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+    (void) cudaGetLastError();
+    return NULL;
+}
+
 void fill_src(SrcCfg *d, const crtx_source *s)
 {
     memset(d, 0, sizeof(*d));
@@ -670,6 +745,8 @@ int crtx_create(crtx_ctx **out, int n)
     CTX_TRY(cudaMalloc(&ctx->d_cfg, sizeof(MonCfg) * n));
     CTX_TRY(cudaMalloc(&ctx->d_state, sizeof(MonState) * n));
     CTX_TRY(cudaMalloc(&ctx->d_src, sizeof(SrcCfg) * n));
+    CTX_TRY(cudaMalloc(&ctx->d_row_jobs, sizeof(RowGather) * n));
+    CTX_TRY(cudaMalloc(&ctx->d_host_out, sizeof(unsigned char *) * n));
     CTX_TRY(cudaMalloc(&ctx->d_lines, sizeof(LineRec) * (size_t) n * kLines));
     CTX_TRY(cudaMalloc(&ctx->d_analog, (size_t) n * kSignalBytes));
     CTX_TRY(cudaMalloc(&ctx->d_inp, (size_t) n * kSignalBytes));
@@ -731,6 +808,8 @@ void crtx_destroy(crtx_ctx *ctx)
     cudaFree(ctx->d_cfg);
     cudaFree(ctx->d_state);
     cudaFree(ctx->d_src);
+    cudaFree(ctx->d_row_jobs);
+    cudaFree(ctx->d_host_out);
     cudaFree(ctx->d_lines);
     cudaFree(ctx->d_analog);
     cudaFree(ctx->d_inp);
@@ -865,11 +944,15 @@ int crtx_write_signal(crtx_ctx *ctx, int i, int which, const signed char *host, 
     return 0;
 }
 
-int crtx_modulate(crtx_ctx *ctx, int first, int count, const crtx_source *src, void *stream)
+// crtx_modulate; compact[i] != 0: src[i].data is a staging slot that holds only the rows the field reads (crtx_frames_host)
+static int modulate_sources(crtx_ctx *ctx, int first, int count, const crtx_source *src, const unsigned char *compact, void *stream)
 {
     if (check_range(ctx, first, count)) return 1;
     ctx->scratch_src.resize(count);
-    for (int i = 0; i < count; i++) fill_src(&ctx->scratch_src[i], &src[i]);
+    for (int i = 0; i < count; i++) {
+        fill_src(&ctx->scratch_src[i], &src[i]);
+        ctx->scratch_src[i].compact = (compact && compact[i]) ? 1 : 0;
+    }
 #if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
     { // the aberration draw happens on the device, from the monitor's rand() replica
         std::vector<int> wants(count);
@@ -880,6 +963,11 @@ int crtx_modulate(crtx_ctx *ctx, int first, int count, const crtx_source *src, v
     }
 #endif
     return modulate_launch(ctx, first, count, ctx->scratch_src.data(), static_cast<cudaStream_t>(stream));
+}
+
+int crtx_modulate(crtx_ctx *ctx, int first, int count, const crtx_source *src, void *stream)
+{
+    return modulate_sources(ctx, first, count, src, NULL, stream);
 }
 
 int crtx_demodulate(crtx_ctx *ctx, int first, int count, void *stream)
@@ -907,30 +995,73 @@ int crtx_frames_host(crtx_ctx *ctx, int first, int count, const crtx_source *src
         ctx->src_slot = need;
     }
     std::vector<crtx_source> dev(src, src + count);
+    std::vector<unsigned char> compact(count, 0);
+    std::vector<RowGather> jobs(count);
+    int row_jobs = 0, max_desth = 0;
     for (int i = 0; i < count; i++) {
         size_t b = (size_t) src[i].w * src[i].h * (kIsNes ? 2 : bpp_of(src[i].format));
+        jobs[i].src = NULL;
         if (ctx->opt_host_src) {
-            // "host_src": the encoder reads a page-locked source image in place over PCIe -- a field only
-            // touches the rows of its own parity (crt_ntsc.c:258-266), about 38 % of an 832x624 image, so
-            // less crosses the link than a whole-image copy moves.  Pageable images still take the copy.
-            cudaPointerAttributes at;
-            if (cudaPointerGetAttributes(&at, src[i].data) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
-                dev[i].data = at.devicePointer;
+            // "host_src": the encoder reads a page-locked source image in place over PCIe (A/B switch; the encoder's
+            // two-deep staging cannot cover the link's latency, the row gather below can).  Pageable images take the copy.
+            void *map = host_mapping(src[i].data);
+            if (map) {
+                dev[i].data = map;
                 continue;
             }
-            (void) cudaGetLastError();
         }
         unsigned char *slot = ctx->d_src_img + ctx->src_slot * (size_t) (first + i);
-        CUDA_TRY(cudaMemcpyAsync(slot, src[i].data, b, cudaMemcpyHostToDevice, st));
         dev[i].data = slot;
+#if CRT_B200_BANDLIMITED
+        const int row_bytes = src[i].w * bpp_of(src[i].format);
+        void *map = (ctx->opt_host_rows && row_bytes > 0 && (row_bytes & 15) == 0 && src[i].h > 0) ? host_mapping(src[i].data) : NULL;
+        if (map && (reinterpret_cast<uintptr_t>(map) & 15) == 0) {
+            RowGather &j = jobs[i];
+            j.src = static_cast<const unsigned char *>(map);
+            j.dst = slot;
+            j.row_bytes = row_bytes;
+            j.h = src[i].h;
+            j.desth = src[i].raw ? (src[i].h < kDestH ? src[i].h : kDestH) : kDestH; // crt_ntsc.c:132-133, 163-172
+            j.field = src[i].field & 1;
+            compact[i] = 1;
+            row_jobs += 1;
+            if (j.desth > max_desth) max_desth = j.desth;
+            continue;
+        }
+#endif
+        CUDA_TRY(cudaMemcpyAsync(slot, src[i].data, b, cudaMemcpyHostToDevice, st));
     }
-    if (crtx_modulate(ctx, first, count, dev.data(), stream)) return 1;
+    if (row_jobs) {
+        CUDA_TRY(cudaMemcpyAsync(static_cast<RowGather *>(ctx->d_row_jobs) + first, jobs.data(), sizeof(RowGather) * count, cudaMemcpyHostToDevice, st));
+        k_rows_gather<<<dim3((max_desth + kRowWarps - 1) / kRowWarps, count), kRowWarps * 32, 0, st>>>(
+            static_cast<const RowGather *>(ctx->d_row_jobs), first);
+        ctx->launches += 1;
+    }
+    if (modulate_sources(ctx, first, count, dev.data(), compact.data(), stream)) return 1;
     if (crtx_demodulate(ctx, first, count, stream)) return 1;
+    std::vector<unsigned char *> maps(count, static_cast<unsigned char *>(NULL));
+    int scatter = 0;
     for (int i = 0; i < count; i++) {
         const MonCfg &c = ctx->h_cfg[first + i];
         if (!out_host || !out_host[i]) continue;
+        const int pitch = c.outw * c.bpp;
+        void *map = (ctx->opt_host_rows && pitch > 0 && (pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(c.out) & 15) == 0
+                     && (long long) c.outh + (long long) c.v_fac >= kLines)
+                        ? host_mapping(out_host[i]) : NULL;
+        if (map && (reinterpret_cast<uintptr_t>(map) & 15) == 0) {
+            maps[i] = static_cast<unsigned char *>(map);
+            scatter += 1;
+            continue;
+        }
         CUDA_TRY(cudaMemcpyAsync(out_host[i], c.out, (size_t) c.outw * c.outh * c.bpp, cudaMemcpyDeviceToHost, st));
     }
+    if (scatter) {
+        CUDA_TRY(cudaMemcpyAsync(ctx->d_host_out + first, maps.data(), sizeof(unsigned char *) * count, cudaMemcpyHostToDevice, st));
+        k_rows_scatter<<<dim3((kLines + kRowWarps - 1) / kRowWarps, count), kRowWarps * 32, 0, st>>>(
+            ctx->d_cfg, ctx->d_lines, ctx->d_host_out, first, ctx->opt_line_lo, ctx->opt_line_hi);
+        ctx->launches += 1;
+    }
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
@@ -1088,6 +1219,7 @@ int crtx_set_option(crtx_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "mod_staged")) ctx->opt_mod_staged = value;
     else if (!strcmp(name, "fused_noise")) ctx->opt_fused_noise = value;
     else if (!strcmp(name, "host_src")) ctx->opt_host_src = value;
+    else if (!strcmp(name, "host_rows")) ctx->opt_host_rows = value;
     else if (!strcmp(name, "mod_bulk")) ctx->opt_mod_bulk = value;
     else if (!strcmp(name, "lines2")) ctx->opt_lines2 = value;
     else if (!strcmp(name, "line_lo")) ctx->opt_line_lo = value;

@@ -17,6 +17,8 @@ struct crtx_ctx {
     crt::MonCfg *d_cfg = nullptr;
     crt::MonState *d_state = nullptr;
     crt::SrcCfg *d_src = nullptr;
+    void *d_row_jobs = nullptr;            // crtx_frames_host: RowGather[n]
+    unsigned char **d_host_out = nullptr;  // crtx_frames_host: device mappings of the callers' host images, [n]
     crtx_line *d_lines = nullptr;
     signed char *d_analog = nullptr;
     signed char *d_inp = nullptr;
@@ -44,6 +46,7 @@ struct crtx_ctx {
     int opt_fused_noise = 1;
     int opt_mod_bulk = 1; // encoder staging: 1 = per-lane bulk copies, 0 = per-lane cp.async (A/B switch; measured equal)
     int opt_lines2 = 1;   // line pass: 1 = k_lines2 where the geometry qualifies (crt_lines2.cuh), 0 = always k_lines (A/B switch)
+    int opt_host_rows = 1; // crtx_frames_host: move only the rows a field reads / writes (page-locked, 16-byte granular images)
     int opt_host_src = 0; // crtx_frames_host: read page-locked source images in place
     int opt_line_lo = 0, opt_line_hi = 1 << 30; // decoded-line window of the line pass (crtx_set_option)
     struct Timed {

@@ -241,9 +241,18 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.001f; return cudaSuccess; } /* (no clock here: a token value) */
-static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *)
+static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p)
 {
     memset(a, 0, sizeof(*a));
+    /* SIMT_HOST_MAPPED=1: every host buffer counts as page-locked and mapped at its own address (what cudaHostAlloc
+     * gives under unified addressing), so that the paths that read / write host images in place can run here */
+    const char *e = getenv("SIMT_HOST_MAPPED");
+    if (e && *e == '1') {
+        a->type = cudaMemoryTypeHost;
+        a->devicePointer = const_cast<void *>(p);
+        a->hostPointer = const_cast<void *>(p);
+        return cudaSuccess;
+    }
     return cudaErrorInvalidValue;
 }
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }

@@ -133,6 +133,72 @@ def test_frames_host_is_the_same_field_with_host_buffers(variant, host_src):
     b.close()
 
 
+@pytest.mark.parametrize("variant,raw", [("ntsc", 0), ("ntsc", 1), ("pv1k", 0), ("nes", 0), ("ntsc_conv", 0)])
+def test_frames_host_moves_only_the_rows_a_field_touches(variant, raw, monkeypatch):
+    """crtx_frames_host with page-locked, 16-byte granular host images: the source rows the field reads are gathered
+    from the host image in place (crt_ntsc.c:258-266) and only the rows the field wrote are stored back into the host
+    image (crt_core.c:428-432, 662-664).  The host image is the monitor's persistent `out`, as in the reference: rows a
+    field does not write keep their previous bytes -- proven with a sentinel the device image never held -- and after
+    every field the rows that WERE written equal the oracle's.  `host_rows` 0 restores whole-image copies."""
+    import torch
+    from ntsc_crt_b200 import capi
+    monkeypatch.setenv("SIMT_HOST_MAPPED", "1")  # (only the CPU interpreter build of the library reads this)
+    n, outw, outh = 3, 832, 624
+    nes = variant == "nes"
+    for host_rows in (1, 0):
+        b = capi.Batch(variant, n)
+        b.set_option("host_rows", host_rows)
+        outs = [torch.zeros(outh, outw, 4, dtype=torch.uint8, device="cuda") for _ in range(n)]
+        host = [torch.full((outh, outw, 4), 0xA5, dtype=torch.uint8).pin_memory() for _ in range(n)]  # sentinel 0xA5
+        oras = []
+        for i in range(n):
+            b.set_monitor(i, outs[i], fmt=layout.PIX_BGRA, noise=3 * i, blend=1, scanlines=1)
+            o = S.OracleEngine(variant, outw, outh)
+            o.set(blend=1, scanlines=1)
+            oras.append(o)
+        b.commit_monitors()
+        written = [np.zeros(outh, dtype=bool) for _ in range(n)]
+        for it in range(3):
+            if nes:
+                imgs = [torch.from_numpy(S.nes_image(seed=60 + i + it).astype(np.int16)).pin_memory() for i in range(n)]
+            elif raw:  # small images placed as they are (crt_ntsc.c:163-172): fewer rows than picture lines
+                imgs = [torch.from_numpy(S.rand_image(320 + 64 * i, 100 + 60 * i, seed=60 + i + it)).pin_memory() for i in range(n)]
+            else:
+                imgs = [torch.from_numpy(S.rand_image(832 - 64 * i, 624 - 100 * i, seed=60 + i + it)).pin_memory() for i in range(n)]
+            for i in range(n):
+                if nes:
+                    kw = dict(dot_crawl_offset=it % 3, hue=10 * i)
+                else:
+                    # (raw images shorter than the picture: an odd field would read the row one past the image in the
+                    # reference, crt_ntsc.c:263 -- outside the reproduced domain, DESIGN.md section 2)
+                    kw = dict(format=layout.PIX_BGRA, as_color=1, field=0 if raw else it & 1, frame=(it >> 1) & 1, raw=raw, dot_crawl_offset=it % 3)
+                b.sources[i].reinit = 1 if (nes and it == 0) else 0
+                b.sources[i].data = imgs[i].data_ptr()
+                b.sources[i].h, b.sources[i].w = imgs[i].shape[0], imgs[i].shape[1]
+                for k, v in kw.items():
+                    setattr(b.sources[i], k, v)
+                src_np = imgs[i].numpy().view(np.uint16) if nes else imgs[i].numpy()
+                oras[i].modulate(src_np, **kw)
+                oras[i].demodulate(3 * i)
+            b.frames_host([h.data_ptr() for h in host])
+            torch.cuda.synchronize()
+            for i in range(n):
+                got = host[i].numpy()
+                assert np.array_equal(outs[i].cpu().numpy(), oras[i].out), (variant, it, i)
+                if not host_rows:
+                    assert np.array_equal(got, oras[i].out), "%s field %d monitor %d: %s" % (variant, it, i, S.diff_report("host image", got, oras[i].out))
+                    continue
+                for l in b.get_lines(i):
+                    if l.beg >= 0:
+                        written[i][l.beg:l.beg + max(1, l.end - 1 - l.beg)] = True
+                w = written[i]
+                assert 0 < w.sum() < outh or it > 0
+                assert np.array_equal(got[w], oras[i].out[w]), "%s field %d monitor %d: %s" % (
+                    variant, it, i, S.diff_report("written rows", got[w], oras[i].out[w]))
+                assert (got[~w] == 0xA5).all(), "%s field %d monitor %d: a row no field wrote changed on the host" % (variant, it, i)
+        b.close()
+
+
 @pytest.mark.parametrize("variant", ["ntsc", "ntsc_conv", "template", "pv1k"])
 @pytest.mark.parametrize("option,value", [("generic_eq", 1), ("mod_staged", 0), ("fused_noise", 0), ("mod_bulk", 0), ("tma", 0)])
 def test_every_switch_of_the_library_gives_the_same_bits(variant, option, value):
