@@ -75,9 +75,16 @@ def block_rows(lo, hi, outh, lines, v_fac=0):
 
 
 class ImageSharder:
-    """Row ownership and the two exchanges of the scanline-block partition of one image.
+    """Row ownership and the exchanges of the scanline-block partition of one image.
 
-    image: this rank's (outh, outw, bpp) uint8 tensor (any device the process group supports)."""
+    image: this rank's (outh, outw, bpp) uint8 tensor (any device the process group supports).
+
+    Per field:  fetch_halo_rows()  ->  the decode of this rank's lines  ->  exchange_spill_rows(written_end).
+    In an odd field every line is shifted down by ratio / 2 rows (crt_core.c:400-407), so the last line of a block
+    reaches into the first rows of the NEXT block: it may only duplicate into them (a taller line) or -- when the line
+    is no taller than the shift -- put its COMPUTED row there, which the blend mixes with what that row held
+    (crt_core.c:584-608).  That content is the next rank's, so the next rank lends it first (the halo) and gets the
+    result back (the spill)."""
 
     def __init__(self, image, lines, rank=None, world=None, v_fac=0, group=None):
         import torch.distributed as dist
@@ -87,10 +94,18 @@ class ImageSharder:
         self.rank = rank if rank is not None else (dist.get_rank(group) if on else 0)
         self.image, self.lines, self.v_fac = image, lines, v_fac
         self.outh = image.shape[0]
+        if self.world > 1 and self.outh + v_fac < lines:
+            # several decoded lines share an output row and the reference applies them in line order
+            # (crt_core.c:409-664 is a sequential loop): lines of two ranks would have to take turns on one row
+            raise ValueError("scanline-block sharding needs at least one output row per decoded line: outh + v_fac = %d < %d lines"
+                             % (self.outh + v_fac, lines))
         self.lo, self.hi = line_block(self.rank, self.world, lines)
         self.blocks = [block_rows(*line_block(r, self.world, lines), self.outh, lines, v_fac)
                        for r in range(self.world)]
         self.r0, self.r1 = self.blocks[self.rank]
+        if self.world > 1 and min(b - a for a, b in self.blocks) < self.max_spill():
+            raise ValueError("scanline-block sharding: %d ranks leave a block with fewer than %d rows (the odd-field shift), "
+                             "use fewer ranks for a %d-row image" % (self.world, self.max_spill(), self.outh))
 
     def apply(self, batch):
         """Restrict a capi.Batch's line pass to this rank's block."""
@@ -98,29 +113,58 @@ class ImageSharder:
         batch.set_option("line_hi", self.hi)
 
     def max_spill(self):
-        """Most rows a block can spill into its successor: ratio / 2 of crt_core.c:400-407."""
-        ratio = ((((self.outh + self.v_fac) << 16) // self.lines) + 32768) >> 16
+        """Most rows a block can reach into its successor: the odd-field shift ratio / 2 of crt_core.c:404-407 (the
+        ratio is taken from outh alone there; v_fac only stretches beg / end, crt_core.c:428-429)."""
+        ratio = (((self.outh << 16) // self.lines) + 32768) >> 16
         return max(1, ratio // 2)
+
+    def _halo_count(self, r):
+        """rows rank r borrows from rank r + 1: the first max_spill() rows of that block"""
+        if r + 1 >= self.world or self.blocks[r + 1][0] != self.blocks[r][1]:
+            return 0
+        a, b = self.blocks[r + 1]
+        return max(0, min(self.max_spill(), b - a))
+
+    def fetch_halo_rows(self):
+        """Before a field: the first max_spill() rows of the next rank's block, as that rank holds them now, into this
+        rank's image -- what this rank's last line will blend with if its computed row lands there.  One small
+        all_gather.  (Cheap enough to do before every field; only odd fields of blended images need it.)"""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return
+        cap = self.max_spill()
+        mine = torch.zeros((cap,) + tuple(self.image.shape[1:]), dtype=self.image.dtype, device=self.image.device)
+        n_mine = min(cap, self.r1 - self.r0)
+        if n_mine:
+            mine[:n_mine].copy_(self.image[self.r0:self.r0 + n_mine])
+        rows = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(rows, mine, group=self.group)
+        cnt = self._halo_count(self.rank)
+        if cnt:
+            self.image[self.r1:self.r1 + cnt].copy_(rows[self.rank + 1][:cnt])
 
     def exchange_spill_rows(self, written_end):
         """After a field.  written_end: one past the last output row this rank's LAST line wrote in this
         field (`end - scanlines` of line hi - 1 from the sync table, or anything <= r1 if it was skipped).
-        Rows [r1, written_end) belong to the next rank, which takes them into its image.  One small
-        all_gather (a few rows per rank)."""
+        Rows [r1, written_end) belong to the next rank, which takes them into its image.  Two small
+        all_gathers (the rows, and how many of them count)."""
         import torch
         import torch.distributed as dist
         if self.world == 1:
             return
         cap = self.max_spill()
         cnt = max(0, min(int(written_end), self.outh, self.r1 + cap) - self.r1) if self.rank + 1 < self.world else 0
-        mine = torch.zeros((cap + 1,) + tuple(self.image.shape[1:]), dtype=self.image.dtype, device=self.image.device)
+        mine = torch.zeros((cap,) + tuple(self.image.shape[1:]), dtype=self.image.dtype, device=self.image.device)
         if cnt:
             mine[:cnt].copy_(self.image[self.r1:self.r1 + cnt])
-        mine[cap].view(-1)[0] = cnt  # (cap rows of pixels, then the count in the first byte of a spare row)
         rows = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(rows, mine, group=self.group)
+        n_mine = torch.tensor([cnt], dtype=torch.int64, device=self.image.device)
+        counts = [torch.empty_like(n_mine) for _ in range(self.world)]
+        dist.all_gather(counts, n_mine, group=self.group)
         if self.rank > 0 and self.blocks[self.rank - 1][1] == self.r0:
-            got = int(rows[self.rank - 1][cap].view(-1)[0])
+            got = int(counts[self.rank - 1].item())
             if got:
                 self.image[self.r0:self.r0 + got].copy_(rows[self.rank - 1][:got])
 

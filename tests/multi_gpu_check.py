@@ -39,6 +39,8 @@ def decode_image(variant, outw, outh, blend, scanlines, img, fields, noise, part
     part = part_of(out, b) if part_of else None
     for it in range(fields):
         b.set_source(0, img, format=layout.PIX_BGRA, as_color=1, field=it & 1, frame=(it >> 1) & 1)
+        if part is not None:
+            part.fetch_halo_rows()
         b.modulate()
         b.demodulate()
         if part is not None:
@@ -61,7 +63,8 @@ def main():
     # ---- 1. one image, scanline blocks
     img = torch.from_numpy(S.rand_image(400, 300, seed=3)).to(dev)
     for variant, outw, outh, blend, scanlines in (("ntsc", 832, 624, 1, 1), ("ntsc", 640, 480, 1, 0),
-                                                  ("ntsc_conv", 832, 624, 1, 1), ("ntsc", 400, 1080, 1, 0)):
+                                                  ("ntsc_conv", 832, 624, 1, 1), ("ntsc", 400, 1080, 1, 0),
+                                                  ("ntsc", 320, 360, 1, 0), ("ntsc", 320, 360, 1, 1)):
         def make(image, batch):
             p = sharding.ImageSharder(image, batch.spec.lines)
             p.apply(batch)

@@ -17,6 +17,8 @@ pytestmark = pytest.mark.gpu
     (832, 624, 1, 1, 2),
     (640, 480, 0, 1, 2),   # spill row travels after odd fields
     (400, 1080, 0, 1, 3),  # two spill rows, uneven blocks
+    (320, 360, 0, 1, 16),  # 1.5 rows per line: a block's last line can be ONE row tall, its computed (blended) row then
+    (320, 360, 1, 1, 16),  # lands in the next block in odd fields -- needs that block's rows first (the halo)
 ])
 def test_two_contexts_decode_one_image(variant, outw, outh, scanlines, blend, world):
     decode_one_image_in_blocks(variant, outw, outh, scanlines, blend, world)
@@ -50,6 +52,11 @@ def decode_one_image_in_blocks(variant, outw, outh, scanlines, blend, world):
         ora.modulate(img, format=layout.PIX_BGRA, as_color=1, field=it & 1, frame=(it >> 1) & 1)
         ora.demodulate(4)
         ends = []
+        for r in range(world - 1):  # what ImageSharder.fetch_halo_rows does over the process group, before the field
+            (_, dst, ps), (_, src, pn) = ranks[r], ranks[r + 1]
+            cnt = ps._halo_count(r)
+            if cnt:
+                dst[ps.r1:ps.r1 + cnt].copy_(src[pn.r0:pn.r0 + cnt])
         for b, out, part in ranks:
             b.set_source(0, dimg, format=layout.PIX_BGRA, as_color=1, field=it & 1, frame=(it >> 1) & 1)
             b.modulate()

@@ -100,6 +100,7 @@ def _image_worker(rank, world, port, q, cfg):
         for it in range(6):
             field = 0 if progressive else it & 1
             eng.modulate(img, format=layout.PIX_BGRA, as_color=1, field=field, frame=(it >> 1) & 1)
+            part.fetch_halo_rows()
             eng.noise_pass(noise)
             _, table = eng.sync_pass()
             eng.line_pass(table, part.lo, part.hi - part.lo)
@@ -116,6 +117,10 @@ def _image_worker(rank, world, port, q, cfg):
     (3, (333, 250, 0, 1, False, 0)),   # uneven blocks
     (2, (256, 240, 0, 0, True, 3)),
     (2, (400, 1080, 0, 1, False, 0)),  # ratio 4.5: two spill rows per odd field
+    (16, (320, 360, 0, 1, False, 0)),  # 1.5 rows per line: blocks whose last line is ONE row tall put their computed,
+    (16, (320, 360, 1, 1, False, 5)),  # blended row into the next block in odd fields (round-1 advisor finding)
+    (7, (320, 300, 0, 1, False, 0)),
+    (5, (200, 241, 0, 1, False, 2)),   # barely one row per line
 ])
 def test_one_image_over_ranks_matches_the_sequential_decode(world, cfg):
     import support as S
@@ -140,3 +145,15 @@ def test_one_image_over_ranks_matches_the_sequential_decode(world, cfg):
         ref.demodulate(noise)
     for rank, full in results:
         assert np.array_equal(full, ref.out), "rank %d: %s" % (rank, S.diff_report("image", full, ref.out))
+
+
+def test_geometries_the_partition_cannot_serve_are_refused():
+    """fewer output rows than decoded lines: lines of two ranks would share a row and must be applied in order
+    (crt_core.c:409-664), which blocks cannot do -- a clear error instead of a wrong image; likewise blocks thinner than
+    the odd-field shift"""
+    img = torch.zeros(120, 64, 4, dtype=torch.uint8)
+    with pytest.raises(ValueError, match="one output row per decoded line"):
+        sharding.ImageSharder(img, 240, rank=0, world=7)
+    sharding.ImageSharder(img, 240, rank=0, world=1)  # a single rank is always fine
+    tall = torch.zeros(2400, 8, 4, dtype=torch.uint8)  # ratio 10: shift 5 rows; 240 ranks x 10 rows is fine, 5-row blocks are not possible
+    sharding.ImageSharder(tall, 240, rank=3, world=240)
