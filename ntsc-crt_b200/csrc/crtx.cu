@@ -55,6 +55,13 @@ static int upload_cfg(crtx_ctx *ctx, cudaStream_t stream)
         ctx->launches += 1;
         ctx->cfg_dirty_lo = ctx->n;
         ctx->cfg_dirty_hi = 0;
+        // a context may be driven from several streams over disjoint monitor ranges (crtx_frames_host, bench.py): the
+        // others must not read d_cfg or the signal tails before this upload has landed
+        if (!ctx->cfg_ready) CUDA_TRY(cudaEventCreateWithFlags(&ctx->cfg_ready, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(ctx->cfg_ready, stream));
+        ctx->cfg_stream = stream;
+    } else if (ctx->cfg_ready && stream != ctx->cfg_stream) {
+        CUDA_TRY(cudaStreamWaitEvent(stream, ctx->cfg_ready, 0)); // (free once the event has completed)
     }
     return 0;
 }
@@ -185,15 +192,22 @@ static cudaError_t lines_attr_all()
 template <int FMT, bool COLOR>
 static void launch_mod_staged_one(crtx_ctx *ctx, int count, int first, cudaStream_t stream)
 {
-    static bool attr_done = false; // per instantiation; cudaFuncSetAttribute is idempotent
-    if (!attr_done) {
-        cudaFuncSetAttribute(k_mod_picture_rgb_staged<FMT, COLOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSSmem);
-        attr_done = true;
-    }
     // staging: 1 = per-lane bulk copies (default), 2 = per-lane cp.async copies ("mod_bulk" 0), 0 = plain loads
     const int staging = ctx->opt_tma ? (ctx->opt_mod_bulk ? 1 : 2) : 0;
     k_mod_picture_rgb_staged<FMT, COLOR><<<count, 256, kModSSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog,
                                                                             first, staging);
+}
+
+// function attributes are per device: set by crtx_create for the context's device
+static cudaError_t mod_staged_attr_all()
+{
+    cudaError_t e = cudaSuccess;
+#define MA(F)                                                                                                                        \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mod_picture_rgb_staged<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSSmem);  \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mod_picture_rgb_staged<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSSmem);
+    MA(0) MA(1) MA(2) MA(3) MA(4) MA(5)
+#undef MA
+    return e;
 }
 
 static void launch_mod_staged(crtx_ctx *ctx, int format, bool color, int count, int first, cudaStream_t stream)
@@ -796,6 +810,7 @@ int crtx_create(crtx_ctx **out, int n)
     CTX_TRY(cudaFuncSetAttribute(k_sync<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSyncSmem));
 #if CRT_B200_BANDLIMITED
     CTX_TRY(cudaFuncSetAttribute(k_mod_picture_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, kModSmem));
+    CTX_TRY(mod_staged_attr_all());
 #endif
 #undef CTX_TRY
     *out = ctx;
@@ -827,12 +842,22 @@ void crtx_destroy(crtx_ctx *ctx)
         cudaEventDestroy(ctx->timed[i].stop);
     }
     for (size_t i = 0; i < ctx->event_pool.size(); i++) cudaEventDestroy(ctx->event_pool[i]);
+    if (ctx->cfg_ready) cudaEventDestroy(ctx->cfg_ready);
     delete ctx;
 }
 
 int crtx_set_monitors(crtx_ctx *ctx, int first, int count, const crtx_monitor *m)
 {
     if (check_range(ctx, first, count)) return 1;
+    // validate every entry before any of them is applied: a rejected call leaves the context exactly as it was
+    for (int i = 0; i < count; i++) {
+        if (m[i].outw < 0 || m[i].outh < 0)
+            return fail("monitor %d: negative output size %d x %d", first + i, m[i].outw, m[i].outh);
+        if (m[i].outw > kMaxOutw)
+            return fail("monitor %d: outw %d above the supported maximum %d", first + i, m[i].outw, kMaxOutw);
+        if (bpp_of(m[i].out_format) == 4 && (reinterpret_cast<uintptr_t>(m[i].out) & 3))
+            return fail("monitor %d: 4-byte pixel formats need a 4-byte aligned device image", first + i);
+    }
     for (int i = 0; i < count; i++) {
         MonCfg &c = ctx->h_cfg[first + i];
         c.out = static_cast<unsigned char *>(m[i].out);
@@ -850,10 +875,6 @@ int crtx_set_monitors(crtx_ctx *ctx, int first, int count, const crtx_monitor *m
         c.blend = m[i].blend;
         c.v_fac = m[i].v_fac;
         c.noise = m[i].noise;
-        if (c.outw > kMaxOutw)
-            return fail("monitor %d: outw %d above the supported maximum %d", first + i, c.outw, kMaxOutw);
-        if (c.bpp == 4 && (reinterpret_cast<uintptr_t>(c.out) & 3))
-            return fail("monitor %d: 4-byte pixel formats need a 4-byte aligned device image", first + i);
     }
     if (first < ctx->cfg_dirty_lo) ctx->cfg_dirty_lo = first;
     if (first + count > ctx->cfg_dirty_hi) ctx->cfg_dirty_hi = first + count;

@@ -37,6 +37,8 @@ struct crtx_ctx {
     std::vector<crt::MonCfg> h_cfg;
     std::vector<crt::SrcCfg> scratch_src;
     int cfg_dirty_lo = 0, cfg_dirty_hi = 0;
+    cudaEvent_t cfg_ready = nullptr;   // recorded behind the last configuration upload; launches on other streams wait on it
+    cudaStream_t cfg_stream = nullptr; // the stream that upload went to
     long launches = 0;
     long lines2_launches = 0; // line passes that took k_lines2 (crtx_lines2_count)
     int opt_tma = 1;

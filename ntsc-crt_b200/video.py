@@ -110,6 +110,11 @@ class VideoConverter:
         rank = dist.get_rank(group) if world > 1 else 0
         prev_in = None
         if world > 1:
+            counts = torch.tensor([n], dtype=torch.int64, device=dev)
+            dist.all_reduce(counts, op=dist.ReduceOp.MIN, group=group)
+            if int(counts.item()) < 2:
+                raise ValueError("VideoConverter: every rank needs at least 2 frames of the sequence (the two-frame halo of the "
+                                 "next rank's first segment); some rank holds %d" % int(counts.item()))
             tails = sharding.allgather_frames(frames[n - 2:n].contiguous(), group)  # (2 * world, h, w, bpp)
             prev_in = tails[2 * (rank - 1):2 * rank] if rank > 0 else None
 
