@@ -20,6 +20,10 @@
 // Decoded Y/I/Q go to a per-lane ring of 24 samples (two filter sub-chunks) + one guard slot that repeats slot 0,
 // so "sample s + 1" is always the next slot; a block of 8 pixels is emitted as soon as its last sample is in the
 // ring, which the host guarantees is before its first one is overwritten (7 * dx <= 10 * 4096).
+// Nothing in the loops waits on DRAM with a register: the signal windows arrive by per-lane asynchronous copies (48
+// bytes per lane and stage: cp.async, or one bulk copy per lane -- `use_tma` 2 / 1), the previous image's pixels of the
+// NEXT tile by cp.async into shared memory while the current tile is being computed, and all shared-memory traffic of
+// the hot loops goes through 32-bit shared addresses held in registers.
 #pragma once
 
 #include "crt_lines.cuh"
@@ -32,18 +36,19 @@ namespace crt {
 
 constexpr int kL2Warps = 15;
 constexpr int kL2Threads = kL2Warps * 32;      // 480 lane-lines = two monitors (kLines == 240)
-constexpr int kL2Stage = 48;                   // samples per staged chunk = 4 filter sub-chunks
-constexpr int kL2StageRow = ((kL2Stage + 15 + 15) / 16) * 16; // 64 bytes: the aligned superset of a window at any byte phase
+constexpr int kL2Stage = 2 * kSub;             // samples per staged chunk = 2 filter sub-chunks
+constexpr int kL2StageRow = ((kL2Stage + 15 + 15) / 16) * 16; // 48 bytes: the aligned superset of a window at any byte phase
 constexpr int kL2StageBytes = 32 * kL2StageRow;
 constexpr int kL2Stages = (kSamplesPadded + kL2Stage - 1) / kL2Stage;
 constexpr int kL2Ring = 2 * kSub;              // slots; slot of sample s is s % kL2Ring
 constexpr int kL2RingPitch = kL2Ring + 1;      // + guard slot; odd => "all lanes, same slot" is conflict free
 constexpr int kL2RingBytes = 32 * kL2RingPitch * 8;
 constexpr int kL2Block = 8;                    // pixels per unrolled block; the tile is flushed every two blocks
-constexpr int kL2WarpSmem = 2 * kL2StageBytes + kTileBytes + kL2RingBytes;
-constexpr int kL2MaxOutw = 2048;               // descriptor table: 16 bytes per pixel of shared memory
+constexpr int kL2OldBytes = 4 * 32 * 16;       // previous-image pixels of the next tile: [row pass][lane] x 16 bytes
+constexpr int kL2WarpSmem = 2 * kL2StageBytes + kTileBytes + kL2RingBytes + kL2OldBytes;
+constexpr int kL2MaxOutw = 1312;               // descriptor table: 16 bytes per pixel of shared memory, what is left of 227 KB
 static_assert(kLines * 2 == kL2Threads, "two monitors per CTA");
-static_assert(kL2Stage % kSub == 0 && kL2StageRow % 16 == 0, "stage layout");
+static_assert(kL2Stage % kSub == 0 && kL2StageRow % 16 == 0 && kSamplesPadded % kSub == 0, "stage layout");
 static_assert(kL2RingPitch % 2 == 1, "ring pitch");
 
 __host__ __device__ constexpr int lines2_desc_count(int outw) { return ((outw + 15) / 16) * 16; }
@@ -59,6 +64,49 @@ __host__ __device__ inline bool lines2_geometry_ok(int outw)
     if (kCc != 4 || outw < 16 || outw > kL2MaxOutw || (outw & 3)) return false;
     const long long dx = ((long long) (kAvLen - 1) << 12) / outw;
     return 7 * dx <= 10 * 4096; // a block's 8 pixels span at most 12 samples: its first is still in the ring (see above)
+}
+
+// Row pointers of the 16-pixel tile a warp is about to write: lane (q = lane & 3, r = lane >> 2) owns the 16-byte quad q of
+// the rows of lines r, r + 8, r + 16, r + 24.  The pointers walk along the rows, 64 bytes per tile.
+struct TileRows {
+    unsigned char *ptr[4]; // current tile, this lane's quad
+    int rows[4];           // rows to write (crt_core.c:662-664), 0 = slot inactive
+};
+
+// Write one tile (crt_core.c:584-664): 4 passes x (LDS.128 of new pixels, LDS.128 of the previous image's pixels that a
+// cp.async put into shared memory a tile ago, blend on whole words, st.global.v4 to every row of the line), then move
+// on to the next tile and request ITS previous pixels.  No register ever waits on DRAM.
+template <bool BLEND>
+__device__ __forceinline__ void flush_tile(unsigned tile_q_a, unsigned old_a, TileRows &tr, int pitch, int cnt, int cnt_next,
+                                           int lane, unsigned blend_mask)
+{
+    __syncwarp();
+    if (BLEND) cp_async_wait<0>(); // (each lane reads back only what it copied itself)
+    const bool mine = 4 * (lane & 3) < cnt, mine_next = 4 * (lane & 3) < cnt_next;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        if (tr.rows[it] > 0 && mine) {
+            uint4 v = (it == 0) ? lds_u4<0>(tile_q_a) : (it == 1) ? lds_u4<8 * kTilePitch * 4>(tile_q_a)
+                    : (it == 2) ? lds_u4<16 * kTilePitch * 4>(tile_q_a) : lds_u4<24 * kTilePitch * 4>(tile_q_a);
+            if (BLEND) {
+                const uint4 o = (it == 0) ? lds_u4<0>(old_a) : (it == 1) ? lds_u4<512>(old_a) : (it == 2) ? lds_u4<1024>(old_a) : lds_u4<1536>(old_a);
+                v.x += (o.x >> 1) & blend_mask;
+                v.y += (o.y >> 1) & blend_mask;
+                v.z += (o.z >> 1) & blend_mask;
+                v.w += (o.w >> 1) & blend_mask;
+            }
+            unsigned char *p = tr.ptr[it];
+            stg_u4(p, v);
+            if (tr.rows[it] > 1) {
+                stg_u4(p + pitch, v);
+                for (int r = 2; r < tr.rows[it]; r++) stg_u4(p + (size_t) r * pitch, v);
+            }
+        }
+        tr.ptr[it] += 64;
+        if (BLEND && tr.rows[it] > 0 && mine_next) cp_async_16a(old_a + it * 512, tr.ptr[it]);
+    }
+    if (BLEND) cp_async_commit();
+    __syncwarp();
 }
 
 template <int MODE, int FMT> // MODE 0: no blend, 1: blend; FMT: one of the four 4-byte CRT_PIX_FORMATs
@@ -88,10 +136,17 @@ k_lines2(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, c
     const int m = first + (present ? mrel : 0);
 
     unsigned char *stage = smem_raw + warp * kL2WarpSmem;
-    unsigned *tile = reinterpret_cast<unsigned *>(stage + 2 * kL2StageBytes);
-    unsigned char *yiq = stage + 2 * kL2StageBytes + kTileBytes + lane * (kL2RingPitch * 8);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + kL2Warps * kL2WarpSmem) + 2 * warp;
-    if (geo.use_tma) {
+    // 32-bit shared-space addresses of everything the hot loops touch
+    const unsigned stage_a = smem_u32(stage);
+    const unsigned tile_a = stage_a + 2 * kL2StageBytes;
+    const unsigned tile_row_a = tile_a + lane * (kTilePitch * 4);                                    // P phase: this lane's line
+    const unsigned tile_q_a = tile_a + ((lane >> 2) * kTilePitch + 4 * (lane & 3)) * 4;             // flush: this lane's quad
+    const unsigned yiq_a = tile_a + kTileBytes + lane * (kL2RingPitch * 8);
+    const unsigned old_a = tile_a + kTileBytes + kL2RingBytes + lane * 16;
+    const unsigned desc_a = smem_u32(desc);
+    const int staging = geo.use_tma; // 0: plain loads, 1: one bulk copy (TMA) per lane, 2: cp.async per lane
+    if (staging == 1) {
         if (lane == 0) {
             mbar_init(&bars[0], 1);
             mbar_init(&bars[1], 1);
@@ -116,17 +171,15 @@ k_lines2(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, c
     const int beg = active ? rec.beg : -1;
     const int nrows = active ? max(1, rec.end - cfg->scanlines - rec.beg) : 0; // crt_core.c:662-664
     const int pitch = geo.outw * 4;
-    RowSlots rs;
-    uint4 oldv[4];
+    TileRows tr;
 #pragma unroll
     for (int it = 0; it < 4; it++) {
         const int l = it * 8 + (lane >> 2);
         const int lbeg = __shfl_sync(0xffffffffu, beg, l);
         const int lrows = __shfl_sync(0xffffffffu, nrows, l);
         const unsigned long long lout = __shfl_sync(0xffffffffu, (unsigned long long) reinterpret_cast<uintptr_t>(out), l);
-        rs.ptr[it] = reinterpret_cast<unsigned char *>((uintptr_t) lout) + (size_t) max(lbeg, 0) * pitch + (size_t) (lane & 3) * 16;
-        rs.rows[it] = (lbeg >= 0) ? lrows : 0;
-        oldv[it] = make_uint4(0u, 0u, 0u, 0u);
+        tr.ptr[it] = reinterpret_cast<unsigned char *>((uintptr_t) lout) + (size_t) max(lbeg, 0) * pitch + (size_t) (lane & 3) * 16;
+        tr.rows[it] = (lbeg >= 0) ? lrows : 0;
     }
 
     // storage byte order of 0x00RRGGBB (+ alpha 0xff) for the 4-byte formats (crt_core.h:62-67)
@@ -146,21 +199,27 @@ k_lines2(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, c
     const int rnd = geo.rnd;
 
     const signed char *inp = inp_base + (size_t) m * kSignalBytes;
-    const int a = rec.pos & 15; // byte offset of the window inside its 16-byte aligned stage row
-    const signed char *src = inp + (rec.pos & ~15);
-    const signed char *row_base = reinterpret_cast<const signed char *>(stage) + lane * kL2StageRow + a;
-    unsigned *tile_row = tile + lane * kTilePitch;
+    // stage c holds samples [c * kL2Stage, + kL2Stage) of the window: copied from the 16-byte aligned address at or
+    // below its first sample (asynchronous copies move whole 16-byte words), found at byte (pos + c * kL2Stage) & 15
+    const signed char *row_base = reinterpret_cast<const signed char *>(stage) + lane * kL2StageRow;
 
-    auto issue = [&](int c) {
+    auto issue = [&](int c) { // request stage c: samples [c * kL2Stage, + kL2Stage) of every active lane's window
         unsigned char *dst = stage + (c & 1) * kL2StageBytes + lane * kL2StageRow;
-        if (geo.use_tma) {
+        const signed char *src = inp + ((rec.pos + c * kL2Stage) & ~15);
+        if (staging == 1) {
             if (lane == 0) mbar_expect_tx(&bars[c & 1], nactive * kL2StageRow);
             __syncwarp();
-            if (active) tma_load_1d(dst, src + c * kL2Stage, kL2StageRow, &bars[c & 1]);
-        } else if (active) { // plain 16-byte loads, kept for A/B testing of the TMA path
+            if (active) tma_load_1d(dst, src, kL2StageRow, &bars[c & 1]);
+        } else if (staging == 2) {
+            if (active) {
+#pragma unroll
+                for (int q = 0; q < kL2StageRow / 16; q++) cp_async_16(dst + 16 * q, src + 16 * q);
+            }
+            cp_async_commit();
+        } else if (active) { // plain 16-byte loads, kept for A/B testing
 #pragma unroll
             for (int q = 0; q < kL2StageRow / 16; q++)
-                reinterpret_cast<uint4 *>(dst)[q] = __ldg(reinterpret_cast<const uint4 *>(src + c * kL2Stage) + q);
+                reinterpret_cast<uint4 *>(dst)[q] = __ldg(reinterpret_cast<const uint4 *>(src) + q);
         }
     };
 
@@ -176,19 +235,27 @@ k_lines2(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, c
     int sub = 0;  // filter sub-chunk counter (uniform)
 
     issue(0);
-    load_old<MODE == 1>(rs, 0, min(16, geo.outw), lane, oldv);
+    if (MODE == 1) { // previous pixels of tile 0
+        const bool mine0 = 4 * (lane & 3) < min(16, geo.outw);
+#pragma unroll
+        for (int it = 0; it < 4; it++)
+            if (tr.rows[it] > 0 && mine0) cp_async_16a(old_a + it * 512, tr.ptr[it]);
+        cp_async_commit();
+    }
 #pragma unroll 1
     for (int c = 0; c < kL2Stages; c++) {
-        if (c + 1 < kL2Stages) issue(c + 1); // the other buffer was drained in iteration c - 1
-        if (geo.use_tma) mbar_wait(&bars[c & 1], (c >> 1) & 1);
-        else __syncwarp();
-        const signed char *row = row_base + (c & 1) * kL2StageBytes;
+        // stage c has had a whole stage of work to arrive
+        if (staging == 1) mbar_wait(&bars[c & 1], (c >> 1) & 1);
+        else if (staging == 2) cp_async_wait<0>();
+        __syncwarp(); // ... and every lane is done with the other buffer, which is refilled now
+        if (c + 1 < kL2Stages) issue(c + 1);
+        const signed char *row = row_base + (c & 1) * kL2StageBytes + ((rec.pos + c * kL2Stage) & 15);
         const int ns = min(kL2Stage, kSamplesPadded - c * kL2Stage); // a multiple of kSub
 #pragma unroll 1
         for (int u = 0; u < ns; u += kSub, sub++) {
             // ---- (F) filter kSub samples, straight line; sample sub * kSub + t -> ring slot (sub & 1) * kSub + t
             const signed char *rp = row + u;
-            unsigned char *yq = yiq + (sub & 1) * (kSub * 8);
+            const unsigned yq_a = yiq_a + (sub & 1) * (kSub * 8);
 #pragma unroll
             for (int t = 0; t < kSub; t++) {
                 const int s = rp[t];
@@ -196,52 +263,57 @@ k_lines2(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, c
                 const int ci = eq_step<kEqIlf, kEqIhf, 65536, kEqIg2, true, false>(ei, wmul(s, wi[t % 4]) >> 9, rnd) >> 3;
                 const int cq = eq_step<kEqQlf, kEqQhf, 65536, 0, true, false>(eq, wmul(s, wq[t % 4]) >> 9, rnd) >> 3;
                 const uint2 e = make_uint2((unsigned) y, __byte_perm((unsigned) ci, (unsigned) cq, 0x5410));
-                *reinterpret_cast<uint2 *>(yq + t * 8) = e;
-                if (t == 0 && !(sub & 1)) *reinterpret_cast<uint2 *>(yiq + kL2Ring * 8) = e; // guard slot = slot 0
+                switch (t) { // (constant offsets: the store is one instruction)
+#define CRT_L2_PUT(T) case T: sts_u2<T * 8>(yq_a, e); break;
+                    CRT_L2_PUT(0) CRT_L2_PUT(1) CRT_L2_PUT(2) CRT_L2_PUT(3) CRT_L2_PUT(4) CRT_L2_PUT(5) CRT_L2_PUT(6) CRT_L2_PUT(7)
+                    CRT_L2_PUT(8) CRT_L2_PUT(9) CRT_L2_PUT(10) CRT_L2_PUT(11)
+#undef CRT_L2_PUT
+                }
+                if (t == 0 && !(sub & 1)) sts_u2<kL2Ring * 8>(yiq_a, e); // guard slot = slot 0
             }
             // ---- (P) every block of 8 pixels whose last sample is now in the ring (crt_core.c:555-659)
             const unsigned have = (unsigned) (sub * kSub + kSub - 1); // newest sample index filtered
 #pragma unroll 1
-            while (blk < nblk && desc[blk * kL2Block + kL2Block - 1].w <= have) {
-                const uint4 *dp = desc + blk * kL2Block;
-                unsigned *tp = tile_row + (blk & 1) * kL2Block;
+            while (blk < nblk) {
+                const unsigned dp_a = desc_a + blk * (kL2Block * 16);
+                if (lds_u1<(kL2Block - 1) * 16 + 12>(dp_a) > have) break;
+                const unsigned tp_a = tile_row_a + (blk & 1) * (kL2Block * 4);
                 // software pipeline: pixel j + 1's descriptor and samples are requested before pixel j's arithmetic
-                // (the tile store below may alias them as far as the compiler knows, so it would not hoist them itself)
-                uint4 d = dp[0];
-                uint2 va = *reinterpret_cast<const uint2 *>(yiq + d.z);
-                uint2 vb = *reinterpret_cast<const uint2 *>(yiq + d.z + 8);
-#pragma unroll
-                for (int j = 0; j < kL2Block; j++) {
-                    const int R4 = (int) d.x, L4 = (int) d.y;
-                    const uint2 ca = va, cb = vb;
-                    if (j + 1 < kL2Block) {
-                        d = dp[j + 1];
-                        va = *reinterpret_cast<const uint2 *>(yiq + d.z);
-                        vb = *reinterpret_cast<const uint2 *>(yiq + d.z + 8);
-                    }
-                    const int ai = (int) (short) (unsigned short) ca.y, aq = ((int) ca.y) >> 16;
-                    const int bi = (int) (short) (unsigned short) cb.y, bq = ((int) cb.y) >> 16;
-                    // (Y*16*L >> 2) + (Y'*16*R >> 2) == 4*(Y*L + Y'*R) exactly; (I*L >> 14) == (I*4L >> 16)
-                    const int y = wadd(wmul((int) ca.x, L4), wadd(wmul((int) cb.x, R4), ybias));
-                    unsigned px = yiq_to_rgb<kHalved>(y, wadd(wmul(ai, L4) >> 16, wmul(bi, R4) >> 16),
-                                                      wadd(wmul(aq, L4) >> 16, wmul(bq, R4) >> 16), contrast);
-                    px = (FMT == CRT_PIX_FORMAT_BGRA) ? (px | alpha_ff) : __byte_perm(px, 0xffu, sel_store);
-                    tp[j] = px;
+                uint4 d = lds_u4<0>(dp_a);
+                uint2 va = lds_u2<0>(yiq_a + d.z), vb = lds_u2<8>(yiq_a + d.z);
+#define CRT_L2_PIXEL(J)                                                                                                   \
+                {                                                                                                         \
+                    const int R4 = (int) d.x, L4 = (int) d.y;                                                             \
+                    const uint2 ca = va, cb = vb;                                                                         \
+                    if (J + 1 < kL2Block) {                                                                               \
+                        d = lds_u4<((J + 1) % kL2Block) * 16>(dp_a);                                                      \
+                        va = lds_u2<0>(yiq_a + d.z);                                                                      \
+                        vb = lds_u2<8>(yiq_a + d.z);                                                                      \
+                    }                                                                                                     \
+                    const int ai = (int) (short) (unsigned short) ca.y, aq = ((int) ca.y) >> 16;                          \
+                    const int bi = (int) (short) (unsigned short) cb.y, bq = ((int) cb.y) >> 16;                          \
+                    /* (Y*16*L >> 2) + (Y'*16*R >> 2) == 4*(Y*L + Y'*R) exactly; (I*L >> 14) == (I*4L >> 16) */           \
+                    const int y = wadd(wmul((int) ca.x, L4), wadd(wmul((int) cb.x, R4), ybias));                          \
+                    unsigned px = yiq_to_rgb<kHalved>(y, wadd(wmul(ai, L4) >> 16, wmul(bi, R4) >> 16),                    \
+                                                      wadd(wmul(aq, L4) >> 16, wmul(bq, R4) >> 16), contrast);            \
+                    px = (FMT == CRT_PIX_FORMAT_BGRA) ? (px | alpha_ff) : __byte_perm(px, 0xffu, sel_store);              \
+                    sts_u1<J * 4>(tp_a, px);                                                                              \
                 }
+                CRT_L2_PIXEL(0) CRT_L2_PIXEL(1) CRT_L2_PIXEL(2) CRT_L2_PIXEL(3) CRT_L2_PIXEL(4) CRT_L2_PIXEL(5) CRT_L2_PIXEL(6) CRT_L2_PIXEL(7)
+#undef CRT_L2_PIXEL
                 blk++;
-                if (!(blk & 1)) { // two blocks = one 16-pixel tile: write it, then fetch the next tile's old pixels
+                if (!(blk & 1)) { // two blocks = one 16-pixel tile
                     const int k0 = (blk - 2) * kL2Block;
-                    flush16_vec<MODE == 1>(tile, rs, pitch, k0, min(16, geo.outw - k0), lane, blend_mask, oldv);
-                    load_old<MODE == 1>(rs, k0 + 16, min(16, geo.outw - k0 - 16), lane, oldv);
+                    flush_tile<MODE == 1>(tile_q_a, old_a, tr, pitch, min(16, geo.outw - k0), min(16, geo.outw - k0 - 16), lane, blend_mask);
                 }
             }
         }
-        __syncwarp(); // all lanes are done with this stage buffer before it is refilled
     }
     if (blk & 1) { // odd number of blocks: the last tile holds one
         const int k0 = (blk - 1) * kL2Block;
-        flush16_vec<MODE == 1>(tile, rs, pitch, k0, geo.outw - k0, lane, blend_mask, oldv);
+        flush_tile<MODE == 1>(tile_q_a, old_a, tr, pitch, geo.outw - k0, 0, lane, blend_mask);
     }
+    if (staging == 2 || MODE == 1) cp_async_wait<0>();
 }
 
 } // namespace crt

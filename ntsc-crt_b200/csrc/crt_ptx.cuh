@@ -77,6 +77,46 @@ template <int PENDING> __device__ __forceinline__ void tma_store_wait_read()
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Shared-memory accesses at 32-bit shared-space ADDRESSES (+ constant byte offset) and global 16-byte accesses by
+// explicit state space: the hot loops of k_lines2 keep absolute shared addresses in registers, so no generic-to-shared
+// conversion or 64-bit pointer arithmetic is ever re-derived inside them, and images reached through pointers that were
+// loaded from memory (generic as far as the compiler knows) are still written with st.global.
+template <int OFF = 0> __device__ __forceinline__ uint4 lds_u4(unsigned addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF = 0> __device__ __forceinline__ uint2 lds_u2(unsigned addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF = 0> __device__ __forceinline__ unsigned lds_u1(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF = 0> __device__ __forceinline__ void sts_u1(unsigned addr, unsigned v)
+{
+    asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "r"(v) : "memory");
+}
+template <int OFF = 0> __device__ __forceinline__ void sts_u2(unsigned addr, uint2 v)
+{
+    asm volatile("st.shared.v2.u32 [%0+%1], {%2, %3};" ::"r"(addr), "n"(OFF), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void stg_u4(void *p, uint4 v)
+{
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 16-byte asynchronous copy global -> shared with the shared side given as an address
+__device__ __forceinline__ void cp_async_16a(unsigned dst_addr, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_addr), "l"(src) : "memory");
+}
+
 // Row element at a shared-memory ADDRESS (+ constant byte offset), sign-extended.  The resampler keeps
 // absolute shared addresses in registers; going through ld.shared directly keeps the address arithmetic
 // out of the pixel loop (a generic pointer would be re-derived from the shared window base every time).

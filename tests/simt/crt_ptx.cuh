@@ -46,6 +46,28 @@ __device__ __forceinline__ void tma_store_commit() { ::simt::bulk_store_commit()
 template <int PENDING> __device__ __forceinline__ void tma_store_wait_read() { ::simt::bulk_store_wait_read(PENDING); }
 __device__ __forceinline__ void fence_async_smem() {}
 
+// explicit-state-space accesses of the real header: plain loads / stores here, with the instructions' alignment rules
+template <typename T> __device__ __forceinline__ T *smem_at(unsigned addr, int off, const char *what)
+{
+    unsigned char *p = ::simt::g_smem_anchor + (int) (addr + (unsigned) off);
+    if ((uintptr_t) p % sizeof(T)) ::simt::ptx_fail(what);
+    return reinterpret_cast<T *>(p);
+}
+template <int OFF = 0> __device__ __forceinline__ uint4 lds_u4(unsigned addr) { return *smem_at<uint4>(addr, OFF, "ld.shared.v4: misaligned address"); }
+template <int OFF = 0> __device__ __forceinline__ uint2 lds_u2(unsigned addr) { return *smem_at<uint2>(addr, OFF, "ld.shared.v2: misaligned address"); }
+template <int OFF = 0> __device__ __forceinline__ unsigned lds_u1(unsigned addr) { return *smem_at<unsigned>(addr, OFF, "ld.shared.u32: misaligned address"); }
+template <int OFF = 0> __device__ __forceinline__ void sts_u1(unsigned addr, unsigned v) { *smem_at<unsigned>(addr, OFF, "st.shared.u32: misaligned address") = v; }
+template <int OFF = 0> __device__ __forceinline__ void sts_u2(unsigned addr, uint2 v) { *smem_at<uint2>(addr, OFF, "st.shared.v2: misaligned address") = v; }
+__device__ __forceinline__ void stg_u4(void *p, uint4 v)
+{
+    if ((uintptr_t) p % 16) ::simt::ptx_fail("st.global.v4: misaligned address");
+    *reinterpret_cast<uint4 *>(p) = v;
+}
+__device__ __forceinline__ void cp_async_16a(unsigned dst_addr, const void *src)
+{
+    ::simt::lane_copy16(::simt::g_smem_anchor + (int) dst_addr, src);
+}
+
 template <typename Elem, int OFF> __device__ __forceinline__ int lds_elem(unsigned addr)
 {
     const unsigned char *p = ::simt::g_smem_anchor + (int) (addr + (unsigned) OFF); // offsets may be "negative"

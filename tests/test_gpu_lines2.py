@@ -68,10 +68,11 @@ def _run(variant, outw, outh, n, fields, fmt=layout.PIX_BGRA, noise=0, expect_li
     return results
 
 
-@pytest.mark.parametrize("outw,outh,blend,scanlines", [(832, 624, 1, 1), (640, 480, 0, 1), (832, 624, 0, 0), (1920, 1080, 1, 0)])
+@pytest.mark.parametrize("outw,outh,blend,scanlines", [(832, 624, 1, 1), (640, 480, 0, 1), (832, 624, 0, 0), (1280, 960, 1, 0), (1920, 1080, 1, 0)])
 def test_driver_geometries(outw, outh, blend, scanlines):
-    """what crt_main.c (blend 1, scanlines 1) and video_convert.c (blend 0) ask for, interlaced, 4 fields, 3 monitors"""
-    _run("ntsc", outw, outh, n=3, fields=4, knobs=dict(blend=blend, scanlines=scanlines), noise=0 if blend else 6)
+    """what crt_main.c (blend 1, scanlines 1) and video_convert.c (blend 0) ask for, interlaced, 4 fields, 3 monitors;
+    1920 is wider than the kernel's descriptor table has room for and stays with k_lines"""
+    _run("ntsc", outw, outh, n=3, fields=4, knobs=dict(blend=blend, scanlines=scanlines), noise=0 if blend else 6, expect_lines2=outw <= 1312)
 
 
 @pytest.mark.parametrize("fmt", FMT4)
@@ -79,7 +80,7 @@ def test_every_four_byte_format(fmt):
     _run("ntsc", 704, 480, n=2, fields=2, fmt=fmt, knobs=dict(blend=1, scanlines=0), noise=4)
 
 
-@pytest.mark.parametrize("outw,expect", [(528, True), (524, False), (1000, True), (2048, True), (2052, False), (830, False), (256, False)])
+@pytest.mark.parametrize("outw,expect", [(528, True), (524, False), (1000, True), (1312, True), (1316, False), (830, False), (256, False)])
 def test_limits_of_the_geometry(outw, expect):
     """narrowest / widest output the ring and the descriptor table cover, widths that are not a multiple of 4 or 16,
     and the widths just outside, which must fall back to k_lines -- same bits either way"""
@@ -108,6 +109,14 @@ def test_generic_monitor_inside_a_pair():
 def test_generic_everywhere_and_plain_loads():
     _run("ntsc", 640, 480, n=2, fields=2, options=(("generic_eq", 1),), knobs=dict(blend=0, scanlines=1))
     _run("ntsc", 640, 480, n=2, fields=2, options=(("tma", 0),), knobs=dict(blend=1, scanlines=0))
+
+
+@pytest.mark.parametrize("tma", [1, 2])
+def test_both_asynchronous_staging_modes(tma):
+    """the signal windows reach shared memory by one bulk copy (TMA) per lane and stage, or by three 16-byte cp.async per
+    lane and stage (option "tma" 1 / 2); odd byte phases of the windows come from the noise-driven hsync"""
+    _run("ntsc", 832, 624, n=3, fields=4, options=(("tma", tma),), knobs=dict(blend=1, scanlines=1), noise=9)
+    _run("ntsc", 640, 480, n=2, fields=2, options=(("tma", tma),), knobs=dict(blend=0, scanlines=1), noise=0)
 
 
 def test_scanline_window():

@@ -33,6 +33,7 @@ import test_gpu_template as _template  # noqa: E402
 import test_gpu_still_cli as _still  # noqa: E402
 import test_gpu_video as _video  # noqa: E402
 import test_gpu_video_driver as _vdriver  # noqa: E402
+import test_gpu_video_convert_unmodified as _vconv  # noqa: E402
 import test_gpu_wire as _wire  # noqa: E402
 
 
@@ -102,6 +103,7 @@ _adopt(_bloom, "bloom")
 _adopt(_api, "api")
 test_cli_unmodified_cli_driver_is_byte_identical = _cli.test_unmodified_cli_driver_is_byte_identical
 _adopt(_still, "still")
+test_vconv_unmodified_video_convert_runs_against_the_library = _vconv.test_unmodified_video_convert_runs_against_the_library
 
 
 def _bare(fn):
