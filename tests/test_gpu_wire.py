@@ -98,3 +98,13 @@ def test_fade_phosphors(npix, skew):
         assert L.crtx_fade_phosphors(d.data_ptr() + 4 * skew, npix, None) == 0
         want[skew:skew + npix] = W.fade_phosphors(want[skew:skew + npix])
     assert np.array_equal(host(d, np.uint32, npix + 8), want)
+    # ... and against the reference's own function, cut out of crt_main.c:437-452 and compiled (oracle/Makefile: libref_fade.so)
+    import ctypes as C
+    import os
+    ref = os.path.join(S.REF_DIR, "libref_fade.so")
+    if os.path.exists(ref):
+        R = C.CDLL(ref)
+        theirs = img[skew:skew + npix].astype(np.int32).copy()
+        for _ in range(4):
+            R.ref_fade_phosphors(theirs.ctypes.data_as(C.c_void_p), npix, 1)
+        assert np.array_equal(host(d, np.uint32, npix + 8)[skew:skew + npix], theirs.view(np.uint32))
