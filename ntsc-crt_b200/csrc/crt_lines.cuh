@@ -142,6 +142,7 @@ constexpr int kMaxOutw = 8192;
 struct LinesGeom { // uniform over a launch: host groups monitors by these (crtx.cu)
     int outw, out_format, bpp, blend;
     int use_tma;
+    int stage2; // k_lines2 only: 0 plain loads, 1 one bulk copy per lane and stage, 2 cp.async (crt_lines2.cuh)
     int pass; // -1: every line; -2: only the last line of each shared-row run; >= 0: lines at this run position
     int rnd; // 32768, passed as an argument so that it lives in a register (see pole())
     int dx;  // ((AV_LEN - 1) << 12) / outw (crt_core.c:527), computed by the host: no division in the kernels

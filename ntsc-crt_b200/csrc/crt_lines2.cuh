@@ -145,7 +145,7 @@ k_lines2(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, c
     const unsigned yiq_a = tile_a + kTileBytes + lane * (kL2RingPitch * 8);
     const unsigned old_a = tile_a + kTileBytes + kL2RingBytes + lane * 16;
     const unsigned desc_a = smem_u32(desc);
-    const int staging = geo.use_tma; // 0: plain loads, 1: one bulk copy (TMA) per lane, 2: cp.async per lane
+    const int staging = geo.stage2; // 0: plain loads, 1: one bulk copy (TMA) per lane and stage, 2: cp.async per lane
     if (staging == 1) {
         if (lane == 0) {
             mbar_init(&bars[0], 1);

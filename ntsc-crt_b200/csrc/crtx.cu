@@ -458,6 +458,7 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
         geo.bpp = c0.bpp;
         geo.blend = c0.blend ? 1 : 0;
         geo.use_tma = ctx->opt_tma;
+        geo.stage2 = ctx->opt_tma ? ctx->opt_lines2_stage : 0;
         geo.rnd = 32768;
         geo.dx = c0.outw > 0 ? ((kAvLen - 1) << 12) / c0.outw : 0;
         geo.line_lo = ctx->opt_line_lo;
@@ -1243,6 +1244,7 @@ int crtx_set_option(crtx_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "host_rows")) ctx->opt_host_rows = value;
     else if (!strcmp(name, "mod_bulk")) ctx->opt_mod_bulk = value;
     else if (!strcmp(name, "lines2")) ctx->opt_lines2 = value;
+    else if (!strcmp(name, "lines2_stage")) ctx->opt_lines2_stage = value;
     else if (!strcmp(name, "line_lo")) ctx->opt_line_lo = value;
     else if (!strcmp(name, "line_hi")) ctx->opt_line_hi = value;
     else return fail("crtx_set_option: unknown option '%s'", name);

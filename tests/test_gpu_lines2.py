@@ -111,12 +111,12 @@ def test_generic_everywhere_and_plain_loads():
     _run("ntsc", 640, 480, n=2, fields=2, options=(("tma", 0),), knobs=dict(blend=1, scanlines=0))
 
 
-@pytest.mark.parametrize("tma", [1, 2])
-def test_both_asynchronous_staging_modes(tma):
+@pytest.mark.parametrize("mode", [1, 2])
+def test_both_asynchronous_staging_modes(mode):
     """the signal windows reach shared memory by one bulk copy (TMA) per lane and stage, or by three 16-byte cp.async per
-    lane and stage (option "tma" 1 / 2); odd byte phases of the windows come from the noise-driven hsync"""
-    _run("ntsc", 832, 624, n=3, fields=4, options=(("tma", tma),), knobs=dict(blend=1, scanlines=1), noise=9)
-    _run("ntsc", 640, 480, n=2, fields=2, options=(("tma", tma),), knobs=dict(blend=0, scanlines=1), noise=0)
+    lane and stage (option "lines2_stage" 1 / 2); odd byte phases of the windows come from the noise-driven hsync"""
+    _run("ntsc", 832, 624, n=3, fields=4, options=(("lines2_stage", mode),), knobs=dict(blend=1, scanlines=1), noise=9)
+    _run("ntsc", 640, 480, n=2, fields=2, options=(("lines2_stage", mode),), knobs=dict(blend=0, scanlines=1), noise=0)
 
 
 def test_scanline_window():
