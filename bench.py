@@ -463,7 +463,9 @@ def config4_block(args, dev, rank, world, noise=0):
         return out
 
     frames = make_frames(lo, hi)
-    segs = max(1, min(args.config4_segments, hi - lo))
+    # time-parallel segments per rank: ~8 frames each (a two-frame halo on top), at most one line-kernel wave (296 monitors)
+    segs = args.config4_segments if args.config4_segments > 0 else max(16, min(296, (hi - lo) // 8))
+    segs = max(1, min(segs, hi - lo))
     conv = video.VideoConverter("ntsc", ow, oh, noise=noise, scanlines=1, segments=segs)
     if world > 1:
         dist.barrier()
@@ -879,8 +881,9 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=128)
     ap.add_argument("--e2e-streams", type=int, default=4)
     ap.add_argument("--sustained-seconds", type=float, default=1.2, help="0: skip the sustained block")
-    ap.add_argument("--config4-frames", type=int, default=2048, help="length of the config-4 video sequence (0: skip)")
-    ap.add_argument("--config4-segments", type=int, default=148, help="time-parallel segments per rank")
+    ap.add_argument("--config4-frames", type=int, default=4999,
+                    help="length of the config-4 video sequence: video_convert.c with num_frames 5000 converts 4999 images (0: skip)")
+    ap.add_argument("--config4-segments", type=int, default=0, help="time-parallel segments per rank (0: about 8 frames per segment)")
     ap.add_argument("--set", action="append", default=[], help="library option name=value (A/B testing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-allgather", action="store_true", help="N > 1: skip the all_gather / gather_to_root blocks")

@@ -35,6 +35,15 @@ class Source(C.Structure):  # crtx_source
                 ("do_aberration", C.c_int), ("dot_crawl_offset", C.c_int), ("reinit", C.c_int)]
 
 
+def source_table(sources):
+    """numpy structured view (shared memory) of a ctypes array of Source: whole columns of settings can be filled with
+    array assignments instead of one Python attribute store per field and monitor (video.VideoConverter)."""
+    import numpy as np
+    dt = np.dtype([(n, "u8" if t is C.c_void_p else "i4") for n, t in Source._fields_], align=True)
+    assert dt.itemsize == C.sizeof(Source), (dt.itemsize, C.sizeof(Source))
+    return np.frombuffer(sources, dtype=dt)
+
+
 class State(C.Structure):  # crtx_state
     _fields_ = [("ccf", (C.c_int * 5) * 5), ("hsync", C.c_int), ("vsync", C.c_int), ("rn", C.c_int)]
 

@@ -95,7 +95,8 @@ class VideoConverter:
         S = max(1, min(self.segments, n))
         spans = [sharding.shard_range(n, s, S) for s in range(S)]  # local frame indices
         b = self._factory(self.variant, S)
-        self._work = [torch.zeros(self.outh, self.outw, bpp, dtype=torch.uint8, device=dev) for _ in range(S)]
+        work_all = torch.zeros(S, self.outh, self.outw, bpp, dtype=torch.uint8, device=dev)
+        self._work = [work_all[s] for s in range(S)]  # the monitors' images: one tensor, so a step's images move with one copy
         for s in range(S):
             b.set_monitor(s, self._work[s], fmt=self.fmt, noise=self.noise, **self.knobs)
         b.commit_monitors()
@@ -151,14 +152,37 @@ class VideoConverter:
             states[s].hsync, states[s].vsync, states[s].rn = hs, vs, rn_before(halo0[s])
         b.set_state(states)
 
+        # the settings table of the batch as numpy columns (the CUDA library's Batch; the CPU test double has none)
+        table = capi.source_table(b.sources) if hasattr(b, "sources") else None
+        frame_bytes = frames[0].numel() * frames[0].element_size() if n else 0
+        if table is not None:
+            import numpy as np
+            table["format"], table["as_color"], table["raw"], table["hue"] = self.fmt, self.as_color, 0, 0
+            table["xoffset"], table["yoffset"] = 0, 0
+            table["h"], table["w"] = frames.shape[1], frames.shape[2]
+            base_mine = frames.data_ptr()
+            base_prev = prev_in.data_ptr() if prev_in is not None else 0
+            b._keep[("video", 0)] = (frames, prev_in)
+
         def step(items):  # items: [(segment, global frame)] with contiguous segment indices
             if not items:
                 return
-            for s, gf in items:
-                field, frame = frame_parity(gf, self.progressive)
-                b.set_source(s, src_frame(gf), format=self.fmt, as_color=self.as_color, field=field, frame=frame,
-                             raw=0, hue=0, xoffset=0, yoffset=0)
             lo_s = min(s for s, _ in items)
+            if table is not None:  # whole columns at once: no per-monitor Python work in the step loop
+                seg = np.fromiter((s for s, _ in items), dtype=np.int64, count=len(items))
+                gf = np.fromiter((g for _, g in items), dtype=np.int64, count=len(items))
+                lf = gf - first_frame
+                ptr = np.where(lf >= 0, base_mine + lf * frame_bytes, base_prev + (2 + lf) * frame_bytes)
+                table["data"][seg] = ptr.astype(np.uint64)
+                if self.progressive:
+                    table["field"][seg], table["frame"][seg] = 0, 0
+                else:
+                    table["field"][seg], table["frame"][seg] = gf & 1, (gf >> 1) & 1  # frame_parity
+            else:
+                for s, gf in items:
+                    field, frame = frame_parity(gf, self.progressive)
+                    b.set_source(s, src_frame(gf), format=self.fmt, as_color=self.as_color, field=field, frame=frame,
+                                 raw=0, hue=0, xoffset=0, yoffset=0)
             b.modulate(first=lo_s, count=len(items))
             b.demodulate(first=lo_s, count=len(items))
 
@@ -170,11 +194,11 @@ class VideoConverter:
         # ---- main steps: step t advances every segment still inside its span by one frame; shard_range puts
         # the longer segments first, so the active ones are always 0 .. count-1
         longest = max(e - a for a, e in spans)
+        span_lo = torch.tensor([a for a, _ in spans], dtype=torch.int64, device=dev)
         for t in range(longest):
-            active = [s for s in range(S) if spans[s][0] + t < spans[s][1]]
+            active = [s for s in range(S) if spans[s][0] + t < spans[s][1]]  # always 0 .. len(active) - 1
             step([(s, starts[s] + t) for s in active])
-            for s in active:
-                outputs[spans[s][0] + t].copy_(self._work[s])
+            outputs.index_copy_(0, span_lo[:len(active)] + t, work_all[:len(active)])  # one copy for the whole step
         finals = [(x.hsync, x.vsync) for x in b.get_state()]
 
         # ---- verification in sequence order, repairing what the speculation got wrong.  Segment s is exact

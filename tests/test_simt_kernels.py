@@ -180,7 +180,8 @@ def test_bench_product_arm_dry_run(variant):
     import json
     import subprocess
     r = subprocess.run([sys.executable, os.path.join(S.ROOT, "tests", "simt", "bench_dry_run.py"), "--variant", variant, "--batch", "4",
-                        "--steps", "2", "--warmup", "1", "--e2e-batch", "8", "--no-cpu-baseline"],
+                        "--steps", "2", "--warmup", "1", "--e2e-batch", "8", "--no-cpu-baseline", "--config4-frames", "8",
+                        "--config4-segments", "2", "--sustained-seconds", "0.001"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=S.ROOT, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
@@ -191,6 +192,10 @@ def test_bench_product_arm_dry_run(variant):
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(line["roofline"])
     assert line["dropin"]["value"] > 0 and line["dropin"]["pairs"] >= 8, line["dropin"]
+    assert line["sustained"]["steps"] >= 2 and "demodulate" in line["roofline"] and line["roofline"]["demodulate"]["frac"] > 0
+    assert line["config"]["workload"] == __import__("bench").workload_name() or variant != "ntsc"
+    if variant == "ntsc":  # BASELINE configs[3] in miniature: bit-identical to the sequential loop
+        assert line["config4"]["bit_identical_to_sequential_loop"] is True and line["config4"]["frames_checked"] == 8
 
 
 def test_interpreter_selftest(tmp_path):

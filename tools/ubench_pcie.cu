@@ -111,5 +111,38 @@ int main()
         cudaEventElapsedTime(&m1, a, b); cudaEventElapsedTime(&m2, a, c);
         printf("SM gather (every 3rd row) + copy-engine D2H:      H2D %7.2f GB/s, D2H %7.2f GB/s\n", total * 6 / m1 / 1e6, total * 6 / m2 / 1e6);
     }
+    { // what crtx_frames_host could do: source rows by the SM gather (236 of 624 rows per frame), decoded rows by the copy
+      // engine as five strided 2-D copies per frame (624 rows / 240 lines: the written rows repeat every 13 rows), at once
+        const int pitch = row_bytes;
+        cudaEvent_t a, b, c;
+        cudaEventCreate(&a); cudaEventCreate(&b); cudaEventCreate(&c);
+        const int starts[5] = { 0, 2, 5, 7, 10 }, widths[5] = { 1, 2, 1, 2, 2 }; // rows written per 13-row period (scanlines 1)
+        for (int mode = 0; mode < 3; mode++) {
+            Job g = { h_a, d_a, frames * 236, n16, 0, n16, 148 * 8, 8, 0 };
+            cudaDeviceSynchronize();
+            cudaEventRecord(a, s1);
+            cudaStreamWaitEvent(s2, a, 0);
+            const int reps = 6;
+            for (int r = 0; r < reps; r++) {
+                if (mode != 1) { // gather: row y of the compact image <- row (y * 624) / 236 of the frame (k_rows_gather's pattern, approximated by stride)
+                    g.ss = n16 * 624 / 236; // average stride; the kernel reads rows at src + row * ss
+                    run_kernel(s1, &g);
+                }
+                if (mode != 0)
+                    for (int f = 0; f < frames; f++)
+                        for (int q = 0; q < 5; q++)
+                            cudaMemcpy2DAsync((char *) h_b + (size_t) f * img + (size_t) starts[q] * pitch, (size_t) 13 * pitch,
+                                              (char *) d_b + (size_t) f * img + (size_t) starts[q] * pitch, (size_t) 13 * pitch,
+                                              (size_t) widths[q] * pitch, 48, cudaMemcpyDeviceToHost, s2);
+            }
+            cudaEventRecord(b, s1); cudaEventRecord(c, s2);
+            cudaDeviceSynchronize();
+            float m1, m2; cudaEventElapsedTime(&m1, a, b); cudaEventElapsedTime(&m2, a, c);
+            const double up = (double) frames * 236 * row_bytes * reps, down = (double) frames * 384 * row_bytes * reps;
+            printf("mode %d (%s): H2D rows %7.2f GB/s (%.1f us/frame)   D2H rows by 2-D copy engine %7.2f GB/s (%.1f us/frame)\n", mode,
+                   mode == 0 ? "SM gather alone" : mode == 1 ? "2-D copies alone" : "both at once", mode != 1 ? up / m1 / 1e6 : 0.0,
+                   mode != 1 ? m1 * 1e3 / (frames * reps) : 0.0, mode != 0 ? down / m2 / 1e6 : 0.0, mode != 0 ? m2 * 1e3 / (frames * reps) : 0.0);
+        }
+    }
     return 0;
 }
