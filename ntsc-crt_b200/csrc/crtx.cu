@@ -50,9 +50,14 @@ static int upload_cfg(crtx_ctx *ctx, cudaStream_t stream)
         // pageable source: staged before the call returns, so h_cfg may be edited right after
         CUDA_TRY(cudaMemcpyAsync(ctx->d_cfg + lo, ctx->h_cfg.data() + lo, sizeof(MonCfg) * (hi - lo),
                                  cudaMemcpyHostToDevice, stream));
-        // the bytes that follow inp[] in the reference's struct CRT depend on the output geometry (crt_sync.cuh)
-        k_struct_tail<<<(hi - lo + 63) / 64, 64, 0, stream>>>(ctx->d_cfg, ctx->d_analog, ctx->d_inp, lo, hi - lo);
-        ctx->launches += 1;
+        // the bytes that follow inp[] in the reference's struct CRT depend on the output geometry alone (crt_sync.cuh)
+        if (ctx->tail_dirty_lo < ctx->tail_dirty_hi) {
+            const int tlo = ctx->tail_dirty_lo, thi = ctx->tail_dirty_hi;
+            k_struct_tail<<<(thi - tlo + 63) / 64, 64, 0, stream>>>(ctx->d_cfg, ctx->d_analog, ctx->d_inp, tlo, thi - tlo);
+            ctx->launches += 1;
+            ctx->tail_dirty_lo = ctx->n;
+            ctx->tail_dirty_hi = 0;
+        }
         ctx->cfg_dirty_lo = ctx->n;
         ctx->cfg_dirty_hi = 0;
         // a context may be driven from several streams over disjoint monitor ranges (crtx_frames_host, bench.py): the
@@ -743,6 +748,8 @@ int crtx_create(crtx_ctx **out, int n)
     memset(ctx->h_cfg.data(), 0, sizeof(MonCfg) * n);
     ctx->cfg_dirty_lo = 0;
     ctx->cfg_dirty_hi = n;
+    ctx->tail_dirty_lo = 0;
+    ctx->tail_dirty_hi = n;
     ctx->opt_tma = 1;
     ctx->opt_generic = 0;
     const char *e = getenv("CRT_B200_NO_TMA");
@@ -859,8 +866,11 @@ int crtx_set_monitors(crtx_ctx *ctx, int first, int count, const crtx_monitor *m
         if (bpp_of(m[i].out_format) == 4 && (reinterpret_cast<uintptr_t>(m[i].out) & 3))
             return fail("monitor %d: 4-byte pixel formats need a 4-byte aligned device image", first + i);
     }
+    // only what really changed travels to the device (the drop-in calls re-send every knob before every call)
+    int lo = ctx->n, hi = 0, tlo = ctx->n, thi = 0;
     for (int i = 0; i < count; i++) {
-        MonCfg &c = ctx->h_cfg[first + i];
+        MonCfg c;
+        memset(&c, 0, sizeof(c));
         c.out = static_cast<unsigned char *>(m[i].out);
         c.outw = m[i].outw;
         c.outh = m[i].outh;
@@ -876,9 +886,20 @@ int crtx_set_monitors(crtx_ctx *ctx, int first, int count, const crtx_monitor *m
         c.blend = m[i].blend;
         c.v_fac = m[i].v_fac;
         c.noise = m[i].noise;
+        MonCfg &old = ctx->h_cfg[first + i];
+        if (memcmp(&c, &old, sizeof(MonCfg)) == 0) continue;
+        if (c.outw != old.outw || c.outh != old.outh || c.out_format != old.out_format) {
+            if (first + i < tlo) tlo = first + i;
+            thi = first + i + 1;
+        }
+        old = c;
+        if (first + i < lo) lo = first + i;
+        hi = first + i + 1;
     }
-    if (first < ctx->cfg_dirty_lo) ctx->cfg_dirty_lo = first;
-    if (first + count > ctx->cfg_dirty_hi) ctx->cfg_dirty_hi = first + count;
+    if (lo < ctx->cfg_dirty_lo) ctx->cfg_dirty_lo = lo;
+    if (hi > ctx->cfg_dirty_hi) ctx->cfg_dirty_hi = hi;
+    if (tlo < ctx->tail_dirty_lo) ctx->tail_dirty_lo = tlo;
+    if (thi > ctx->tail_dirty_hi) ctx->tail_dirty_hi = thi;
     return 0;
 }
 
@@ -886,9 +907,11 @@ int crtx_set_state(crtx_ctx *ctx, int first, int count, const crtx_state *s, voi
 {
     if (check_range(ctx, first, count)) return 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the whole record is rebuilt on the host: its other fields (`field`, `generic`) are outputs of the sync pre-pass that
+    // the line kernels of the SAME crtx_demodulate consume, never inputs of a later call -- so no read-back, no
+    // synchronisation: one asynchronous copy, ordered on `stream` like everything else
     std::vector<MonState> tmp(count);
-    CUDA_TRY(cudaMemcpyAsync(tmp.data(), ctx->d_state + first, sizeof(MonState) * count, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    memset(tmp.data(), 0, sizeof(MonState) * count);
     for (int i = 0; i < count; i++) {
         for (int r = 0; r < kVper; r++)
             for (int x = 0; x < kCc; x++) tmp[i].ccf[r][x] = s[i].ccf[r][x];
@@ -896,8 +919,8 @@ int crtx_set_state(crtx_ctx *ctx, int first, int count, const crtx_state *s, voi
         tmp[i].vsync = s[i].vsync;
         tmp[i].rn = s[i].rn;
     }
+    // (pageable source: staged before the call returns, so `tmp` may go out of scope)
     CUDA_TRY(cudaMemcpyAsync(ctx->d_state + first, tmp.data(), sizeof(MonState) * count, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
     return 0;
 }
 

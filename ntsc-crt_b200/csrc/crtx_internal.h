@@ -37,6 +37,7 @@ struct crtx_ctx {
     std::vector<crt::MonCfg> h_cfg;
     std::vector<crt::SrcCfg> scratch_src;
     int cfg_dirty_lo = 0, cfg_dirty_hi = 0;
+    int tail_dirty_lo = 0, tail_dirty_hi = 0; // monitors whose output geometry changed: k_struct_tail rewrites the bytes behind their signals
     cudaEvent_t cfg_ready = nullptr;   // recorded behind the last configuration upload; launches on other streams wait on it
     cudaStream_t cfg_stream = nullptr; // the stream that upload went to
     long launches = 0;
