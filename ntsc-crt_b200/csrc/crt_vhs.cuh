@@ -17,6 +17,13 @@
 //          constant, so next(p) = p + 2 + [test1(raw[p + 1])] is a function of p alone): 10 doubling
 //          rounds give every sample its position, after which all samples of the line are evaluated in
 //          parallel with the reference's literal expressions.
+// Round 2: the two regions run as two CTAs per monitor at once (blockIdx.y: 0 bulk, 1 tail) -- the tail's start state is the
+// bulk's 256 runs applied as two level-7 jumps -- and the tail only builds tables where the count is really data
+// dependent: within signal line L the first test of sample x >= 1 is (draw % 20) >= 256 - L, so lines up to 236 always
+// take two draws and lines from 256 on always three (closed-form positions); for the 19 lines in between the successor
+// table is doubled five times (1, 2, 4, 8, 16, 32 steps) instead of nine, one thread walks the 29 chunk starts with
+// the 32-step table, and a sample finishes with five look-ups.  The generator state after the call goes to a second
+// array that k_vhs_commit copies back, because the bulk CTA of the same monitor may not have read the old one yet.
 #pragma once
 
 #include "crt_kernels.cuh"
@@ -33,6 +40,9 @@ constexpr int kVhsTailRun = 310;                      // raw values per thread f
 constexpr int kVhsTailRaw = kVhsThreads * kVhsTailRun; // 79 360 >= 3 draws x tail samples
 constexpr int kVhsWin = 2752;                         // raw values visible to one line's walk (>= 3 * 910 + 3)
 constexpr int kVhsLevels = 8;                         // doubling levels: 2^8 = 256 runs
+constexpr int kVhsJLevels = 6;                        // tail walk: successor tables for 1, 2, 4, 8, 16, 32 steps
+constexpr int kVhsChunk = 1 << (kVhsJLevels - 1);     // samples per chunk of the walk (32)
+constexpr int kVhsChunks = (kHres + kVhsChunk - 1) / kVhsChunk + 1;
 static_assert(kVhsBulk <= kInputSize - 25 * kHres, "bulk region must stay clear of the data-dependent band");
 static_assert(kVhsTailRaw >= 3 * kVhsTailSamples + 64 && kVhsWin >= 3 * kHres + 8, "tail stream sizes");
 
@@ -86,8 +96,23 @@ __device__ __forceinline__ void vhs_spread_states(unsigned (*states)[32], const 
 __device__ __forceinline__ bool vhs_test1(int i, unsigned a) { return i > (kInputSize - kHres * (16 + ((int) (a % 20u) - 10))); }
 __device__ __forceinline__ bool vhs_test2(int i, unsigned b) { return i < (kInputSize - kHres * (5 + ((int) (b % 8u) - 4))); }
 
+// new = A * old on chronological states in shared memory (warp 0 computes, everybody synchronises)
+__device__ __forceinline__ void vhs_apply(unsigned *to, const unsigned (*A)[31], const unsigned *from, int tid, unsigned *Am)
+{
+    const unsigned *src = &A[0][0];
+    for (int e = tid; e < 31 * 31; e += kVhsThreads) Am[e] = __ldg(src + e);
+    __syncthreads();
+    if (tid < 31) {
+        unsigned acc = 0;
+#pragma unroll
+        for (int j = 0; j < 31; j++) acc += Am[tid * 31 + j] * from[j];
+        to[tid] = acc;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states_mon,
-                                                           VhsRand *__restrict__ rands,
+                                                           const VhsRand *__restrict__ rands, VhsRand *__restrict__ rands_next,
                                                            const VhsJump *__restrict__ jump,
                                                            unsigned *__restrict__ raw_base,
                                                            const signed char *__restrict__ analog_base,
@@ -95,18 +120,24 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
 {
     extern __shared__ __align__(16) unsigned char vsm[];
     unsigned (*states)[32] = reinterpret_cast<unsigned (*)[32]>(vsm);                 // [257][32]
-    short *terms = reinterpret_cast<short *>(vsm + 257 * 32 * 4);                       // [256][32]
-    unsigned *win = reinterpret_cast<unsigned *>(vsm + 257 * 32 * 4);                   // tail: [kVhsWin + 8]
-    unsigned short *jt = reinterpret_cast<unsigned short *>(win + kVhsWin + 8);         // tail: [10][kVhsWin + 8]
+    short *terms = reinterpret_cast<short *>(vsm + 257 * 32 * 4);                       // bulk: [256][32]
+    // the tail's tables overlay the run states, which are dead once the raw stream is generated
+    unsigned *win = reinterpret_cast<unsigned *>(vsm);                                  // tail: [kVhsWin + 8]
+    unsigned short *jt = reinterpret_cast<unsigned short *>(win + kVhsWin + 8);         // tail: [kVhsJLevels][kVhsWin + 8]
+    int *cs = reinterpret_cast<int *>(jt + kVhsJLevels * (kVhsWin + 8));                // tail: [kVhsChunks] chunk start positions
     __shared__ int s_wobble, s_adv, s_start;
     __shared__ unsigned s_mat[31 * 31];
     const int m = first + blockIdx.x, tid = threadIdx.x;
-    if (cfgs[m].bpp == 0) return; // crt_core.c:312-315
+    const bool tail_role = blockIdx.y != 0;
+    if (cfgs[m].bpp == 0) { // crt_core.c:312-315: no draws, the generator state stays
+        if (tail_role && tid < 32) reinterpret_cast<unsigned *>(&rands_next[m])[tid] = reinterpret_cast<const unsigned *>(&rands[m])[tid];
+        return;
+    }
     const int noise = cfgs[m].noise;
     const signed char *analog = analog_base + (size_t) m * kSignalBytes;
     signed char *inp = inp_base + (size_t) m * kSignalBytes;
     unsigned *raw = raw_base + (size_t) blockIdx.x * kVhsTailRaw;
-    VhsRand *rs = &rands[m];
+    const VhsRand *rs = &rands[m];
 
     // ---- the wobble draw (crt_core.c:344), then the run start states
     if (tid == 0) {
@@ -116,10 +147,10 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
         for (int j = 0; j < 31; j++) states[0][j] = h[j];
     }
     __syncthreads();
-    vhs_spread_states(states, jump->bulk, tid, s_mat);
 
-    // ---- bulk: thread t owns samples [t * kVhsRun, (t + 1) * kVhsRun), two draws each
-    {
+    if (!tail_role) {
+        vhs_spread_states(states, jump->bulk, tid, s_mat);
+        // ---- bulk: thread t owns samples [t * kVhsRun, (t + 1) * kVhsRun), two draws each
         unsigned h[31];
 #pragma unroll
         for (int j = 0; j < 31; j++) h[j] = states[tid][j];
@@ -160,11 +191,12 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
             }
             __syncthreads();
         }
+        return;
     }
 
-    // ---- tail raw stream: kVhsTailRaw values continuing after the bulk, to global scratch
-    if (tid < 31) states[0][tid] = states[256][tid];
-    __syncthreads();
+    // ---- tail CTA: the state after the bulk's 256 runs = two jumps of 128 runs (level 7), then the raw stream
+    vhs_apply(states[1], jump->bulk[kVhsLevels - 1], states[0], tid, s_mat);
+    vhs_apply(states[0], jump->bulk[kVhsLevels - 1], states[1], tid, s_mat);
     vhs_spread_states(states, jump->tail, tid, s_mat);
     {
         unsigned h[31];
@@ -178,14 +210,16 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
             }
         }
     }
-    __syncthreads();
+    __syncthreads(); // (block-wide: the stream is visible to every thread; `states` may now be overlaid)
 
     // ---- tail walk, one signal line (or the partial first one) at a time
     const int wobble = s_wobble;
     int D = 0;            // raw values consumed so far in the tail
-    int last_rn = 0;
     for (int i0 = kVhsBulk; i0 < kInputSize;) {
         const int line = i0 / kHres, xa = i0 - line * kHres, nx = kHres - xa; // samples xa .. 909 of this line
+        // for x >= 1 of this line the first test is (draw % 20) >= need (crt_core.c:350 with i = line * HRES + x)
+        const int need = (kInputSize / kHres - 6) - line;
+        const int fixed = (need > 19) ? 2 : (need <= 0) ? 3 : 0; // draws per regular sample when it is not data dependent
         { // all of a thread's window loads in flight together
             constexpr int kPer = (kVhsWin + 8 + kVhsThreads - 1) / kVhsThreads;
             unsigned v[kPer];
@@ -208,25 +242,42 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
             if (xa == 0) p = 2 + (vhs_test1(i0, win[1] >> 1) ? 1 : 0);
             s_start = p; // position of the first "regular" sample
         }
-        const int irep = line * kHres + 1;
-        for (int p = tid; p < kVhsWin + 8; p += kVhsThreads)
-            jt[p] = (unsigned short) ((p + 3 < kVhsWin) ? p + 2 + (vhs_test1(irep, win[p + 1] >> 1) ? 1 : 0) : kVhsWin);
-        __syncthreads();
-        for (int k = 1; k < 10; k++) { // jt[k][p] = 2^k-th successor
-            unsigned short *prev = jt + (k - 1) * (kVhsWin + 8), *cur = jt + k * (kVhsWin + 8);
-#pragma unroll 4
-            for (int p = tid; p < kVhsWin + 8; p += kVhsThreads) cur[p] = prev[min((int) prev[p], kVhsWin)];
-            __syncthreads();
-        }
         const int x0 = (xa == 0) ? 1 : xa; // first regular sample
+        if (!fixed) {
+            const int irep = line * kHres + 1;
+            for (int p = tid; p < kVhsWin + 8; p += kVhsThreads)
+                jt[p] = (unsigned short) ((p + 3 < kVhsWin) ? p + 2 + (vhs_test1(irep, win[p + 1] >> 1) ? 1 : 0) : kVhsWin);
+            __syncthreads();
+            for (int k = 1; k < kVhsJLevels; k++) { // jt[k][p] = 2^k-th successor
+                unsigned short *prev = jt + (k - 1) * (kVhsWin + 8), *cur = jt + k * (kVhsWin + 8);
+#pragma unroll 4
+                for (int p = tid; p < kVhsWin + 8; p += kVhsThreads) cur[p] = prev[min((int) prev[p], kVhsWin)];
+                __syncthreads();
+            }
+            if (tid == 0) { // chunk c starts kVhsChunk * c regular samples after the first one
+                const unsigned short *far = jt + (kVhsJLevels - 1) * (kVhsWin + 8);
+                int p = s_start;
+                const int chunks = (kHres - x0 + kVhsChunk - 1) / kVhsChunk;
+                for (int c = 0; c < chunks; c++) {
+                    cs[c] = p;
+                    p = far[min(p, kVhsWin)];
+                }
+            }
+        }
+        __syncthreads();
         for (int x = xa + tid; x < kHres; x += kVhsThreads) {
             const int sig = analog[line * kHres + x]; // requested before the (dependent) table walk
             int P = 0;
             if (!(xa == 0 && x == 0)) {
-                P = s_start;
                 const int e = x - x0;
-                for (int k = 0; k < 10; k++)
-                    if ((e >> k) & 1) P = jt[k * (kVhsWin + 8) + min(P, kVhsWin)];
+                if (fixed) {
+                    P = s_start + fixed * e;
+                } else {
+                    P = cs[e / kVhsChunk];
+#pragma unroll
+                    for (int k = 0; k < kVhsJLevels - 1; k++)
+                        if ((e >> k) & 1) P = jt[k * (kVhsWin + 8) + min(P, kVhsWin)];
+                }
             }
             const int i = line * kHres + x;
             const int rn = (int) (win[P] >> 1);
@@ -234,16 +285,15 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
             if (vhs_test1(i, win[P + 1] >> 1)) { // crt_core.c:350-357
                 used = 3;
                 if (vhs_test2(i, win[P + 2] >> 1)) {
-                    int sn, cs;
-                    sincos14_d(sn, cs, ((i * wobble) / kHres) * 8192 / 180);
-                    gain = cs >> 8;
+                    int sn, cs14;
+                    sincos14_d(sn, cs14, ((i * wobble) / kHres) * 8192 / 180);
+                    gain = cs14 >> 8;
                 }
             }
             const int s = sig + (wmul(((rn >> 16) & 0xff) - 0x7f, gain) >> 8);
             inp[i] = (signed char) clampi(s, -127, 127);
             if (x == kHres - 1) { // the line's last sample closes the walk
                 s_adv = P + used;
-                last_rn = rn;
                 if (i == kInputSize - 1) states_mon[m].rn = rn; // crt_core.c:367
             }
         }
@@ -252,12 +302,19 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
         i0 += nx;
         __syncthreads();
     }
-    (void) last_rn;
     // ---- the generator state after the call: the last 31 raw values consumed
     if (tid < 31) {
         // total draws: 1 + 2 * kVhsBulk + D; D >= 31 always (the tail spans > 24 000 samples)
-        rs->hist[tid] = raw[D - 31 + tid];
+        rands_next[m].hist[tid] = raw[D - 31 + tid];
     }
+}
+
+// rands_next -> rands for monitors [first, first + count): runs after k_noise_vhs on the same stream
+__global__ void k_vhs_commit(VhsRand *__restrict__ rands, const VhsRand *__restrict__ rands_next, int first, int count)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count * 32) return;
+    reinterpret_cast<unsigned *>(rands + first)[k] = reinterpret_cast<const unsigned *>(rands_next + first)[k];
 }
 
 // the aberration draw of crt_modulate (crt_ntscvhs.c:205-207), one thread per monitor
@@ -271,9 +328,11 @@ __global__ void k_vhs_aberration(SrcCfg *__restrict__ srcs, const int *__restric
     srcs[first + k].aberration = ab;
 }
 
-constexpr int kVhsSmem = 257 * 32 * 4 + ((256 * 32 * 2 > (kVhsWin + 8) * 4 + 10 * (kVhsWin + 8) * 2)
-                                             ? 256 * 32 * 2
-                                             : (kVhsWin + 8) * 4 + 10 * (kVhsWin + 8) * 2);
+constexpr int kVhsSmemBulk = 257 * 32 * 4 + 256 * 32 * 2;
+constexpr int kVhsSmemTail = (kVhsWin + 8) * 4 + kVhsJLevels * (kVhsWin + 8) * 2 + kVhsChunks * 4 + 16;
+constexpr int kVhsSmem = (kVhsSmemBulk > kVhsSmemTail ? kVhsSmemBulk : kVhsSmemTail) > 257 * 32 * 4
+                             ? (kVhsSmemBulk > kVhsSmemTail ? kVhsSmemBulk : kVhsSmemTail) : 257 * 32 * 4;
+static_assert(kInputSize % kHres == 0, "the tail's per-line test assumes whole signal lines");
 
 } // namespace crt
 

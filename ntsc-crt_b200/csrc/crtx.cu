@@ -405,10 +405,14 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
         k_noise_terms<<<tgrid, 256, 0, stream>>>(ctx->d_cfg, ctx->d_analog, ctx->d_inp, d_noise_terms, first);
     } else { // batch path: the per-monitor rand() replica (crt_vhs.cuh)
         LaunchTimer lt(ctx, stream, 2);
-        k_noise_vhs<<<count, kVhsThreads, kVhsSmem, stream>>>(ctx->d_cfg, ctx->d_state, static_cast<VhsRand *>(ctx->d_vhs_rand),
-                                                              static_cast<const VhsJump *>(ctx->d_vhs_jump),
-                                                              ctx->d_vhs_raw + (size_t) first * kVhsTailRaw, ctx->d_analog,
-                                                              ctx->d_inp, first);
+        // two CTAs per monitor, side by side: (x, 0) the bulk of the field, (x, 1) its data-dependent tail
+        k_noise_vhs<<<dim3(count, 2), kVhsThreads, kVhsSmem, stream>>>(ctx->d_cfg, ctx->d_state, static_cast<const VhsRand *>(ctx->d_vhs_rand),
+                                                                       static_cast<VhsRand *>(ctx->d_vhs_rand_next),
+                                                                       static_cast<const VhsJump *>(ctx->d_vhs_jump),
+                                                                       ctx->d_vhs_raw + (size_t) first * kVhsTailRaw, ctx->d_analog,
+                                                                       ctx->d_inp, first);
+        k_vhs_commit<<<(count * 32 + 255) / 256, 256, 0, stream>>>(static_cast<VhsRand *>(ctx->d_vhs_rand),
+                                                                   static_cast<const VhsRand *>(ctx->d_vhs_rand_next), first, count);
     }
     {
         LaunchTimer lt(ctx, stream, 3);
@@ -800,6 +804,7 @@ int crtx_create(crtx_ctx **out, int n)
 #if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
     {
         CTX_TRY(cudaMalloc(&ctx->d_vhs_rand, sizeof(VhsRand) * n));
+        CTX_TRY(cudaMalloc(&ctx->d_vhs_rand_next, sizeof(VhsRand) * n));
         CTX_TRY(cudaMalloc(&ctx->d_vhs_jump, sizeof(VhsJump)));
         CTX_TRY(cudaMalloc(&ctx->d_vhs_raw, sizeof(unsigned) * (size_t) kVhsTailRaw * n));
         CTX_TRY(cudaMalloc(&ctx->d_vhs_wants, sizeof(int) * n));
@@ -842,6 +847,7 @@ void crtx_destroy(crtx_ctx *ctx)
     cudaFree(ctx->d_nes_tab);
     cudaFree(ctx->d_bloom);
     cudaFree(ctx->d_vhs_rand);
+    cudaFree(ctx->d_vhs_rand_next);
     cudaFree(ctx->d_vhs_jump);
     cudaFree(ctx->d_vhs_raw);
     cudaFree(ctx->d_vhs_wants);

@@ -27,6 +27,7 @@ struct crtx_ctx {
     signed char *d_nes_tab = nullptr; // NES: per-monitor 512 x 12 sample table + burst rows
     void *d_bloom = nullptr;      // CRT_DO_BLOOM build: BloomLine[n][CRT_LINES], each line's resampling step and start
     void *d_vhs_rand = nullptr;   // VHS: VhsRand[n], glibc rand() replica per monitor
+    void *d_vhs_rand_next = nullptr; // VHS: the state after the running call (k_vhs_commit copies it back)
     void *d_vhs_jump = nullptr;   // VHS: jump-ahead matrices
     unsigned *d_vhs_raw = nullptr; // VHS: tail raw-stream scratch
     int *d_vhs_wants = nullptr;   // VHS: do_aberration flags of the current modulate

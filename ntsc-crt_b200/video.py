@@ -64,6 +64,7 @@ class VideoConverter:
         import torch
         self.torch = torch
         self._factory = batch_factory if batch_factory is not None else capi.Batch
+        self._pool = {}  # monitors are kept between convert() calls: creating and freeing a context costs tens of ms
         self.variant, self.spec = variant, layout.system_spec(variant)
         if self.spec.system != layout.SYS_NTSC:
             raise ValueError("the video path covers CRT_SYSTEM_NTSC (what video_convert.c is built for)")
@@ -72,6 +73,25 @@ class VideoConverter:
         self.as_color, self.progressive = as_color, progressive
         self.segments = segments
         self.recomputed = 0  # segments that failed verification in the last convert()
+
+    def _batch(self, n):
+        """a context of n monitors, reused across calls (every call sets all of their state; the parts of analog[] no
+        crt_modulate writes are zero in a fresh context and stay zero, because this class never varies raw / offsets)"""
+        b = self._pool.get(n)
+        if b is None:
+            b = self._pool[n] = self._factory(self.variant, n)
+        return b
+
+    def close(self):
+        for b in self._pool.values():
+            b.close()
+        self._pool = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     # one sequential pass over local frames [lo, hi) on monitor `i` (the repair path)
     def _run_sequential(self, b, i, frames, lo, hi, outputs, first_frame):
@@ -94,7 +114,7 @@ class VideoConverter:
         bpp = layout.bpp4fmt(self.fmt)
         S = max(1, min(self.segments, n))
         spans = [sharding.shard_range(n, s, S) for s in range(S)]  # local frame indices
-        b = self._factory(self.variant, S)
+        b = self._batch(S)
         work_all = torch.zeros(S, self.outh, self.outw, bpp, dtype=torch.uint8, device=dev)
         self._work = [work_all[s] for s in range(S)]  # the monitors' images: one tensor, so a step's images move with one copy
         for s in range(S):
@@ -124,10 +144,13 @@ class VideoConverter:
             return frames[lf] if lf >= 0 else prev_in[2 + lf]
 
         # ---- speculated sync state: what a steady decode holds after a field of each parity (4 probe fields)
-        probe = self._factory(self.variant, 1)
+        probe = self._batch(1) if S != 1 else self._factory(self.variant, 1)
         scratch = torch.zeros(self.outh, self.outw, bpp, dtype=torch.uint8, device=dev)
         probe.set_monitor(0, scratch, fmt=self.fmt, noise=0, **self.knobs)
         probe.commit_monitors()
+        fresh = (capi.State * 1)()  # what crt_init leaves (crt_core.c:250-269): the probe monitor may have been used before
+        fresh[0].hsync, fresh[0].vsync, fresh[0].rn = 0, 0, 194
+        probe.set_state(fresh)
         after = {}
         for f in range(min(4, n)):
             field, frame = frame_parity(first_frame + f, self.progressive)
@@ -136,7 +159,8 @@ class VideoConverter:
             probe.demodulate()
             st = probe.get_state()[0]
             after[(first_frame + f) & 1] = (st.hsync, st.vsync)
-        probe.close()
+        if S == 1:
+            probe.close()
 
         # ---- every segment but the sequence's very first decodes a halo of up to two frames first: the
         # output buffer holds rows of the last two fields, so after the halo it must EQUAL the predecessor's
@@ -255,5 +279,4 @@ class VideoConverter:
                 break
         if dev.type == "cuda":
             torch.cuda.synchronize(dev)
-        b.close()
         return outputs
