@@ -114,13 +114,12 @@ __device__ __forceinline__ void vhs_apply(unsigned *to, const unsigned (*A)[31],
 __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states_mon,
                                                            const VhsRand *__restrict__ rands, VhsRand *__restrict__ rands_next,
                                                            const VhsJump *__restrict__ jump,
-                                                           unsigned *__restrict__ raw_base,
+                                                           unsigned *__restrict__ raw_base, short *__restrict__ terms_base,
                                                            const signed char *__restrict__ analog_base,
                                                            signed char *__restrict__ inp_base, int first)
 {
     extern __shared__ __align__(16) unsigned char vsm[];
     unsigned (*states)[32] = reinterpret_cast<unsigned (*)[32]>(vsm);                 // [257][32]
-    short *terms = reinterpret_cast<short *>(vsm + 257 * 32 * 4);                       // bulk: [256][32]
     // the tail's tables overlay the run states, which are dead once the raw stream is generated
     unsigned *win = reinterpret_cast<unsigned *>(vsm);                                  // tail: [kVhsWin + 8]
     unsigned short *jt = reinterpret_cast<unsigned short *>(win + kVhsWin + 8);         // tail: [kVhsJLevels][kVhsWin + 8]
@@ -150,46 +149,53 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
 
     if (!tail_role) {
         vhs_spread_states(states, jump->bulk, tid, s_mat);
-        // ---- bulk: thread t owns samples [t * kVhsRun, (t + 1) * kVhsRun), two draws each
-        unsigned h[31];
+        // ---- bulk, phase A: thread t owns samples [t * kVhsRun, (t + 1) * kVhsRun), two draws each; it only GENERATES --
+        // the noise term of every sample goes, as a 16-bit value, to this monitor's scratch in flat sample order ...
+        short *tflat = terms_base + (size_t) blockIdx.x * kVhsBulk;
+        {
+            unsigned h[31];
 #pragma unroll
-        for (int j = 0; j < 31; j++) h[j] = states[tid][j];
-        constexpr int kApply = kVhsThreads / (kVhsThreads / 32); // slices each warp applies per block (32)
-        for (int it = 0; it < kVhsRun / 31; it++) {
-            // The signal bytes this thread will combine with the terms below do not depend on the draws:
-            // request them all now, so the 32 small loads are in flight while the generator runs (issued
-            // after the barrier, one wait per load, they were 37 % of the kernel's time).
-            signed char sig[kApply];
-            {
-                const int j = tid & 31;
+            for (int j = 0; j < 31; j++) h[j] = states[tid][j];
+            short *mine = tflat + tid * kVhsRun;
+            for (int it = 0; it < kVhsRun / 31; it++) {
 #pragma unroll
-                for (int q = 0; q < kApply; q++) {
-                    const int u = (tid >> 5) + q * (kVhsThreads / 32);
-                    sig[q] = (j < 31) ? analog[u * kVhsRun + it * 31 + j] : (signed char) 0;
+                for (int d = 0; d < 62; d++) { // draw d of the block uses slot d % 31 (31-periodic alignment)
+                    const int slot = d % 31;
+                    h[slot] += h[(slot + 28) % 31];
+                    if ((d & 1) == 0) { // the noise draw; the odd draw feeds the never-true first test
+                        const int rn = (int) (h[slot] >> 1);
+                        int t = wmul(((rn >> 16) & 0xff) - 0x7f, noise) >> 8;
+                        t = clampi(t, -255, 255); // analog is within [-128, 127]: beyond +-255 the sum saturates anyway
+                        mine[it * 31 + (d >> 1)] = (short) t;
+                    }
                 }
             }
+        }
+        __syncthreads(); // (block-wide: the terms are visible to every thread of the CTA)
+        // ... phase B: the whole CTA adds them to the signal, 16 samples per thread and step, every access 16 bytes wide
+        const uint4 *a16 = reinterpret_cast<const uint4 *>(analog);
+        const uint4 *t16 = reinterpret_cast<const uint4 *>(tflat);
+        uint4 *o16 = reinterpret_cast<uint4 *>(inp);
+        static_assert(kVhsBulk % 16 == 0, "bulk region in 16-sample groups");
+#pragma unroll 2
+        for (int g = tid; g < kVhsBulk / 16; g += kVhsThreads) {
+            const uint4 sv = __ldg(a16 + g);
+            const uint4 t0 = t16[2 * g], t1 = t16[2 * g + 1];
+            const unsigned sw[4] = { sv.x, sv.y, sv.z, sv.w };
+            const unsigned tw[8] = { t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w };
+            unsigned ow[4];
 #pragma unroll
-            for (int d = 0; d < 62; d++) { // draw d of the block uses slot d % 31 (31-periodic alignment)
-                const int slot = d % 31;
-                h[slot] += h[(slot + 28) % 31];
-                if ((d & 1) == 0) { // the noise draw; the odd draw feeds the never-true first test
-                    const int rn = (int) (h[slot] >> 1);
-                    int t = wmul(((rn >> 16) & 0xff) - 0x7f, noise) >> 8;
-                    t = clampi(t, -255, 255); // analog is within [-128, 127]: beyond +-255 the sum saturates anyway
-                    terms[tid * 32 + (d >> 1)] = (short) t;
-                }
-            }
-            __syncthreads();
-            // apply, coalesced over the 31 samples of each thread's slice
-            {
-                const int j = tid & 31;
+            for (int w = 0; w < 4; w++) {
+                unsigned o = 0;
 #pragma unroll
-                for (int q = 0; q < kApply; q++) {
-                    const int u = (tid >> 5) + q * (kVhsThreads / 32);
-                    if (j < 31) inp[u * kVhsRun + it * 31 + j] = (signed char) clampi(sig[q] + terms[u * 32 + j], -127, 127);
+                for (int b = 0; b < 4; b++) {
+                    const int sg = (int) (signed char) (sw[w] >> (8 * b));
+                    const int tm = (int) (short) (tw[2 * w + (b >> 1)] >> (16 * (b & 1)));
+                    o |= ((unsigned) clampi(sg + tm, -127, 127) & 0xffu) << (8 * b);
                 }
+                ow[w] = o;
             }
-            __syncthreads();
+            o16[g] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
         return;
     }
@@ -328,7 +334,7 @@ __global__ void k_vhs_aberration(SrcCfg *__restrict__ srcs, const int *__restric
     srcs[first + k].aberration = ab;
 }
 
-constexpr int kVhsSmemBulk = 257 * 32 * 4 + 256 * 32 * 2;
+constexpr int kVhsSmemBulk = 257 * 32 * 4;
 constexpr int kVhsSmemTail = (kVhsWin + 8) * 4 + kVhsJLevels * (kVhsWin + 8) * 2 + kVhsChunks * 4 + 16;
 constexpr int kVhsSmem = (kVhsSmemBulk > kVhsSmemTail ? kVhsSmemBulk : kVhsSmemTail) > 257 * 32 * 4
                              ? (kVhsSmemBulk > kVhsSmemTail ? kVhsSmemBulk : kVhsSmemTail) : 257 * 32 * 4;
