@@ -17,7 +17,9 @@
 //          constant, so next(p) = p + 2 + [test1(raw[p + 1])] is a function of p alone): 10 doubling
 //          rounds give every sample its position, after which all samples of the line are evaluated in
 //          parallel with the reference's literal expressions.
-// Round 2: the two regions run as two CTAs per monitor at once (blockIdx.y: 0 bulk, 1 tail) -- the tail's start state is the
+// Round 2: runs of 868 samples = 7 blocks of 124 (four generator periods), so that every thread's share of a block is
+// 31 aligned 32-bit words: the terms meet the signal 4 samples per lane with word loads and stores.  The two regions run as
+// two CTAs per monitor at once (blockIdx.y: 0 tail, 1 bulk) -- the tail's start state is the
 // bulk's 256 runs applied as two level-7 jumps -- and the tail only builds tables where the count is really data
 // dependent: within signal line L the first test of sample x >= 1 is (draw % 20) >= 256 - L, so lines up to 236 always
 // take two draws and lines from 256 on always three (closed-form positions); for the 19 lines in between the successor
@@ -33,8 +35,11 @@
 namespace crt {
 
 constexpr int kVhsThreads = 256;
-constexpr int kVhsRun = 31 * 27;                      // samples per thread in the bulk region (2 draws each)
-constexpr int kVhsBulk = kVhsThreads * kVhsRun;       // 214 272 <= INPUT_SIZE - 25 lines
+constexpr int kVhsPeriods = 4;                        // generator periods (31 samples, 62 draws) per block of a run
+constexpr int kVhsSlice = 31 * kVhsPeriods;           // 124 samples: a thread's share of one block -- a whole number of 32-bit words
+constexpr int kVhsRun = kVhsSlice * 7;                // 868 samples per run (2 draws each); every slice starts 4-byte aligned
+constexpr int kVhsRuns = 248;                         // runs = generating threads of the bulk CTA (the doubling tree makes 256 states)
+constexpr int kVhsBulk = kVhsRuns * kVhsRun;          // 215 264 <= INPUT_SIZE - 25 lines
 constexpr int kVhsTailSamples = kInputSize - kVhsBulk;
 constexpr int kVhsTailRun = 310;                      // raw values per thread for the tail (10 x 31)
 constexpr int kVhsTailRaw = kVhsThreads * kVhsTailRun; // 79 360 >= 3 draws x tail samples
@@ -44,6 +49,7 @@ constexpr int kVhsJLevels = 6;                        // tail walk: successor ta
 constexpr int kVhsChunk = 1 << (kVhsJLevels - 1);     // samples per chunk of the walk (32)
 constexpr int kVhsChunks = (kHres + kVhsChunk - 1) / kVhsChunk + 1;
 static_assert(kVhsBulk <= kInputSize - 25 * kHres, "bulk region must stay clear of the data-dependent band");
+static_assert(kVhsRun % 4 == 0 && kVhsSlice % 4 == 0 && kVhsRuns <= kVhsThreads, "bulk slices are whole aligned words");
 static_assert(kVhsTailRaw >= 3 * kVhsTailSamples + 64 && kVhsWin >= 3 * kHres + 8, "tail stream sizes");
 
 struct VhsRand { // generator state: the last 31 raw values, oldest first
@@ -111,10 +117,10 @@ __device__ __forceinline__ void vhs_apply(unsigned *to, const unsigned (*A)[31],
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states_mon,
+__global__ void __launch_bounds__(kVhsThreads, 4) k_noise_vhs(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states_mon,
                                                            const VhsRand *__restrict__ rands, VhsRand *__restrict__ rands_next,
                                                            const VhsJump *__restrict__ jump,
-                                                           unsigned *__restrict__ raw_base, short *__restrict__ terms_base,
+                                                           unsigned *__restrict__ raw_base,
                                                            const signed char *__restrict__ analog_base,
                                                            signed char *__restrict__ inp_base, int first)
 {
@@ -127,7 +133,7 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
     __shared__ int s_wobble, s_adv, s_start;
     __shared__ unsigned s_mat[31 * 31];
     const int m = first + blockIdx.x, tid = threadIdx.x;
-    const bool tail_role = blockIdx.y != 0;
+    const bool tail_role = blockIdx.y == 0; // (the tail CTAs are the longer ones: they are scheduled first)
     if (cfgs[m].bpp == 0) { // crt_core.c:312-315: no draws, the generator state stays
         if (tail_role && tid < 32) reinterpret_cast<unsigned *>(&rands_next[m])[tid] = reinterpret_cast<const unsigned *>(&rands[m])[tid];
         return;
@@ -149,60 +155,81 @@ __global__ void __launch_bounds__(kVhsThreads) k_noise_vhs(const MonCfg *__restr
 
     if (!tail_role) {
         vhs_spread_states(states, jump->bulk, tid, s_mat);
-        // ---- bulk, phase A: thread t owns samples [t * kVhsRun, (t + 1) * kVhsRun), two draws each; it only GENERATES --
-        // the noise term of every sample goes, as a 16-bit value, to this monitor's scratch in flat sample order ...
-        short *tflat = terms_base + (size_t) blockIdx.x * kVhsBulk;
-        {
-            unsigned h[31];
+        // ---- bulk: thread t < kVhsRuns owns samples [t * kVhsRun, (t + 1) * kVhsRun), two draws each.  Per block of
+        // kVhsSlice samples: (1) every thread generates its slice's noise terms into shared memory, (2) the CTA adds
+        // them to the signal -- slice by slice, 31 lanes x one aligned 32-bit word (4 samples) each, so global traffic
+        // is whole words and coalesced although a thread's slices lie kVhsRun bytes apart.
+        unsigned h[31];
 #pragma unroll
-            for (int j = 0; j < 31; j++) h[j] = states[tid][j];
-            short *mine = tflat + tid * kVhsRun;
-            for (int it = 0; it < kVhsRun / 31; it++) {
+        for (int j = 0; j < 31; j++) h[j] = states[min(tid, kVhsRuns - 1)][j];
+        __syncthreads(); // the run states are in registers: the terms buffer may overlay them
+        short *terms = reinterpret_cast<short *>(vsm); // [kVhsRuns][kVhsSlice]
+        constexpr int kSlicesPerWarp = (kVhsRuns + 7) / 8; // 31 slices per warp per block
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int it = 0; it < kVhsRun / kVhsSlice; it++) {
+            if (tid < kVhsRuns) {
 #pragma unroll
-                for (int d = 0; d < 62; d++) { // draw d of the block uses slot d % 31 (31-periodic alignment)
-                    const int slot = d % 31;
-                    h[slot] += h[(slot + 28) % 31];
-                    if ((d & 1) == 0) { // the noise draw; the odd draw feeds the never-true first test
-                        const int rn = (int) (h[slot] >> 1);
-                        int t = wmul(((rn >> 16) & 0xff) - 0x7f, noise) >> 8;
-                        t = clampi(t, -255, 255); // analog is within [-128, 127]: beyond +-255 the sum saturates anyway
-                        mine[it * 31 + (d >> 1)] = (short) t;
+                for (int pr = 0; pr < kVhsPeriods; pr++) {
+#pragma unroll
+                    for (int d = 0; d < 62; d++) { // draw d of a period uses slot d % 31 (31-periodic alignment)
+                        const int slot = d % 31;
+                        h[slot] += h[(slot + 28) % 31];
+                        if ((d & 1) == 0) { // the noise draw; the odd draw feeds the never-true first test
+                            const int rn = (int) (h[slot] >> 1);
+                            int t = wmul(((rn >> 16) & 0xff) - 0x7f, noise) >> 8;
+                            t = clampi(t, -255, 255); // analog is within [-128, 127]: beyond +-255 the sum saturates anyway
+                            terms[tid * kVhsSlice + pr * 31 + (d >> 1)] = (short) t;
+                        }
                     }
                 }
             }
-        }
-        __syncthreads(); // (block-wide: the terms are visible to every thread of the CTA)
-        // ... phase B: the whole CTA adds them to the signal, 16 samples per thread and step, every access 16 bytes wide
-        const uint4 *a16 = reinterpret_cast<const uint4 *>(analog);
-        const uint4 *t16 = reinterpret_cast<const uint4 *>(tflat);
-        uint4 *o16 = reinterpret_cast<uint4 *>(inp);
-        static_assert(kVhsBulk % 16 == 0, "bulk region in 16-sample groups");
-#pragma unroll 2
-        for (int g = tid; g < kVhsBulk / 16; g += kVhsThreads) {
-            const uint4 sv = __ldg(a16 + g);
-            const uint4 t0 = t16[2 * g], t1 = t16[2 * g + 1];
-            const unsigned sw[4] = { sv.x, sv.y, sv.z, sv.w };
-            const unsigned tw[8] = { t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w };
-            unsigned ow[4];
+            __syncthreads();
+            // apply: eight slices per batch, their signal words requested together (the register budget of the whole kernel
+            // is what lets every CTA of a launch be resident at once)
+#pragma unroll 1
+            for (int q0 = 0; q0 < kSlicesPerWarp; q0 += 8) {
+                unsigned sig[8];
 #pragma unroll
-            for (int w = 0; w < 4; w++) {
-                unsigned o = 0;
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int sg = (int) (signed char) (sw[w] >> (8 * b));
-                    const int tm = (int) (short) (tw[2 * w + (b >> 1)] >> (16 * (b & 1)));
-                    o |= ((unsigned) clampi(sg + tm, -127, 127) & 0xffu) << (8 * b);
+                for (int q = 0; q < 8; q++) {
+                    const int u = warp + 8 * (q0 + q);
+                    sig[q] = (q0 + q < kSlicesPerWarp && u < kVhsRuns && lane < kVhsSlice / 4)
+                                 ? __ldg(reinterpret_cast<const unsigned *>(analog + u * kVhsRun + it * kVhsSlice) + lane) : 0u;
                 }
-                ow[w] = o;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int u = warp + 8 * (q0 + q);
+                    if (q0 + q < kSlicesPerWarp && u < kVhsRuns && lane < kVhsSlice / 4) {
+                        const uint2 tw = *reinterpret_cast<const uint2 *>(terms + u * kVhsSlice + 4 * lane);
+                        const unsigned tws[2] = { tw.x, tw.y };
+                        unsigned o = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            const int sg = (int) (signed char) (sig[q] >> (8 * b));
+                            const int tm = (int) (short) (tws[b >> 1] >> (16 * (b & 1)));
+                            o |= ((unsigned) clampi(sg + tm, -127, 127) & 0xffu) << (8 * b);
+                        }
+                        reinterpret_cast<unsigned *>(inp + u * kVhsRun + it * kVhsSlice)[lane] = o;
+                    }
+                }
             }
-            o16[g] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            __syncthreads();
         }
         return;
     }
 
     // ---- tail CTA: the state after the bulk's 256 runs = two jumps of 128 runs (level 7), then the raw stream
-    vhs_apply(states[1], jump->bulk[kVhsLevels - 1], states[0], tid, s_mat);
-    vhs_apply(states[0], jump->bulk[kVhsLevels - 1], states[1], tid, s_mat);
+    { // kVhsRuns = 248 = 128 + 64 + 32 + 16 + 8 runs: one jump per set bit (levels 7, 6, 5, 4, 3)
+        int cur = 0;
+        for (int k = kVhsLevels - 1; k >= 0; k--)
+            if ((kVhsRuns >> k) & 1) {
+                vhs_apply(states[cur ^ 1], jump->bulk[k], states[cur], tid, s_mat);
+                cur ^= 1;
+            }
+        if (cur) {
+            if (tid < 31) states[0][tid] = states[1][tid];
+            __syncthreads();
+        }
+    }
     vhs_spread_states(states, jump->tail, tid, s_mat);
     {
         unsigned h[31];
@@ -334,7 +361,7 @@ __global__ void k_vhs_aberration(SrcCfg *__restrict__ srcs, const int *__restric
     srcs[first + k].aberration = ab;
 }
 
-constexpr int kVhsSmemBulk = 257 * 32 * 4;
+constexpr int kVhsSmemBulk = (257 * 32 * 4 > kVhsRuns * kVhsSlice * 2) ? 257 * 32 * 4 : kVhsRuns * kVhsSlice * 2;
 constexpr int kVhsSmemTail = (kVhsWin + 8) * 4 + kVhsJLevels * (kVhsWin + 8) * 2 + kVhsChunks * 4 + 16;
 constexpr int kVhsSmem = (kVhsSmemBulk > kVhsSmemTail ? kVhsSmemBulk : kVhsSmemTail) > 257 * 32 * 4
                              ? (kVhsSmemBulk > kVhsSmemTail ? kVhsSmemBulk : kVhsSmemTail) : 257 * 32 * 4;

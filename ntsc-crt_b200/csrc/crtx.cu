@@ -405,12 +405,11 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
         k_noise_terms<<<tgrid, 256, 0, stream>>>(ctx->d_cfg, ctx->d_analog, ctx->d_inp, d_noise_terms, first);
     } else { // batch path: the per-monitor rand() replica (crt_vhs.cuh)
         LaunchTimer lt(ctx, stream, 2);
-        // two CTAs per monitor, side by side: (x, 0) the bulk of the field, (x, 1) its data-dependent tail
+        // two CTAs per monitor, side by side: (x, 0) the data-dependent tail of the field, (x, 1) its bulk
         k_noise_vhs<<<dim3(count, 2), kVhsThreads, kVhsSmem, stream>>>(ctx->d_cfg, ctx->d_state, static_cast<const VhsRand *>(ctx->d_vhs_rand),
                                                                        static_cast<VhsRand *>(ctx->d_vhs_rand_next),
                                                                        static_cast<const VhsJump *>(ctx->d_vhs_jump),
-                                                                       ctx->d_vhs_raw + (size_t) first * kVhsTailRaw,
-                                                                       ctx->d_vhs_terms + (size_t) first * kVhsBulk, ctx->d_analog,
+                                                                       ctx->d_vhs_raw + (size_t) first * kVhsTailRaw, ctx->d_analog,
                                                                        ctx->d_inp, first);
         k_vhs_commit<<<(count * 32 + 255) / 256, 256, 0, stream>>>(static_cast<VhsRand *>(ctx->d_vhs_rand),
                                                                    static_cast<const VhsRand *>(ctx->d_vhs_rand_next), first, count);
@@ -808,7 +807,6 @@ int crtx_create(crtx_ctx **out, int n)
         CTX_TRY(cudaMalloc(&ctx->d_vhs_rand_next, sizeof(VhsRand) * n));
         CTX_TRY(cudaMalloc(&ctx->d_vhs_jump, sizeof(VhsJump)));
         CTX_TRY(cudaMalloc(&ctx->d_vhs_raw, sizeof(unsigned) * (size_t) kVhsTailRaw * n));
-        CTX_TRY(cudaMalloc(&ctx->d_vhs_terms, sizeof(short) * (size_t) kVhsBulk * n));
         CTX_TRY(cudaMalloc(&ctx->d_vhs_wants, sizeof(int) * n));
         std::vector<VhsJump> j(1);
         vhs_build_jump(&j[0]);
@@ -852,7 +850,6 @@ void crtx_destroy(crtx_ctx *ctx)
     cudaFree(ctx->d_vhs_rand_next);
     cudaFree(ctx->d_vhs_jump);
     cudaFree(ctx->d_vhs_raw);
-    cudaFree(ctx->d_vhs_terms);
     cudaFree(ctx->d_vhs_wants);
     for (size_t i = 0; i < ctx->timed.size(); i++) {
         cudaEventDestroy(ctx->timed[i].start);

@@ -30,7 +30,6 @@ struct crtx_ctx {
     void *d_vhs_rand_next = nullptr; // VHS: the state after the running call (k_vhs_commit copies it back)
     void *d_vhs_jump = nullptr;   // VHS: jump-ahead matrices
     unsigned *d_vhs_raw = nullptr; // VHS: tail raw-stream scratch
-    short *d_vhs_terms = nullptr;  // VHS: the bulk region's noise terms in flat sample order, [n][kVhsBulk]
     int *d_vhs_wants = nullptr;   // VHS: do_aberration flags of the current modulate
     bool vhs_seeded = false;
     int vhs_draw_aberration = 0;
