@@ -63,7 +63,6 @@ struct SyncShared {
     int rowcount[kVper > 3 ? kVper : 3];
     int vs_found[2 * kVsyncWindow]; // per vsync candidate: crossing index or -1
     int generic;
-    int linemax[kVres + 1]; // FUSED: largest |inp| on each signal line (filled by the noise warps)
 };
 
 // hsync search of one decoded line given the hsync it enters with (crt_core.c:437-447):
@@ -227,7 +226,6 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
     // |bright| bound of the fast equaliser path (crt_lines.cuh); halved for the PV-1000, whose luma cascade
     // (hf = 80024) is only proven wrap-free up to there
     if (tid == 0) sh.generic = force_generic || abs(cfg.brightness - (kBlack + cfg.black_point)) > (kCc == 5 ? 2048 : 4096);
-    for (int j = tid; j <= kVres; j += kSyncThreads) sh.linemax[j] = FUSED ? 0 : 127;
     __syncthreads();
 
     // ---- 2. vsync (crt_core.c:379-396): candidate c = line posmod(vsync + c - W); first crossing wins
@@ -382,7 +380,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
     } else if (FUSED) {
         // ---- 3c. the noise pass proper (crt_core.c:346-367), by the 7 warps that would otherwise wait:
         // analog -> inp, 16 samples per thread per step, 128-bit accesses
-        constexpr int kNB = 4; // loads in flight per thread: the 7 warps must cover DRAM latency by themselves
+        constexpr int kNB = 8; // loads in flight per thread: the 7 warps must cover DRAM latency by themselves (4 in round 1)
         for (int tb = tid - 32; tb < kNoiseThreads; tb += kNB * (kSyncThreads - 32)) {
             uint4 in[kNB];
 #pragma unroll
@@ -420,13 +418,6 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
                 } else {
                     for (int b = 0; i0 + b < kInputSize; b++) inp_w[i0 + b] = (signed char) (w[b >> 2] >> (8 * (b & 3)));
                 }
-                // largest magnitude in this chunk, credited to the (at most two) lines it touches
-                unsigned a4 = __vmaxu4(__vmaxu4(__vabsss4(w[0]), __vabsss4(w[1])), __vmaxu4(__vabsss4(w[2]), __vabsss4(w[3])));
-                a4 = __vmaxu4(a4, a4 >> 16);
-                const int mx = (int) (__vmaxu4(a4, a4 >> 8) & 0xffu);
-                const int l0 = i0 / kHres, l1 = min(i0 + kNoiseVec - 1, kInputSize - 1) / kHres;
-                if (mx > sh.linemax[l0]) atomicMax(&sh.linemax[l0], mx);
-                if (l1 != l0 && mx > sh.linemax[l1]) atomicMax(&sh.linemax[l1], mx);
             }
         }
     }
@@ -484,7 +475,17 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
             // within +-16383 (crt_lines.cuh).  |s| is bounded by the largest sample of the one or two
             // signal lines the decode window covers -- measured by the noise warps when the noise pass is
             // fused, 127 (the clamp of crt_core.c:363-364) otherwise.
-            const int smax = max(sh.linemax[g.ypos], sh.linemax[min(g.ypos + 1, kVres)]);
+            // |s| <= 127 always (the clamp of crt_core.c:363-364).  With the stock saturation that bound already passes and
+            // nothing more is needed; only a line whose carrier is large enough to fail it has its two signal lines scanned for
+            // the real maximum -- by this one thread, from the inp[] this CTA wrote before the barrier above.  (Round 1 tracked
+            // the maximum of every 16-byte chunk inside the noise loop: 13 % of the kernel's instructions for a rare case.)
+            int smax = 127;
+            if (FUSED && ((smax * wmax) >> 9) + 1 > 16383) {
+                const int lo = (g.ypos * kHres) & ~15, hi = min((g.ypos + 2) * kHres, kInputSize);
+                int mx = 0;
+                for (int i = lo; i < hi; i++) mx = max(mx, abs((int) inp_w[i]));
+                smax = mx;
+            }
             if (((smax * wmax) >> 9) + 1 > 16383) sh.generic = 1;
         }
         lines[k] = rec;
