@@ -138,36 +138,18 @@ __device__ __forceinline__ void enc_tables(const SrcCfg &s, int row, int x, int 
 constexpr int kEquAHi = kIsPv1k ? -1 : kIsTemp ? 2 : 3, kEquBLo = 7, kEquBHi = 9;
 constexpr int kVsyncLo = kIsPv1k ? 258 : kIsTemp ? 3 : 4, kVsyncHi = kIsPv1k ? 260 : 6;
 
-// One CTA per monitor.  Lines above CRT_TOP are written whole, active lines only up to AV_BEG
-// (the rest of an active line belongs to the picture pass or keeps its old content).
-__global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restrict__ srcs,
-                                                          MonState *__restrict__ states,
-                                                          signed char *__restrict__ analog_base, int first)
+// Lines above CRT_TOP are written whole, active lines only up to AV_BEG (the rest of an active line belongs to the
+// picture pass or keeps its old content).  One warp per line (lines w0, w0 + wstride, ...); every line is a handful of
+// constant runs (crt_ntsc.c:205-252), written as warp-wide byte fills -- no per-byte classification.
+__device__ __forceinline__ void mod_skeleton_lines(const SrcCfg &s, signed char *analog, const int (*burst)[kCc], int w0,
+                                                   int wstride, int lane)
 {
     static_assert(kHres % 2 == 0 && kAvBeg % 2 == 0, "pairs");
-    constexpr int kFullPairs = kHres / 2, kHeadPairs = kAvBeg / 2;
-    constexpr int kTotal = kTop * kFullPairs + (kVres - kTop) * kHeadPairs;
-    const SrcCfg s = srcs[blockIdx.x];
-    signed char *analog = analog_base + (size_t) (first + blockIdx.x) * kSignalBytes;
-    __shared__ int burst[kVper][kCc];
-
-    if (bpp_of(s.format) == 0) return; // crt_ntsc.c:190-193
-    if (threadIdx.x < kCc * kVper) {
-        int b, mi, mq;
-        enc_tables(s, (int) threadIdx.x / kCc, (int) threadIdx.x % kCc, b, mi, mq);
-        burst[threadIdx.x / kCc][threadIdx.x % kCc] = b;
-    }
-    __syncthreads();
     const int field = s.field & 1, frame = s.frame & 1;
     const int flip = kRowCarrier ? 0 : (field == frame); // the template system and the PV-1000 have no phase inversion
-
-    (void) kTotal;
-    // One warp per line; every line is a handful of constant runs (crt_ntsc.c:205-252), written as
-    // warp-wide byte fills -- no per-byte classification.
     const int aberration = s.aberration;
-    const int lane = threadIdx.x & 31;
     constexpr int H = kHres;
-    for (int n = threadIdx.x >> 5; n < kVres; n += blockDim.x >> 5) {
+    for (int n = w0; n < kVres; n += wstride) {
         signed char *line = analog + n * H;
         auto fill = [&](int from, int to, int level) {
             for (int t = from + lane; t < to; t += 32) line[t] = (signed char) level;
@@ -192,16 +174,40 @@ __global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restri
             fill(kCbBeg + kBurstLen, (n < kTop) ? H : kAvBeg, kBlank);
         }
     }
-    if (threadIdx.x < kCc * kVper) { // prime the burst lock (crt_ntsc.c:325-329 / crt_ntscvhs.c:332-336)
-        MonState *st = &states[first + blockIdx.x];
-        const int row = threadIdx.x / kCc, x = threadIdx.x % kCc;
-        // template / PV-1000 (crt_template.c:239, 331-335; crt_pv1k.c:236, 326-330): every video line n stores its
-        // burst bytes in row (n + 3) % VPER, so row r ends up with the bytes of the lines with n % VPER == r - 3
-        const int from = kRowCarrier ? posmod(row - 3, kVper) : 0;
-        int p = (int) (signed char) ((kBlank + burst[from][(x + flip * 2) % kCc] * kBurst) >> 5);
-        st->ccf[row][x] = kIsVhs ? 0 : p * 128;
-        if (kIsVhs && threadIdx.x == 0) st->hsync = 0; // crt_ntscvhs.c:258-259
+}
+
+// prime the burst lock (crt_ntsc.c:325-329 / crt_ntscvhs.c:332-336): thread e < CC_SAMPLES * CC_VPER writes ccf[e / CC][e % CC]
+__device__ __forceinline__ void mod_skeleton_prime(const SrcCfg &s, MonState *st, const int (*burst)[kCc], int e)
+{
+    const int field = s.field & 1, frame = s.frame & 1;
+    const int flip = kRowCarrier ? 0 : (field == frame);
+    const int row = e / kCc, x = e % kCc;
+    // template / PV-1000 (crt_template.c:239, 331-335; crt_pv1k.c:236, 326-330): every video line n stores its
+    // burst bytes in row (n + 3) % VPER, so row r ends up with the bytes of the lines with n % VPER == r - 3
+    const int from = kRowCarrier ? posmod(row - 3, kVper) : 0;
+    int p = (int) (signed char) ((kBlank + burst[from][(x + flip * 2) % kCc] * kBurst) >> 5);
+    st->ccf[row][x] = kIsVhs ? 0 : p * 128;
+    if (kIsVhs && e == 0) st->hsync = 0; // crt_ntscvhs.c:258-259
+}
+
+// One CTA per monitor (the stand-alone form; the staged picture kernel can carry the same work on a ninth warp).
+__global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restrict__ srcs,
+                                                          MonState *__restrict__ states,
+                                                          signed char *__restrict__ analog_base, int first)
+{
+    const SrcCfg s = srcs[blockIdx.x];
+    signed char *analog = analog_base + (size_t) (first + blockIdx.x) * kSignalBytes;
+    __shared__ int burst[kVper][kCc];
+
+    if (bpp_of(s.format) == 0) return; // crt_ntsc.c:190-193
+    if (threadIdx.x < kCc * kVper) {
+        int b, mi, mq;
+        enc_tables(s, (int) threadIdx.x / kCc, (int) threadIdx.x % kCc, b, mi, mq);
+        burst[threadIdx.x / kCc][threadIdx.x % kCc] = b;
     }
+    __syncthreads();
+    mod_skeleton_lines(s, analog, burst, (int) (threadIdx.x >> 5), (int) (blockDim.x >> 5), (int) (threadIdx.x & 31));
+    if (threadIdx.x < kCc * kVper) mod_skeleton_prime(s, &states[first + blockIdx.x], burst, (int) threadIdx.x);
 }
 
 // Picture pass.  One CTA (8 warps) per monitor; a warp owns 32 consecutive picture lines.
@@ -230,8 +236,8 @@ __device__ __forceinline__ void load_rgb(const unsigned char *data, size_t pix, 
     }
 }
 
-__device__ __forceinline__ bool mod_staged_ok(const SrcCfg &s, int destw);
-template <bool STAGED> __device__ __forceinline__ bool mod_takes(const SrcCfg &s);
+__host__ __device__ __forceinline__ bool mod_staged_ok(const SrcCfg &s, int destw);
+template <bool STAGED> __host__ __device__ __forceinline__ bool mod_takes(const SrcCfg &s);
 
 __global__ void __launch_bounds__(256) k_mod_picture_rgb(const SrcCfg *__restrict__ srcs,
                                                          const MonCfg *__restrict__ cfgs,
@@ -386,7 +392,7 @@ constexpr int kModSOutPitch = kModSChunk / 4 + 1;  // words
 constexpr int kModSWarpSmem = 2 * 32 * kModSRow + 32 * kModSOutPitch * 4 + 32 * 4;
 constexpr int kModSSmem = 8 * kModSWarpSmem + 8 * 2 * 8;
 
-__device__ __forceinline__ bool mod_staged_ok(const SrcCfg &s, int destw)
+__host__ __device__ __forceinline__ bool mod_staged_ok(const SrcCfg &s, int destw)
 {
     const int bpp = bpp_of(s.format);
     if (bpp == 0 || destw <= 0 || s.w <= 0 || kCc != 4) return false; // (four samples per carrier period only)
@@ -397,24 +403,44 @@ __device__ __forceinline__ bool mod_staged_ok(const SrcCfg &s, int destw)
 }
 
 template <bool STAGED>
-__device__ __forceinline__ bool mod_takes(const SrcCfg &s)
+__host__ __device__ __forceinline__ bool mod_takes(const SrcCfg &s)
 {
     int destw = kDestW;
-    if (s.raw) destw = min(s.w, kDestW);
+    if (s.raw) destw = s.w < kDestW ? s.w : kDestW;
     return mod_staged_ok(s, destw) == STAGED;
 }
+
+// The sync skeleton and the picture write disjoint bytes of analog[] when the picture is not moved up or left of its
+// place (lines below CRT_TOP and bytes before AV_BEG belong to the skeleton): then the staged picture kernel may carry
+// the skeleton on a ninth warp instead of waiting for a kernel of its own (crt_ntsc.c:194-203 for the picture's origin).
+__host__ __device__ __forceinline__ bool mod_skeleton_fusable(const SrcCfg &s) { return s.xoffset >= 0 && s.yoffset >= 0; }
+constexpr int kModSThreads = 9 * 32; // 8 picture warps + the skeleton warp
 
 // FMT / COLOR are launch-uniform (the host groups monitors by them) so byte extraction and the
 // chroma path compile to straight-line code; monitors that do not match return at once.
 template <int FMT, bool COLOR>
-__global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg *__restrict__ srcs,
-                                                                   const MonCfg *__restrict__ cfgs,
-                                                                   signed char *__restrict__ analog_base, int first,
-                                                                   int use_tma)
+__global__ void __launch_bounds__(kModSThreads, 2) k_mod_picture_rgb_staged(const SrcCfg *__restrict__ srcs,
+                                                                            const MonCfg *__restrict__ cfgs,
+                                                                            MonState *__restrict__ states,
+                                                                            signed char *__restrict__ analog_base, int first,
+                                                                            int use_tma, int with_skeleton)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SrcCfg s = srcs[blockIdx.x];
+    if (warp == 8) { // the skeleton warp: store-latency bound work beside eight issue-bound picture warps
+        __shared__ int sk_burst[kVper][kCc];
+        if (!with_skeleton || bpp_of(s.format) == 0) return; // crt_ntsc.c:190-193
+        for (int e = lane; e < kCc * kVper; e += 32) {
+            int b, mi, mq;
+            enc_tables(s, e / kCc, e % kCc, b, mi, mq);
+            sk_burst[e / kCc][e % kCc] = b;
+        }
+        __syncwarp();
+        mod_skeleton_lines(s, analog_base + (size_t) (first + blockIdx.x) * kSignalBytes, sk_burst, 0, 1, lane);
+        for (int e = lane; e < kCc * kVper; e += 32) mod_skeleton_prime(s, &states[first + blockIdx.x], sk_burst, e);
+        return;
+    }
     if (!mod_takes<true>(s) || s.format != FMT || (s.as_color != 0) != COLOR) return;
     const MonCfg cfg = cfgs[first + blockIdx.x];
     signed char *analog = analog_base + (size_t) (first + blockIdx.x) * kSignalBytes;

@@ -200,7 +200,8 @@ def test_frames_host_moves_only_the_rows_a_field_touches(variant, raw, monkeypat
 
 
 @pytest.mark.parametrize("variant", ["ntsc", "ntsc_conv", "template", "pv1k"])
-@pytest.mark.parametrize("option,value", [("generic_eq", 1), ("mod_staged", 0), ("fused_noise", 0), ("mod_bulk", 0), ("tma", 0)])
+@pytest.mark.parametrize("option,value", [("generic_eq", 1), ("mod_staged", 0), ("fused_noise", 0), ("mod_bulk", 0), ("tma", 0), ("mod_fuse", 0),
+                                          ("lines2", 0), ("lines2_stage", 1)])
 def test_every_switch_of_the_library_gives_the_same_bits(variant, option, value):
     """the A/B switches of crtx_set_option select other code paths (the wrap-exact equaliser on every monitor, the
     gather encoder, the separate noise kernel, per-lane cp.async staging, plain loads instead of bulk copies): all of
@@ -275,4 +276,44 @@ def test_images_that_are_not_16_byte_aligned(variant, out_skew, src_skew, src_fm
         assert np.array_equal(got, ora.out), "%s field %d: %s" % (variant, it, S.diff_report("out", got, ora.out))
         assert np.array_equal(b.signal(0, "analog"), ora.analog)
     assert not big[:base + out_skew].any() and not big[base + out_skew + outw * outh * 4:].any(), "wrote outside the image"
+    b.close()
+
+
+@pytest.mark.parametrize("variant", ["ntsc", "vhs", "template"])
+def test_picture_moved_into_the_skeleton_keeps_the_reference_order(variant):
+    """crt_modulate writes the sync / blank / burst skeleton first and the picture over it (crt_ntsc.c:205-324).  The
+    library normally lets the staged picture kernel carry the skeleton on a ninth warp -- legal only while the two write
+    disjoint bytes; negative offsets move the picture into the skeleton's bytes (above CRT_TOP, left of AV_BEG), and the
+    call must then fall back to two ordered kernels.  A batch that mixes both kinds, against the oracle, analog[] included."""
+    import torch
+    from ntsc_crt_b200 import capi
+    n = 3
+    offs = [(0, 0), (-12, -4), (8, 3)]
+    b = capi.Batch(variant, n)
+    outs = [torch.zeros(480, 640, 4, dtype=torch.uint8, device="cuda") for _ in range(n)]
+    imgs = [S.rand_image(300, 200, seed=90 + i) for i in range(n)]
+    dimgs = [torch.from_numpy(im).cuda() for im in imgs]
+    oras = []
+    for i in range(n):
+        b.set_monitor(i, outs[i], fmt=layout.PIX_BGRA, noise=0 if variant == "vhs" else 5, blend=0, scanlines=0)
+        o = S.OracleEngine(variant, 640, 480)
+        o.set(blend=0, scanlines=0)
+        oras.append(o)
+    b.commit_monitors()
+    for f in range(3):
+        for i in range(n):
+            kw = dict(format=layout.PIX_BGRA, as_color=1, field=f & 1, frame=(f >> 1) & 1, xoffset=offs[i][0], yoffset=offs[i][1],
+                      dot_crawl_offset=f % 2)
+            b.set_source(i, dimgs[i], **kw)
+            oras[i].modulate(imgs[i], **kw)
+        b.modulate()
+        for i in range(n):
+            assert np.array_equal(b.signal(i, "analog"), oras[i].analog), "%s field %d monitor %d: %s" % (
+                variant, f, i, S.diff_report("analog", b.signal(i, "analog"), oras[i].analog))
+        if variant != "vhs":  # (VHS noise comes from rand(): the stream comparison has its own tests)
+            b.demodulate()
+            torch.cuda.synchronize()
+            for i in range(n):
+                oras[i].demodulate(5)
+                assert np.array_equal(outs[i].cpu().numpy(), oras[i].out), (variant, f, i)
     b.close()
