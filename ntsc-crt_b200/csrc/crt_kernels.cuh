@@ -190,7 +190,9 @@ __device__ __forceinline__ void mod_skeleton_prime(const SrcCfg &s, MonState *st
     if (kIsVhs && e == 0) st->hsync = 0; // crt_ntscvhs.c:258-259
 }
 
-// One CTA per monitor (the stand-alone form; the staged picture kernel can carry the same work on a ninth warp).
+// One CTA per monitor.  (Round 2 tried carrying this work on a ninth warp of the staged picture kernel: 155 us against
+// 21 + 130 separately, and the picture of a line shifted right by xoffset >= 4 spills three bytes into the next line's
+// porch, which the reference's write order resolves -- dropped.)
 __global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restrict__ srcs,
                                                           MonState *__restrict__ states,
                                                           signed char *__restrict__ analog_base, int first)
@@ -410,37 +412,18 @@ __host__ __device__ __forceinline__ bool mod_takes(const SrcCfg &s)
     return mod_staged_ok(s, destw) == STAGED;
 }
 
-// The sync skeleton and the picture write disjoint bytes of analog[] when the picture is not moved up or left of its
-// place (lines below CRT_TOP and bytes before AV_BEG belong to the skeleton): then the staged picture kernel may carry
-// the skeleton on a ninth warp instead of waiting for a kernel of its own (crt_ntsc.c:194-203 for the picture's origin).
-__host__ __device__ __forceinline__ bool mod_skeleton_fusable(const SrcCfg &s) { return s.xoffset >= 0 && s.yoffset >= 0; }
-constexpr int kModSThreads = 9 * 32; // 8 picture warps + the skeleton warp
 
 // FMT / COLOR are launch-uniform (the host groups monitors by them) so byte extraction and the
 // chroma path compile to straight-line code; monitors that do not match return at once.
 template <int FMT, bool COLOR>
-__global__ void __launch_bounds__(kModSThreads, 2) k_mod_picture_rgb_staged(const SrcCfg *__restrict__ srcs,
-                                                                            const MonCfg *__restrict__ cfgs,
-                                                                            MonState *__restrict__ states,
-                                                                            signed char *__restrict__ analog_base, int first,
-                                                                            int use_tma, int with_skeleton)
+__global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg *__restrict__ srcs,
+                                                                   const MonCfg *__restrict__ cfgs,
+                                                                   signed char *__restrict__ analog_base, int first,
+                                                                   int use_tma)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SrcCfg s = srcs[blockIdx.x];
-    if (warp == 8) { // the skeleton warp: store-latency bound work beside eight issue-bound picture warps
-        __shared__ int sk_burst[kVper][kCc];
-        if (!with_skeleton || bpp_of(s.format) == 0) return; // crt_ntsc.c:190-193
-        for (int e = lane; e < kCc * kVper; e += 32) {
-            int b, mi, mq;
-            enc_tables(s, e / kCc, e % kCc, b, mi, mq);
-            sk_burst[e / kCc][e % kCc] = b;
-        }
-        __syncwarp();
-        mod_skeleton_lines(s, analog_base + (size_t) (first + blockIdx.x) * kSignalBytes, sk_burst, 0, 1, lane);
-        for (int e = lane; e < kCc * kVper; e += 32) mod_skeleton_prime(s, &states[first + blockIdx.x], sk_burst, e);
-        return;
-    }
     if (!mod_takes<true>(s) || s.format != FMT || (s.as_color != 0) != COLOR) return;
     const MonCfg cfg = cfgs[first + blockIdx.x];
     signed char *analog = analog_base + (size_t) (first + blockIdx.x) * kSignalBytes;

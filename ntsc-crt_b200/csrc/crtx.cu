@@ -195,12 +195,12 @@ static cudaError_t lines_attr_all()
 
 #if CRT_B200_BANDLIMITED
 template <int FMT, bool COLOR>
-static void launch_mod_staged_one(crtx_ctx *ctx, int count, int first, cudaStream_t stream, int with_skeleton)
+static void launch_mod_staged_one(crtx_ctx *ctx, int count, int first, cudaStream_t stream)
 {
     // staging: 1 = per-lane bulk copies (default), 2 = per-lane cp.async copies ("mod_bulk" 0), 0 = plain loads
     const int staging = ctx->opt_tma ? (ctx->opt_mod_bulk ? 1 : 2) : 0;
-    k_mod_picture_rgb_staged<FMT, COLOR><<<count, kModSThreads, kModSSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_state,
-                                                                                     ctx->d_analog, first, staging, with_skeleton);
+    k_mod_picture_rgb_staged<FMT, COLOR><<<count, 256, kModSSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog,
+                                                                            first, staging);
 }
 
 // function attributes are per device: set by crtx_create for the context's device
@@ -215,12 +215,12 @@ static cudaError_t mod_staged_attr_all()
     return e;
 }
 
-static void launch_mod_staged(crtx_ctx *ctx, int format, bool color, int count, int first, cudaStream_t stream, int with_skeleton)
+static void launch_mod_staged(crtx_ctx *ctx, int format, bool color, int count, int first, cudaStream_t stream)
 {
-#define MS(F)                                                                                       \
-    case F:                                                                                         \
-        if (color) launch_mod_staged_one<F, true>(ctx, count, first, stream, with_skeleton);        \
-        else launch_mod_staged_one<F, false>(ctx, count, first, stream, with_skeleton);             \
+#define MS(F)                                                                        \
+    case F:                                                                          \
+        if (color) launch_mod_staged_one<F, true>(ctx, count, first, stream);        \
+        else launch_mod_staged_one<F, false>(ctx, count, first, stream);             \
         break;
     switch (format) { MS(0) MS(1) MS(2) MS(3) MS(4) MS(5) default: break; }
 #undef MS
@@ -368,16 +368,12 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
     int extra = 0;
     // (the staged kernel steps four samples per carrier period: not for the PV-1000's five, which takes the gather kernel)
     const bool staged = ctx->opt_mod_staged && kCc == 4;
-    // Which kernels does this call need?  The staged picture kernel carries the sync skeleton on a ninth warp when no
-    // picture of the call is moved into the skeleton's bytes; the gather kernel only runs for sources the staged one
-    // cannot take (their span does not fit a stage row), or for all of them when staging is off.
-    bool fuse = staged && ctx->opt_mod_fuse, gather = !staged;
-    for (int i = 0; i < count; i++) {
-        if (bpp_of(src[i].format) == 0) continue; // silent no-op in every kernel (crt_ntsc.c:190-193)
-        if (!mod_skeleton_fusable(src[i])) fuse = false;
-        if (staged && !mod_takes<true>(src[i])) gather = true;
-    }
-    if (!fuse) {
+    // The gather kernel only runs for sources the staged one cannot take (their span does not fit a stage row), or for all of
+    // them when staging is off: the host can tell (mod_takes is a pure function of the settings), so the usual call saves a launch.
+    bool gather = !staged;
+    for (int i = 0; i < count; i++)
+        if (bpp_of(src[i].format) != 0 && staged && !mod_takes<true>(src[i])) gather = true;
+    {
         LaunchTimer lt(ctx, stream, 0);
         k_mod_skeleton_rgb<<<count, 256, 0, stream>>>(ctx->d_src + first, ctx->d_state, ctx->d_analog, first);
         extra += 1;
@@ -389,7 +385,7 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
                 int hi = lo + 1;
                 while (hi < count && src[hi].format == src[lo].format && (src[hi].as_color != 0) == (src[lo].as_color != 0)) hi++;
                 if (bpp_of(src[lo].format) != 0) {
-                    launch_mod_staged(ctx, src[lo].format, src[lo].as_color != 0, hi - lo, first + lo, stream, fuse ? 1 : 0);
+                    launch_mod_staged(ctx, src[lo].format, src[lo].as_color != 0, hi - lo, first + lo, stream);
                     extra += 1;
                 }
                 lo = hi;
@@ -1328,7 +1324,6 @@ int crtx_set_option(crtx_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "host_src")) ctx->opt_host_src = value;
     else if (!strcmp(name, "host_rows")) ctx->opt_host_rows = value;
     else if (!strcmp(name, "mod_bulk")) ctx->opt_mod_bulk = value;
-    else if (!strcmp(name, "mod_fuse")) ctx->opt_mod_fuse = value;
     else if (!strcmp(name, "lines2")) ctx->opt_lines2 = value;
     else if (!strcmp(name, "lines2_stage")) ctx->opt_lines2_stage = value;
     else if (!strcmp(name, "line_lo")) ctx->opt_line_lo = value;

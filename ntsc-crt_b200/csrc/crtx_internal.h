@@ -48,7 +48,6 @@ struct crtx_ctx {
     int opt_timing = 0;
     int opt_mod_staged = 1;
     int opt_fused_noise = 1;
-    int opt_mod_fuse = 1; // the staged picture kernel carries the sync skeleton on a ninth warp (0: a kernel of its own, as in round 1)
     int opt_mod_bulk = 1; // encoder staging: 1 = per-lane bulk copies, 0 = per-lane cp.async (A/B switch; measured equal)
     int opt_lines2 = 1;   // line pass: 1 = k_lines2 where the geometry qualifies (crt_lines2.cuh), 0 = always k_lines (A/B switch)
     int opt_lines2_stage = 2; // k_lines2's signal staging: 2 = three 16-byte cp.async per lane and stage (measured 261 us per 296 fields),

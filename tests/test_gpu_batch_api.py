@@ -200,7 +200,7 @@ def test_frames_host_moves_only_the_rows_a_field_touches(variant, raw, monkeypat
 
 
 @pytest.mark.parametrize("variant", ["ntsc", "ntsc_conv", "template", "pv1k"])
-@pytest.mark.parametrize("option,value", [("generic_eq", 1), ("mod_staged", 0), ("fused_noise", 0), ("mod_bulk", 0), ("tma", 0), ("mod_fuse", 0),
+@pytest.mark.parametrize("option,value", [("generic_eq", 1), ("mod_staged", 0), ("fused_noise", 0), ("mod_bulk", 0), ("tma", 0),
                                           ("lines2", 0), ("lines2_stage", 1)])
 def test_every_switch_of_the_library_gives_the_same_bits(variant, option, value):
     """the A/B switches of crtx_set_option select other code paths (the wrap-exact equaliser on every monitor, the
@@ -281,10 +281,10 @@ def test_images_that_are_not_16_byte_aligned(variant, out_skew, src_skew, src_fm
 
 @pytest.mark.parametrize("variant", ["ntsc", "vhs", "template"])
 def test_picture_moved_into_the_skeleton_keeps_the_reference_order(variant):
-    """crt_modulate writes the sync / blank / burst skeleton first and the picture over it (crt_ntsc.c:205-324).  The
-    library normally lets the staged picture kernel carry the skeleton on a ninth warp -- legal only while the two write
-    disjoint bytes; negative offsets move the picture into the skeleton's bytes (above CRT_TOP, left of AV_BEG), and the
-    call must then fall back to two ordered kernels.  A batch that mixes both kinds, against the oracle, analog[] included."""
+    """crt_modulate writes the sync / blank / burst skeleton first and the picture over it (crt_ntsc.c:205-324); offsets
+    move the picture into the skeleton's bytes (above CRT_TOP, left of AV_BEG, or -- xoffset >= 4 -- three bytes into the
+    next line's porch), where that order decides the result.  A batch that mixes such pictures with ordinary ones, against
+    the oracle, analog[] included."""
     import torch
     from ntsc_crt_b200 import capi
     n = 3
