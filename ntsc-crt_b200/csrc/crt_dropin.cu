@@ -36,16 +36,7 @@ struct Shadow {
     size_t img_bytes = 0;
     short *d_terms = nullptr; // VHS noise terms
     bool out_valid = false;   // device image mirrors the host image (non-strict mode)
-    bool sig_valid = false;   // device analog[] mirrors the host's (non-strict mode)
     const unsigned char *out_host = nullptr;
-    // rows-only transfers: the caller's images are pageable (and may be freed and reallocated at the same address between
-    // calls, as video_convert.c does, so they cannot be registered): the rows a field reads are gathered by the CPU into a
-    // library-owned page-locked buffer and cross PCIe as one DMA; the rows it wrote come back packed and are scattered
-    unsigned char *h_stage = nullptr; // page-locked
-    size_t stage_bytes = 0;
-    unsigned char *d_pack = nullptr;  // packed written rows (+ 16 bytes: the row count)
-    size_t pack_bytes = 0;
-    struct Tail { crtx_line lines[CRT_LINES]; int total; } *h_tail = nullptr; // page-locked: line table + packed row count
 };
 
 std::mutex g_mutex;
@@ -83,9 +74,6 @@ void drop_shadow(Shadow *sh)
     cudaFree(sh->d_out);
     cudaFree(sh->d_img);
     cudaFree(sh->d_terms);
-    cudaFree(sh->d_pack);
-    cudaFreeHost(sh->h_stage);
-    cudaFreeHost(sh->h_tail);
     crtx_destroy(sh->ctx);
     if (sh->stream) cudaStreamDestroy(sh->stream);
     delete sh;
@@ -125,28 +113,6 @@ void ensure(unsigned char **buf, size_t *have, size_t need, cudaStream_t st)
     cuda_or_die(cudaMalloc(buf, need), "cudaMalloc");
     cuda_or_die(cudaMemsetAsync(*buf, 0, need, st), "cudaMemset");
     *have = need;
-}
-
-void ensure_stage(Shadow *sh, size_t need)
-{
-    if (need <= sh->stage_bytes) return;
-    cuda_or_die(cudaStreamSynchronize(sh->stream), "cudaStreamSynchronize");
-    cudaFreeHost(sh->h_stage);
-    sh->h_stage = nullptr;
-    sh->stage_bytes = 0;
-    need = (need + 65535) & ~(size_t) 65535;
-    cuda_or_die(cudaHostAlloc(&sh->h_stage, need, cudaHostAllocDefault), "cudaHostAlloc");
-    sh->stage_bytes = need;
-}
-
-bool rows_mode()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("CRT_B200_ROWS"); // 0: whole-image copies as in round 1 (A/B switch)
-        v = (e && *e == '0') ? 0 : 1;
-    }
-    return v != 0;
 }
 
 void push_state(Shadow *sh, const struct CRT *v)
@@ -289,30 +255,8 @@ void crt_modulate(struct CRT *v, struct NTSC_SETTINGS *s)
     const size_t img_bytes = (size_t) s->w * s->h * bpp;
 #endif
     ensure(&sh->d_img, &sh->img_bytes, img_bytes ? img_bytes : 4, sh->stream);
-    bool compact = false;
-#if CRT_B200_BANDLIMITED
-    if (rows_mode() && s->w > 0 && s->h > 0) {
-        // only the rows this field reads (crt_ntsc.c:258-266), gathered into page-locked staging: picture line y <- row
-        // (y * h) / desth + field offset, as the encoder kernels compute it (the reference's one-row over-read clamped alike)
-        const size_t rb = (size_t) s->w * bpp;
-        const int desth = src.raw ? (s->h < kDestH ? s->h : kDestH) : kDestH; // crt_ntsc.c:132-133, 163-172
-        if (desth > 0 && (size_t) desth < (size_t) s->h) {
-            ensure_stage(sh, rb * desth);
-            const unsigned char *img = reinterpret_cast<const unsigned char *>(s->data);
-            const int field = src.field & 1;
-            for (int y = 0; y < desth; y++) {
-                int row = (int) (((long long) y * s->h) / desth) + (field * s->h + desth) / desth / 2;
-                if (row >= s->h) row = s->h - 1;
-                memcpy(sh->h_stage + (size_t) y * rb, img + (size_t) row * rb, rb);
-            }
-            cuda_or_die(cudaMemcpyAsync(sh->d_img, sh->h_stage, rb * desth, cudaMemcpyHostToDevice, sh->stream), "image rows upload");
-            compact = true;
-        }
-    }
-#endif
-    if (!compact) cuda_or_die(cudaMemcpyAsync(sh->d_img, s->data, img_bytes, cudaMemcpyHostToDevice, sh->stream), "image upload");
+    cuda_or_die(cudaMemcpyAsync(sh->d_img, s->data, img_bytes, cudaMemcpyHostToDevice, sh->stream), "image upload");
     src.data = sh->d_img;
-    src.compact = compact ? 1 : 0;
 
     push_monitor(sh, v, 0); // black_point / white_point feed the encoder
     push_state(sh, v);
@@ -335,19 +279,11 @@ void crt_demodulate(struct CRT *v, int noise)
     push_state(sh, v);
     const size_t out_bytes = (size_t) v->outw * v->outh * bpp;
     signed char *d_analog = crtx_analog(sh->ctx, 0);
-    // (with fewer output rows than decoded lines several lines share a row and the packed copy would exceed the image: whole copies)
-    const bool rows = rows_mode() && v->outw > 0 && (long long) v->outh + (long long) v->v_fac >= CRT_LINES;
-    // `synced`: the device image equals the caller's image on every row when the kernels start
-    bool synced = !strict_mode() && sh->out_valid;
-    if (!synced && (v->blend || !rows)) {
-        // the previous image is only ever READ by the blend (crt_core.c:584-608): without it the rows a field does not
-        // write never leave the device (rows-only download below), so the upload is only made when it can matter
+    if (strict_mode() || !sh->out_valid) {
         cuda_or_die(cudaMemcpyAsync(sh->d_out, v->out, out_bytes, cudaMemcpyHostToDevice, sh->stream), "image upload");
-        synced = true;
-    }
-    if (strict_mode() || !sh->sig_valid)
         cuda_or_die(cudaMemcpyAsync(d_analog, v->analog, CRT_INPUT_SIZE, cudaMemcpyHostToDevice, sh->stream),
                     "analog upload");
+    }
     const short *d_terms = nullptr;
 #if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
     /* The VHS noise pass draws from the process's libc rand() (crt_core.c:343-357); to stay a
@@ -383,45 +319,9 @@ void crt_demodulate(struct CRT *v, int noise)
     if (demodulate_launch(sh->ctx, 0, 1, sh->stream, d_terms)) die("crt_demodulate");
     cuda_or_die(cudaMemcpyAsync(v->inp, crtx_inp(sh->ctx, 0), CRT_INPUT_SIZE, cudaMemcpyDeviceToHost, sh->stream),
                 "inp download");
-    if (!rows) {
-        cuda_or_die(cudaMemcpyAsync(v->out, sh->d_out, out_bytes, cudaMemcpyDeviceToHost, sh->stream), "image download");
-        pull_state(sh, v); // synchronises the stream
-    } else {
-        // rows-only download: the rows the line table says this field wrote (crt_core.c:428-432, 662-664), packed on the
-        // device, one DMA into page-locked staging, scattered into the caller's image by the CPU; every other row of the
-        // caller's image is left alone, as the reference leaves it
-        const size_t pitch = (size_t) v->outw * bpp;
-        if (sh->pack_bytes < out_bytes + 32) {
-            cuda_or_die(cudaStreamSynchronize(sh->stream), "cudaStreamSynchronize");
-            cudaFree(sh->d_pack);
-            sh->d_pack = nullptr;
-            cuda_or_die(cudaMalloc(&sh->d_pack, out_bytes + 32), "cudaMalloc");
-            sh->pack_bytes = out_bytes + 32;
-        }
-        if (!sh->h_tail) cuda_or_die(cudaHostAlloc(&sh->h_tail, sizeof(Shadow::Tail), cudaHostAllocDefault), "cudaHostAlloc");
-        ensure_stage(sh, out_bytes);
-        int *d_total = reinterpret_cast<int *>(sh->d_pack + ((out_bytes + 15) & ~(size_t) 15)); // behind the packed rows
-        if (pack_rows_launch(sh->ctx, 0, sh->d_pack, d_total, sh->stream)) die("pack_rows_launch");
-        cuda_or_die(cudaMemcpyAsync(sh->h_tail->lines, sh->ctx->d_lines, sizeof(crtx_line) * CRT_LINES, cudaMemcpyDeviceToHost, sh->stream), "line table download");
-        cuda_or_die(cudaMemcpyAsync(&sh->h_tail->total, d_total, sizeof(int), cudaMemcpyDeviceToHost, sh->stream), "row count download");
-        pull_state(sh, v); // synchronises the stream: table, count and state are here
-        const int total = sh->h_tail->total;
-        if (total > 0) {
-            cuda_or_die(cudaMemcpyAsync(sh->h_stage, sh->d_pack, (size_t) total * pitch, cudaMemcpyDeviceToHost, sh->stream), "image rows download");
-            cuda_or_die(cudaStreamSynchronize(sh->stream), "cudaStreamSynchronize");
-            size_t at = 0;
-            for (int k = 0; k < CRT_LINES; k++) {
-                const crtx_line &l = sh->h_tail->lines[k];
-                if (l.beg < 0) continue;
-                int n = l.end - v->scanlines - l.beg; // crt_core.c:662-664
-                if (n < 1) n = 1;
-                memcpy(v->out + (size_t) l.beg * pitch, sh->h_stage + at, (size_t) n * pitch);
-                at += (size_t) n * pitch;
-            }
-        }
-    }
-    sh->out_valid = synced; // every row the kernels wrote has been brought back: equal before, equal now
-    sh->sig_valid = true;
+    cuda_or_die(cudaMemcpyAsync(v->out, sh->d_out, out_bytes, cudaMemcpyDeviceToHost, sh->stream), "image download");
+    pull_state(sh, v); // synchronises the stream
+    sh->out_valid = true;
 #if (CRT_SYSTEM == CRT_SYSTEM_NTSCVHS)
     v->rn = last_rn; /* crt_core.c:367 */
 #endif

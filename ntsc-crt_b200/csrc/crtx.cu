@@ -698,48 +698,6 @@ k_rows_scatter(const MonCfg *__restrict__ cfgs, const LineRec *__restrict__ line
     }
 }
 
-// ---- the drop-in calls' image download: the rows monitor `m` wrote in its last field, packed in line order (crt_dropin.cu).
-// One CTA: an exclusive scan of the lines' row counts gives every line its place in `pack`; `total[0]` = rows packed.
-__global__ void __launch_bounds__(256) k_rows_pack(const MonCfg *__restrict__ cfgs, const LineRec *__restrict__ lines, int m,
-                                                   unsigned char *__restrict__ pack, int *__restrict__ total)
-{
-    __shared__ int offs[kLines + 1];
-    const MonCfg cfg = cfgs[m];
-    const int pitch = cfg.outw * cfg.bpp;
-    const LineRec *tab = lines + (size_t) m * kLines;
-    for (int k = threadIdx.x; k < kLines; k += blockDim.x) {
-        const LineRec r = tab[k];
-        offs[k + 1] = (r.beg >= 0) ? max(1, r.end - cfg.scanlines - r.beg) : 0; // crt_core.c:662-664
-    }
-    if (threadIdx.x == 0) offs[0] = 0;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < kLines; k++) offs[k + 1] += offs[k];
-        total[0] = offs[kLines];
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool wide = (pitch & 15) == 0 && ((reinterpret_cast<uintptr_t>(cfg.out) | reinterpret_cast<uintptr_t>(pack)) & 15) == 0;
-    for (int k = warp; k < kLines; k += (int) (blockDim.x >> 5)) {
-        const int n = offs[k + 1] - offs[k];
-        if (n <= 0) continue;
-        const unsigned char *src = cfg.out + (size_t) tab[k].beg * pitch;
-        unsigned char *dst = pack + (size_t) offs[k] * pitch;
-        if (wide) copy_row16(reinterpret_cast<const uint4 *>(src), reinterpret_cast<uint4 *>(dst), n * pitch / 16, lane);
-        else
-            for (int i = lane; i < n * pitch; i += 32) dst[i] = src[i];
-    }
-}
-
-int pack_rows_launch(crtx_ctx *ctx, int m, unsigned char *d_pack, int *d_total, cudaStream_t stream)
-{
-    if (check_range(ctx, m, 1)) return 1;
-    k_rows_pack<<<1, 256, 0, stream>>>(ctx->d_cfg, ctx->d_lines, m, d_pack, d_total);
-    ctx->launches += 1;
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
-
 // device mapping of a page-locked host buffer (NULL if `p` is pageable or not mapped)
 static void *host_mapping(const void *p)
 {

@@ -69,6 +69,4 @@ void fill_src(SrcCfg *d, const crtx_source *s);
 int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cudaStream_t stream);
 // d_noise_terms: VHS only -- per-sample noise term already drawn on the host from libc rand()
 int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, const short *d_noise_terms);
-// the rows monitor m wrote in its last field -> d_pack in line order, their number -> d_total[0] (crt_dropin.cu's download)
-int pack_rows_launch(crtx_ctx *ctx, int m, unsigned char *d_pack, int *d_total, cudaStream_t stream);
 } // namespace crt
