@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(256) k_mod_skeleton_rgb(const SrcCfg *__restri
                                                           MonState *__restrict__ states,
                                                           signed char *__restrict__ analog_base, int first)
 {
+    grid_dep_launch(); // the picture kernel behind this one may be scheduled as SMs free up (it waits before it writes)
     const SrcCfg s = srcs[blockIdx.x];
     signed char *analog = analog_base + (size_t) (first + blockIdx.x) * kSignalBytes;
     __shared__ int burst[kVper][kCc];
@@ -421,6 +422,8 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
                                                                    signed char *__restrict__ analog_base, int first,
                                                                    int use_tma)
 {
+    grid_dep_launch();
+    grid_dep_wait(); // (programmatic launch behind the skeleton kernel: its bytes must be in place first, crt_ntsc.c:205-324)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SrcCfg s = srcs[blockIdx.x];

@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kLinesWarps * 32, (FAST && kCc == 4) ? 2 : 1) 
 k_lines(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, const LineRec *__restrict__ lines_base,
         const signed char *__restrict__ inp_base, int first, const LinesGeom geo)
 {
+    grid_dep_wait(); // (programmatic launch behind k_sync / k_lines2)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kWarpSmem = lines_warp_smem<FAST>();
     constexpr int kEntry = YiqRow<FAST>::kEntryBytes;

@@ -118,6 +118,7 @@ k_lines2(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint4 *desc = reinterpret_cast<uint4 *>(smem_raw + kL2Warps * kL2WarpSmem + kL2Warps * 2 * 8);
     const int dx = geo.dx;
+    grid_dep_launch();
 
     // ---- descriptor table, once per CTA (pixels past outw repeat the last one: they are computed and never stored)
     const int ndesc = lines2_desc_count(geo.outw);
@@ -126,6 +127,9 @@ k_lines2(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, c
         const unsigned s = npos >> 12, R = npos & 0xfffu;
         desc[k] = make_uint4(4u * R, 4u * (0xfffu - R), (s % (unsigned) kL2Ring) * 8u, s + 1u);
     }
+    // (programmatic launch behind k_sync: everything above depends on the kernel arguments only and runs while k_sync's
+    // last CTAs finish; the line table, the state records and inp[] are read below)
+    grid_dep_wait();
     __syncthreads();
 
     const int gl = warp * 32 + lane;           // lane-line of the CTA

@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(kFirWarps * 32, FAST ? 2 : 1)
 k_lines_fir(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, const LineRec *__restrict__ lines_base,
             const signed char *__restrict__ inp_base, int first, const LinesGeom geo)
 {
+    grid_dep_wait(); // (programmatic launch behind k_sync)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using Elem = typename FirRow<FAST>::Elem;
     constexpr int kComp = FirRow<FAST>::kCompBytes / (int) sizeof(Elem); // elements between the Y, I and Q rows

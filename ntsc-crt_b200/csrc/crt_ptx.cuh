@@ -117,6 +117,14 @@ __device__ __forceinline__ void cp_async_16a(unsigned dst_addr, const void *src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_addr), "l"(src) : "memory");
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
+// scheduled while its predecessor in the stream is still running -- its CTAs take SMs as the predecessor's CTAs leave them and
+// run whatever depends on kernel arguments only -- and `grid_dep_wait` holds it until the predecessor grid has completed and
+// its memory is visible.  `grid_dep_launch` is the predecessor's side: "my dependents may be scheduled now".  Both are
+// no-ops in a kernel that was launched the ordinary way.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Row element at a shared-memory ADDRESS (+ constant byte offset), sign-extended.  The resampler keeps
 // absolute shared addresses in registers; going through ld.shared directly keeps the address arithmetic
 // out of the pixel loop (a generic pointer would be re-derived from the shared window base every time).

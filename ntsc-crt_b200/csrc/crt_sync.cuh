@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
                                                        const Affine *__restrict__ jump_hi, int first,
                                                        int force_generic)
 {
+    grid_dep_launch();
+    grid_dep_wait(); // (programmatic launch behind the encoder: analog[] must be complete)
     extern __shared__ __align__(16) unsigned heads[]; // [kHeadLines][kHeadWords]
     __shared__ SyncShared sh;
     const int m = first + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

@@ -36,6 +36,27 @@ int fail(const char *fmt, ...)
         if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// Launch `kernel`; with `pdl` as a programmatic dependent of the kernel launched just before it on `stream`: it may be
+// scheduled while that one is still running and waits for it inside (grid_dep_wait, crt_ptx.cuh).  Only kernels that call
+// grid_dep_wait before their first read of global memory are launched this way.
+template <typename... KA, typename... A>
+static cudaError_t launch_kernel(bool pdl, void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A &&...args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    memset(attr, 0, sizeof(attr));
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
+}
+
 static int check_range(const crtx_ctx *ctx, int first, int count)
 {
     if (!ctx) return fail("null context");
@@ -80,11 +101,13 @@ static void launch_lines_one(crtx_ctx *ctx, int count, int lo, const LinesGeom &
         int gx = FAST ? (4 * ctx->sm_count + count - 1) / count : 1;
         gx = gx < 1 ? 1 : (gx > kFirGroups ? kFirGroups : gx);
         const dim3 grid(gx, count);
-        k_lines_fir<FAST, MODE, FMT><<<grid, kFirWarps * 32, fir_smem<FAST>(), stream>>>(ctx->d_cfg, ctx->d_state,
-                                                                                         ctx->d_lines, ctx->d_inp, lo, geo);
+        (void) launch_kernel(ctx->opt_pdl != 0, k_lines_fir<FAST, MODE, FMT>, grid, dim3(kFirWarps * 32), (size_t) fir_smem<FAST>(), stream,
+                             (const MonCfg *) ctx->d_cfg, (const MonState *) ctx->d_state, (const LineRec *) ctx->d_lines,
+                             (const signed char *) ctx->d_inp, lo, geo);
     } else { // (only the kernel a build uses is instantiated)
-        k_lines<FAST, MODE, FMT><<<count, kLinesWarps * 32, lines_smem<FAST>(), stream>>>(ctx->d_cfg, ctx->d_state,
-                                                                                          ctx->d_lines, ctx->d_inp, lo, geo);
+        (void) launch_kernel(ctx->opt_pdl != 0, k_lines<FAST, MODE, FMT>, dim3(count), dim3(kLinesWarps * 32), (size_t) lines_smem<FAST>(), stream,
+                             (const MonCfg *) ctx->d_cfg, (const MonState *) ctx->d_state, (const LineRec *) ctx->d_lines,
+                             (const signed char *) ctx->d_inp, lo, geo);
     }
 }
 
@@ -118,8 +141,9 @@ static bool lines2_eligible(const crtx_ctx *ctx, int count, int lo, const LinesG
 template <int MODE, int FMT>
 static void launch_lines2_one(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
 {
-    k_lines2<MODE, FMT><<<(count + 1) / 2, kL2Threads, lines2_smem(geo.outw), stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines,
-                                                                                       ctx->d_inp, lo, count, geo);
+    (void) launch_kernel(ctx->opt_pdl != 0, k_lines2<MODE, FMT>, dim3((count + 1) / 2), dim3(kL2Threads), (size_t) lines2_smem(geo.outw), stream,
+                         (const MonCfg *) ctx->d_cfg, (const MonState *) ctx->d_state, (const LineRec *) ctx->d_lines,
+                         (const signed char *) ctx->d_inp, lo, count, geo);
 }
 
 static void launch_lines2(crtx_ctx *ctx, int count, int lo, const LinesGeom &geo, cudaStream_t stream)
@@ -199,8 +223,8 @@ static void launch_mod_staged_one(crtx_ctx *ctx, int count, int first, cudaStrea
 {
     // staging: 1 = per-lane bulk copies (default), 2 = per-lane cp.async copies ("mod_bulk" 0), 0 = plain loads
     const int staging = ctx->opt_tma ? (ctx->opt_mod_bulk ? 1 : 2) : 0;
-    k_mod_picture_rgb_staged<FMT, COLOR><<<count, 256, kModSSmem, stream>>>(ctx->d_src + first, ctx->d_cfg, ctx->d_analog,
-                                                                            first, staging);
+    (void) launch_kernel(ctx->opt_pdl != 0, k_mod_picture_rgb_staged<FMT, COLOR>, dim3(count), dim3(256), (size_t) kModSSmem, stream,
+                         (const SrcCfg *) (ctx->d_src + first), (const MonCfg *) ctx->d_cfg, ctx->d_analog, first, staging);
 }
 
 // function attributes are per device: set by crtx_create for the context's device
@@ -436,9 +460,11 @@ int demodulate_launch(crtx_ctx *ctx, int first, int count, cudaStream_t stream, 
     int pre = 1;
     if (ctx->opt_fused_noise) { // the noise pass runs inside k_sync (crt_sync.cuh)
         LaunchTimer lt(ctx, stream, 3);
-        k_sync<true><<<count, kSyncThreads, kSyncSmem, stream>>>(ctx->d_cfg, ctx->d_state, ctx->d_lines, ctx->d_analog,
-                                                                 ctx->d_inp, ctx->d_jump_lo, ctx->d_jump_hi, first,
-                                                                 ctx->opt_generic);
+        // (a programmatic dependent of the encoder only when the encoder's last kernel is right in front of it on this stream:
+        // the batch path's crtx_modulate -> crtx_demodulate; any other predecessor is waited for in full, as always)
+        (void) launch_kernel(ctx->opt_pdl != 0, k_sync<true>, dim3(count), dim3(kSyncThreads), (size_t) kSyncSmem, stream,
+                             (const MonCfg *) ctx->d_cfg, ctx->d_state, ctx->d_lines, (const signed char *) ctx->d_analog,
+                             ctx->d_inp, (const Affine *) ctx->d_jump_lo, (const Affine *) ctx->d_jump_hi, first, ctx->opt_generic);
     } else {
         dim3 ngrid(kNoiseBlocks, count);
         {
@@ -1282,6 +1308,7 @@ int crtx_set_option(crtx_ctx *ctx, const char *name, int value)
     else if (!strcmp(name, "host_src")) ctx->opt_host_src = value;
     else if (!strcmp(name, "host_rows")) ctx->opt_host_rows = value;
     else if (!strcmp(name, "mod_bulk")) ctx->opt_mod_bulk = value;
+    else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
     else if (!strcmp(name, "lines2")) ctx->opt_lines2 = value;
     else if (!strcmp(name, "lines2_stage")) ctx->opt_lines2_stage = value;
     else if (!strcmp(name, "line_lo")) ctx->opt_line_lo = value;

@@ -68,6 +68,10 @@ __device__ __forceinline__ void cp_async_16a(unsigned dst_addr, const void *src)
     ::simt::lane_copy16(::simt::g_smem_anchor + (int) dst_addr, src);
 }
 
+// (kernels run one after the other here: nothing to wait for)
+__device__ __forceinline__ void grid_dep_wait() {}
+__device__ __forceinline__ void grid_dep_launch() {}
+
 template <typename Elem, int OFF> __device__ __forceinline__ int lds_elem(unsigned addr)
 {
     const unsigned char *p = ::simt::g_smem_anchor + (int) (addr + (unsigned) OFF); // offsets may be "negative"
