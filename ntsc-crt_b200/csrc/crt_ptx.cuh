@@ -6,6 +6,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace crt {
 
@@ -134,6 +135,30 @@ template <typename Elem, int OFF> __device__ __forceinline__ int lds_elem(unsign
     if (sizeof(Elem) == 2) asm volatile("ld.shared.s16 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
     else asm volatile("ld.shared.s32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
     return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side of the same feature
+// ---------------------------------------------------------------------------------------
+// Launch `kernel`; with `pdl` as a programmatic dependent of the kernel launched just before it on `stream`: it may be
+// scheduled while that one is still running and waits for it inside (grid_dep_wait, crt_ptx.cuh).  Only kernels that call
+// grid_dep_wait before their first read of global memory are launched this way.
+template <typename... KA, typename... A>
+inline cudaError_t launch_kernel(bool pdl, void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A &&...args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    memset(attr, 0, sizeof(attr));
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
 }
 
 } // namespace crt

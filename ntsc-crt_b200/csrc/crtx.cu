@@ -36,27 +36,6 @@ int fail(const char *fmt, ...)
         if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-// Launch `kernel`; with `pdl` as a programmatic dependent of the kernel launched just before it on `stream`: it may be
-// scheduled while that one is still running and waits for it inside (grid_dep_wait, crt_ptx.cuh).  Only kernels that call
-// grid_dep_wait before their first read of global memory are launched this way.
-template <typename... KA, typename... A>
-static cudaError_t launch_kernel(bool pdl, void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A &&...args)
-{
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    memset(attr, 0, sizeof(attr));
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1u : 0u;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
-}
-
 static int check_range(const crtx_ctx *ctx, int first, int count)
 {
     if (!ctx) return fail("null context");

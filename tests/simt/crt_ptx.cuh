@@ -79,4 +79,13 @@ template <typename Elem, int OFF> __device__ __forceinline__ int lds_elem(unsign
     return (int) *reinterpret_cast<const Elem *>(p);
 }
 
+// host side: here a kernel always starts after its predecessor has finished, so "programmatic dependent" launches are
+// ordinary ones
+template <typename... KA, typename... A>
+inline cudaError_t launch_kernel(bool, void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t, A &&...args)
+{
+    ::simt::launch(grid, block, smem, [&]() { kernel(static_cast<KA>(args)...); });
+    return cudaSuccess;
+}
+
 } // namespace crt

@@ -244,18 +244,6 @@ static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigne
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.001f; return cudaSuccess; } /* (no clock here: a token value) */
-/* cudaLaunchKernelEx with launch attributes (programmatic dependent launch): here a kernel always starts after its
- * predecessor has finished, so the attributes are accepted and ignored */
-enum cudaLaunchAttributeID { cudaLaunchAttributeProgrammaticStreamSerialization = 6 };
-struct cudaLaunchAttributeValue { int programmaticStreamSerializationAllowed; };
-struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
-struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes; cudaStream_t stream; cudaLaunchAttribute *attrs; unsigned numAttrs; };
-template <typename... KA, typename... A>
-static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t *cfg, void (*kernel)(KA...), A &&...args)
-{
-    ::simt::launch(cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, [&]() { kernel(static_cast<KA>(args)...); });
-    return cudaSuccess;
-}
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void *p)
 {
     memset(a, 0, sizeof(*a));
