@@ -12,7 +12,7 @@ Contents (only what the hot path needs):
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(PKG_DIR, "lib")
+LIB_DIR = os.environ.get("CRT_B200_LIB_DIR") or os.path.join(PKG_DIR, "lib")  # (the override is for debug builds, tools/phase_clocks.py)
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 REPO_ROOT = os.path.dirname(PKG_DIR)
 

@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
 {
     grid_dep_launch();
     grid_dep_wait(); // (programmatic launch behind the skeleton kernel: its bytes must be in place first, crt_ntsc.c:205-324)
+    phase_mark(2, 0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const SrcCfg s = srcs[blockIdx.x];
@@ -615,6 +616,8 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
         }
         __syncwarp();
     }
+    phase_mark(2, 14);
+    phase_mark(2, 12, 7 * 32);
 }
 
 #endif // RGB systems

@@ -119,6 +119,7 @@ k_lines2(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, c
     uint4 *desc = reinterpret_cast<uint4 *>(smem_raw + kL2Warps * kL2WarpSmem + kL2Warps * 2 * 8);
     const int dx = geo.dx;
     grid_dep_launch();
+    phase_mark(1, 0);
 
     // ---- descriptor table, once per CTA (pixels past outw repeat the last one: they are computed and never stored)
     const int ndesc = lines2_desc_count(geo.outw);
@@ -131,6 +132,7 @@ k_lines2(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, c
     // last CTAs finish; the line table, the state records and inp[] are read below)
     grid_dep_wait();
     __syncthreads();
+    phase_mark(1, 1);
 
     const int gl = warp * 32 + lane;           // lane-line of the CTA
     const int half = gl >= kLines ? 1 : 0;
@@ -318,6 +320,8 @@ k_lines2(const MonCfg *__restrict__ cfgs, const MonState *__restrict__ states, c
         flush_tile<MODE == 1>(tile_q_a, old_a, tr, pitch, geo.outw - k0, 0, lane, blend_mask);
     }
     if (staging == 2 || MODE == 1) cp_async_wait<0>();
+    phase_mark(1, 14);
+    phase_mark(1, 12, 7 * 32);
 }
 
 } // namespace crt

@@ -62,6 +62,11 @@ __device__ __forceinline__ void cp_async_16(void *dst, const void *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+// 4-byte flavour (.ca: the only cache operator the small sizes have)
+__device__ __forceinline__ void cp_async_4(void *dst, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int PENDING> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
@@ -125,6 +130,28 @@ __device__ __forceinline__ void cp_async_16a(unsigned dst_addr, const void *src)
 // no-ops in a kernel that was launched the ordinary way.
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Debug builds only (-DCRTX_PHASE_CLOCKS=1, `make custom`): thread `who` of every CTA stamps the SM's cycle counter at the
+// phase boundaries of a kernel, and crtx_debug_clocks() (crtx.cu) hands the table to tools/phase_clocks.py.  Compiled out otherwise.
+#if defined(CRTX_PHASE_CLOCKS) && CRTX_PHASE_CLOCKS
+constexpr int kClkCtas = 512, kClkPhases = 16;
+static __device__ unsigned long long g_phase_clk[4][kClkCtas][kClkPhases]; // [kernel][CTA][phase]
+__device__ __forceinline__ void phase_mark(int kernel, int phase, int who = 0)
+{
+    if ((int) threadIdx.x == who) {
+        const int cta = (int) (blockIdx.x + blockIdx.y * gridDim.x);
+        if (cta < kClkCtas) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            // phase 0 = start, phase 14 = end: wall clock (ns) for the skew between CTAs, with the cycle counter beside it
+            g_phase_clk[kernel][cta][phase] = (phase == 0 || phase == 14) ? t : (unsigned long long) clock64();
+            if (phase == 0 || phase == 14) g_phase_clk[kernel][cta][phase == 0 ? 15 : 13] = (unsigned long long) clock64();
+        }
+    }
+}
+#else
+__device__ __forceinline__ void phase_mark(int, int, int = 0) {}
+#endif
 
 // Row element at a shared-memory ADDRESS (+ constant byte offset), sign-extended.  The resampler keeps
 // absolute shared addresses in registers; going through ld.shared directly keeps the address arithmetic

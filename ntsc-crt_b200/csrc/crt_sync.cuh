@@ -58,11 +58,12 @@ struct SyncShared {
     SyncLine ln[kLines];
     int hs[kLines];     // hsync after each decoded line's search
     int ccr[kLines][kCc]; // burst-lock accumulator of the line's colour row after its 10 steps
-    signed char burst[kLines][kBurstLen]; // the 40 (PV-1000: 50) burst samples each decoded line locks onto
+    uint4 burst[kLines][kCc]; // the burst samples each decoded line locks onto, by carrier phase: bytes 0 .. 9 of [line][phase]
     short rowlist[kVper > 3 ? kVper : 3][kLines]; // decoded lines of each colour row, in order
     int rowcount[kVper > 3 ? kVper : 3];
     int vs_found[2 * kVsyncWindow]; // per vsync candidate: crossing index or -1
     int generic;
+    int noise_next; // next chunk of the noise pass to hand out (FUSED)
 };
 
 // hsync search of one decoded line given the hsync it enters with (crt_core.c:437-447):
@@ -153,11 +154,21 @@ __device__ __forceinline__ unsigned noisy_word(const signed char *__restrict__ a
     return noisy_apply(__ldg(reinterpret_cast<const unsigned *>(analog + p)), p, noise, rn0, jump_lo, jump_hi);
 }
 
-// FUSED (LCG systems): the kernel reads analog[], applies the noise itself to what it stages, and its
-// otherwise idle warps write the whole inp[] while warp 0 runs the burst-lock chain -- the separate noise
-// pass disappears.  !FUSED (VHS, whose noise comes from rand()): inp[] was written by k_noise_terms.
+// FUSED (LCG systems): the kernel reads analog[], applies the noise itself to what it stages, and writes the whole
+// inp[] -- the separate noise pass disappears.  That copy is pure memory traffic and the sync phases are pure latency, so they
+// are interleaved: the signal is cut into chunks of 4 KB (one warp-wide batch of 16-byte loads per thread); every warp takes a
+// chunk and issues its loads BEFORE each sync phase and applies the noise and stores AFTER it, and while the last warp runs the
+// burst-lock chain the others work the remaining chunks off (a counter in shared memory hands them out).
+// !FUSED (VHS, whose noise comes from rand()): inp[] was written by k_noise_vhs.
+constexpr int kNoiseNB = 8;                                   // 16-byte loads in flight per thread
+constexpr int kNoiseChunkVecs = 32 * kNoiseNB;                // vectors per chunk (one warp, kNoiseNB rounds)
+constexpr int kNoiseChunks = (kNoiseThreads + kNoiseChunkVecs - 1) / kNoiseChunkVecs;
+constexpr int kChainWarp = kSyncThreads / 32 - 1;             // the arbiter favours the highest warp id: the serial chain gets it
+constexpr int kBurstSteps = kBurstLen / kCc;                  // burst samples per carrier phase and line (10)
+static_assert(kBurstSteps <= 16 && kBurstLen % kCc == 0, "one 16-byte record per (line, phase)");
+
 template <bool FUSED>
-__global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states,
+__global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states,
                                                        LineRec *__restrict__ lines_base,
                                                        const signed char *__restrict__ analog_base,
                                                        signed char *__restrict__ inp_base,
@@ -167,6 +178,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
 {
     grid_dep_launch();
     grid_dep_wait(); // (programmatic launch behind the encoder: analog[] must be complete)
+    phase_mark(0, 0);
     extern __shared__ __align__(16) unsigned heads[]; // [kHeadLines][kHeadWords]
     __shared__ SyncShared sh;
     const int m = first + blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -189,48 +201,102 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
         return (int) (signed char) (w >> (8 * (p & 3)));
     };
 
+    // ---- the noise pass (crt_core.c:346-367), in chunks: analog -> inp, 16 samples per thread per round, 128-bit accesses
+    uint4 nz_in[kNoiseNB];
+    int nz_chunk = kNoiseChunks; // chunk whose loads are in flight (none)
+    auto nz_load = [&](int c) { // whole warp
+        nz_chunk = c;
+        if (!FUSED || c >= kNoiseChunks) return;
+#pragma unroll
+        for (int u = 0; u < kNoiseNB; u++) {
+            const int t = c * kNoiseChunkVecs + u * 32 + lane;
+            nz_in[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (t < kNoiseThreads) nz_in[u] = *reinterpret_cast<const uint4 *>(analog + t * kNoiseVec);
+        }
+    };
+    auto nz_issue = [&]() { // the next chunk nobody has taken
+        if (!FUSED) return;
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&sh.noise_next, 1);
+        nz_load(__shfl_sync(0xffffffffu, c, 0));
+    };
+    auto nz_finish = [&]() {
+        if (!FUSED || nz_chunk >= kNoiseChunks) return;
+#pragma unroll
+        for (int u = 0; u < kNoiseNB; u++) {
+            const int t = nz_chunk * kNoiseChunkVecs + u * 32 + lane;
+            if (t >= kNoiseThreads) continue;
+            const int i0 = t * kNoiseVec;
+            unsigned w[4] = { nz_in[u].x, nz_in[u].y, nz_in[u].z, nz_in[u].w };
+            if (noise == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) w[k] = __vmaxs4(w[k], 0x81818181u);
+            } else {
+                const Affine lo = jump_lo[t % kJumpLo], hi = jump_hi[t / kJumpLo];
+                unsigned rn = (rn0 * hi.mul + hi.add) * lo.mul + lo.add;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    unsigned o = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        rn = rn * kLcgMul + kLcgAdd;
+                        int v = (int) (signed char) (w[k] >> (8 * b)) + (wmul((int) ((rn >> 16) & 0xff) - 0x7f, noise) >> 8);
+                        o |= ((unsigned) clampi(v, -127, 127) & 0xffu) << (8 * b);
+                    }
+                    w[k] = o;
+                }
+            }
+            if (i0 + kNoiseVec <= kInputSize) {
+                *reinterpret_cast<uint4 *>(inp_w + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+                for (int b = 0; i0 + b < kInputSize; b++) inp_w[i0 + b] = (signed char) (w[b >> 2] >> (8 * (b & 3)));
+            }
+        }
+        nz_chunk = kNoiseChunks;
+    };
+    if (tid == 0) sh.noise_next = kSyncThreads / 32; // the first round is dealt out statically: chunk = warp
+    nz_load(warp);
+
     // ---- 1. stage line heads (heads[j][w] = the aligned word at ((j * H - 16) & ~3) + 4w) and the 2W
-    // vsync candidate lines in full (cand[c][w] = aligned words covering line posmod(vsync + c - W)).
-    // All loads of a batch are issued before any is stored, so the copy runs at memory-level parallelism
-    // instead of one L2 round trip per word.
+    // vsync candidate lines in full (cand[c][w] = aligned words covering line posmod(vsync + c - W)): every word is one
+    // asynchronous copy straight into shared memory, all of them in flight at once (a register-staged copy in batches of 8
+    // spent 16 us here on 9 round trips to memory); the noise is then applied in place.
     unsigned *cand = heads + kHeadLines * kHeadWords; // [2W][kCandWords]
     const int vs_in = st->vsync;
     {
-        constexpr int kBatch = 8;
         constexpr int kHeadTotal = kHeadLines * kHeadWords, kCandTotal = 2 * kVsyncWindow * kCandWords;
         const signed char *from = FUSED ? analog : inp;
-        for (int base = 0; base < kHeadTotal + kCandTotal; base += kBatch * kSyncThreads) {
-            unsigned v[kBatch];
-            int pos[kBatch];
-#pragma unroll
-            for (int b = 0; b < kBatch; b++) { // where each word comes from (-1: nothing to load)
-                const int idx = base + b * kSyncThreads + tid;
-                pos[b] = -1;
-                if (idx < kHeadTotal) {
-                    const int j = idx / kHeadWords, w = idx - j * kHeadWords;
-                    pos[b] = ((j * kHres - kHeadBefore) & ~3) + 4 * w;
-                } else if (idx < kHeadTotal + kCandTotal) {
-                    const int q = idx - kHeadTotal, c = q / kCandWords, w = q - c * kCandWords;
-                    pos[b] = (posmod(vs_in + c - kVsyncWindow, kVres) * kHres & ~3) + 4 * w;
-                }
+        auto pos_of = [&](int idx) { // where staged word idx comes from
+            if (idx < kHeadTotal) {
+                const int j = idx / kHeadWords, w = idx - j * kHeadWords;
+                return ((j * kHres - kHeadBefore) & ~3) + 4 * w;
             }
-#pragma unroll
-            for (int b = 0; b < kBatch; b++) // the raw loads, back to back
-                v[b] = (pos[b] >= 0) ? __ldg(reinterpret_cast<const unsigned *>(from + pos[b])) : 0u;
-#pragma unroll
-            for (int b = 0; b < kBatch; b++) {
-                const int idx = base + b * kSyncThreads + tid;
-                if (FUSED && pos[b] >= 0) v[b] = noisy_apply(v[b], pos[b], noise, rn0, jump_lo, jump_hi);
-                if (idx < kHeadTotal + kCandTotal) heads[idx] = v[b];
+            const int q = idx - kHeadTotal, c = q / kCandWords, w = q - c * kCandWords;
+            return (posmod(vs_in + c - kVsyncWindow, kVres) * kHres & ~3) + 4 * w;
+        };
+        for (int idx = tid; idx < kHeadTotal + kCandTotal; idx += kSyncThreads) {
+            const int pos = pos_of(idx);
+            if (pos >= 0) cp_async_4(&heads[idx], from + pos);
+            else heads[idx] = 0u;
+        }
+        cp_async_commit();
+        cp_async_wait<0>(); // (a thread only touches the words it copied itself until the barrier below)
+        if (FUSED) {
+            for (int idx = tid; idx < kHeadTotal + kCandTotal; idx += kSyncThreads) {
+                const int pos = pos_of(idx);
+                if (pos >= 0) heads[idx] = noisy_apply(heads[idx], pos, noise, rn0, jump_lo, jump_hi);
             }
         }
     }
     // |bright| bound of the fast equaliser path (crt_lines.cuh); halved for the PV-1000, whose luma cascade
     // (hf = 80024) is only proven wrap-free up to there
     if (tid == 0) sh.generic = force_generic || abs(cfg.brightness - (kBlack + cfg.black_point)) > (kCc == 5 ? 2048 : 4096);
+    nz_finish();
     __syncthreads();
+    phase_mark(0, 1);
 
     // ---- 2. vsync (crt_core.c:379-396): candidate c = line posmod(vsync + c - W); first crossing wins
+    nz_issue();
     constexpr int kSeg = (kHres + 31) / 32;
     for (int c = warp; c < 2 * kVsyncWindow; c += kSyncThreads / 32) {
         const int lstart = posmod(vs_in + c - kVsyncWindow, kVres) * kHres;
@@ -247,7 +313,9 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
         const int j = hit ? __shfl_sync(0xffffffffu, idx, __ffs(hit) - 1) : -1;
         if (lane == 0) sh.vs_found[c] = j;
     }
+    nz_finish();
     __syncthreads();
+    phase_mark(0, 2);
     int vs = posmod(vs_in + kVsyncWindow - 1, kVres), jcross = kHres; // "gave up" defaults
     for (int c = 0; c < 2 * kVsyncWindow; c++) {
         if (sh.vs_found[c] >= 0) {
@@ -275,6 +343,8 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
         sh.hs[k] = hs_in; // initial guess of the chain
     }
     __syncthreads();
+    phase_mark(0, 3);
+    nz_issue();
     // Decoded lines of each colour row, in order (skipped lines do not touch ccf).  Warp r compacts row r
     // with ballots, 32 lines per step -- a 240-iteration loop on one thread per row here made every other
     // thread wait ~13 % of the kernel at the next barrier.
@@ -283,9 +353,9 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
         for (int k0 = 0; k0 < kLines; k0 += 32) {
             const int k = k0 + lane;
             const bool mine = (k < kLines) && sh.ln[k].beg >= 0 && sh.ln[k].row == warp;
-            const unsigned m = __ballot_sync(0xffffffffu, mine);
-            if (mine) sh.rowlist[warp][n + __popc(m & ((1u << lane) - 1u))] = (short) k;
-            n += __popc(m);
+            const unsigned mm = __ballot_sync(0xffffffffu, mine);
+            if (mine) sh.rowlist[warp][n + __popc(mm & ((1u << lane) - 1u))] = (short) k;
+            n += __popc(mm);
         }
         if (lane == 0) sh.rowcount[warp] = n;
     }
@@ -315,62 +385,76 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
         }
         if (!__syncthreads_or(changed)) break;
     }
+    nz_finish();
+    phase_mark(0, 4);
 
     // ---- 3b. burst lock (crt_core.c:456-467): ccr = ccr * 127 / 128 + sample, 10 samples per phase per line.
-    // First every thread gathers the 40 burst samples of its lines (their position depends on hsync, now
-    // known) into shared memory, so the serial chain below is nothing but the recurrence.
-    for (int idx = tid; idx < kLines * kBurstLen; idx += kSyncThreads) {
-        const int k = idx / kBurstLen, t = idx - k * kBurstLen;
-        int v = 0;
-        if (sh.ln[k].beg >= 0) {
-            const int hs = sh.hs[k], jl = sh.ln[k].jl;
-            const int p = jl * kHres + (hs - hs % kCc) + kCbBeg + t; // crt_core.c:458-462 (hs >= 0: "& ~3" when kCc == 4)
-            const int j = (hs > kHres / 2) ? jl + 1 : jl;
-            const int off = p - ((j * kHres - kHeadBefore) & ~3);
-            if (j < kHeadLines && off >= 0 && off < kHeadWords * 4)
-                v = (int) (signed char) (heads[j * kHeadWords + (off >> 2)] >> (8 * (off & 3)));
-            else
-                v = fetch_byte(p);
+    // First one thread per decoded line gathers the line's 40 burst samples (their position depends on hsync, now known)
+    // into shared memory, sorted by carrier phase -- sample t belongs to phase (t + CB_BEG) % CC, step t / CC -- so that the
+    // serial chain below is nothing but one 16-byte load per line and the recurrence.
+    nz_issue();
+    for (int k = tid; k < kLines; k += kSyncThreads) {
+        if (sh.ln[k].beg < 0) continue; // (never on a colour row's list)
+        const int hs = sh.hs[k], jl = sh.ln[k].jl;
+        const int p = jl * kHres + (hs - hs % kCc) + kCbBeg; // crt_core.c:458-462 (hs >= 0: "& ~3" when kCc == 4)
+        const int j = (hs > kHres / 2) ? jl + 1 : jl;
+        const int off = p - ((j * kHres - kHeadBefore) & ~3);
+        signed char *dst = reinterpret_cast<signed char *>(&sh.burst[k][0]);
+        if (j < kHeadLines && off >= 0 && off + kBurstLen <= kHeadWords * 4) {
+            const signed char *hb = reinterpret_cast<const signed char *>(heads + j * kHeadWords) + off;
+#pragma unroll
+            for (int t = 0; t < kBurstLen; t++) dst[((t + kCbBeg) % kCc) * 16 + t / kCc] = hb[t];
+        } else {
+            for (int t = 0; t < kBurstLen; t++) dst[((t + kCbBeg) % kCc) * 16 + t / kCc] = (signed char) fetch_byte(p + t);
         }
-        sh.burst[k][t] = (signed char) v;
     }
+    nz_finish();
     __syncthreads();
-    if (warp == 0) {
+    phase_mark(0, 5);
+    if (warp == kChainWarp) {
         // Lane = kCc * row + phase walks its own colour row's lines (at most 5 x 5 = 25 lanes).
         static_assert(kCc * kVper <= 32, "one lane per (colour row, phase)");
-        const int row = lane / kCc, phase = lane % kCc;
         const bool chain_lane = lane < kCc * kVper;
-        const int t0 = posmod(phase - kCbBeg, kCc); // burst samples of this phase: t0, t0 + kCc, ...
+        const int row = chain_lane ? lane / kCc : 0, phase = chain_lane ? lane % kCc : 0;
         int x = chain_lane ? st->ccf[row][phase] : 0;
         const int count = chain_lane ? sh.rowcount[row] : 0;
+        const short *rl = sh.rowlist[row];
+        // the line after the current one is loaded while the current one's ten dependent steps run
+        int k = (count > 0) ? rl[0] : 0, k1 = (count > 1) ? rl[1] : k;
+        uint4 cur = sh.burst[k][phase];
         for (int n = 0; n < count; n++) {
-            const int k = sh.rowlist[row][n];
-            const signed char *bs = &sh.burst[k][t0];
+            const uint4 nxt = sh.burst[k1][phase];
+            const int k2 = (n + 2 < count) ? rl[n + 2] : k1;
+            const unsigned cw[4] = { cur.x, cur.y, cur.z, cur.w };
+            int bs[kBurstSteps];
+#pragma unroll
+            for (int q = 0; q < kBurstSteps; q++) bs[q] = (int) (signed char) (cw[q >> 2] >> (8 * (q & 3)));
             // C's x * 127 / 128 truncates towards zero.  While the product cannot wrap it equals
             // x - ((x + (x >= 0 ? 127 : 0)) >> 7): ceil(x / 128) for x >= 0, floor for x < 0.
-            if (abs(x) < (1 << 23)) {
-                // The sign of x almost never changes within a line, so the rounding bias is taken from the
-                // line's first x and the 10 dependent steps are add, shift, add; the sign bits of the
-                // intermediate values are collected off the critical path and the rare line on which one
-                // differs is redone with the per-step bias.
-                const int bias = (x >= 0) ? 127 : 0;
-                int y = x, flips = 0;
+            // The sign of x almost never changes within a line, so the rounding bias is taken from the line's first x
+            // and carried INSIDE the running value (z = x + bias): a step is then shift, three-input add -- two
+            // dependent instructions.  The sign bits of the intermediate values are collected off the critical path and
+            // the rare line on which one differs, or whose x is too large for the shortcut, is redone exactly.
+            const int bias = (x >= 0) ? 127 : 0;
+            int z = x + bias, flips = 0;
 #pragma unroll
-                for (int q = 0; q < kBurstLen / kCc; q++) {
-                    flips |= y ^ x;
-                    y = y - ((y + bias) >> 7) + bs[kCc * q];
-                }
-                if (flips < 0) {
+            for (int q = 0; q < kBurstSteps; q++) {
+                flips |= (z - bias) ^ x;
+                z = z - (z >> 7) + bs[q];
+            }
+            if (abs(x) >= (1 << 23)) {
 #pragma unroll
-                    for (int q = 0; q < kBurstLen / kCc; q++) x = x - ((x + ((x >= 0) ? 127 : 0)) >> 7) + bs[kCc * q];
-                } else {
-                    x = y;
-                }
+                for (int q = 0; q < kBurstSteps; q++) x = wadd(wmul(x, 127) / 128, bs[q]);
+            } else if (flips < 0) {
+#pragma unroll
+                for (int q = 0; q < kBurstSteps; q++) x = x - ((x + ((x >= 0) ? 127 : 0)) >> 7) + bs[q];
             } else {
-#pragma unroll
-                for (int q = 0; q < kBurstLen / kCc; q++) x = wadd(wmul(x, 127) / 128, bs[kCc * q]);
+                x = z - bias;
             }
             sh.ccr[k][phase] = x;
+            k = k1;
+            k1 = k2;
+            cur = nxt;
         }
         if (chain_lane) st->ccf[row][phase] = x;
         if (lane == 0) {
@@ -379,51 +463,19 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
             st->field = field;
             if (!kIsVhs) st->rn = (int) (rn0 * kLcgField.mul + kLcgField.add); // crt_core.c:367
         }
-    } else if (FUSED) {
-        // ---- 3c. the noise pass proper (crt_core.c:346-367), by the 7 warps that would otherwise wait:
-        // analog -> inp, 16 samples per thread per step, 128-bit accesses
-        constexpr int kNB = 8; // loads in flight per thread: the 7 warps must cover DRAM latency by themselves (4 in round 1)
-        for (int tb = tid - 32; tb < kNoiseThreads; tb += kNB * (kSyncThreads - 32)) {
-            uint4 in[kNB];
-#pragma unroll
-            for (int u = 0; u < kNB; u++) {
-                const int t = tb + u * (kSyncThreads - 32);
-                in[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (t < kNoiseThreads) in[u] = *reinterpret_cast<const uint4 *>(analog + t * kNoiseVec);
-            }
-#pragma unroll
-            for (int u = 0; u < kNB; u++) {
-                const int t = tb + u * (kSyncThreads - 32);
-                if (t >= kNoiseThreads) continue;
-                const int i0 = t * kNoiseVec;
-                unsigned w[4] = { in[u].x, in[u].y, in[u].z, in[u].w };
-                if (noise == 0) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) w[k] = __vmaxs4(w[k], 0x81818181u);
-                } else {
-                    const Affine lo = jump_lo[t % kJumpLo], hi = jump_hi[t / kJumpLo];
-                    unsigned rn = (rn0 * hi.mul + hi.add) * lo.mul + lo.add;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        unsigned o = 0;
-#pragma unroll
-                        for (int b = 0; b < 4; b++) {
-                            rn = rn * kLcgMul + kLcgAdd;
-                            int v = (int) (signed char) (w[k] >> (8 * b)) + (wmul((int) ((rn >> 16) & 0xff) - 0x7f, noise) >> 8);
-                            o |= ((unsigned) clampi(v, -127, 127) & 0xffu) << (8 * b);
-                        }
-                        w[k] = o;
-                    }
-                }
-                if (i0 + kNoiseVec <= kInputSize) {
-                    *reinterpret_cast<uint4 *>(inp_w + i0) = make_uint4(w[0], w[1], w[2], w[3]);
-                } else {
-                    for (int b = 0; i0 + b < kInputSize; b++) inp_w[i0 + b] = (signed char) (w[b >> 2] >> (8 * (b & 3)));
-                }
-            }
+        phase_mark(0, 6, kChainWarp * 32);
+    }
+    // ---- 3c. the rest of the noise pass, by whoever has nothing else to do (the chain warp joins when it is through)
+    if (FUSED) {
+        for (;;) {
+            nz_issue();
+            if (nz_chunk >= kNoiseChunks) break;
+            nz_finish();
         }
+        phase_mark(0, 7);
     }
     __syncthreads();
+    phase_mark(0, 8);
 
     // ---- 4. per-line records for k_lines (crt_core.c:452-454, 469-479), all threads
     int huesn, huecs;
@@ -474,13 +526,11 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
                 for (int i = 0; i < 5; i++) wmax = max(wmax, max(llabs((long long) wi[i]), llabs((long long) wq[i])));
             }
             // The fast equaliser path of k_lines is exact while every chroma input (s * wave) >> 9 stays
-            // within +-16383 (crt_lines.cuh).  |s| is bounded by the largest sample of the one or two
-            // signal lines the decode window covers -- measured by the noise warps when the noise pass is
-            // fused, 127 (the clamp of crt_core.c:363-364) otherwise.
-            // |s| <= 127 always (the clamp of crt_core.c:363-364).  With the stock saturation that bound already passes and
-            // nothing more is needed; only a line whose carrier is large enough to fail it has its two signal lines scanned for
-            // the real maximum -- by this one thread, from the inp[] this CTA wrote before the barrier above.  (Round 1 tracked
-            // the maximum of every 16-byte chunk inside the noise loop: 13 % of the kernel's instructions for a rare case.)
+            // within +-16383 (crt_lines.cuh).  |s| <= 127 always (the clamp of crt_core.c:363-364).  With the stock
+            // saturation that bound already passes and nothing more is needed; only a line whose carrier is large enough
+            // to fail it has its two signal lines scanned for the real maximum -- by this one thread, from the inp[] this
+            // CTA wrote before the barrier above.  (Round 1 tracked the maximum of every 16-byte chunk inside the noise
+            // loop: 13 % of the kernel's instructions for a rare case.)
             int smax = 127;
             if (FUSED && ((smax * wmax) >> 9) + 1 > 16383) {
                 const int lo = (g.ypos * kHres) & ~15, hi = min((g.ypos + 2) * kHres, kInputSize);
@@ -494,6 +544,7 @@ __global__ void __launch_bounds__(kSyncThreads) k_sync(const MonCfg *__restrict_
     }
     __syncthreads();
     if (tid == 0) st->generic = sh.generic;
+    phase_mark(0, 14);
 }
 
 } // namespace crt

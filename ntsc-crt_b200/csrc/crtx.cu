@@ -1143,6 +1143,14 @@ int crtx_get_lines(crtx_ctx *ctx, int i, crtx_line *table, void *stream)
 long crtx_launch_count(crtx_ctx *ctx) { return ctx ? ctx->launches : 0; }
 long crtx_lines2_count(crtx_ctx *ctx) { return ctx ? ctx->lines2_launches : 0; }
 
+#if defined(CRTX_PHASE_CLOCKS) && CRTX_PHASE_CLOCKS
+// debug builds only (crt_ptx.cuh: phase_mark): the table of phase stamps, 4 x 512 x 16 values
+extern "C" int crtx_debug_clocks(unsigned long long *dst)
+{
+    return (int) cudaMemcpyFromSymbol(dst, crt::g_phase_clk, sizeof(crt::g_phase_clk));
+}
+#endif
+
 int crtx_get_timing(crtx_ctx *ctx, float *ms, long *launches)
 {
     if (!ctx || !ms || !launches) return fail("crtx_get_timing: bad arguments");

@@ -19,6 +19,7 @@ void mbar_expect_tx(uint64_t *bar, unsigned bytes);
 void mbar_wait(uint64_t *bar, unsigned parity);
 void bulk_load(void *dst, const void *src, unsigned bytes, uint64_t *bar);
 void lane_copy16(void *dst, const void *src);
+void lane_copy4(void *dst, const void *src);
 void lane_commit();
 void lane_wait(int pending);
 void bulk_store(void *dst, const void *src, unsigned bytes);
@@ -38,6 +39,7 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
     ::simt::bulk_load(dst, src, bytes, bar);
 }
 __device__ __forceinline__ void cp_async_16(void *dst, const void *src) { ::simt::lane_copy16(dst, src); }
+__device__ __forceinline__ void cp_async_4(void *dst, const void *src) { ::simt::lane_copy4(dst, src); }
 __device__ __forceinline__ void cp_async_commit() { ::simt::lane_commit(); }
 template <int PENDING> __device__ __forceinline__ void cp_async_wait() { ::simt::lane_wait(PENDING); }
 
@@ -71,6 +73,7 @@ __device__ __forceinline__ void cp_async_16a(unsigned dst_addr, const void *src)
 // (kernels run one after the other here: nothing to wait for)
 __device__ __forceinline__ void grid_dep_wait() {}
 __device__ __forceinline__ void grid_dep_launch() {}
+__device__ __forceinline__ void phase_mark(int, int, int = 0) {}
 
 template <typename Elem, int OFF> __device__ __forceinline__ int lds_elem(unsigned addr)
 {
