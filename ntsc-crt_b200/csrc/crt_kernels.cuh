@@ -414,6 +414,52 @@ __host__ __device__ __forceinline__ bool mod_takes(const SrcCfg &s)
 }
 
 
+// cr * R + cg * G + cb * B of a 4-byte pixel whose channels sit in bytes RP, GP, BP (crt_ntsc.c:308-310) as two-way dot
+// products on the pixel word itself (IDP.2A, crt_ptx.cuh): the coefficients of bytes (0, 1) and of bytes (2, 3) are packed as
+// 16-bit pairs at compile time.  A pair of non-negative coefficients takes the unsigned form (up to 65535), a pair within
+// +-32767 the signed one, and a pair with a coefficient outside both (39059 next to a negative one, -34275) is split into two
+// signed halves.  Exact: the sum is the same 32-bit integer the three multiplications give.
+constexpr bool fits_s16(int c) { return c >= -32768 && c <= 32767; }
+constexpr unsigned pack_h2(int c0, int c1) { return ((unsigned) c0 & 0xffffu) | (((unsigned) c1 & 0xffffu) << 16); }
+template <int C0, int C1, bool HI> struct YiqDotPair { // coefficients of bytes (0, 1) or (2, 3), pinned in registers by init()
+    static constexpr int kKind = (C0 == 0 && C1 == 0) ? 0 : (C0 >= 0 && C1 >= 0) ? 1 : (fits_s16(C0) && fits_s16(C1)) ? 2 : 3;
+    static constexpr int A0 = C0 / 2, B0 = C0 - A0, A1 = C1 / 2, B1 = C1 - A1; // the two signed halves (kind 3)
+    static_assert(C0 <= 65535 && C1 <= 65535 && fits_s16(A0) && fits_s16(B0) && fits_s16(A1) && fits_s16(B1), "16-bit coefficients");
+    unsigned a, b;
+    // `zero` is a 0 the compiler cannot know to be one: OR-ing it in keeps the constants in registers -- ptxas otherwise
+    // re-materialises each of them with a move at every use, six issue slots per four samples in the encoder's loop
+    __device__ __forceinline__ void init(unsigned zero)
+    {
+        a = b = 0u;
+        if (kKind == 1 || kKind == 2) a = pack_h2(C0, C1) | zero;
+        if (kKind == 3) {
+            a = pack_h2(A0, A1) | zero;
+            b = pack_h2(B0, B1) | zero;
+        }
+    }
+    __device__ __forceinline__ int dot(unsigned v, int acc) const
+    {
+        if (kKind == 1) return dp2a_u8<HI, false>(a, v, acc);
+        if (kKind == 2) return dp2a_u8<HI, true>(a, v, acc);
+        if (kKind == 3) return dp2a_u8<HI, true>(b, v, dp2a_u8<HI, true>(a, v, acc));
+        return acc;
+    }
+};
+template <int CR, int CG, int CB, int RP, int GP, int BP> struct YiqDot {
+    static constexpr int c0 = (RP == 0) ? CR : (GP == 0) ? CG : (BP == 0) ? CB : 0;
+    static constexpr int c1 = (RP == 1) ? CR : (GP == 1) ? CG : (BP == 1) ? CB : 0;
+    static constexpr int c2 = (RP == 2) ? CR : (GP == 2) ? CG : (BP == 2) ? CB : 0;
+    static constexpr int c3 = (RP == 3) ? CR : (GP == 3) ? CG : (BP == 3) ? CB : 0;
+    YiqDotPair<c0, c1, false> lo;
+    YiqDotPair<c2, c3, true> hi;
+    __device__ __forceinline__ void init(unsigned zero)
+    {
+        lo.init(zero);
+        hi.init(zero);
+    }
+    __device__ __forceinline__ int operator()(unsigned v) const { return hi.dot(v, lo.dot(v, 0)); }
+};
+
 // FMT / COLOR are launch-uniform (the host groups monitors by them) so byte extraction and the
 // chroma path compile to straight-line code; monitors that do not match return at once.
 template <int FMT, bool COLOR>
@@ -528,6 +574,18 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
         }
     };
 
+    // the rows of the RGB -> YIQ matrix (crt_ntsc.c:308-310) for 4-byte pixels, see YiqDot
+    YiqDot<19595, 38470, 7471, rp, gp, bp> dot_y;
+    YiqDot<39059, -18022, -21103, rp, gp, bp> dot_i;
+    YiqDot<13894, -34275, 20382, rp, gp, bp> dot_q;
+    if (bpp == 4) {
+        const unsigned zero = (unsigned) use_tma >> 8; // (0: the staging mode is 0, 1 or 2)
+        dot_y.init(zero);
+        if (color) {
+            dot_i.init(zero);
+            dot_q.init(zero);
+        }
+    }
     int hy = 0, hi = 0, hq = 0;
     int col_cur = colof(0);
     issue(0, col_cur);
@@ -556,14 +614,12 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
         for (int x4 = 0; x4 < nx; x4 += 4) { // kModSChunk is a multiple of 4: coltab[x4 .. x4 + 3] exist
             unsigned packed = 0;
             int rr[4], gg[4], bb[4];
+            unsigned pix[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) { // all four pixel fetches first, then the dependent arithmetic
                 const int off = coltab[x4 + k];
                 if (bpp == 4) {
-                    const unsigned v = *reinterpret_cast<const unsigned *>(srow + off);
-                    rr[k] = (v >> (8 * rp)) & 0xff;
-                    gg[k] = (v >> (8 * gp)) & 0xff;
-                    bb[k] = (v >> (8 * bp)) & 0xff;
+                    pix[k] = *reinterpret_cast<const unsigned *>(srow + off);
                 } else {
                     rr[k] = srow[off + rp];
                     gg[k] = srow[off + gp];
@@ -572,13 +628,24 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
             }
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int r = rr[k], g = gg[k], b = bb[k];
-                const int fy = (19595 * r + 38470 * g + 7471 * b) >> 14; // crt_ntsc.c:308-310
+                int fy, fi = 0, fq = 0; // crt_ntsc.c:308-310
+                if (bpp == 4) { // the matrix rows as dot products straight on the pixel word: no byte is ever extracted
+                    fy = dot_y(pix[k]) >> 14;
+                    if (color) {
+                        fi = dot_i(pix[k]) >> 14;
+                        fq = dot_q(pix[k]) >> 14;
+                    }
+                } else {
+                    const int r = rr[k], g = gg[k], b = bb[k];
+                    fy = (19595 * r + 38470 * g + 7471 * b) >> 14;
+                    if (color) {
+                        fi = (39059 * r - 18022 * g - 21103 * b) >> 14;
+                        fq = (13894 * r - 34275 * g + 20382 * b) >> 14;
+                    }
+                }
                 hy += wmul(fy - hy, kIirY) >> 11; // iirf, crt_ntsc.c:117-126
                 int sum = hy;
                 if (color) {
-                    const int fi = (39059 * r - 18022 * g - 21103 * b) >> 14;
-                    const int fq = (13894 * r - 34275 * g + 20382 * b) >> 14;
                     hi += wmul(fi - hi, kIirI) >> 11;
                     hq += wmul(fq - hq, kIirQ) >> 11;
                     // (x + xo) & 3 == k: xo, c0 and x4 are multiples of 4

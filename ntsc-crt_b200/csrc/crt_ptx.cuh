@@ -131,6 +131,22 @@ __device__ __forceinline__ void cp_async_16a(unsigned dst_addr, const void *src)
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Two-way dot product of 16-bit by 8-bit values with 32-bit accumulate (IDP.2A): a holds two 16-bit values (signed when
+// SIGNED_A, else unsigned), b four unsigned bytes of which the low (HI = false: bytes 0, 1) or the high pair (bytes 2, 3)
+// takes part:  c + a.h0 * b.byte[0 | 2] + a.h1 * b.byte[1 | 3]  (mod 2^32).
+template <bool HI, bool SIGNED_A> __device__ __forceinline__ int dp2a_u8(unsigned a, unsigned b, int c)
+{
+    int d;
+    if (HI) {
+        if (SIGNED_A) asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+        else asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    } else {
+        if (SIGNED_A) asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+        else asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    }
+    return d;
+}
+
 // Debug builds only (-DCRTX_PHASE_CLOCKS=1, `make custom`): thread `who` of every CTA stamps the SM's cycle counter at the
 // phase boundaries of a kernel, and crtx_debug_clocks() (crtx.cu) hands the table to tools/phase_clocks.py.  Compiled out otherwise.
 #if defined(CRTX_PHASE_CLOCKS) && CRTX_PHASE_CLOCKS

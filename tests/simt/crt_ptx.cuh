@@ -70,6 +70,14 @@ __device__ __forceinline__ void cp_async_16a(unsigned dst_addr, const void *src)
     ::simt::lane_copy16(::simt::g_smem_anchor + (int) dst_addr, src);
 }
 
+template <bool HI, bool SIGNED_A> __device__ __forceinline__ int dp2a_u8(unsigned a, unsigned b, int c)
+{
+    const unsigned b0 = (b >> (HI ? 16 : 0)) & 0xffu, b1 = (b >> (HI ? 24 : 8)) & 0xffu;
+    const unsigned h0 = SIGNED_A ? (unsigned) (int) (short) (a & 0xffffu) : (a & 0xffffu);
+    const unsigned h1 = SIGNED_A ? (unsigned) (int) (short) (a >> 16) : (a >> 16);
+    return (int) ((unsigned) c + h0 * b0 + h1 * b1);
+}
+
 // (kernels run one after the other here: nothing to wait for)
 __device__ __forceinline__ void grid_dep_wait() {}
 __device__ __forceinline__ void grid_dep_launch() {}
