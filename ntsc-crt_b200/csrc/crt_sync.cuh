@@ -154,11 +154,18 @@ __device__ __forceinline__ unsigned noisy_word(const signed char *__restrict__ a
     return noisy_apply(__ldg(reinterpret_cast<const unsigned *>(analog + p)), p, noise, rn0, jump_lo, jump_hi);
 }
 
+// max(b, -127) on four packed samples (the clamp of crt_core.c:363-364 when the noise term is zero: only -128 moves).
+// A byte is 0x80 iff its top bit is set and its low seven bits are zero; (low7 + 0x7f) carries into the top bit iff they are not.
+__device__ __forceinline__ unsigned clamp127_4(unsigned x)
+{
+    const unsigned nz = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return x | ((x & ~nz & 0x80808080u) >> 7);
+}
+
 // FUSED (LCG systems): the kernel reads analog[], applies the noise itself to what it stages, and writes the whole
-// inp[] -- the separate noise pass disappears.  That copy is pure memory traffic and the sync phases are pure latency, so they
-// are interleaved: the signal is cut into chunks of 4 KB (one warp-wide batch of 16-byte loads per thread); every warp takes a
-// chunk and issues its loads BEFORE each sync phase and applies the noise and stores AFTER it, and while the last warp runs the
-// burst-lock chain the others work the remaining chunks off (a counter in shared memory hands them out).
+// inp[] -- the separate noise pass disappears.  That copy is pure memory traffic and the burst-lock chain pure latency on one
+// warp, so they overlap: while the last warp runs the chain the other seven copy, 4 KB chunks handed out by a counter in shared
+// memory (the chain warp joins when it is through).
 // !FUSED (VHS, whose noise comes from rand()): inp[] was written by k_noise_vhs.
 constexpr int kNoiseNB = 8;                                   // 16-byte loads in flight per thread
 constexpr int kNoiseChunkVecs = 32 * kNoiseNB;                // vectors per chunk (one warp, kNoiseNB rounds)
@@ -166,15 +173,21 @@ constexpr int kNoiseChunks = (kNoiseThreads + kNoiseChunkVecs - 1) / kNoiseChunk
 constexpr int kChainWarp = kSyncThreads / 32 - 1;             // the arbiter favours the highest warp id: the serial chain gets it
 constexpr int kBurstSteps = kBurstLen / kCc;                  // burst samples per carrier phase and line (10)
 static_assert(kBurstSteps <= 16 && kBurstLen % kCc == 0, "one 16-byte record per (line, phase)");
+// staging (phase 1) moves 16-byte vectors: a head row is covered by kHeadVecs of them from the 16-byte aligned address at or
+// below its first word, a vsync candidate line by kCandVecs
+constexpr int kHeadVecs = (12 + 4 * kHeadWords + 15) / 16;
+constexpr int kCandVecs = (12 + 4 * kCandWords + 15) / 16;
+constexpr int kStageVecs = kHeadLines * kHeadVecs + 2 * kVsyncWindow * kCandVecs;
+constexpr int kStageBatch = 6;                                // vector loads in flight per thread
 
 template <bool FUSED>
 __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states,
-                                                       LineRec *__restrict__ lines_base,
-                                                       const signed char *__restrict__ analog_base,
-                                                       signed char *__restrict__ inp_base,
-                                                       const Affine *__restrict__ jump_lo,
-                                                       const Affine *__restrict__ jump_hi, int first,
-                                                       int force_generic)
+                                                          LineRec *__restrict__ lines_base,
+                                                          const signed char *__restrict__ analog_base,
+                                                          signed char *__restrict__ inp_base,
+                                                          const Affine *__restrict__ jump_lo,
+                                                          const Affine *__restrict__ jump_hi, int first,
+                                                          int force_generic)
 {
     grid_dep_launch();
     grid_dep_wait(); // (programmatic launch behind the encoder: analog[] must be complete)
@@ -200,103 +213,73 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
         const unsigned w = fetch(p & ~3);
         return (int) (signed char) (w >> (8 * (p & 3)));
     };
-
-    // ---- the noise pass (crt_core.c:346-367), in chunks: analog -> inp, 16 samples per thread per round, 128-bit accesses
-    uint4 nz_in[kNoiseNB];
-    int nz_chunk = kNoiseChunks; // chunk whose loads are in flight (none)
-    auto nz_load = [&](int c) { // whole warp
-        nz_chunk = c;
-        if (!FUSED || c >= kNoiseChunks) return;
-#pragma unroll
-        for (int u = 0; u < kNoiseNB; u++) {
-            const int t = c * kNoiseChunkVecs + u * 32 + lane;
-            nz_in[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (t < kNoiseThreads) nz_in[u] = *reinterpret_cast<const uint4 *>(analog + t * kNoiseVec);
-        }
-    };
-    auto nz_issue = [&]() { // the next chunk nobody has taken
-        if (!FUSED) return;
-        int c = 0;
-        if (lane == 0) c = atomicAdd(&sh.noise_next, 1);
-        nz_load(__shfl_sync(0xffffffffu, c, 0));
-    };
-    auto nz_finish = [&]() {
-        if (!FUSED || nz_chunk >= kNoiseChunks) return;
-#pragma unroll
-        for (int u = 0; u < kNoiseNB; u++) {
-            const int t = nz_chunk * kNoiseChunkVecs + u * 32 + lane;
-            if (t >= kNoiseThreads) continue;
-            const int i0 = t * kNoiseVec;
-            unsigned w[4] = { nz_in[u].x, nz_in[u].y, nz_in[u].z, nz_in[u].w };
-            if (noise == 0) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) w[k] = __vmaxs4(w[k], 0x81818181u);
-            } else {
-                const Affine lo = jump_lo[t % kJumpLo], hi = jump_hi[t / kJumpLo];
-                unsigned rn = (rn0 * hi.mul + hi.add) * lo.mul + lo.add;
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    unsigned o = 0;
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        rn = rn * kLcgMul + kLcgAdd;
-                        int v = (int) (signed char) (w[k] >> (8 * b)) + (wmul((int) ((rn >> 16) & 0xff) - 0x7f, noise) >> 8);
-                        o |= ((unsigned) clampi(v, -127, 127) & 0xffu) << (8 * b);
-                    }
-                    w[k] = o;
-                }
-            }
-            if (i0 + kNoiseVec <= kInputSize) {
-                *reinterpret_cast<uint4 *>(inp_w + i0) = make_uint4(w[0], w[1], w[2], w[3]);
-            } else {
-                for (int b = 0; i0 + b < kInputSize; b++) inp_w[i0 + b] = (signed char) (w[b >> 2] >> (8 * (b & 3)));
-            }
-        }
-        nz_chunk = kNoiseChunks;
-    };
-    if (tid == 0) sh.noise_next = kSyncThreads / 32; // the first round is dealt out statically: chunk = warp
-    nz_load(warp);
+    if (tid == 0) sh.noise_next = 0;
 
     // ---- 1. stage line heads (heads[j][w] = the aligned word at ((j * H - 16) & ~3) + 4w) and the 2W
-    // vsync candidate lines in full (cand[c][w] = aligned words covering line posmod(vsync + c - W)): every word is one
-    // asynchronous copy straight into shared memory, all of them in flight at once (a register-staged copy in batches of 8
-    // spent 16 us here on 9 round trips to memory); the noise is then applied in place.
+    // vsync candidate lines in full (cand[c][w] = aligned words covering line posmod(vsync + c - W)).  The signal is
+    // read in 16-byte vectors, kStageBatch of them in flight per thread (word-sized loads in batches of 8 spent 16 us here,
+    // most of it on index arithmetic), the noise applied, and the four words land at their places in the row.
     unsigned *cand = heads + kHeadLines * kHeadWords; // [2W][kCandWords]
     const int vs_in = st->vsync;
     {
-        constexpr int kHeadTotal = kHeadLines * kHeadWords, kCandTotal = 2 * kVsyncWindow * kCandWords;
         const signed char *from = FUSED ? analog : inp;
-        auto pos_of = [&](int idx) { // where staged word idx comes from
-            if (idx < kHeadTotal) {
-                const int j = idx / kHeadWords, w = idx - j * kHeadWords;
-                return ((j * kHres - kHeadBefore) & ~3) + 4 * w;
+        for (int base = 0; base < kStageVecs; base += kStageBatch * kSyncThreads) {
+            uint4 v[kStageBatch];
+            int pos[kStageBatch], w0[kStageBatch], nw[kStageBatch]; // source position, first word of the row it feeds, row length
+            unsigned *rowp[kStageBatch];
+#pragma unroll
+            for (int b = 0; b < kStageBatch; b++) {
+                const int idx = base + b * kSyncThreads + tid;
+                int start4, i;
+                nw[b] = 0;
+                rowp[b] = heads;
+                if (idx < kHeadLines * kHeadVecs) {
+                    const int j = idx / kHeadVecs;
+                    i = idx - j * kHeadVecs;
+                    start4 = (j * kHres - kHeadBefore) & ~3;
+                    rowp[b] = heads + j * kHeadWords;
+                    nw[b] = kHeadWords;
+                } else {
+                    const int q = idx - kHeadLines * kHeadVecs, c = q / kCandVecs;
+                    i = q - c * kCandVecs;
+                    start4 = (posmod(vs_in + c - kVsyncWindow, kVres) * kHres) & ~3;
+                    rowp[b] = cand + c * kCandWords;
+                    if (idx < kStageVecs) nw[b] = kCandWords;
+                }
+                const int start16 = start4 & ~15; // (arithmetic: also right for the negative start of line 0)
+                pos[b] = start16 + 16 * i;
+                w0[b] = (pos[b] - start4) >> 2; // row word the vector's first word is (-3 .. nw)
+                v[b] = make_uint4(0u, 0u, 0u, 0u);
+                if (nw[b] > 0 && pos[b] >= 0) v[b] = __ldg(reinterpret_cast<const uint4 *>(from + pos[b]));
             }
-            const int q = idx - kHeadTotal, c = q / kCandWords, w = q - c * kCandWords;
-            return (posmod(vs_in + c - kVsyncWindow, kVres) * kHres & ~3) + 4 * w;
-        };
-        for (int idx = tid; idx < kHeadTotal + kCandTotal; idx += kSyncThreads) {
-            const int pos = pos_of(idx);
-            if (pos >= 0) cp_async_4(&heads[idx], from + pos);
-            else heads[idx] = 0u;
-        }
-        cp_async_commit();
-        cp_async_wait<0>(); // (a thread only touches the words it copied itself until the barrier below)
-        if (FUSED) {
-            for (int idx = tid; idx < kHeadTotal + kCandTotal; idx += kSyncThreads) {
-                const int pos = pos_of(idx);
-                if (pos >= 0) heads[idx] = noisy_apply(heads[idx], pos, noise, rn0, jump_lo, jump_hi);
+#pragma unroll
+            for (int b = 0; b < kStageBatch; b++) {
+                if (nw[b] == 0) continue;
+                unsigned w[4] = { v[b].x, v[b].y, v[b].z, v[b].w };
+                if (FUSED && pos[b] >= 0) {
+                    if (noise == 0 && pos[b] + 16 <= kInputSize) {
+#pragma unroll
+                        for (int e = 0; e < 4; e++) w[e] = clamp127_4(w[e]);
+                    } else {
+#pragma unroll 1
+                        for (int e = 0; e < 4; e++) w[e] = noisy_apply(w[e], pos[b] + 4 * e, noise, rn0, jump_lo, jump_hi);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int wi = w0[b] + e;
+                    if (wi >= 0 && wi < nw[b]) rowp[b][wi] = w[e];
+                }
             }
         }
     }
     // |bright| bound of the fast equaliser path (crt_lines.cuh); halved for the PV-1000, whose luma cascade
     // (hf = 80024) is only proven wrap-free up to there
     if (tid == 0) sh.generic = force_generic || abs(cfg.brightness - (kBlack + cfg.black_point)) > (kCc == 5 ? 2048 : 4096);
-    nz_finish();
     __syncthreads();
     phase_mark(0, 1);
 
     // ---- 2. vsync (crt_core.c:379-396): candidate c = line posmod(vsync + c - W); first crossing wins
-    nz_issue();
     constexpr int kSeg = (kHres + 31) / 32;
     for (int c = warp; c < 2 * kVsyncWindow; c += kSyncThreads / 32) {
         const int lstart = posmod(vs_in + c - kVsyncWindow, kVres) * kHres;
@@ -313,7 +296,6 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
         const int j = hit ? __shfl_sync(0xffffffffu, idx, __ffs(hit) - 1) : -1;
         if (lane == 0) sh.vs_found[c] = j;
     }
-    nz_finish();
     __syncthreads();
     phase_mark(0, 2);
     int vs = posmod(vs_in + kVsyncWindow - 1, kVres), jcross = kHres; // "gave up" defaults
@@ -344,7 +326,6 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
     }
     __syncthreads();
     phase_mark(0, 3);
-    nz_issue();
     // Decoded lines of each colour row, in order (skipped lines do not touch ccf).  Warp r compacts row r
     // with ballots, 32 lines per step -- a 240-iteration loop on one thread per row here made every other
     // thread wait ~13 % of the kernel at the next barrier.
@@ -385,14 +366,12 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
         }
         if (!__syncthreads_or(changed)) break;
     }
-    nz_finish();
     phase_mark(0, 4);
 
     // ---- 3b. burst lock (crt_core.c:456-467): ccr = ccr * 127 / 128 + sample, 10 samples per phase per line.
     // First one thread per decoded line gathers the line's 40 burst samples (their position depends on hsync, now known)
     // into shared memory, sorted by carrier phase -- sample t belongs to phase (t + CB_BEG) % CC, step t / CC -- so that the
     // serial chain below is nothing but one 16-byte load per line and the recurrence.
-    nz_issue();
     for (int k = tid; k < kLines; k += kSyncThreads) {
         if (sh.ln[k].beg < 0) continue; // (never on a colour row's list)
         const int hs = sh.hs[k], jl = sh.ln[k].jl;
@@ -408,7 +387,6 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
             for (int t = 0; t < kBurstLen; t++) dst[((t + kCbBeg) % kCc) * 16 + t / kCc] = (signed char) fetch_byte(p + t);
         }
     }
-    nz_finish();
     __syncthreads();
     phase_mark(0, 5);
     if (warp == kChainWarp) {
@@ -419,6 +397,29 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
         int x = chain_lane ? st->ccf[row][phase] : 0;
         const int count = chain_lane ? sh.rowcount[row] : 0;
         const short *rl = sh.rowlist[row];
+        // One line, exactly.  C's x * 127 / 128 truncates towards zero; while the product cannot wrap it equals
+        // x - ((x + (x >= 0 ? 127 : 0)) >> 7): ceil(x / 128) for x >= 0, floor for x < 0.
+        auto exact_line = [&](int v, const int (&b)[kBurstSteps]) {
+            if (abs(v) < (1 << 23)) {
+#pragma unroll
+                for (int q = 0; q < kBurstSteps; q++) v = v - ((v + ((v >= 0) ? 127 : 0)) >> 7) + b[q];
+            } else {
+#pragma unroll
+                for (int q = 0; q < kBurstSteps; q++) v = wadd(wmul(v, 127) / 128, b[q]);
+            }
+            return v;
+        };
+        // The sign of x almost never changes, within a line or from one line to the next, so the rounding bias is carried
+        // INSIDE the running value (z = x + bias) for as long as it holds: a step is then shift, three-input add -- two
+        // dependent instructions -- and nothing but the 10 steps of a line separates it from the next.  Whether a line kept
+        // the sign (and was small enough for the shortcut) is worked out beside the chain and looked at one line LATE, so
+        // that no branch waits for the end of a chain; a line that did not is redone exactly together with its successor.
+        int bias = (x >= 0) ? 127 : 0;
+        int z = x + bias;
+        int pend_k = 0, pend_x = 0, pend_verdict = 0; // the line before the current one: record, starting value, < 0 = redo
+        int pend_bs[kBurstSteps];
+#pragma unroll
+        for (int q = 0; q < kBurstSteps; q++) pend_bs[q] = 0;
         // the line after the current one is loaded while the current one's ten dependent steps run
         int k = (count > 0) ? rl[0] : 0, k1 = (count > 1) ? rl[1] : k;
         uint4 cur = sh.burst[k][phase];
@@ -429,32 +430,40 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
             int bs[kBurstSteps];
 #pragma unroll
             for (int q = 0; q < kBurstSteps; q++) bs[q] = (int) (signed char) (cw[q >> 2] >> (8 * (q & 3)));
-            // C's x * 127 / 128 truncates towards zero.  While the product cannot wrap it equals
-            // x - ((x + (x >= 0 ? 127 : 0)) >> 7): ceil(x / 128) for x >= 0, floor for x < 0.
-            // The sign of x almost never changes within a line, so the rounding bias is taken from the line's first x
-            // and carried INSIDE the running value (z = x + bias): a step is then shift, three-input add -- two
-            // dependent instructions.  The sign bits of the intermediate values are collected off the critical path and
-            // the rare line on which one differs, or whose x is too large for the shortcut, is redone exactly.
-            const int bias = (x >= 0) ? 127 : 0;
-            int z = x + bias, flips = 0;
+            const int xin = z - bias;
+            int zz = z, sgn = 0;
 #pragma unroll
             for (int q = 0; q < kBurstSteps; q++) {
-                flips |= (z - bias) ^ x;
-                z = z - (z >> 7) + bs[q];
+                zz = zz - (zz >> 7) + bs[q];
+                sgn |= (zz - bias) ^ xin;
             }
-            if (abs(x) >= (1 << 23)) {
-#pragma unroll
-                for (int q = 0; q < kBurstSteps; q++) x = wadd(wmul(x, 127) / 128, bs[q]);
-            } else if (flips < 0) {
-#pragma unroll
-                for (int q = 0; q < kBurstSteps; q++) x = x - ((x + ((x >= 0) ? 127 : 0)) >> 7) + bs[q];
+            const int verdict = sgn | ((abs(xin) >= (1 << 23)) ? -1 : 0);
+            if (pend_verdict < 0) { // (rare) the previous line's shortcut did not hold: this line started from a wrong value
+                x = exact_line(pend_x, pend_bs);
+                sh.ccr[pend_k][phase] = x;
+                x = exact_line(x, bs);
+                sh.ccr[k][phase] = x;
+                bias = (x >= 0) ? 127 : 0;
+                z = x + bias;
+                pend_verdict = 0;
             } else {
-                x = z - bias;
+                sh.ccr[k][phase] = zz - bias; // (provisional if this line's verdict says so: rewritten next time round)
+                pend_k = k;
+                pend_x = xin;
+                pend_verdict = verdict;
+#pragma unroll
+                for (int q = 0; q < kBurstSteps; q++) pend_bs[q] = bs[q];
+                z = zz;
             }
-            sh.ccr[k][phase] = x;
             k = k1;
             k1 = k2;
             cur = nxt;
+        }
+        if (pend_verdict < 0) {
+            x = exact_line(pend_x, pend_bs);
+            sh.ccr[pend_k][phase] = x;
+        } else {
+            x = z - bias;
         }
         if (chain_lane) st->ccf[row][phase] = x;
         if (lane == 0) {
@@ -465,12 +474,60 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
         }
         phase_mark(0, 6, kChainWarp * 32);
     }
-    // ---- 3c. the rest of the noise pass, by whoever has nothing else to do (the chain warp joins when it is through)
+    // ---- 3c. the noise pass proper (crt_core.c:346-367): analog -> inp, 16 samples per thread per round, 128-bit accesses,
+    // by the seven warps that would otherwise wait for the chain (which joins them when it is through)
     if (FUSED) {
         for (;;) {
-            nz_issue();
-            if (nz_chunk >= kNoiseChunks) break;
-            nz_finish();
+            int c = 0;
+            if (lane == 0) c = atomicAdd(&sh.noise_next, 1);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= kNoiseChunks) break;
+            const int t0 = c * kNoiseChunkVecs + lane;
+            if (noise == 0 && (c + 1) * kNoiseChunkVecs * kNoiseVec <= kInputSize) { // whole vectors, no noise term: the stock case
+                uint4 in[kNoiseNB];
+#pragma unroll
+                for (int u = 0; u < kNoiseNB; u++) in[u] = *reinterpret_cast<const uint4 *>(analog + (t0 + 32 * u) * kNoiseVec);
+#pragma unroll
+                for (int u = 0; u < kNoiseNB; u++) {
+                    in[u].x = clamp127_4(in[u].x);
+                    in[u].y = clamp127_4(in[u].y);
+                    in[u].z = clamp127_4(in[u].z);
+                    in[u].w = clamp127_4(in[u].w);
+                    *reinterpret_cast<uint4 *>(inp_w + (t0 + 32 * u) * kNoiseVec) = in[u];
+                }
+                continue;
+            }
+#pragma unroll 2
+            for (int u = 0; u < kNoiseNB; u++) {
+                const int t = t0 + 32 * u;
+                if (t >= kNoiseThreads) continue;
+                const int i0 = t * kNoiseVec;
+                const uint4 in = *reinterpret_cast<const uint4 *>(analog + i0);
+                unsigned w[4] = { in.x, in.y, in.z, in.w };
+                if (noise == 0) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) w[e] = clamp127_4(w[e]);
+                } else {
+                    const Affine lo = jump_lo[t % kJumpLo], hi = jump_hi[t / kJumpLo];
+                    unsigned rn = (rn0 * hi.mul + hi.add) * lo.mul + lo.add;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        unsigned o = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; b++) {
+                            rn = rn * kLcgMul + kLcgAdd;
+                            int v = (int) (signed char) (w[e] >> (8 * b)) + (wmul((int) ((rn >> 16) & 0xff) - 0x7f, noise) >> 8);
+                            o |= ((unsigned) clampi(v, -127, 127) & 0xffu) << (8 * b);
+                        }
+                        w[e] = o;
+                    }
+                }
+                if (i0 + kNoiseVec <= kInputSize) {
+                    *reinterpret_cast<uint4 *>(inp_w + i0) = make_uint4(w[0], w[1], w[2], w[3]);
+                } else {
+                    for (int b = 0; i0 + b < kInputSize; b++) inp_w[i0 + b] = (signed char) (w[b >> 2] >> (8 * (b & 3)));
+                }
+            }
         }
         phase_mark(0, 7);
     }

@@ -85,6 +85,30 @@ def test_dropin_ntsc_pixel_formats(fmt):
         check(gpu, ora, ref, "fmt %d call %d" % (fmt, it))
 
 
+@pytest.mark.parametrize("variant", ["ntsc", "nes", "pv1k"])
+def test_burst_lock_from_poked_accumulators(variant):
+    """crt->ccf is a public field (crt_core.h:74-92) and only the encoders re-prime it: accumulators far from the lock
+    value, of either sign, beyond the range in which the kernel's shortcut for x * 127 / 128 holds (2^23) and changing
+    sign on the way down must decay exactly as in the reference (crt_core.c:462-467), call after call"""
+    nes = variant == "nes"
+    img = S.nes_image(seed=11) if nes else S.rand_image(256, 240, seed=11)
+    gpu, ora, ref = trio(variant, 400, 300)
+    run_all((gpu, ora, ref), lambda e: e.set(blend=0, scanlines=1))
+    kw = dict(dot_crawl_offset=1) if nes else dict(format=layout.PIX_BGRA, as_color=1, field=0, frame=0)
+    run_all((gpu, ora, ref), lambda e: e.modulate(img, **kw))
+    vals = [9000000, -9000000, 16000000, -1, -16000000]
+
+    def poke(e):
+        tab = e.crt.ccf if hasattr(e, "crt") else e.mon.ccf
+        for r in range(e.spec.vper):
+            for x in range(e.spec.cc_samples):
+                tab[r][x] = vals[(r + x) % len(vals)] - 12345 * r
+    run_all((gpu, ora, ref), poke)
+    for it in range(3):
+        run_all((gpu, ora, ref), lambda e: e.demodulate(0 if it == 0 else 7))
+        check(gpu, ora, ref, "%s poked ccf, call %d" % (variant, it))
+
+
 def test_dropin_ntsc_knobs_raw_mono_offsets():
     img = S.bars_image(300, 200)
     gpu, ora, ref = trio("ntsc", 512, 448)

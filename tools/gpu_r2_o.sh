@@ -1,0 +1,12 @@
+#!/bin/bash
+set -u
+TAG=${1:-r2o}
+OUT=gpurun_out
+mkdir -p $OUT
+python tools/phase_clocks.py pdl=0 > $OUT/${TAG}_phase_clocks.txt 2>&1
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --config4-frames 0 --set pdl=0 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+python bench.py --steps 20 --warmup 5 --no-cpu-baseline --config4-frames 0 --set pdl=1 > $OUT/${TAG}_bench_pdl.json 2> $OUT/${TAG}_bench_pdl.err
+python -m pytest tests -m gpu -q -x > $OUT/${TAG}_tests.log 2>&1
+echo "pytest exit $?" >> $OUT/${TAG}_tests.log
+cat $OUT/${TAG}_phase_clocks.txt
+tail -3 $OUT/${TAG}_tests.log
