@@ -178,7 +178,7 @@ static_assert(kBurstSteps <= 16 && kBurstLen % kCc == 0, "one 16-byte record per
 constexpr int kHeadVecs = (12 + 4 * kHeadWords + 15) / 16;
 constexpr int kCandVecs = (12 + 4 * kCandWords + 15) / 16;
 constexpr int kStageVecs = kHeadLines * kHeadVecs + 2 * kVsyncWindow * kCandVecs;
-constexpr int kStageBatch = 6;                                // vector loads in flight per thread
+constexpr int kStageBatch = (kStageVecs + kSyncThreads - 1) / kSyncThreads; // vector loads per thread, all in flight at once
 
 template <bool FUSED>
 __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restrict__ cfgs, MonState *__restrict__ states,
@@ -223,53 +223,55 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
     const int vs_in = st->vsync;
     {
         const signed char *from = FUSED ? analog : inp;
-        for (int base = 0; base < kStageVecs; base += kStageBatch * kSyncThreads) {
-            uint4 v[kStageBatch];
-            int pos[kStageBatch], w0[kStageBatch], nw[kStageBatch]; // source position, first word of the row it feeds, row length
-            unsigned *rowp[kStageBatch];
+        // where staged vector idx comes from and which row words it feeds (computed twice -- for the load and again for the
+        // stores -- rather than kept: with every load of the phase in flight at once the registers belong to the data)
+        auto place = [&](int idx, int &pos, int &w0, int &nw) -> unsigned * {
+            int start4, i;
+            unsigned *row;
+            if (idx < kHeadLines * kHeadVecs) {
+                const int j = idx / kHeadVecs;
+                i = idx - j * kHeadVecs;
+                start4 = (j * kHres - kHeadBefore) & ~3;
+                row = heads + j * kHeadWords;
+                nw = kHeadWords;
+            } else {
+                const int q = idx - kHeadLines * kHeadVecs, c = q / kCandVecs;
+                i = q - c * kCandVecs;
+                start4 = (posmod(vs_in + c - kVsyncWindow, kVres) * kHres) & ~3;
+                row = cand + c * kCandWords;
+                nw = (idx < kStageVecs) ? kCandWords : 0;
+            }
+            pos = (start4 & ~15) + 16 * i; // (arithmetic "& ~15": also right for the negative start of line 0)
+            w0 = (pos - start4) >> 2;      // row word the vector's first word is (-3 .. nw)
+            return row;
+        };
+        uint4 v[kStageBatch];
 #pragma unroll
-            for (int b = 0; b < kStageBatch; b++) {
-                const int idx = base + b * kSyncThreads + tid;
-                int start4, i;
-                nw[b] = 0;
-                rowp[b] = heads;
-                if (idx < kHeadLines * kHeadVecs) {
-                    const int j = idx / kHeadVecs;
-                    i = idx - j * kHeadVecs;
-                    start4 = (j * kHres - kHeadBefore) & ~3;
-                    rowp[b] = heads + j * kHeadWords;
-                    nw[b] = kHeadWords;
+        for (int b = 0; b < kStageBatch; b++) {
+            int pos, w0, nw;
+            (void) place(b * kSyncThreads + tid, pos, w0, nw);
+            v[b] = make_uint4(0u, 0u, 0u, 0u);
+            if (nw > 0 && pos >= 0) v[b] = __ldg(reinterpret_cast<const uint4 *>(from + pos));
+        }
+#pragma unroll
+        for (int b = 0; b < kStageBatch; b++) {
+            int pos, w0, nw;
+            unsigned *row = place(b * kSyncThreads + tid, pos, w0, nw);
+            if (nw == 0) continue;
+            unsigned w[4] = { v[b].x, v[b].y, v[b].z, v[b].w };
+            if (FUSED && pos >= 0) {
+                if (noise == 0 && pos + 16 <= kInputSize) {
+#pragma unroll
+                    for (int e = 0; e < 4; e++) w[e] = clamp127_4(w[e]);
                 } else {
-                    const int q = idx - kHeadLines * kHeadVecs, c = q / kCandVecs;
-                    i = q - c * kCandVecs;
-                    start4 = (posmod(vs_in + c - kVsyncWindow, kVres) * kHres) & ~3;
-                    rowp[b] = cand + c * kCandWords;
-                    if (idx < kStageVecs) nw[b] = kCandWords;
+#pragma unroll 1
+                    for (int e = 0; e < 4; e++) w[e] = noisy_apply(w[e], pos + 4 * e, noise, rn0, jump_lo, jump_hi);
                 }
-                const int start16 = start4 & ~15; // (arithmetic: also right for the negative start of line 0)
-                pos[b] = start16 + 16 * i;
-                w0[b] = (pos[b] - start4) >> 2; // row word the vector's first word is (-3 .. nw)
-                v[b] = make_uint4(0u, 0u, 0u, 0u);
-                if (nw[b] > 0 && pos[b] >= 0) v[b] = __ldg(reinterpret_cast<const uint4 *>(from + pos[b]));
             }
 #pragma unroll
-            for (int b = 0; b < kStageBatch; b++) {
-                if (nw[b] == 0) continue;
-                unsigned w[4] = { v[b].x, v[b].y, v[b].z, v[b].w };
-                if (FUSED && pos[b] >= 0) {
-                    if (noise == 0 && pos[b] + 16 <= kInputSize) {
-#pragma unroll
-                        for (int e = 0; e < 4; e++) w[e] = clamp127_4(w[e]);
-                    } else {
-#pragma unroll 1
-                        for (int e = 0; e < 4; e++) w[e] = noisy_apply(w[e], pos[b] + 4 * e, noise, rn0, jump_lo, jump_hi);
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const int wi = w0[b] + e;
-                    if (wi >= 0 && wi < nw[b]) rowp[b][wi] = w[e];
-                }
+            for (int e = 0; e < 4; e++) {
+                const int wi = w0 + e;
+                if (wi >= 0 && wi < nw) row[wi] = w[e];
             }
         }
     }
@@ -409,61 +411,72 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
             }
             return v;
         };
-        // The sign of x almost never changes, within a line or from one line to the next, so the rounding bias is carried
-        // INSIDE the running value (z = x + bias) for as long as it holds: a step is then shift, three-input add -- two
-        // dependent instructions -- and nothing but the 10 steps of a line separates it from the next.  Whether a line kept
-        // the sign (and was small enough for the shortcut) is worked out beside the chain and looked at one line LATE, so
-        // that no branch waits for the end of a chain; a line that did not is redone exactly together with its successor.
-        int bias = (x >= 0) ? 127 : 0;
-        int z = x + bias;
-        int pend_k = 0, pend_x = 0, pend_verdict = 0; // the line before the current one: record, starting value, < 0 = redo
-        int pend_bs[kBurstSteps];
+        // The serial part proper.  floor and ceil differ by a sign: with v = -x while x >= 0 (and the samples subtracted) and
+        // v = x while x < 0, BOTH cases are v -= v >> 7 (v <= 0: floor(v / 128)), then the sample -- a step is shift,
+        // three-input add, two dependent instructions, for as long as v stays <= 0, which it does: the sign of x almost never
+        // changes, within a line or from one line to the next.  Whether a line kept it (every v after a step negative: one
+        // AND per step, beside the chain) and was small enough for the shortcut is looked at one line LATE, so that no branch
+        // waits for the end of a chain; a line that did not is redone exactly together with its successor.
+        auto samples = [&](const uint4 &c, int (&b)[kBurstSteps]) {
+            const unsigned cw[4] = { c.x, c.y, c.z, c.w };
 #pragma unroll
-        for (int q = 0; q < kBurstSteps; q++) pend_bs[q] = 0;
+            for (int q = 0; q < kBurstSteps; q++) b[q] = (int) (signed char) (cw[q >> 2] >> (8 * (q & 3)));
+        };
+        int mode = (x >= 0) ? 1 : 0; // 1: v = -x
+        int v = mode ? -x : x;
+        int pend_k = 0, pend_x = 0, pend_verdict = -1; // the line before the current one: record, starting x, >= 0 = redo
         // the line after the current one is loaded while the current one's ten dependent steps run
         int k = (count > 0) ? rl[0] : 0, k1 = (count > 1) ? rl[1] : k;
         uint4 cur = sh.burst[k][phase];
         for (int n = 0; n < count; n++) {
             const uint4 nxt = sh.burst[k1][phase];
             const int k2 = (n + 2 < count) ? rl[n + 2] : k1;
-            const unsigned cw[4] = { cur.x, cur.y, cur.z, cur.w };
             int bs[kBurstSteps];
+            samples(cur, bs);
+            const int v0 = v;
+            int vv = v, acc = -1;
+            if (mode) {
 #pragma unroll
-            for (int q = 0; q < kBurstSteps; q++) bs[q] = (int) (signed char) (cw[q >> 2] >> (8 * (q & 3)));
-            const int xin = z - bias;
-            int zz = z, sgn = 0;
+                for (int q = 0; q < kBurstSteps; q++) {
+                    vv = vv - (vv >> 7) - bs[q];
+                    acc &= vv;
+                }
+            } else {
 #pragma unroll
-            for (int q = 0; q < kBurstSteps; q++) {
-                zz = zz - (zz >> 7) + bs[q];
-                sgn |= (zz - bias) ^ xin;
+                for (int q = 0; q < kBurstSteps; q++) {
+                    vv = vv - (vv >> 7) + bs[q];
+                    acc &= vv;
+                }
             }
-            const int verdict = sgn | ((abs(xin) >= (1 << 23)) ? -1 : 0);
-            if (pend_verdict < 0) { // (rare) the previous line's shortcut did not hold: this line started from a wrong value
-                x = exact_line(pend_x, pend_bs);
+            const int verdict = (v0 > -(1 << 23)) ? acc : 0; // negative: the shortcut held for this line and holds for the next
+            if (pend_verdict >= 0) { // (rare) the previous line's did not: this line started from a wrong value
+                int pb[kBurstSteps];
+                samples(sh.burst[pend_k][phase], pb);
+                x = exact_line(pend_x, pb);
                 sh.ccr[pend_k][phase] = x;
                 x = exact_line(x, bs);
                 sh.ccr[k][phase] = x;
-                bias = (x >= 0) ? 127 : 0;
-                z = x + bias;
-                pend_verdict = 0;
+                mode = (x >= 0) ? 1 : 0;
+                v = mode ? -x : x;
+                pend_verdict = -1;
             } else {
-                sh.ccr[k][phase] = zz - bias; // (provisional if this line's verdict says so: rewritten next time round)
+                sh.ccr[k][phase] = mode ? -vv : vv; // (provisional if this line's verdict says so: rewritten next time round)
                 pend_k = k;
-                pend_x = xin;
+                pend_x = mode ? -v0 : v0;
                 pend_verdict = verdict;
-#pragma unroll
-                for (int q = 0; q < kBurstSteps; q++) pend_bs[q] = bs[q];
-                z = zz;
+                v = vv;
             }
             k = k1;
             k1 = k2;
             cur = nxt;
         }
-        if (pend_verdict < 0) {
-            x = exact_line(pend_x, pend_bs);
+        if (pend_verdict >= 0) {
+            int pb[kBurstSteps];
+            samples(sh.burst[pend_k][phase], pb);
+            x = exact_line(pend_x, pb);
             sh.ccr[pend_k][phase] = x;
         } else {
-            x = z - bias;
+            x = mode ? -v : v;
         }
         if (chain_lane) st->ccf[row][phase] = x;
         if (lane == 0) {
