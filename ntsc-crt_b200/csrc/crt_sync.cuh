@@ -435,18 +435,17 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
             samples(cur, bs);
             const int v0 = v;
             int vv = v, acc = -1;
-            if (mode) {
+            // (one instruction stream for both directions -- the lanes of a warp differ in theirs: the samples take the sign)
+            const int sg = mode ? -1 : 1;
+            int be[kBurstSteps];
 #pragma unroll
-                for (int q = 0; q < kBurstSteps; q++) {
-                    vv = vv - (vv >> 7) - bs[q];
-                    acc &= vv;
-                }
-            } else {
+            for (int q = 0; q < kBurstSteps; q++) {
+                be[q] = mode ? -bs[q] : bs[q]; // (not "* sg": ptxas folds a multiplication into the chain's add, a third dependent instruction per step)
+            }
 #pragma unroll
-                for (int q = 0; q < kBurstSteps; q++) {
-                    vv = vv - (vv >> 7) + bs[q];
-                    acc &= vv;
-                }
+            for (int q = 0; q < kBurstSteps; q++) {
+                vv = vv - (vv >> 7) + be[q];
+                acc &= vv;
             }
             const int verdict = (v0 > -(1 << 23)) ? acc : 0; // negative: the shortcut held for this line and holds for the next
             if (pend_verdict >= 0) { // (rare) the previous line's did not: this line started from a wrong value
@@ -460,9 +459,9 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
                 v = mode ? -x : x;
                 pend_verdict = -1;
             } else {
-                sh.ccr[k][phase] = mode ? -vv : vv; // (provisional if this line's verdict says so: rewritten next time round)
+                sh.ccr[k][phase] = wmul(vv, sg); // (provisional if this line's verdict says so: rewritten next time round)
                 pend_k = k;
-                pend_x = mode ? -v0 : v0;
+                pend_x = wmul(v0, sg);
                 pend_verdict = verdict;
                 v = vv;
             }
