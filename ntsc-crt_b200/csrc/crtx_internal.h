@@ -49,7 +49,7 @@ struct crtx_ctx {
     int opt_mod_staged = 1;
     int opt_fused_noise = 1;
     int opt_mod_bulk = 1; // encoder staging: 1 = per-lane bulk copies, 0 = per-lane cp.async (A/B switch; measured equal)
-    int opt_pdl = 1;      // programmatic dependent launch of picture / sync / line kernels behind their predecessors (0: ordinary launches)
+    int opt_pdl = 0;      // 1: programmatic dependent launch of picture / sync / line kernels behind their predecessors (measured: no gain -- every kernel is one wave that ends within microseconds across the SMs -- so ordinary launches are the default)
     int opt_lines2 = 1;   // line pass: 1 = k_lines2 where the geometry qualifies (crt_lines2.cuh), 0 = always k_lines (A/B switch)
     int opt_lines2_stage = 2; // k_lines2's signal staging: 2 = three 16-byte cp.async per lane and stage (measured 261 us per 296 fields),
                               // 1 = one bulk copy (TMA) per lane and stage (286 us: 32 serial issues per warp), "tma" 0 = plain loads
