@@ -414,8 +414,8 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
         // The serial part proper.  floor and ceil differ by a sign: with v = -x while x >= 0 (and the samples subtracted) and
         // v = x while x < 0, BOTH cases are v -= v >> 7 (v <= 0: floor(v / 128)), then the sample -- a step is shift,
         // three-input add, two dependent instructions, for as long as v stays <= 0, which it does: the sign of x almost never
-        // changes, within a line or from one line to the next.  Whether a line kept it (every v after a step negative: one
-        // AND per step, beside the chain) and was small enough for the shortcut is looked at one line LATE, so that no branch
+        // changes, within a line or from one line to the next.  Whether a line kept it (the largest v after any step: one
+        // max per step, beside the chain) and was small enough for the shortcut is looked at one line LATE, so that no branch
         // waits for the end of a chain; a line that did not is redone exactly together with its successor.
         auto samples = [&](const uint4 &c, int (&b)[kBurstSteps]) {
             const unsigned cw[4] = { c.x, c.y, c.z, c.w };
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
             int bs[kBurstSteps];
             samples(cur, bs);
             const int v0 = v;
-            int vv = v, acc = -1;
+            int vv = v, top = -0x7fffffff - 1; // (the largest v after any step)
             // (one instruction stream for both directions -- the lanes of a warp differ in theirs: the samples take the sign)
             const int sg = mode ? -1 : 1;
             int be[kBurstSteps];
@@ -445,9 +445,12 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
 #pragma unroll
             for (int q = 0; q < kBurstSteps; q++) {
                 vv = vv - (vv >> 7) + be[q];
-                acc &= vv;
+                top = max(top, vv);
             }
-            const int verdict = (v0 > -(1 << 23)) ? acc : 0; // negative: the shortcut held for this line and holds for the next
+            // negative: the shortcut held for this line (no step started from a v > 0) and holds for the start of the next.
+            // v == 0 is fine -- floor and ceil agree there -- and must be: a carrier phase that samples the burst at its zero
+            // crossing (the NES has one) keeps its accumulator at exactly 0.
+            const int verdict = (top <= 0 && v0 > -(1 << 23)) ? -1 : 0;
             if (pend_verdict >= 0) { // (rare) the previous line's did not: this line started from a wrong value
                 int pb[kBurstSteps];
                 samples(sh.burst[pend_k][phase], pb);
