@@ -24,7 +24,9 @@ struct MonState { // device resident, the persistent decoder state of struct CRT
     int hsync, vsync, rn;
     int field;   // detected field * (ratio / 2) of the last demodulate (crt_core.c:398-407)
     int generic; // last sync pass: some line needs the wrap-exact (generic) equaliser path
-    int pad[2];
+    int track_max; // last sync pass: some line's carrier was large enough for the fast path to hinge on the line's largest sample:
+                   // the next pass measures every signal line's while it copies it (crt_sync.cuh); device-managed
+    int pad;
 };
 
 struct SrcCfg { // host -> device, struct NTSC_SETTINGS

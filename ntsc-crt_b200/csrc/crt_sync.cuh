@@ -64,6 +64,8 @@ struct SyncShared {
     int vs_found[2 * kVsyncWindow]; // per vsync candidate: crossing index or -1
     int generic;
     int noise_next; // next chunk of the noise pass to hand out (FUSED)
+    int need_max;   // some line of this pass needed its signal lines' largest sample
+    int linemax[kVres + 2]; // largest |sample| of each signal line of inp[], measured by the noise pass when MonState::track_max says so
 };
 
 // hsync search of one decoded line given the hsync it enters with (crt_core.c:437-447):
@@ -154,6 +156,20 @@ __device__ __forceinline__ unsigned noisy_word(const signed char *__restrict__ a
     return noisy_apply(__ldg(reinterpret_cast<const unsigned *>(analog + p)), p, noise, rn0, jump_lo, jump_hi);
 }
 
+// |b| of four packed samples in -127 .. 127, and the larger of two such words byte by byte (values <= 127: bit 7 is free to
+// catch the borrow of a per-byte subtraction)
+__device__ __forceinline__ unsigned abs127_4(unsigned x)
+{
+    const unsigned neg = (x >> 7) & 0x01010101u;
+    return (x ^ (neg * 0xffu)) + neg; // ~b + 1 where b < 0: at most 127, no carry leaves the byte
+}
+__device__ __forceinline__ unsigned max127_4(unsigned a, unsigned b)
+{
+    const unsigned ge = (((a | 0x80808080u) - b) >> 7) & 0x01010101u; // 1 where a >= b
+    const unsigned sel = ge * 0xffu;
+    return (a & sel) | (b & ~sel);
+}
+
 // max(b, -127) on four packed samples (the clamp of crt_core.c:363-364 when the noise term is zero: only -128 moves).
 // A byte is 0x80 iff its top bit is set and its low seven bits are zero; (low7 + 0x7f) carries into the top bit iff they are not.
 __device__ __forceinline__ unsigned clamp127_4(unsigned x)
@@ -213,7 +229,13 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
         const unsigned w = fetch(p & ~3);
         return (int) (signed char) (w >> (8 * (p & 3)));
     };
-    if (tid == 0) sh.noise_next = 0;
+    const int track = FUSED ? st->track_max : 0; // measure every signal line's largest sample during the copy (see step 4)
+    if (tid == 0) {
+        sh.noise_next = 0;
+        sh.need_max = 0;
+    }
+    if (track)
+        for (int l = tid; l < kVres + 2; l += kSyncThreads) sh.linemax[l] = 0;
 
     // ---- 1. stage line heads (heads[j][w] = the aligned word at ((j * H - 16) & ~3) + 4w) and the 2W
     // vsync candidate lines in full (cand[c][w] = aligned words covering line posmod(vsync + c - W)).  The signal is
@@ -498,6 +520,15 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c >= kNoiseChunks) break;
             const int t0 = c * kNoiseChunkVecs + lane;
+            // largest |sample| of the vector's 16 bytes (already clamped to +-127), credited to the signal line(s) they lie in
+            auto track_vec = [&](unsigned w0, unsigned w1, unsigned w2, unsigned w3, int i0) {
+                unsigned a = max127_4(max127_4(abs127_4(w0), abs127_4(w1)), max127_4(abs127_4(w2), abs127_4(w3)));
+                a = max127_4(a, a >> 16);
+                const int mx = (int) (max127_4(a, a >> 8) & 0xffu);
+                const int l0 = i0 / kHres, l1 = min(i0 + kNoiseVec - 1, kInputSize - 1) / kHres;
+                if (mx > sh.linemax[l0]) atomicMax(&sh.linemax[l0], mx);
+                if (l1 != l0 && mx > sh.linemax[l1]) atomicMax(&sh.linemax[l1], mx);
+            };
             if (noise == 0 && (c + 1) * kNoiseChunkVecs * kNoiseVec <= kInputSize) { // whole vectors, no noise term: the stock case
                 uint4 in[kNoiseNB];
 #pragma unroll
@@ -509,6 +540,10 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
                     in[u].z = clamp127_4(in[u].z);
                     in[u].w = clamp127_4(in[u].w);
                     *reinterpret_cast<uint4 *>(inp_w + (t0 + 32 * u) * kNoiseVec) = in[u];
+                }
+                if (track) {
+#pragma unroll
+                    for (int u = 0; u < kNoiseNB; u++) track_vec(in[u].x, in[u].y, in[u].z, in[u].w, (t0 + 32 * u) * kNoiseVec);
                 }
                 continue;
             }
@@ -541,7 +576,13 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
                     *reinterpret_cast<uint4 *>(inp_w + i0) = make_uint4(w[0], w[1], w[2], w[3]);
                 } else {
                     for (int b = 0; i0 + b < kInputSize; b++) inp_w[i0 + b] = (signed char) (w[b >> 2] >> (8 * (b & 3)));
+#pragma unroll
+                    for (int e = 0; e < 4; e++) { // (what lies behind inp[] is not signal)
+                        const int left = kInputSize - i0 - 4 * e; // bytes of word e inside inp[]
+                        w[e] = (left <= 0) ? 0u : (left >= 4) ? w[e] : (w[e] & (0xffffffffu >> (8 * (4 - left))));
+                    }
                 }
+                if (track) track_vec(w[0], w[1], w[2], w[3], i0);
             }
         }
         phase_mark(0, 7);
@@ -600,22 +641,31 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
             // The fast equaliser path of k_lines is exact while every chroma input (s * wave) >> 9 stays
             // within +-16383 (crt_lines.cuh).  |s| <= 127 always (the clamp of crt_core.c:363-364).  With the stock
             // saturation that bound already passes and nothing more is needed; only a line whose carrier is large enough
-            // to fail it has its two signal lines scanned for the real maximum -- by this one thread, from the inp[] this
-            // CTA wrote before the barrier above.  (Round 1 tracked the maximum of every 16-byte chunk inside the noise
-            // loop: 13 % of the kernel's instructions for a rare case.)
+            // to fail it needs the real maximum of its two signal lines.  Measuring that costs about as much as the copy itself,
+            // so it is done only for monitors that needed it the last time (MonState::track_max: the NES and NES-RGB
+            // systems at their stock saturation, nothing else at stock settings), inside the copy that runs beside the
+            // burst-lock chain; the first pass of such a monitor scans the two lines here instead, one thread per line, slowly.
             int smax = 127;
             if (FUSED && ((smax * wmax) >> 9) + 1 > 16383) {
-                const int lo = (g.ypos * kHres) & ~15, hi = min((g.ypos + 2) * kHres, kInputSize);
-                int mx = 0;
-                for (int i = lo; i < hi; i++) mx = max(mx, abs((int) inp_w[i]));
-                smax = mx;
+                sh.need_max = 1; // (the next pass of this monitor measures while it copies)
+                if (track) {
+                    smax = max(sh.linemax[g.ypos], sh.linemax[g.ypos + 1]);
+                } else {
+                    const int lo = (g.ypos * kHres) & ~15, hi = min((g.ypos + 2) * kHres, kInputSize);
+                    int mx = 0;
+                    for (int i = lo; i < hi; i++) mx = max(mx, abs((int) inp_w[i]));
+                    smax = mx;
+                }
             }
             if (((smax * wmax) >> 9) + 1 > 16383) sh.generic = 1;
         }
         lines[k] = rec;
     }
     __syncthreads();
-    if (tid == 0) st->generic = sh.generic;
+    if (tid == 0) {
+        st->generic = sh.generic;
+        if (FUSED) st->track_max = sh.need_max;
+    }
     phase_mark(0, 14);
 }
 

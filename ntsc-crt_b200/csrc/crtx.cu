@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cstddef>
 #include <vector>
 
 #include "crt_kernels.cuh"
@@ -940,8 +941,11 @@ int crtx_set_state(crtx_ctx *ctx, int first, int count, const crtx_state *s, voi
         tmp[i].vsync = s[i].vsync;
         tmp[i].rn = s[i].rn;
     }
-    // (pageable source: staged before the call returns, so `tmp` may go out of scope)
-    CUDA_TRY(cudaMemcpyAsync(ctx->d_state + first, tmp.data(), sizeof(MonState) * count, cudaMemcpyHostToDevice, st));
+    // only the caller's part of each record travels (a strided copy): behind it sit outputs of the sync pre-pass and
+    // MonState::track_max, which the device manages across calls.  (pageable source: staged before the call returns, so
+    // `tmp` may go out of scope)
+    CUDA_TRY(cudaMemcpy2DAsync(ctx->d_state + first, sizeof(MonState), tmp.data(), sizeof(MonState), offsetof(MonState, field),
+                               (size_t) count, cudaMemcpyHostToDevice, st));
     return 0;
 }
 
