@@ -243,6 +243,9 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
     // most of it on index arithmetic), the noise applied, and the four words land at their places in the row.
     unsigned *cand = heads + kHeadLines * kHeadWords; // [2W][kCandWords]
     const int vs_in = st->vsync;
+    // candidate c is line posmod(vsync + c - W, VRES) (crt->vsync is the caller's to poke: any value); one modulo per thread
+    const int cand0 = posmod(vs_in - kVsyncWindow, kVres);
+    auto cand_line = [&](int c) { return (cand0 + c >= kVres) ? cand0 + c - kVres : cand0 + c; };
     {
         const signed char *from = FUSED ? analog : inp;
         // where staged vector idx comes from and which row words it feeds (computed twice -- for the load and again for the
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
             } else {
                 const int q = idx - kHeadLines * kHeadVecs, c = q / kCandVecs;
                 i = q - c * kCandVecs;
-                start4 = (posmod(vs_in + c - kVsyncWindow, kVres) * kHres) & ~3;
+                start4 = (cand_line(c) * kHres) & ~3;
                 row = cand + c * kCandWords;
                 nw = (idx < kStageVecs) ? kCandWords : 0;
             }
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
     // ---- 2. vsync (crt_core.c:379-396): candidate c = line posmod(vsync + c - W); first crossing wins
     constexpr int kSeg = (kHres + 31) / 32;
     for (int c = warp; c < 2 * kVsyncWindow; c += kSyncThreads / 32) {
-        const int lstart = posmod(vs_in + c - kVsyncWindow, kVres) * kHres;
+        const int lstart = cand_line(c) * kHres;
         const signed char *sig = reinterpret_cast<const signed char *>(cand + c * kCandWords) + (lstart & 3);
         const int b0 = lane * kSeg, b1 = min(kHres, b0 + kSeg);
         int sum = 0;
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
     int vs = posmod(vs_in + kVsyncWindow - 1, kVres), jcross = kHres; // "gave up" defaults
     for (int c = 0; c < 2 * kVsyncWindow; c++) {
         if (sh.vs_found[c] >= 0) {
-            vs = posmod(vs_in + c - kVsyncWindow, kVres);
+            vs = cand_line(c);
             jcross = sh.vs_found[c];
             break;
         }
