@@ -6,10 +6,9 @@
 // line, and a row may keep part of its previous content.  That does not fit the launch-uniform pixel loop of
 // k_lines; this option (off in the reference's stock build) gets its own, functional-not-tuned kernels:
 //   k_bloom        CTA per monitor: line sums in parallel (warp per line), the 240-step energy chain on one thread
-//   k_lines_bloom  a warp per group of lines: lanes 3 g .. 3 g + 2 run the Y / I / Q equalisers of the group's line g
-//                  (same code, per-lane coefficients), then all lanes resample, convert and store the pixels of one line
-//                  after the other, and replicate duplicated rows whole (crt_core.c:662-664 copies the complete row,
-//                  including what this line did not write).
+//   k_lines_bloom  warp per line: lanes 0..2 run the Y / I / Q equalisers (same code, per-lane coefficients),
+//                  then all lanes resample, convert and store pixels, and replicate duplicated rows whole
+//                  (crt_core.c:662-664 copies the complete row, including what this line did not write).
 #pragma once
 
 #include "crt_lines.cuh"
@@ -65,17 +64,10 @@ __global__ void __launch_bounds__(256) k_bloom(const MonCfg *__restrict__ cfgs, 
     }
 }
 
-// Lines in flight per CTA = what fits next to each other in shared memory as three rows of 32-bit values; a warp takes kBloomG
-// consecutive decoded lines and runs their 3 x kBloomG equalisers side by side, lane 3 g + c = component c of its line g
-// (round 1 ran ONE line per warp: 3 busy lanes through the 753 dependent steps that are 94 % of this kernel).
+constexpr int kBloomWarps = 8;
 constexpr int kBloomRow = kAvLen + 1;                       // ints per component and line
-constexpr int kBloomFit = (200 * 1024) / (3 * kBloomRow * 4);
-constexpr int kBloomWarps = kBloomFit >= 20 ? 4 : (kBloomFit >= 9 ? 3 : 2);
-constexpr int kBloomG = (kBloomFit / kBloomWarps) > 10 ? 10 : (kBloomFit / kBloomWarps);
-constexpr int kBloomCtaLines = kBloomWarps * kBloomG;
-constexpr int kBloomSmem = kBloomCtaLines * 3 * kBloomRow * 4; // Y, I, Q rows of the lines in flight
-constexpr int kBloomGroups = (kLines + kBloomCtaLines - 1) / kBloomCtaLines;
-static_assert(kBloomG >= 1 && 3 * kBloomG <= 32 && kBloomSmem <= 227 * 1024, "a warp's lines fit its lanes and shared memory");
+constexpr int kBloomSmem = kBloomWarps * 3 * kBloomRow * 4; // Y, I, Q rows of the lines in flight
+constexpr int kBloomGroups = (kLines + kBloomWarps - 1) / kBloomWarps;
 
 __global__ void __launch_bounds__(kBloomWarps * 32) k_lines_bloom(const MonCfg *__restrict__ cfgs,
                                                                  const LineRec *__restrict__ lines_base,
@@ -86,57 +78,41 @@ __global__ void __launch_bounds__(kBloomWarps * 32) k_lines_bloom(const MonCfg *
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = first + blockIdx.y;
-    const int kbase = (blockIdx.x * kBloomWarps + warp) * kBloomG; // first decoded line of this warp
-    if (kbase >= kLines || geo.bpp == 0 || geo.outw <= 0) return;
-    const MonCfg cfg = cfgs[m];
-    int *comp = reinterpret_cast<int *>(smem_raw) + warp * kBloomG * 3 * kBloomRow;
-    const unsigned scan_r = (unsigned) ((kAvLen - 1) << 12);
-    const int f_hi = (int) (scan_r >> 12); // crt_core.c:524-525: sample AV_LEN - 1 is NOT filtered
-
-    // this lane's line (lanes 3 g .. 3 g + 2 share it) and whether it is decoded in this launch
-    const int g = lane / 3, ch = lane - 3 * g;
-    const int k = kbase + g;
-    LineRec rec;
-    rec.pos = 0; rec.wave0 = rec.wave1 = 0; rec.beg = -1; rec.end = -1; rec.hsync = 0; rec.pad0 = rec.pad1 = 0;
-    BloomLine bl;
-    bl.dx = 0;
-    bl.scan_l = 0;
-    const bool mine = g < kBloomG && k < kLines;
-    if (mine) {
-        rec = lines_base[(size_t) m * kLines + k];
-        bl = bloom_base[(size_t) m * kLines + k];
-    }
-    const bool active = mine && rec.beg >= 0 && k >= geo.line_lo && k < geo.line_hi
+    const int k = blockIdx.x * kBloomWarps + warp; // decoded line of this warp
+    if (k >= kLines || geo.bpp == 0 || geo.outw <= 0) return;
+    const LineRec rec = lines_base[(size_t) m * kLines + k];
+    const bool active = rec.beg >= 0 && k >= geo.line_lo && k < geo.line_hi
                      && (geo.pass == -1 || (geo.pass == -2 ? rec.pad1 != 0 : rec.pad0 == geo.pass));
-    const int f_lo = (int) ((unsigned) bl.scan_l >> 12);
+    if (!active) return; // (warp-uniform)
+    const MonCfg cfg = cfgs[m];
+    const BloomLine bl = bloom_base[(size_t) m * kLines + k];
+    int *comp = reinterpret_cast<int *>(smem_raw) + warp * 3 * kBloomRow;
+    int *yy = comp, *ii = comp + kBloomRow, *qq = comp + 2 * kBloomRow;
+    const signed char *sig = inp_base + (size_t) m * kSignalBytes + rec.pos;
+    const unsigned scan_l = (unsigned) bl.scan_l, scan_r = (unsigned) ((kAvLen - 1) << 12);
+    const int f_lo = (int) (scan_l >> 12), f_hi = (int) (scan_r >> 12); // crt_core.c:524-525: sample AV_LEN - 1 is NOT filtered
 
-    // ---- equalisers (crt_core.c:534-543, literal wrap-exact form): component 0 = Y, 1 = I, 2 = Q; every line starts
-    // at its own first sample (the state before it is zero), the loop at the earliest of them
-    {
-        int i_lo = active ? f_lo : f_hi;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) i_lo = min(i_lo, __shfl_xor_sync(0xffffffffu, i_lo, d));
-        const int lf = ch == 0 ? kEqYlf : ch == 1 ? kEqIlf : kEqQlf;
-        const int hf = ch == 0 ? kEqYhf : ch == 1 ? kEqIhf : kEqQhf;
-        const int g1 = ch == 0 ? kEqYg1 : 65536;
-        const int g2 = ch == 0 ? kEqYg2 : ch == 1 ? kEqIg2 : 0;
+    // ---- equalisers (crt_core.c:534-543, literal wrap-exact form): lane 0 = Y, 1 = I, 2 = Q
+    if (lane < 3 && f_lo >= 0) {
+        const int lf = lane == 0 ? kEqYlf : lane == 1 ? kEqIlf : kEqQlf;
+        const int hf = lane == 0 ? kEqYhf : lane == 1 ? kEqIhf : kEqQhf;
+        const int g1 = lane == 0 ? kEqYg1 : 65536;
+        const int g2 = lane == 0 ? kEqYg2 : lane == 1 ? kEqIg2 : 0;
         const int bright = cfg.brightness - (kBlack + cfg.black_point);
-        const int off = ch == 2 ? 3 : 0; // wave[(i + 0) & 3] feeds I, wave[(i + 3) & 3] feeds Q
-        int w5[5] = { 0, 0, 0, 0, 0 };     // five carrier phases (PV-1000): this lane's table, waveI or waveQ
+        const int off = lane == 2 ? 3 : 0; // wave[(i + 0) & 3] feeds I, wave[(i + 3) & 3] feeds Q
+        int w5[5] = { 0, 0, 0, 0, 0 };      // five carrier phases (PV-1000): this lane's table, waveI or waveQ
         if (kCc == 5) {
             int wi5[5], wq5[5];
             pv1k_waves(rec.wave0, rec.wave1, cfg.hue, cfg.saturation, wi5, wq5);
 #pragma unroll
-            for (int q = 0; q < 5; q++) w5[q] = (ch == 2) ? wq5[q] : wi5[q];
+            for (int q = 0; q < 5; q++) w5[q] = (lane == 2) ? wq5[q] : wi5[q];
         }
         int l0 = 0, l1 = 0, l2 = 0, l3 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0, s1 = 0, s2 = 0, s3 = 0;
-        const signed char *sig = inp_base + (size_t) m * kSignalBytes + rec.pos;
-        int *dst = comp + (g * 3 + ch) * kBloomRow;
-        for (int i = i_lo; i < f_hi; i++) {
-            if (!active || i < f_lo) continue;
+        int *dst = comp + lane * kBloomRow;
+        for (int i = f_lo; i < f_hi; i++) {
             const int s = sig[i];
             int in;
-            if (ch == 0) {
+            if (lane == 0) {
                 in = s + bright;
             } else if (kCc == 5) { // waveI[i % 5] / waveQ[i % 5] (crt_core.c:545-549)
                 const int ph = i % 5;
@@ -162,51 +138,42 @@ __global__ void __launch_bounds__(kBloomWarps * 32) k_lines_bloom(const MonCfg *
             s2 = s1;
             s1 = in;
             const int r = wadd(wadd(r0, r1), r2);
-            dst[i] = ch == 0 ? wmul(r, 16) : (r >> 3);
+            dst[i] = lane == 0 ? wmul(r, 16) : (r >> 3);
         }
         // never filtered with bloom on, and the reference's static scratch array holds its initial zero there
-        if (active) dst[kAvLen - 1] = 0;
+        dst[kAvLen - 1] = 0;
     }
     __syncwarp();
 
-    // ---- pixels (crt_core.c:551-664), one line after the other, the whole warp on each
+    // ---- pixels (crt_core.c:551-664)
     const int bpp = geo.bpp, pitch = geo.outw * bpp;
     int rp, gp, bp;
     fmt_positions(geo.out_format, rp, gp, bp);
     const int ap = (bpp == 4) ? (6 - rp - gp - bp) : -1; // the remaining byte of a 4-byte pixel
-#pragma unroll 1
-    for (int gg = 0; gg < kBloomG; gg++) {
-        const int src = 3 * gg; // a lane that holds line gg's records
-        if (!__shfl_sync(0xffffffffu, (int) active, src)) continue; // (warp-uniform)
-        const int l_beg = __shfl_sync(0xffffffffu, rec.beg, src), l_end = __shfl_sync(0xffffffffu, rec.end, src);
-        const int l_dx = __shfl_sync(0xffffffffu, bl.dx, src);
-        const unsigned scan_l = (unsigned) __shfl_sync(0xffffffffu, bl.scan_l, src);
-        const int *yy = comp + gg * 3 * kBloomRow, *ii = yy + kBloomRow, *qq = yy + 2 * kBloomRow;
-        unsigned char *row = cfg.out + (size_t) l_beg * pitch;
-        const int nrows = max(1, l_end - cfg.scanlines - l_beg); // crt_core.c:662-664
-        for (int j = lane; j < geo.outw; j += 32) {
-            const unsigned pos = scan_l + (unsigned) j * (unsigned) l_dx;
-            const bool wr = pos < scan_r; // the written pixels are a prefix of the row (crt_core.c:555)
-            unsigned char *p = row + (size_t) j * bpp;
-            unsigned char px[4];
-            px[0] = p[0]; px[1] = p[1]; px[2] = p[2]; px[3] = (bpp == 4) ? p[3] : 0;
-            if (wr) {
-                const int s = (int) (pos >> 12), R = (int) (pos & 0xfffu), L = 0xfff - R;
-                unsigned rgb = yiq_pixel(yy[s], ii[s], qq[s], yy[s + 1], ii[s + 1], qq[s + 1], R, L, cfg.contrast);
-                if (geo.blend) { // crt_core.c:584-609
-                    const unsigned old = (unsigned) px[rp] << 16 | (unsigned) px[gp] << 8 | (unsigned) px[bp];
-                    rgb = ((rgb & 0xfefeffu) >> 1) + ((old & 0xfefeffu) >> 1);
-                }
-                px[rp] = (unsigned char) (rgb >> 16);
-                px[gp] = (unsigned char) (rgb >> 8);
-                px[bp] = (unsigned char) rgb;
-                if (ap >= 0) px[ap] = 0xff;
+    unsigned char *row = cfg.out + (size_t) rec.beg * pitch;
+    const int nrows = max(1, rec.end - cfg.scanlines - rec.beg); // crt_core.c:662-664
+    for (int j = lane; j < geo.outw; j += 32) {
+        const unsigned pos = scan_l + (unsigned) j * (unsigned) bl.dx;
+        const bool wr = f_lo >= 0 && pos < scan_r; // the written pixels are a prefix of the row (crt_core.c:555)
+        unsigned char *p = row + (size_t) j * bpp;
+        unsigned char px[4];
+        px[0] = p[0]; px[1] = p[1]; px[2] = p[2]; px[3] = (bpp == 4) ? p[3] : 0;
+        if (wr) {
+            const int s = (int) (pos >> 12), R = (int) (pos & 0xfffu), L = 0xfff - R;
+            unsigned rgb = yiq_pixel(yy[s], ii[s], qq[s], yy[s + 1], ii[s + 1], qq[s + 1], R, L, cfg.contrast);
+            if (geo.blend) { // crt_core.c:584-609
+                const unsigned old = (unsigned) px[rp] << 16 | (unsigned) px[gp] << 8 | (unsigned) px[bp];
+                rgb = ((rgb & 0xfefeffu) >> 1) + ((old & 0xfefeffu) >> 1);
             }
-            for (int r = wr ? 0 : 1; r < nrows; r++) { // row `beg` itself only where the line wrote
-                unsigned char *d = p + (size_t) r * pitch;
-                d[0] = px[0]; d[1] = px[1]; d[2] = px[2];
-                if (bpp == 4) d[3] = px[3];
-            }
+            px[rp] = (unsigned char) (rgb >> 16);
+            px[gp] = (unsigned char) (rgb >> 8);
+            px[bp] = (unsigned char) rgb;
+            if (ap >= 0) px[ap] = 0xff;
+        }
+        for (int r = wr ? 0 : 1; r < nrows; r++) { // row `beg` itself only where the line wrote
+            unsigned char *d = p + (size_t) r * pitch;
+            d[0] = px[0]; d[1] = px[1]; d[2] = px[2];
+            if (bpp == 4) d[3] = px[3];
         }
     }
 }
