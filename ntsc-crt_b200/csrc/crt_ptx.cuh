@@ -131,14 +131,6 @@ __device__ __forceinline__ void cp_async_16a(unsigned dst_addr, const void *src)
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// The hardware slot of the calling warp on its SM; slot % 4 is the scheduler (SM sub-partition) that issues for it.
-__device__ __forceinline__ unsigned hw_warp_id()
-{
-    unsigned w;
-    asm volatile("mov.u32 %0, %%warpid;" : "=r"(w));
-    return w;
-}
-
 // Two-way dot product of 16-bit by 8-bit values with 32-bit accumulate (IDP.2A): a holds two 16-bit values (signed when
 // SIGNED_A, else unsigned), b four unsigned bytes of which the low (HI = false: bytes 0, 1) or the high pair (bytes 2, 3)
 // takes part:  c + a.h0 * b.byte[0 | 2] + a.h1 * b.byte[1 | 3]  (mod 2^32).

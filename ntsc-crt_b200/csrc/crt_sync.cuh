@@ -65,7 +65,6 @@ struct SyncShared {
     int generic;
     int noise_next; // next chunk of the noise pass to hand out (FUSED)
     int need_max;   // some line of this pass needed its signal lines' largest sample
-    unsigned hwid[kSyncThreads / 32]; // hardware slot of each warp (see the choice of the chain warp)
     int linemax[kVres + 2]; // largest |sample| of each signal line of inp[], measured by the noise pass when MonState::track_max says so
 };
 
@@ -187,6 +186,7 @@ __device__ __forceinline__ unsigned clamp127_4(unsigned x)
 constexpr int kNoiseNB = 8;                                   // 16-byte loads in flight per thread
 constexpr int kNoiseChunkVecs = 32 * kNoiseNB;                // vectors per chunk (one warp, kNoiseNB rounds)
 constexpr int kNoiseChunks = (kNoiseThreads + kNoiseChunkVecs - 1) / kNoiseChunkVecs;
+constexpr int kChainWarp = kSyncThreads / 32 - 1;             // the arbiter favours the highest warp id: the serial chain gets it
 constexpr int kBurstSteps = kBurstLen / kCc;                  // burst samples per carrier phase and line (10)
 static_assert(kBurstSteps <= 16 && kBurstLen % kCc == 0, "one 16-byte record per (line, phase)");
 // staging (phase 1) moves 16-byte vectors: a head row is covered by kHeadVecs of them from the 16-byte aligned address at or
@@ -236,7 +236,6 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
     }
     if (track)
         for (int l = tid; l < kVres + 2; l += kSyncThreads) sh.linemax[l] = 0;
-    if (lane == 0) sh.hwid[warp] = hw_warp_id();
 
     // ---- 1. stage line heads (heads[j][w] = the aligned word at ((j * H - 16) & ~3) + 4w) and the 2W
     // vsync candidate lines in full (cand[c][w] = aligned words covering line posmod(vsync + c - W)).  The signal is
@@ -417,25 +416,7 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
     }
     __syncthreads();
     phase_mark(0, 5);
-    // Which warp runs the serial chain.  Two CTAs share an SM, and a chain is ~50 alu-pipe instructions per line on ONE
-    // scheduler's half-rate pipe: with both CTAs' chains on the same scheduler (warp 7 of each: slots 7 and 15, both
-    // scheduler 3) the two took turns -- 220 cycles per line.  So the CTA in the lower slots takes its warp on scheduler 3 and
-    // the one in the upper slots its warp on scheduler 2; within a scheduler the higher slot, which the arbiter favours.
-    int chain_warp = kSyncThreads / 32 - 1;
-    {
-        unsigned lowest = sh.hwid[0];
-#pragma unroll
-        for (int w = 1; w < kSyncThreads / 32; w++) lowest = min(lowest, sh.hwid[w]);
-        const unsigned want = ((lowest >> 3) & 1u) ? 2u : 3u;
-        int best = -1;
-#pragma unroll
-        for (int w = 0; w < kSyncThreads / 32; w++)
-            if ((sh.hwid[w] & 3u) == want && (int) sh.hwid[w] > best) {
-                best = (int) sh.hwid[w];
-                chain_warp = w;
-            }
-    }
-    if (warp == chain_warp) {
+    if (warp == kChainWarp) {
         // Lane = kCc * row + phase walks its own colour row's lines (at most 5 x 5 = 25 lanes).
         static_assert(kCc * kVper <= 32, "one lane per (colour row, phase)");
         const bool chain_lane = lane < kCc * kVper;
@@ -531,7 +512,7 @@ __global__ void __launch_bounds__(kSyncThreads, 2) k_sync(const MonCfg *__restri
             st->field = field;
             if (!kIsVhs) st->rn = (int) (rn0 * kLcgField.mul + kLcgField.add); // crt_core.c:367
         }
-        phase_mark(0, 6, chain_warp * 32);
+        phase_mark(0, 6, kChainWarp * 32);
     }
     // ---- 3c. the noise pass proper (crt_core.c:346-367): analog -> inp, 16 samples per thread per round, 128-bit accesses,
     // by the seven warps that would otherwise wait for the chain (which joins them when it is through)

@@ -70,7 +70,6 @@ __device__ __forceinline__ void cp_async_16a(unsigned dst_addr, const void *src)
     ::simt::lane_copy16(::simt::g_smem_anchor + (int) dst_addr, src);
 }
 
-__device__ __forceinline__ unsigned hw_warp_id() { return threadIdx.x >> 5; }
 template <bool HI, bool SIGNED_A> __device__ __forceinline__ int dp2a_u8(unsigned a, unsigned b, int c)
 {
     const unsigned b0 = (b >> (HI ? 16 : 0)) & 0xffu, b1 = (b >> (HI ? 24 : 8)) & 0xffu;
