@@ -144,5 +144,35 @@ int main()
                    mode != 1 ? m1 * 1e3 / (frames * reps) : 0.0, mode != 0 ? down / m2 / 1e6 : 0.0, mode != 0 ? m2 * 1e3 / (frames * reps) : 0.0);
         }
     }
+    { // the other pairing: source rows by the copy engine (five strided 2-D copies per frame, one row of every 13-row period
+      // each: 240 of 624 rows) while the decoded rows leave by the SM scatter (384 of 624 rows per frame)
+        const int pitch = row_bytes;
+        cudaEvent_t a, b, c;
+        cudaEventCreate(&a); cudaEventCreate(&b); cudaEventCreate(&c);
+        const int starts[5] = { 0, 2, 5, 7, 10 };
+        for (int mode = 0; mode < 3; mode++) {
+            Job sc = { d_b, h_b, frames * 384, n16, n16, n16 * 624 / 384, 148 * 8, 8, 0 };
+            cudaDeviceSynchronize();
+            cudaEventRecord(a, s1);
+            cudaStreamWaitEvent(s2, a, 0);
+            const int reps = 6;
+            for (int r = 0; r < reps; r++) {
+                if (mode != 1) run_kernel(s1, &sc);
+                if (mode != 0)
+                    for (int f = 0; f < frames; f++)
+                        for (int q = 0; q < 5; q++)
+                            cudaMemcpy2DAsync((char *) d_a + (size_t) f * img + (size_t) starts[q] * pitch, (size_t) 13 * pitch,
+                                              (char *) h_a + (size_t) f * img + (size_t) starts[q] * pitch, (size_t) 13 * pitch,
+                                              (size_t) pitch, 48, cudaMemcpyHostToDevice, s2);
+            }
+            cudaEventRecord(b, s1); cudaEventRecord(c, s2);
+            cudaDeviceSynchronize();
+            float m1, m2; cudaEventElapsedTime(&m1, a, b); cudaEventElapsedTime(&m2, a, c);
+            const double down = (double) frames * 384 * row_bytes * reps, up = (double) frames * 240 * row_bytes * reps;
+            printf("pairing B mode %d (%s): D2H rows by SM scatter %7.2f GB/s (%.1f us/frame)   H2D rows by 2-D copy engine %7.2f GB/s (%.1f us/frame)\n", mode,
+                   mode == 0 ? "SM scatter alone" : mode == 1 ? "2-D copies alone" : "both at once", mode != 1 ? down / m1 / 1e6 : 0.0,
+                   mode != 1 ? m1 * 1e3 / (frames * reps) : 0.0, mode != 0 ? up / m2 / 1e6 : 0.0, mode != 0 ? m2 * 1e3 / (frames * reps) : 0.0);
+        }
+    }
     return 0;
 }
