@@ -398,7 +398,7 @@ constexpr int kModSSmem = 8 * kModSWarpSmem + 8 * 2 * 8;
 __host__ __device__ __forceinline__ bool mod_staged_ok(const SrcCfg &s, int destw)
 {
     const int bpp = bpp_of(s.format);
-    if (bpp == 0 || destw <= 0 || s.w <= 0 || kCc != 4) return false; // (four samples per carrier period only)
+    if (bpp == 0 || destw <= 0 || s.w <= 0 || (kCc != 4 && kCc != 5)) return false; // (four or five samples per carrier period)
     // widest source span of a chunk: ceil(32 * w / destw) + 1 pixels, plus 15 bytes of alignment
     const long long span = ((long long) kModSChunk * s.w + destw - 1) / destw + 1;
     return span * bpp + 15 + 16 <= kModSSpan && s.w <= 65535
@@ -493,6 +493,17 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
         desth = min(s.h, kDestH);
     }
     if (desth <= 0 || s.h <= 0) return;
+    // five carrier phases (PV-1000): the phase of a sample is not a compile-time constant of the 4-sample inner step, so the
+    // tables live in shared memory, [I | Q][colour row][phase], as in the gather kernel
+    __shared__ int mtab[2][kVper][kCc];
+    if (kCc == 5) {
+        if (threadIdx.x < kCc * kVper) {
+            int b;
+            enc_tables(s, (int) threadIdx.x / kCc, (int) threadIdx.x % kCc, b, mtab[0][threadIdx.x / kCc][threadIdx.x % kCc],
+                       mtab[1][threadIdx.x / kCc][threadIdx.x % kCc]);
+        }
+        __syncthreads(); // (every return above is block-uniform)
+    }
     const int y0 = warp * 32;
     if (y0 >= desth) return;
     const int nlines = min(32, desth - y0);
@@ -610,6 +621,7 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
         __syncwarp();
         const unsigned char *srow = stage + (c & 1) * 32 * kModSRow + lane * kModSRow
                                   + (int) (reinterpret_cast<uintptr_t>(rowp + (size_t) f0 * bpp) & 15);
+        int p5 = c0 % 5; // carrier phase of the chunk's first sample (five-phase systems)
 #pragma unroll 1
         for (int x4 = 0; x4 < nx; x4 += 4) { // kModSChunk is a multiple of 4: coltab[x4 .. x4 + 3] exist
             unsigned packed = 0;
@@ -648,8 +660,12 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
                 if (color) {
                     hi += wmul(fi - hi, kIirI) >> 11;
                     hq += wmul(fq - hq, kIirQ) >> 11;
-                    // (x + xo) & 3 == k: xo, c0 and x4 are multiples of 4
-                    sum += (wmul(hi, mI[k]) >> 4) + (wmul(hq, mQ[k]) >> 4);
+                    if (kCc == 5) { // (x + xo) % 5 == x % 5: xo is a multiple of 5; p5 walks 0 .. 4 along the line
+                        sum += (wmul(hi, mtab[0][crow][p5]) >> 4) + (wmul(hq, mtab[1][crow][p5]) >> 4);
+                        p5 = (p5 == 4) ? 0 : p5 + 1;
+                    } else { // (x + xo) & 3 == k: xo, c0 and x4 are multiples of 4
+                        sum += (wmul(hi, mI[k]) >> 4) + (wmul(hq, mQ[k]) >> 4);
+                    }
                 }
                 int ire = ire0 + (wmul(sum, white) >> 10);
                 ire = __vimin_s32_relu(ire, 110); // clamp to 0..110 in one instruction
@@ -663,7 +679,18 @@ __global__ void __launch_bounds__(256, 2) k_mod_picture_rgb_staged(const SrcCfg 
             const int j = lane & 15;
             const unsigned short *ob = reinterpret_cast<const unsigned short *>(obuf) + (lane >> 4) * (2 * kModSOutPitch) + j;
             signed char *dst = analog + (c0 + xo) + (y0 + (lane >> 4) + yo) * kHres + 2 * j;
-            if (nx == kModSChunk) { // full chunk: no edge tests
+            // the pair is 2-byte aligned when xo is even: always with four carrier phases (xo is a multiple of 4 and CRT_HRES is
+            // even), not with the PV-1000's five (xo is a multiple of 5); dst moves by whole pairs of lines, so its parity stays
+            if (kCc == 5 && (reinterpret_cast<uintptr_t>(dst) & 1)) {
+                for (int l2 = 0; l2 < nlines; l2 += 2) {
+                    if (l2 + (lane >> 4) < nlines) {
+                        const unsigned short two = ob[l2 * (2 * kModSOutPitch)];
+                        if (2 * j < nx) dst[0] = (signed char) (two & 0xff);
+                        if (2 * j + 1 < nx) dst[1] = (signed char) (two >> 8);
+                    }
+                    dst += 2 * kHres;
+                }
+            } else if (nx == kModSChunk) { // full chunk: no edge tests
 #pragma unroll 4
                 for (int l2 = 0; l2 + 1 < nlines; l2 += 2) {
                     *reinterpret_cast<unsigned short *>(dst) = ob[l2 * (2 * kModSOutPitch)];

@@ -371,7 +371,7 @@ int modulate_launch(crtx_ctx *ctx, int first, int count, const SrcCfg *src, cuda
 #else
     int extra = 0;
     // (the staged kernel steps four samples per carrier period: not for the PV-1000's five, which takes the gather kernel)
-    const bool staged = ctx->opt_mod_staged && kCc == 4;
+    const bool staged = ctx->opt_mod_staged && (kCc == 4 || kCc == 5);
     // The gather kernel only runs for sources the staged one cannot take (their span does not fit a stage row), or for all of
     // them when staging is off: the host can tell (mod_takes is a pure function of the settings), so the usual call saves a launch.
     bool gather = !staged;

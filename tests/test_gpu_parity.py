@@ -109,6 +109,23 @@ def test_burst_lock_from_poked_accumulators(variant):
         check(gpu, ora, ref, "%s poked ccf, call %d" % (variant, it))
 
 
+@pytest.mark.parametrize("fmt", [layout.PIX_BGRA, layout.PIX_RGB, layout.PIX_ARGB])
+def test_pv1k_staged_encoder_offsets_and_formats(fmt):
+    """the PV-1000 takes the staged encoder since round 2 (five carrier phases from shared-memory tables, crt_pv1k.c:262-318):
+    x offsets of either parity (the picture then starts on an odd or an even sample: 2-byte or byte stores), raw and scaled
+    pictures, colour and monochrome, walking dot-crawl rows, 3- and 4-byte sources"""
+    rgb = S.rand_image(300, 200, bpp=3, seed=21)
+    img = S.pack_rgb(rgb, fmt)
+    gpu, ora, ref = trio("pv1k", 512, 384)
+    run_all((gpu, ora, ref), lambda e: e.set(blend=0, scanlines=0, saturation=12))
+    cases = [dict(xoffset=0, raw=0, as_color=1), dict(xoffset=1, raw=0, as_color=1), dict(xoffset=3, raw=1, as_color=1),
+             dict(xoffset=5, raw=0, as_color=0), dict(xoffset=7, raw=1, as_color=1), dict(xoffset=2, raw=0, as_color=1)]
+    for it, kw in enumerate(cases):
+        run_all((gpu, ora, ref), lambda e: e.modulate(img, format=fmt, field=it & 1, frame=0, dot_crawl_offset=it, **kw))
+        run_all((gpu, ora, ref), lambda e: e.demodulate(2 * it))
+        check(gpu, ora, ref, "pv1k fmt %d case %d %r" % (fmt, it, kw))
+
+
 def test_dropin_ntsc_knobs_raw_mono_offsets():
     img = S.bars_image(300, 200)
     gpu, ora, ref = trio("ntsc", 512, 448)
