@@ -126,6 +126,37 @@ def test_pv1k_staged_encoder_offsets_and_formats(fmt):
         check(gpu, ora, ref, "pv1k fmt %d case %d %r" % (fmt, it, kw))
 
 
+@pytest.mark.parametrize("variant", ["ntsc", "nes"])
+def test_poked_signal_extremes(variant):
+    """crt->analog is the caller's to poke (crt_main.c:430 clears it): -128 -- which no encoder writes, and which the
+    noise pass alone turns into -127 (crt_core.c:363-364) -- and +-127 / +-126, scattered over the picture area of a dozen
+    lines and the last bytes of the buffer (the copy's partial 16-byte vector), at noise 0 (the packed-byte clamp of
+    crt_sync.cuh) and with noise"""
+    nes = variant == "nes"
+    img = S.nes_image(seed=3) if nes else S.rand_image(256, 240, seed=3)
+    gpu, ora, ref = trio(variant, 400, 300)
+    run_all((gpu, ora, ref), lambda e: e.set(blend=0, scanlines=0))
+    kw = dict(dot_crawl_offset=2) if nes else dict(format=layout.PIX_BGRA, as_color=1, field=0, frame=0)
+    n = gpu.spec.input_size
+    h = gpu.spec.hres
+    rng = np.random.default_rng(17)
+    pos = np.concatenate([line * h + rng.integers(300, 800, size=60) for line in range(40, 220, 15)] + [np.arange(n - 21, n)])
+    vals = rng.choice(np.array([-128, -128, -127, 127, 126, -126, 0], dtype=np.int8), size=pos.size)
+
+    def poke(e):
+        if hasattr(e, "crt"):
+            buf = np.frombuffer(e.crt, dtype=np.int8, count=n, offset=0)  # analog[] leads the struct (crt_core.h:74-92)
+        else:
+            buf = np.ctypeslib.as_array(e.mon.analog, shape=(n,)).view(np.int8)
+        buf[pos] = vals
+    for it, noise in enumerate((0, 9, 0)):
+        run_all((gpu, ora, ref), lambda e: e.modulate(img, **kw))
+        run_all((gpu, ora, ref), poke)
+        run_all((gpu, ora, ref), lambda e: e.demodulate(noise))
+        check(gpu, ora, ref, "%s poked analog, call %d (noise %d)" % (variant, it, noise))
+    assert (gpu.inp >= -127).all() and (gpu.inp[pos[vals == -128]] == -127).any()
+
+
 def test_dropin_ntsc_knobs_raw_mono_offsets():
     img = S.bars_image(300, 200)
     gpu, ora, ref = trio("ntsc", 512, 448)

@@ -212,3 +212,23 @@ def test_interpreter_selftest(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:]
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0 and "selftest ok" in r.stdout, r.stdout[-2000:]
+
+
+def test_packed_byte_helpers(tmp_path):
+    """tests/simt/helpers_check.cpp: clamp127_4 / abs127_4 / max127_4 (crt_sync.cuh: max(b, -127), |b| and the larger of two
+    values on four packed bytes with plain integer instructions) against their byte-wise definitions, exhaustively per pair
+    of bytes and positions.  Picture content never produces the -128 that clamp127_4 exists for, and a too small maximum
+    would only show on a monitor at the edge of the fast equaliser's range: both get their own check here."""
+    import subprocess
+    from simt import build as B  # noqa: F401  (the prepared copy of the product sources: tests/simt/_build/src)
+    here = os.path.join(S.ROOT, "tests", "simt")
+    src = os.path.join(here, "_build", "src")
+    B.prepare(src)
+    exe = str(tmp_path / "helpers_check")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fwrapv", "-fno-strict-aliasing", "-Wno-unknown-pragmas", "-Wno-attributes",
+           "-I" + src, "-I" + os.path.join(S.ROOT, "include"), "-DCRT_SYSTEM=0",
+           os.path.join(here, "helpers_check.cpp"), os.path.join(src, "simt_runtime.cpp"), "-o", exe]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "helpers ok" in r.stdout, r.stdout[-2000:]
